@@ -1,0 +1,1056 @@
+// Host side of libaudiolcm_b200: weight preparation, per-(B,T) plans (buffers + kernel list +
+// CUDA graph) and the C-ABI declared in include/audiolcm_b200.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/audiolcm_b200.h"
+#include "act1d.cuh"
+#include "common.cuh"
+#include "conv.cuh"
+#include "misc_kernels.cuh"
+
+using namespace alcm;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err = "";
+struct AlcmError : std::runtime_error {
+  int code;
+  AlcmError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+#define CUDA_CHECK(expr)                                                                                   \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess)                                                                                 \
+      throw AlcmError(ALCM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                                         std::to_string(__LINE__) + ")");                                  \
+  } while (0)
+#define REQUIRE(cond, msg)                                              \
+  do {                                                                  \
+    if (!(cond)) throw AlcmError(ALCM_ERR_INVALID, std::string(msg));   \
+  } while (0)
+
+template <class F>
+static int guarded(F&& f) {
+  try {
+    f();
+    return ALCM_OK;
+  } catch (const AlcmError& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return ALCM_ERR_INTERNAL;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ ctx
+struct alcm_ctx {
+  int device = 0;
+  int sm_count = 148;
+};
+
+struct Arena {  // owns device allocations
+  std::vector<void*> ptrs;
+  size_t total = 0;
+  void* alloc(size_t bytes, bool zero = true) {
+    void* p = nullptr;
+    bytes = std::max<size_t>(bytes, 16);
+    CUDA_CHECK(cudaMalloc(&p, bytes));
+    if (zero) CUDA_CHECK(cudaMemset(p, 0, bytes));
+    ptrs.push_back(p);
+    total += bytes;
+    return p;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+    total = 0;
+  }
+  ~Arena() { release(); }
+};
+
+struct PlaneT {
+  uint8_t* p = nullptr;
+  int B = 0, C = 0, T = 0, esz = 4;
+  PlaneGeom g{0, 0, 0};
+  size_t bytes = 0;
+  float* f() const { return reinterpret_cast<float*>(p); }
+};
+
+static PlaneT make_planes(Arena& ar, int B, int C, int T, int esz) {
+  PlaneT t;
+  t.B = B; t.C = C; t.T = T; t.esz = esz;
+  const int E = 16 / esz;
+  t.g.nchunk = round_up(C, 16) / E;
+  t.g.pad = kPad;
+  t.g.Tp = T + 2 * kPad;
+  t.bytes = (size_t)B * t.g.nchunk * t.g.Tp * 16;
+  t.p = static_cast<uint8_t*>(ar.alloc(t.bytes, true));
+  return t;
+}
+
+static inline int opnd_esz(int prec) { return prec == ALCM_PREC_BF16 ? 2 : 4; }
+
+// ------------------------------------------------------------------------------------------ conv layers
+enum ConvKind { KIND_CONV = 0, KIND_CONVT = 1, KIND_UPCONV3 = 2 };
+
+struct ConvLayer {
+  int Cin = 0, Cout = 0, nphase = 1, ntaps = 1;
+  int tap_off[kMaxPhase][kMaxTaps];
+  int min_off[kMaxPhase];
+  int span = 0;
+  float* weff = nullptr;   // fp32 [nphase][ntaps][Cout][Cin]   (kept only for ALCM_PREC_FP32)
+  uint8_t* wpack = nullptr;
+  size_t phase_stride = 0;
+  float* bias = nullptr;   // padded
+  int NT = 0, n_tiles = 0, kchunks = 0, kblk = 0, nkb = 0, tmem_cols = 0, w_stages = 0;
+  uint32_t idesc = 0, smem = 0;
+  int prec = 0;
+};
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+// w: folded weight on device (Conv1d [Cout,Cin,K] or ConvTranspose1d [Cin,Cout,K]); bias may be null
+static ConvLayer prepare_conv(Arena& ar, int prec, ConvKind kind, const float* w, const float* bias, int Cout, int Cin, int K,
+                              int dil_or_stride) {
+  ConvLayer L;
+  L.Cin = Cin; L.Cout = Cout; L.prec = prec;
+  WeffRecipe rc;
+  memset(&rc, 0xff, sizeof(rc));  // all -1
+  if (kind == KIND_CONV) {
+    const int d = dil_or_stride;
+    REQUIRE(K >= 1 && K <= kMaxTaps && (K % 2) == 1, "conv1d: odd kernel size <= 11 required");
+    const int pad = (K * d - d) / 2;
+    REQUIRE(pad <= kPad, "conv1d: padding exceeds plane halo");
+    L.nphase = 1; L.ntaps = K;
+    for (int j = 0; j < K; ++j) { L.tap_off[0][j] = j * d - pad; rc.src_k[0][j][0] = j; }
+  } else if (kind == KIND_CONVT) {
+    const int u = dil_or_stride;
+    REQUIRE(K == 2 * u && (u % 2) == 0 && u <= kMaxPhase, "conv_transpose1d: kernel 2u, even stride u<=4, padding u/2 only");
+    L.nphase = u; L.ntaps = 2;
+    for (int r = 0; r < u; ++r) {
+      const int s = r + u / 2;
+      if (s < u) { L.tap_off[r][0] = 0; rc.src_k[r][0][0] = s; L.tap_off[r][1] = -1; rc.src_k[r][1][0] = s + u; }
+      else       { L.tap_off[r][0] = 1; rc.src_k[r][0][0] = s - u; L.tap_off[r][1] = 0; rc.src_k[r][1][0] = s; }
+    }
+  } else {
+    REQUIRE(K == 3, "upsample conv: k=3 only");
+    L.nphase = 2; L.ntaps = 2;
+    L.tap_off[0][0] = -1; rc.src_k[0][0][0] = 0;
+    L.tap_off[0][1] = 0;  rc.src_k[0][1][0] = 1; rc.src_k[0][1][1] = 2;
+    L.tap_off[1][0] = 0;  rc.src_k[1][0][0] = 0; rc.src_k[1][0][1] = 1;
+    L.tap_off[1][1] = 1;  rc.src_k[1][1][0] = 2;
+  }
+  rc.nphase = L.nphase; rc.ntaps = L.ntaps;
+  L.span = 0;
+  for (int p = 0; p < L.nphase; ++p) {
+    int mn = L.tap_off[p][0], mx = L.tap_off[p][0];
+    for (int j = 1; j < L.ntaps; ++j) { mn = std::min(mn, L.tap_off[p][j]); mx = std::max(mx, L.tap_off[p][j]); }
+    L.min_off[p] = mn;
+    L.span = std::max(L.span, mx - mn);
+  }
+  // effective weights
+  const size_t nweff = (size_t)L.nphase * L.ntaps * Cout * Cin;
+  Arena tmp;
+  Arena& weff_owner = (prec == ALCM_PREC_FP32) ? ar : tmp;
+  L.weff = static_cast<float*>(weff_owner.alloc(nweff * 4, false));
+  weff_kernel<<<(unsigned)std::min<size_t>((nweff + 255) / 256, 4096), 256>>>(w, L.weff, rc, Cout, Cin, K, kind == KIND_CONVT);
+  CUDA_CHECK(cudaGetLastError());
+
+  if (prec == ALCM_PREC_FP32) {
+    L.bias = nullptr;
+    if (bias) {
+      L.bias = static_cast<float*>(ar.alloc((size_t)Cout * 4, false));
+      CUDA_CHECK(cudaMemcpy(L.bias, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice));
+    }
+    CUDA_CHECK(cudaDeviceSynchronize());
+    return L;
+  }
+  const int E = (prec == ALCM_PREC_BF16) ? 8 : 4;
+  const int cout_pad = round_up(Cout, 16);
+  int nt_pref = env_int("ALCM_NT", 128);
+  if (cout_pad <= 256 && (cout_pad <= nt_pref || cout_pad % nt_pref != 0)) L.NT = cout_pad;
+  else L.NT = nt_pref;
+  REQUIRE(L.NT % 16 == 0 && L.NT >= 16 && L.NT <= 256, "bad N tile");
+  L.n_tiles = (cout_pad + L.NT - 1) / L.NT;
+  L.tmem_cols = 32;
+  while (L.tmem_cols < L.NT) L.tmem_cols *= 2;
+  L.kchunks = round_up(Cin, 16) / E;
+  L.kblk = 0;
+  if (L.kchunks <= 12) L.kblk = L.kchunks;
+  else for (int d = 8; d >= 2; d -= 2) if (L.kchunks % d == 0) { L.kblk = d; break; }
+  REQUIRE(L.kblk >= 2 && L.kblk % 2 == 0, "bad k-block");
+  L.nkb = L.kchunks / L.kblk;
+  L.idesc = umma_idesc(prec == ALCM_PREC_BF16 ? 1 : 2, L.NT);
+  const uint32_t budget = (uint32_t)env_int("ALCM_SMEM_BUDGET", 100 * 1024);
+  const uint32_t a2 = 2u * L.kblk * (kTileM + L.span) * 16, ws = (uint32_t)L.kblk * L.NT * 16;
+  int S = (budget > a2 + 256) ? (int)((budget - a2 - 256) / ws) : 0;
+  S = std::max(2, std::min(8, S));
+  S = std::min(S, std::max(2, L.nkb * L.ntaps));
+  L.w_stages = S;
+  L.smem = conv_smem_layout(L.kblk, L.span, L.NT, S).total;
+  REQUIRE(L.smem <= 227 * 1024, "conv tile does not fit shared memory");
+  L.phase_stride = (size_t)L.n_tiles * L.nkb * L.ntaps * L.kblk * L.NT * 16;
+  L.wpack = static_cast<uint8_t*>(ar.alloc(L.phase_stride * L.nphase, false));
+  const size_t units = L.phase_stride * L.nphase / 16;
+  const unsigned blocks = (unsigned)std::min<size_t>((units + 255) / 256, 8192);
+  if (E == 8) pack_w_kernel<8><<<blocks, 256>>>(L.weff, L.wpack, L.nphase, L.ntaps, Cout, Cin, L.NT, L.n_tiles, L.kblk, L.nkb);
+  else pack_w_kernel<4><<<blocks, 256>>>(L.weff, L.wpack, L.nphase, L.ntaps, Cout, Cin, L.NT, L.n_tiles, L.kblk, L.nkb);
+  CUDA_CHECK(cudaGetLastError());
+  L.bias = static_cast<float*>(ar.alloc((size_t)L.n_tiles * L.NT * 4, true));
+  if (bias) CUDA_CHECK(cudaMemcpy(L.bias, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice));
+  CUDA_CHECK(cudaDeviceSynchronize());
+  L.weff = nullptr;  // tmp arena frees it
+  return L;
+}
+
+// weight_norm fold into a temp buffer (dim0 x inner)
+static float* fold_wn(Arena& tmp, const float* g, const float* v, int dim0, int inner) {
+  float* w = static_cast<float*>(tmp.alloc((size_t)dim0 * inner * 4, false));
+  wn_fold_kernel<<<dim0, 256>>>(v, g, w, inner);
+  CUDA_CHECK(cudaGetLastError());
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------ ops
+struct Op {
+  int cls;
+  double flops, bytes;
+  std::function<void(cudaStream_t)> fn;
+};
+
+static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const float* res, int M, float scale, int accum,
+                        cudaStream_t st) {
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x.p; a.xg = x.g;
+  a.bias = L.bias;
+  a.out = out.f(); a.og = out.g;
+  a.res = res;
+  a.M = M;
+  a.ostride = L.nphase; a.nphase = L.nphase; a.ntaps = L.ntaps;
+  memcpy(a.tap_off, L.tap_off, sizeof(a.tap_off));
+  memcpy(a.min_off, L.min_off, sizeof(a.min_off));
+  a.span = L.span;
+  a.Cin = L.Cin; a.Cout = L.Cout;
+  a.scale = scale; a.accum = accum;
+  a.desc_swap = env_int("ALCM_DESC_SWAP", 0);
+  const int B = x.B;
+  if (L.prec == ALCM_PREC_FP32) {
+    a.w = reinterpret_cast<const uint8_t*>(L.weff);
+    dim3 grid((M + kSimtTM - 1) / kSimtTM, (L.Cout + kSimtTN - 1) / kSimtTN, B * L.nphase);
+    conv_simt_kernel<<<grid, 256, 0, st>>>(a);
+  } else {
+    a.w = L.wpack;
+    a.kchunks = L.kchunks; a.kblk = L.kblk; a.nkb = L.nkb;
+    a.NT = L.NT; a.n_tiles = L.n_tiles; a.tmem_cols = L.tmem_cols; a.w_stages = L.w_stages;
+    a.idesc = L.idesc; a.w_phase_stride = L.phase_stride;
+    dim3 grid((M + kTileM - 1) / kTileM, L.n_tiles, B * L.nphase);
+    if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0><<<grid, 192, L.smem, st>>>(a);
+    else conv_umma_kernel<1><<<grid, 192, L.smem, st>>>(a);
+  }
+}
+
+struct OpList {
+  std::vector<Op> ops;
+  void conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const PlaneT* res, float scale = 1.f, int accum = 0) {
+    const int M = x.T;  // rows per batch item are input time steps (== output steps / nphase)
+    REQUIRE(x.esz == opnd_esz(L.prec), "conv: operand dtype mismatch");
+    REQUIRE(out.esz == 4 && out.T == x.T * L.nphase, "conv: bad output planes");
+    REQUIRE(x.g.nchunk * (16 / x.esz) >= L.Cin && out.g.nchunk * 4 >= L.Cout, "conv: channel mismatch");
+    Op op;
+    op.cls = ALCM_CLS_CONV;
+    op.flops = 2.0 * L.Cin * L.Cout * L.ntaps * L.nphase * (double)M * x.B;
+    op.bytes = (double)x.B * x.T * ((double)L.Cin * x.esz + (double)L.Cout * L.nphase * 4 * (res ? 2 : 1));
+    const float* rp = res ? res->f() : nullptr;
+    ConvLayer Lc = L;
+    PlaneT xc = x, oc = out;
+    op.fn = [=](cudaStream_t st) { launch_conv(Lc, xc, oc, rp, M, scale, accum, st); };
+    ops.push_back(op);
+  }
+  void act(const PlaneT& x, const PlaneT& out, const float* ea, const float* ib, int round_tf32) {
+    REQUIRE(x.esz == 4 && x.T == out.T && x.B == out.B, "act: bad planes");
+    ActArgs a;
+    a.x = x.f(); a.xg = x.g; a.out = out.p; a.og = out.g; a.ea = ea; a.ib = ib; a.T = x.T; a.round_tf32 = round_tf32;
+    const int B = x.B, T = x.T;
+    const int nch = out.g.nchunk, oesz = out.esz;
+    Op op;
+    op.cls = ALCM_CLS_ACT;
+    op.flops = 0;
+    op.bytes = (double)B * T * round_up(x.C, 16) * (4.0 + oesz);
+    op.fn = [=](cudaStream_t st) {
+      if (oesz == 4) act1d_kernel<1, 512><<<dim3((T + 511) / 512, nch, B), kActThreads, 0, st>>>(a);
+      else act1d_kernel<2, 256><<<dim3((T + 255) / 256, nch, B), kActThreads, 0, st>>>(a);
+    };
+    ops.push_back(op);
+  }
+  // fp32 planes -> operand planes (bf16 / tf32-rounded)
+  void cast(const PlaneT& x, const PlaneT& out) {
+    REQUIRE(x.esz == 4 && x.T == out.T, "cast: bad planes");
+    const int B = x.B, T = x.T, nch = out.g.nchunk, oesz = out.esz;
+    PlaneT xc = x, oc = out;
+    Op op;
+    op.cls = ALCM_CLS_MISC; op.flops = 0; op.bytes = (double)B * T * round_up(x.C, 16) * (4.0 + oesz);
+    op.fn = [=](cudaStream_t st) {
+      dim3 grid((T + 255) / 256, nch, B);
+      if (oesz == 2) cast_planes_kernel<8><<<grid, 256, 0, st>>>(xc.f(), xc.g, oc.p, oc.g, T);
+      else cast_planes_kernel<4><<<grid, 256, 0, st>>>(xc.f(), xc.g, oc.p, oc.g, T);
+    };
+    ops.push_back(op);
+  }
+  void run(cudaStream_t st) const {
+    for (const Op& o : ops) o.fn(st);
+  }
+};
+
+static void launch_pack(const float* in, const PlaneT& out, int C, int T, float mul, int prec, cudaStream_t st) {
+  dim3 grid((T + 255) / 256, out.g.nchunk, out.B);
+  if (out.esz == 2) pack_cf_kernel<8><<<grid, 256, 0, st>>>(in, out.p, out.g, C, T, mul, 0);
+  else pack_cf_kernel<4><<<grid, 256, 0, st>>>(in, out.p, out.g, C, T, mul, prec == ALCM_PREC_TF32);
+}
+static void launch_unpack(const PlaneT& in, float* out, int C, int T, cudaStream_t st) {
+  dim3 grid((T + 255) / 256, (C + 3) / 4, in.B);
+  unpack_cf_kernel<<<grid, 256, 0, st>>>(in.f(), in.g, out, C, T);
+}
+
+struct GraphExec {
+  cudaGraphExec_t exec = nullptr;
+  ~GraphExec() { if (exec) cudaGraphExecDestroy(exec); }
+};
+
+static bool use_graph() { return env_int("ALCM_GRAPH", 1) != 0; }
+
+static void capture_graph(const OpList& ol, GraphExec& ge) {
+  cudaStream_t cs;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (e == cudaSuccess) {
+    ol.run(cs);
+    e = cudaStreamEndCapture(cs, &graph);
+  }
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&ge.exec, graph, 0);
+  if (graph) cudaGraphDestroy(graph);
+  cudaStreamDestroy(cs);
+  if (e != cudaSuccess) {
+    ge.exec = nullptr;
+    throw AlcmError(ALCM_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ vocoder
+struct SnakeP { float* ea; float* ib; };
+
+struct AmpBlock {
+  ConvLayer c1[3], c2[3];
+  SnakeP a[6];
+};
+struct VocStage {
+  ConvLayer up;
+  std::vector<AmpBlock> blocks;
+  int C, u;
+};
+
+struct VocPlan {
+  Arena ar;
+  int B, T, Tout;
+  PlaneT mel_in;   // operand planes
+  PlaneT post_in;  // fp32 planes feeding conv_post
+  OpList ol;
+  GraphExec ge;
+};
+
+struct alcm_vocoder {
+  alcm_ctx* ctx;
+  alcm_bigvgan_cfg cfg;
+  int prec;
+  Arena war;  // weights
+  ConvLayer conv_pre;
+  std::vector<VocStage> stages;
+  SnakeP act_post;
+  float* post_w = nullptr;  // [7][Cpad] tap-major fp32
+  float post_bias = 0.f;
+  int post_C = 0, hop = 1;
+  std::map<std::pair<int, int>, std::unique_ptr<VocPlan>> plans;
+};
+
+static SnakeP make_snake(Arena& ar, const float* alpha, const float* beta, int C) {
+  const int Cpad = round_up(C, 16);
+  SnakeP s;
+  s.ea = static_cast<float*>(ar.alloc((size_t)Cpad * 4, false));
+  s.ib = static_cast<float*>(ar.alloc((size_t)Cpad * 4, false));
+  snake_params_kernel<<<(Cpad + 127) / 128, 128>>>(alpha, beta, s.ea, s.ib, C, Cpad);
+  CUDA_CHECK(cudaGetLastError());
+  return s;
+}
+
+static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
+  auto key = std::make_pair(B, T);
+  auto it = v->plans.find(key);
+  if (it != v->plans.end()) return it->second.get();
+  std::unique_ptr<VocPlan> pl(new VocPlan());
+  VocPlan& P = *pl;
+  P.B = B; P.T = T;
+  const int prec = v->prec, oe = opnd_esz(prec);
+  const int rtf = (prec == ALCM_PREC_TF32);
+  const int nk = v->cfg.num_kernels;
+  P.mel_in = make_planes(P.ar, B, v->cfg.num_mels, T, oe);
+  int C = v->cfg.upsample_initial_channel, Tc = T;
+  PlaneT xprev = make_planes(P.ar, B, C, Tc, 4);
+  P.ol.conv(v->conv_pre, P.mel_in, xprev, nullptr);
+  for (size_t i = 0; i < v->stages.size(); ++i) {
+    const VocStage& S = v->stages[i];
+    PlaneT up_in = xprev;
+    if (prec == ALCM_PREC_BF16) {
+      up_in = make_planes(P.ar, B, C, Tc, 2);
+      P.ol.cast(xprev, up_in);
+    }
+    C = S.C; Tc *= S.u;
+    PlaneT X = make_planes(P.ar, B, C, Tc, 4), R = make_planes(P.ar, B, C, Tc, 4), Y = make_planes(P.ar, B, C, Tc, 4);
+    PlaneT XS = make_planes(P.ar, B, C, Tc, 4), A = make_planes(P.ar, B, C, Tc, oe);
+    P.ol.conv(S.up, up_in, X, nullptr);
+    for (int j = 0; j < nk; ++j) {
+      const AmpBlock& bk = S.blocks[j];
+      const PlaneT* cur = &X;
+      for (int l = 0; l < 3; ++l) {  // models.py:72-81
+        P.ol.act(*cur, A, bk.a[2 * l].ea, bk.a[2 * l].ib, rtf);
+        P.ol.conv(bk.c1[l], A, Y, nullptr);
+        P.ol.act(Y, A, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, rtf);
+        if (l < 2) {
+          P.ol.conv(bk.c2[l], A, R, cur);
+          cur = &R;
+        } else {  // x = xs / num_kernels, models.py:190-196, folded into the last conv of each block
+          P.ol.conv(bk.c2[l], A, XS, cur, 1.0f / nk, j > 0);
+        }
+      }
+    }
+    xprev = XS;
+  }
+  P.post_in = make_planes(P.ar, B, C, Tc, 4);
+  P.ol.act(xprev, P.post_in, v->act_post.ea, v->act_post.ib, 0);
+  P.Tout = Tc;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  if (use_graph()) capture_graph(P.ol, P.ge);
+  VocPlan* raw = pl.get();
+  v->plans[key] = std::move(pl);
+  return raw;
+}
+
+static void voc_run(alcm_vocoder* v, VocPlan* P, const float* mel, const PlaneT* mel_planes, float* wav, cudaStream_t st) {
+  // mel either as [B,C,T] device tensor (packed here) or already resident in P->mel_in (decode_to_wav)
+  if (mel) launch_pack(mel, P->mel_in, v->cfg.num_mels, P->T, 1.f, v->prec, st);
+  (void)mel_planes;
+  if (P->ge.exec) CUDA_CHECK(cudaGraphLaunch(P->ge.exec, st));
+  else P->ol.run(st);
+  const int threads = 256;
+  dim3 grid((P->Tout + threads - 1) / threads, P->B);
+  const size_t sm = (size_t)7 * P->post_in.g.nchunk * 4 * sizeof(float);
+  conv_post_tanh_kernel<<<grid, threads, sm, st>>>(P->post_in.f(), P->post_in.g, v->post_w, v->post_bias, wav, P->Tout, 7);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------ VAE
+struct GnP { float* gamma; float* beta; int C; };
+struct ResBlock {
+  GnP n1, n2;
+  ConvLayer c1, c2, nin;
+  bool has_nin = false;
+  int Cin, Cout;
+};
+struct AttnBlk { GnP norm; ConvLayer q, k, v, proj; int C; };
+struct VaeLevel { std::vector<ResBlock> blocks; bool has_up = false; ConvLayer up; int C; };
+
+struct VaePlan {
+  Arena ar;
+  int B, T, Tout;
+  PlaneT z_in, mel_out;
+  OpList ol;
+  GraphExec ge;
+};
+
+struct alcm_vae {
+  alcm_ctx* ctx;
+  alcm_vae_cfg cfg;
+  int prec;
+  Arena war;
+  ConvLayer post_quant, conv_in, conv_out;
+  ResBlock mid1, mid2;
+  AttnBlk attn;
+  std::vector<VaeLevel> levels;  // in execution order (highest level first)
+  GnP norm_out;
+  int up_factor = 1;
+  std::map<std::pair<int, int>, std::unique_ptr<VaePlan>> plans;
+};
+
+static void op_gn(OpList& ol, Arena& ar, const PlaneT& x, const PlaneT& out, const GnP& n, int swish, int prec) {
+  const int B = x.B, C = x.C, T = x.T, groups = 32;
+  REQUIRE(C % groups == 0, "GroupNorm: C must be a multiple of 32");
+  float2* stats = static_cast<float2*>(ar.alloc((size_t)B * groups * sizeof(float2), false));
+  PlaneT xc = x, oc = out;
+  GnP nn = n;
+  Op a;
+  a.cls = ALCM_CLS_NORM; a.flops = 0; a.bytes = (double)B * C * T * 4;
+  a.fn = [=](cudaStream_t st) { gn_stats_kernel<<<dim3(groups, B), 256, 0, st>>>(xc.f(), xc.g, C, T, groups, 1e-6f, stats); };
+  ol.ops.push_back(a);
+  Op b;
+  b.cls = ALCM_CLS_NORM; b.flops = 0; b.bytes = (double)B * C * T * (4.0 + out.esz);
+  const int oesz = out.esz, nch = out.g.nchunk, rtf = (prec == ALCM_PREC_TF32);
+  b.fn = [=](cudaStream_t st) {
+    dim3 grid((T + 127) / 128, nch, B);
+    if (oesz == 2) gn_apply_kernel<8><<<grid, 128, 0, st>>>(xc.f(), xc.g, oc.p, oc.g, C, T, groups, stats, nn.gamma, nn.beta, swish, 0);
+    else gn_apply_kernel<4><<<grid, 128, 0, st>>>(xc.f(), xc.g, oc.p, oc.g, C, T, groups, stats, nn.gamma, nn.beta, swish, rtf);
+  };
+  ol.ops.push_back(b);
+}
+
+// operand-dtype view of an fp32 tensor: bf16 needs a cast copy, tf32/fp32 read the fp32 planes directly
+static PlaneT as_operand(OpList& ol, Arena& ar, const PlaneT& x, int prec) {
+  if (prec != ALCM_PREC_BF16) return x;
+  PlaneT o = make_planes(ar, x.B, x.C, x.T, 2);
+  ol.cast(x, o);
+  return o;
+}
+
+static PlaneT op_resblock(OpList& ol, Arena& ar, const ResBlock& rb, const PlaneT& x, int prec) {  // autoencoder1d.py:215-235
+  const int oe = opnd_esz(prec);
+  PlaneT a1 = make_planes(ar, x.B, rb.Cin, x.T, oe);
+  op_gn(ol, ar, x, a1, rb.n1, 1, prec);
+  PlaneT h = make_planes(ar, x.B, rb.Cout, x.T, 4);
+  ol.conv(rb.c1, a1, h, nullptr);
+  PlaneT a2 = make_planes(ar, x.B, rb.Cout, x.T, oe);
+  op_gn(ol, ar, h, a2, rb.n2, 1, prec);
+  PlaneT sc = x;
+  if (rb.has_nin) {
+    sc = make_planes(ar, x.B, rb.Cout, x.T, 4);
+    ol.conv(rb.nin, as_operand(ol, ar, x, prec), sc, nullptr);
+  }
+  PlaneT out = make_planes(ar, x.B, rb.Cout, x.T, 4);
+  ol.conv(rb.c2, a2, out, &sc);
+  return out;
+}
+
+static PlaneT op_attn(OpList& ol, Arena& ar, const AttnBlk& at, const PlaneT& x, int prec) {  // autoencoder1d.py:257-278
+  const int oe = opnd_esz(prec), B = x.B, C = at.C, T = x.T;
+  PlaneT hn = make_planes(ar, B, C, T, oe);
+  op_gn(ol, ar, x, hn, at.norm, 0, prec);
+  PlaneT q = make_planes(ar, B, C, T, 4), k = make_planes(ar, B, C, T, 4), v = make_planes(ar, B, C, T, 4);
+  ol.conv(at.q, hn, q, nullptr);
+  ol.conv(at.k, hn, k, nullptr);
+  ol.conv(at.v, hn, v, nullptr);
+  float* S = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
+  PlaneT h = make_planes(ar, B, C, T, 4);
+  const float scale = 1.0f / sqrtf((float)C);  // reference unpacks (b,c,t) as (b,t,c): scale = C^-0.5
+  Op s1;
+  s1.cls = ALCM_CLS_ATTN; s1.flops = 2.0 * B * (double)T * T * C; s1.bytes = (double)B * (2.0 * C * T + (double)T * T) * 4;
+  s1.fn = [=](cudaStream_t st) {
+    attn_scores_kernel<<<dim3((T + 31) / 32, (T + 31) / 32, B), 256, 0, st>>>(q.f(), k.f(), q.g, C, T, scale, S);
+  };
+  ol.ops.push_back(s1);
+  Op s2;
+  s2.cls = ALCM_CLS_ATTN; s2.flops = 0; s2.bytes = 2.0 * B * (double)T * T * 4;
+  s2.fn = [=](cudaStream_t st) { softmax_rows_kernel<<<B * T, 128, 0, st>>>(S, T); };
+  ol.ops.push_back(s2);
+  Op s3;
+  s3.cls = ALCM_CLS_ATTN; s3.flops = 2.0 * B * (double)T * T * C; s3.bytes = (double)B * (2.0 * C * T + (double)T * T) * 4;
+  s3.fn = [=](cudaStream_t st) {
+    attn_pv_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), 256, 0, st>>>(v.f(), v.g, S, C, T, h.f(), h.g);
+  };
+  ol.ops.push_back(s3);
+  PlaneT out = make_planes(ar, B, C, T, 4);
+  ol.conv(at.proj, as_operand(ol, ar, h, prec), out, &x);
+  return out;
+}
+
+static VaePlan* vae_plan(alcm_vae* v, int B, int T) {
+  auto key = std::make_pair(B, T);
+  auto it = v->plans.find(key);
+  if (it != v->plans.end()) return it->second.get();
+  std::unique_ptr<VaePlan> pl(new VaePlan());
+  VaePlan& P = *pl;
+  P.B = B; P.T = T;
+  const int prec = v->prec, oe = opnd_esz(prec);
+  P.z_in = make_planes(P.ar, B, v->cfg.embed_dim, T, oe);
+  PlaneT h0 = make_planes(P.ar, B, v->cfg.z_channels, T, 4);
+  P.ol.conv(v->post_quant, P.z_in, h0, nullptr);
+  PlaneT h = make_planes(P.ar, B, v->conv_in.Cout, T, 4);
+  P.ol.conv(v->conv_in, as_operand(P.ol, P.ar, h0, prec), h, nullptr);
+  h = op_resblock(P.ol, P.ar, v->mid1, h, prec);
+  h = op_attn(P.ol, P.ar, v->attn, h, prec);
+  h = op_resblock(P.ol, P.ar, v->mid2, h, prec);
+  for (const VaeLevel& lv : v->levels) {
+    for (const ResBlock& rb : lv.blocks) h = op_resblock(P.ol, P.ar, rb, h, prec);
+    if (lv.has_up) {
+      PlaneT up = make_planes(P.ar, B, lv.C, h.T * 2, 4);
+      P.ol.conv(lv.up, as_operand(P.ol, P.ar, h, prec), up, nullptr);
+      h = up;
+    }
+  }
+  PlaneT a = make_planes(P.ar, B, h.C, h.T, oe);
+  op_gn(P.ol, P.ar, h, a, v->norm_out, 1, prec);
+  P.mel_out = make_planes(P.ar, B, v->cfg.out_ch, h.T, 4);
+  P.ol.conv(v->conv_out, a, P.mel_out, nullptr);
+  P.Tout = h.T;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  if (use_graph()) capture_graph(P.ol, P.ge);
+  VaePlan* raw = pl.get();
+  v->plans[key] = std::move(pl);
+  return raw;
+}
+
+static void vae_run(alcm_vae* v, VaePlan* P, const float* z, float inv_scale, cudaStream_t st) {
+  launch_pack(z, P->z_in, v->cfg.embed_dim, P->T, inv_scale, v->prec, st);
+  if (P->ge.exec) CUDA_CHECK(cudaGraphLaunch(P->ge.exec, st));
+  else P->ol.run(st);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------ C-ABI
+static void set_kernel_attrs() {
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
+
+extern "C" {
+
+const char* alcm_last_error(void) { return g_err.c_str(); }
+
+int alcm_ctx_create(alcm_ctx** out, int device) {
+  return guarded([&] {
+    REQUIRE(out != nullptr, "ctx_create: out is NULL");
+    int n = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&n));
+    REQUIRE(device >= 0 && device < n, "ctx_create: no such CUDA device");
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    REQUIRE(prop.major == 10, "audiolcm_b200 requires an sm_100 (Blackwell B200) GPU; there is no fallback path");
+    set_kernel_attrs();
+    alcm_ctx* c = new alcm_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    *out = c;
+  });
+}
+void alcm_ctx_destroy(alcm_ctx* ctx) { delete ctx; }
+
+int alcm_vocoder_num_tensors(const alcm_bigvgan_cfg* c) {
+  if (!c) return -1;
+  return 3 + c->num_upsamples * (3 + c->num_kernels * (18 + 12)) + 2 + 3;
+}
+
+int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float* const* t, int n_tensors, int precision,
+                        alcm_vocoder** out) {
+  return guarded([&] {
+    REQUIRE(ctx && cfg && t && out, "vocoder_create: NULL argument");
+    REQUIRE(precision >= 0 && precision <= 2, "vocoder_create: bad precision");
+    REQUIRE(cfg->num_upsamples >= 1 && cfg->num_upsamples <= 8 && cfg->num_kernels >= 1 && cfg->num_kernels <= 4,
+            "vocoder_create: bad config");
+    REQUIRE(n_tensors == alcm_vocoder_num_tensors(cfg), "vocoder_create: wrong tensor count");
+    for (int i = 0; i < n_tensors; ++i) REQUIRE(t[i] != nullptr, "vocoder_create: NULL tensor");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    std::unique_ptr<alcm_vocoder> v(new alcm_vocoder());
+    v->ctx = ctx; v->cfg = *cfg; v->prec = precision;
+    Arena tmp;
+    int ti = 0;
+    const int c0 = cfg->upsample_initial_channel;
+    {
+      const float* w = fold_wn(tmp, t[ti], t[ti + 1], c0, cfg->num_mels * 7);
+      v->conv_pre = prepare_conv(v->war, precision, KIND_CONV, w, t[ti + 2], c0, cfg->num_mels, 7, 1);
+      ti += 3;
+    }
+    int C = c0;
+    v->hop = 1;
+    for (int i = 0; i < cfg->num_upsamples; ++i) {
+      const int u = cfg->upsample_rates[i], k = cfg->upsample_kernel_sizes[i];
+      REQUIRE(C % 2 == 0, "vocoder_create: channel count must halve per stage");
+      VocStage S;
+      S.u = u; S.C = C / 2;
+      v->hop *= u;
+      {  // ConvTranspose1d weight (Cin,Cout,k): weight_norm dim 0 = input channel
+        const float* w = fold_wn(tmp, t[ti], t[ti + 1], C, S.C * k);
+        S.up = prepare_conv(v->war, precision, KIND_CONVT, w, t[ti + 2], S.C, C, k, u);
+        ti += 3;
+      }
+      C = S.C;
+      for (int j = 0; j < cfg->num_kernels; ++j) {
+        AmpBlock bk;
+        const int kk = cfg->resblock_kernel_sizes[j];
+        for (int l = 0; l < 3; ++l) {
+          const float* w = fold_wn(tmp, t[ti], t[ti + 1], C, C * kk);
+          bk.c1[l] = prepare_conv(v->war, precision, KIND_CONV, w, t[ti + 2], C, C, kk, cfg->resblock_dilation_sizes[j][l]);
+          ti += 3;
+        }
+        for (int l = 0; l < 3; ++l) {
+          const float* w = fold_wn(tmp, t[ti], t[ti + 1], C, C * kk);
+          bk.c2[l] = prepare_conv(v->war, precision, KIND_CONV, w, t[ti + 2], C, C, kk, 1);
+          ti += 3;
+        }
+        for (int m = 0; m < 6; ++m) {
+          bk.a[m] = make_snake(v->war, t[ti], t[ti + 1], C);
+          ti += 2;
+        }
+        S.blocks.push_back(bk);
+        tmp.release();
+      }
+      v->stages.push_back(std::move(S));
+    }
+    v->act_post = make_snake(v->war, t[ti], t[ti + 1], C);
+    ti += 2;
+    {  // conv_post (1,C,7) -> tap-major [7][Cpad] fp32 on device
+      const float* w = fold_wn(tmp, t[ti], t[ti + 1], 1, C * 7);
+      std::vector<float> hw((size_t)C * 7), hp((size_t)7 * round_up(C, 16), 0.f);
+      CUDA_CHECK(cudaMemcpy(hw.data(), w, hw.size() * 4, cudaMemcpyDeviceToHost));
+      for (int c = 0; c < C; ++c)
+        for (int j = 0; j < 7; ++j) hp[(size_t)j * round_up(C, 16) + c] = hw[(size_t)c * 7 + j];
+      v->post_w = static_cast<float*>(v->war.alloc(hp.size() * 4, false));
+      CUDA_CHECK(cudaMemcpy(v->post_w, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(&v->post_bias, t[ti + 2], 4, cudaMemcpyDeviceToHost));
+      v->post_C = C;
+      ti += 3;
+    }
+    CUDA_CHECK(cudaDeviceSynchronize());
+    *out = v.release();
+  });
+}
+void alcm_vocoder_destroy(alcm_vocoder* v) { delete v; }
+
+int alcm_vocode(alcm_vocoder* v, const float* mel, int B, int T, float* wav, void* stream) {
+  return guarded([&] {
+    REQUIRE(v && mel && wav, "vocode: NULL argument");
+    REQUIRE(B >= 1 && T >= 1, "vocode: B and T must be positive");
+    REQUIRE((long long)T * v->hop < (1ll << 30), "vocode: clip too long for one call; shard it along time");
+    CUDA_CHECK(cudaSetDevice(v->ctx->device));
+    VocPlan* P = voc_plan(v, B, T);
+    voc_run(v, P, mel, nullptr, wav, static_cast<cudaStream_t>(stream));
+  });
+}
+
+// ---- VAE
+static GnP make_gn(Arena& ar, const float* w, const float* b, int C) {
+  GnP g;
+  g.C = C;
+  g.gamma = static_cast<float*>(ar.alloc((size_t)C * 4, false));
+  g.beta = static_cast<float*>(ar.alloc((size_t)C * 4, false));
+  CUDA_CHECK(cudaMemcpy(g.gamma, w, (size_t)C * 4, cudaMemcpyDeviceToDevice));
+  CUDA_CHECK(cudaMemcpy(g.beta, b, (size_t)C * 4, cudaMemcpyDeviceToDevice));
+  return g;
+}
+
+static int vae_resblock_tensors(int cin, int cout) { return 8 + (cin != cout ? 2 : 0); }
+
+int alcm_vae_num_tensors(const alcm_vae_cfg* c) {
+  if (!c) return -1;
+  int n = 2 + 2;
+  int block_in = c->ch * c->ch_mult[c->n_levels - 1];
+  n += vae_resblock_tensors(block_in, block_in) * 2 + 10;
+  for (int lv = c->n_levels - 1; lv >= 0; --lv) {
+    const int block_out = c->ch * c->ch_mult[lv];
+    for (int i = 0; i <= c->num_res_blocks; ++i) {
+      n += vae_resblock_tensors(block_in, block_out);
+      block_in = block_out;
+    }
+    if (c->upsample_levels[lv]) n += 2;
+  }
+  return n + 2 + 2;
+}
+
+int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* t, int n_tensors, int precision, alcm_vae** out) {
+  return guarded([&] {
+    REQUIRE(ctx && cfg && t && out, "vae_create: NULL argument");
+    REQUIRE(precision >= 0 && precision <= 2, "vae_create: bad precision");
+    REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= 8, "vae_create: bad n_levels");
+    REQUIRE(n_tensors == alcm_vae_num_tensors(cfg), "vae_create: wrong tensor count");
+    for (int i = 0; i < n_tensors; ++i) REQUIRE(t[i] != nullptr, "vae_create: NULL tensor");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    std::unique_ptr<alcm_vae> v(new alcm_vae());
+    v->ctx = ctx; v->cfg = *cfg; v->prec = precision;
+    int ti = 0;
+    auto conv = [&](int cout, int cin, int k, ConvKind kind = KIND_CONV) {
+      ConvLayer L = prepare_conv(v->war, precision, kind, t[ti], t[ti + 1], cout, cin, k, 1);
+      ti += 2;
+      return L;
+    };
+    auto gn = [&](int C) {
+      GnP g = make_gn(v->war, t[ti], t[ti + 1], C);
+      ti += 2;
+      return g;
+    };
+    auto resblock = [&](int cin, int cout) {
+      ResBlock rb;
+      rb.Cin = cin; rb.Cout = cout;
+      rb.n1 = gn(cin);
+      rb.c1 = conv(cout, cin, 3);
+      rb.n2 = gn(cout);
+      rb.c2 = conv(cout, cout, 3);
+      rb.has_nin = cin != cout;
+      if (rb.has_nin) rb.nin = conv(cout, cin, 1);
+      return rb;
+    };
+    v->post_quant = conv(cfg->z_channels, cfg->embed_dim, 1);
+    int block_in = cfg->ch * cfg->ch_mult[cfg->n_levels - 1];
+    v->conv_in = conv(block_in, cfg->z_channels, cfg->kernel_size);
+    v->mid1 = resblock(block_in, block_in);
+    v->attn.C = block_in;
+    v->attn.norm = gn(block_in);
+    v->attn.q = conv(block_in, block_in, 1);
+    v->attn.k = conv(block_in, block_in, 1);
+    v->attn.v = conv(block_in, block_in, 1);
+    v->attn.proj = conv(block_in, block_in, 1);
+    v->mid2 = resblock(block_in, block_in);
+    v->up_factor = 1;
+    for (int lv = cfg->n_levels - 1; lv >= 0; --lv) {
+      VaeLevel L;
+      const int block_out = cfg->ch * cfg->ch_mult[lv];
+      for (int i = 0; i <= cfg->num_res_blocks; ++i) {
+        L.blocks.push_back(resblock(block_in, block_out));
+        block_in = block_out;
+      }
+      L.C = block_in;
+      L.has_up = cfg->upsample_levels[lv] != 0;
+      if (L.has_up) {
+        L.up = conv(block_in, block_in, 3, KIND_UPCONV3);
+        v->up_factor *= 2;
+      }
+      v->levels.push_back(std::move(L));
+    }
+    v->norm_out = gn(block_in);
+    v->conv_out = conv(cfg->out_ch, block_in, cfg->kernel_size);
+    REQUIRE(ti == n_tensors, "vae_create: tensor walk mismatch");
+    CUDA_CHECK(cudaDeviceSynchronize());
+    *out = v.release();
+  });
+}
+void alcm_vae_destroy(alcm_vae* v) { delete v; }
+
+int alcm_vae_decode(alcm_vae* v, const float* z, int B, int T, float inv_scale, float* mel, void* stream) {
+  return guarded([&] {
+    REQUIRE(v && z && mel, "vae_decode: NULL argument");
+    REQUIRE(B >= 1 && T >= 1, "vae_decode: B and T must be positive");
+    CUDA_CHECK(cudaSetDevice(v->ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VaePlan* P = vae_plan(v, B, T);
+    vae_run(v, P, z, inv_scale, st);
+    launch_unpack(P->mel_out, mel, v->cfg.out_ch, P->Tout, st);
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+int alcm_decode_to_wav(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, int T, float inv_scale, float* mel_out,
+                       float* wav, void* stream) {
+  return guarded([&] {
+    REQUIRE(vae && voc && z && wav, "decode_to_wav: NULL argument");
+    REQUIRE(B >= 1 && T >= 1, "decode_to_wav: B and T must be positive");
+    REQUIRE(vae->cfg.out_ch == voc->cfg.num_mels, "decode_to_wav: VAE out_ch != vocoder num_mels");
+    REQUIRE(vae->ctx->device == voc->ctx->device, "decode_to_wav: handles live on different devices");
+    CUDA_CHECK(cudaSetDevice(vae->ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    VaePlan* PV = vae_plan(vae, B, T);
+    VocPlan* PW = voc_plan(voc, B, PV->Tout);
+    vae_run(vae, PV, z, inv_scale, st);
+    if (mel_out) launch_unpack(PV->mel_out, mel_out, vae->cfg.out_ch, PV->Tout, st);
+    // mel stays on the device in plane form: fp32 planes -> the vocoder's operand planes
+    {
+      const PlaneT& src = PV->mel_out;
+      const PlaneT& dst = PW->mel_in;
+      dim3 grid((src.T + 255) / 256, dst.g.nchunk, B);
+      if (dst.esz == 2) cast_planes_kernel<8><<<grid, 256, 0, st>>>(src.f(), src.g, dst.p, dst.g, src.T);
+      else if (voc->prec == ALCM_PREC_TF32) cast_planes_kernel<4><<<grid, 256, 0, st>>>(src.f(), src.g, dst.p, dst.g, src.T);
+      else CUDA_CHECK(cudaMemcpyAsync(dst.p, src.p, src.bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    voc_run(voc, PW, nullptr, nullptr, wav, st);
+  });
+}
+
+// ---- single-op entry points ---------------------------------------------------------------
+static void sync_free(cudaStream_t st) { CUDA_CHECK(cudaStreamSynchronize(st)); }
+
+int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, const float* beta, float* y, int B, int C, int T,
+                          int precision, void* stream) {
+  return guarded([&] {
+    REQUIRE(ctx && x && alpha && beta && y, "activation1d: NULL argument");
+    REQUIRE(B >= 1 && C >= 1 && T >= 1, "activation1d: empty tensor");
+    REQUIRE(precision >= 0 && precision <= 2, "activation1d: bad precision");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar;
+    PlaneT xin = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, opnd_esz(precision));
+    SnakeP sp = make_snake(ar, alpha, beta, C);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    launch_pack(x, xin, C, T, 1.f, ALCM_PREC_FP32, st);
+    OpList ol;
+    ol.act(xin, out, sp.ea, sp.ib, precision == ALCM_PREC_TF32);
+    ol.run(st);
+    if (precision == ALCM_PREC_BF16) {
+      dim3 grid((T + 255) / 256, out.g.nchunk, B);
+      unpack_cf_bf16_kernel<<<grid, 256, 0, st>>>(out.p, out.g, y, C, T);
+    } else {
+      launch_unpack(out, y, C, T, st);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    sync_free(st);
+  });
+}
+
+static void run_conv_test(alcm_ctx* ctx, ConvKind kind, const float* x, const float* w, const float* bias, const float* res,
+                          float* y, int B, int Cin, int Cout, int T, int K, int p, int precision, cudaStream_t st) {
+  REQUIRE(ctx && x && w && y, "conv: NULL argument");
+  REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T >= 1, "conv: empty tensor");
+  REQUIRE(precision >= 0 && precision <= 2, "conv: bad precision");
+  CUDA_CHECK(cudaSetDevice(ctx->device));
+  Arena ar;
+  ConvLayer L = prepare_conv(ar, precision, kind, w, bias, Cout, Cin, K, p);
+  PlaneT xin = make_planes(ar, B, Cin, T, opnd_esz(precision));
+  PlaneT out = make_planes(ar, B, Cout, T * L.nphase, 4);
+  PlaneT rp;
+  if (res) rp = make_planes(ar, B, Cout, T * L.nphase, 4);
+  CUDA_CHECK(cudaDeviceSynchronize());
+  launch_pack(x, xin, Cin, T, 1.f, precision, st);
+  if (res) launch_pack(res, rp, Cout, T * L.nphase, 1.f, ALCM_PREC_FP32, st);
+  OpList ol;
+  ol.conv(L, xin, out, res ? &rp : nullptr);
+  ol.run(st);
+  launch_unpack(out, y, Cout, T * L.nphase, st);
+  CUDA_CHECK(cudaGetLastError());
+  sync_free(st);
+}
+
+int alcm_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, float* y, int B, int Cin,
+                    int Cout, int T, int K, int dilation, int precision, void* stream) {
+  return guarded([&] {
+    REQUIRE(dilation >= 1, "conv1d: dilation must be >= 1");
+    run_conv_test(ctx, KIND_CONV, x, w, bias, res, y, B, Cin, Cout, T, K, dilation, precision, static_cast<cudaStream_t>(stream));
+  });
+}
+int alcm_conv_transpose1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
+                              int T, int stride, int precision, void* stream) {
+  return guarded([&] {
+    run_conv_test(ctx, KIND_CONVT, x, w, bias, nullptr, y, B, Cin, Cout, T, 2 * stride, stride, precision,
+                  static_cast<cudaStream_t>(stream));
+  });
+}
+int alcm_upsample_conv3_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
+                            int T, int precision, void* stream) {
+  return guarded([&] {
+    run_conv_test(ctx, KIND_UPCONV3, x, w, bias, nullptr, y, B, Cin, Cout, T, 3, 1, precision, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int alcm_groupnorm_swish_fwd(alcm_ctx* ctx, const float* x, const float* gamma, const float* beta, float* y, int B, int C, int T,
+                             int groups, float eps, int swish, void* stream) {
+  return guarded([&] {
+    REQUIRE(ctx && x && gamma && beta && y, "groupnorm: NULL argument");
+    REQUIRE(B >= 1 && C >= 1 && T >= 1, "groupnorm: empty tensor");
+    REQUIRE(groups == 32 && fabsf(eps - 1e-6f) < 1e-12f, "groupnorm: only GroupNorm(32, eps=1e-6) is on the path");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar;
+    PlaneT xin = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, 4);
+    GnP g = make_gn(ar, gamma, beta, C);
+    OpList ol;
+    op_gn(ol, ar, xin, out, g, swish, ALCM_PREC_FP32);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    launch_pack(x, xin, C, T, 1.f, ALCM_PREC_FP32, st);
+    ol.run(st);
+    launch_unpack(out, y, C, T, st);
+    CUDA_CHECK(cudaGetLastError());
+    sync_free(st);
+  });
+}
+
+int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* v, float* out, int B, int C, int T, void* stream) {
+  return guarded([&] {
+    REQUIRE(ctx && q && k && v && out, "attn: NULL argument");
+    REQUIRE(B >= 1 && C >= 1 && T >= 1, "attn: empty tensor");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar;
+    PlaneT pq = make_planes(ar, B, C, T, 4), pk = make_planes(ar, B, C, T, 4), pv = make_planes(ar, B, C, T, 4);
+    PlaneT ph = make_planes(ar, B, C, T, 4);
+    float* S = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
+    CUDA_CHECK(cudaDeviceSynchronize());
+    launch_pack(q, pq, C, T, 1.f, ALCM_PREC_FP32, st);
+    launch_pack(k, pk, C, T, 1.f, ALCM_PREC_FP32, st);
+    launch_pack(v, pv, C, T, 1.f, ALCM_PREC_FP32, st);
+    attn_scores_kernel<<<dim3((T + 31) / 32, (T + 31) / 32, B), 256, 0, st>>>(pq.f(), pk.f(), pq.g, C, T, 1.0f / sqrtf((float)C), S);
+    softmax_rows_kernel<<<B * T, 128, 0, st>>>(S, T);
+    attn_pv_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), 256, 0, st>>>(pv.f(), pv.g, S, C, T, ph.f(), ph.g);
+    launch_unpack(ph, out, C, T, st);
+    CUDA_CHECK(cudaGetLastError());
+    sync_free(st);
+  });
+}
+
+// ---- measurement ----------------------------------------------------------------------------
+static void profile_ops(const OpList& ol, int iters, alcm_profile* out, cudaStream_t st) {
+  std::vector<cudaEvent_t> ev(ol.ops.size() + 1);
+  for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+  for (int it = 0; it < iters; ++it) {
+    CUDA_CHECK(cudaEventRecord(ev[0], st));
+    for (size_t i = 0; i < ol.ops.size(); ++i) {
+      ol.ops[i].fn(st);
+      CUDA_CHECK(cudaEventRecord(ev[i + 1], st));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < ol.ops.size(); ++i) {
+      float ms = 0.f;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+      out->ms[ol.ops[i].cls] += ms;
+    }
+  }
+  for (const Op& o : ol.ops) {
+    out->flops[o.cls] += o.flops;
+    out->bytes[o.cls] += o.bytes;
+    out->launches[o.cls] += 1;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+}
+
+int alcm_profile_decode(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iters, alcm_profile* out, void* stream) {
+  return guarded([&] {
+    REQUIRE(voc && out && iters >= 1, "profile: bad argument");
+    memset(out, 0, sizeof(*out));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_CHECK(cudaSetDevice(voc->ctx->device));
+    int Tmel = T;
+    if (vae) {
+      VaePlan* PV = vae_plan(vae, B, T);
+      profile_ops(PV->ol, iters, out, st);
+      Tmel = PV->Tout;
+    }
+    VocPlan* PW = voc_plan(voc, B, Tmel);
+    profile_ops(PW->ol, iters, out, st);
+  });
+}
+
+int alcm_vocoder_launches(alcm_vocoder* v, int B, int T) {
+  int n = -1;
+  guarded([&] {
+    REQUIRE(v, "NULL vocoder");
+    n = (int)voc_plan(v, B, T)->ol.ops.size() + 2;  // + mel pack + conv_post
+  });
+  return n;
+}
+int alcm_vae_launches(alcm_vae* v, int B, int T) {
+  int n = -1;
+  guarded([&] {
+    REQUIRE(v, "NULL vae");
+    n = (int)vae_plan(v, B, T)->ol.ops.size() + 2;  // + latent pack + mel unpack
+  });
+  return n;
+}
+
+}  // extern "C"

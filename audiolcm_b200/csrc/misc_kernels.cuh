@@ -1,0 +1,368 @@
+// Layout conversion, weight preparation, conv_post+tanh, GroupNorm+swish and the VAE's single
+// attention block.  All of these are small memory-bound helpers around the two hot kernels
+// (conv.cuh, act1d.cuh).
+#pragma once
+#include "common.cuh"
+
+namespace alcm {
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------- layout
+// [B][C][T] fp32 channel-first  ->  planes (fp32 E=4, optional tf32 rounding, or bf16 E=8); x*mul
+template <int E>
+__global__ void pack_cf_kernel(const float* __restrict__ in, void* __restrict__ out, PlaneGeom og, int C, int T, float mul,
+                               int rtf32) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  float v[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int c = chunk * E + e;
+    v[e] = (c < C) ? in[((size_t)b * C + c) * T + t] * mul : 0.f;
+  }
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out) + plane_row_off(og, b, chunk, t);
+  if (E == 4) {
+    if (rtf32) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = round_tf32(v[e]);
+    }
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
+    *reinterpret_cast<uint4*>(dst) = o;
+  }
+}
+
+// fp32 planes -> [B][C][T] fp32 channel-first
+__global__ void unpack_cf_kernel(const float* __restrict__ in, PlaneGeom ig, float* __restrict__ out, int C, int T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, chunk, t));
+  const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = chunk * 4 + e;
+    if (c < C) out[((size_t)b * C + c) * T + t] = vv[e];
+  }
+}
+
+// bf16 planes (E=8) -> [B][C][T] fp32 channel-first (test entry points only)
+__global__ void unpack_cf_bf16_kernel(const uint8_t* __restrict__ in, PlaneGeom ig, float* __restrict__ out, int C, int T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const uint4 v = *reinterpret_cast<const uint4*>(in + plane_row_off(ig, b, chunk, t));
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = chunk * 8 + e;
+    const uint32_t bits = (e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16);
+    if (c < C) out[((size_t)b * C + c) * T + t] = __uint_as_float(bits);
+  }
+}
+
+// fp32 planes -> operand planes: bf16 (E=8, two in-planes per out-plane) or tf32-rounded fp32 copy
+template <int E>
+__global__ void cast_planes_kernel(const float* __restrict__ in, PlaneGeom ig, void* __restrict__ out, PlaneGeom og, int T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oc = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out) + plane_row_off(og, b, oc, t);
+  if (E == 8) {
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, 2 * oc, t));
+    const float4 c = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, 2 * oc + 1, t));
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(c.x, c.y); o.w = pack_bf16x2(c.z, c.w);
+    *reinterpret_cast<uint4*>(dst) = o;
+  } else {
+    float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, oc, t));
+    a.x = round_tf32(a.x); a.y = round_tf32(a.y); a.z = round_tf32(a.z); a.w = round_tf32(a.w);
+    *reinterpret_cast<float4*>(dst) = a;
+  }
+}
+
+// ------------------------------------------------------------------------------- weights
+// weight_norm fold (torch.nn.utils.weight_norm dim=0; models.py:36-51,143,152,174):
+// w[i,:,:] = g[i] * v[i,:,:] / ||v[i,:,:]||.  One block per dim-0 slice.
+__global__ void wn_fold_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int inner) {
+  __shared__ double red[256];
+  const int i = blockIdx.x;
+  const float* vi = v + (size_t)i * inner;
+  double s = 0.0;
+  for (int k = threadIdx.x; k < inner; k += blockDim.x) s += (double)vi[k] * (double)vi[k];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const float scale = g[i] / (float)sqrt(red[0]);
+  for (int k = threadIdx.x; k < inner; k += blockDim.x) w[(size_t)i * inner + k] = vi[k] * scale;
+}
+
+// Effective per-(phase,tap) weight matrices Weff[phase][tap][Cout][Cin] (fp32) from a folded conv
+// weight.  transposed=0: src is Conv1d (Cout,Cin,K); transposed=1: ConvTranspose1d (Cin,Cout,K).
+// src_k[phase][tap][2]: up to two source taps summed (-1 = none) - the sum is used by the
+// nearest-2x-upsample + k3 conv polyphase form (autoencoder1d.py:291-295).
+struct WeffRecipe {
+  int nphase, ntaps;
+  int src_k[kMaxPhase][kMaxTaps][2];
+};
+__global__ void weff_kernel(const float* __restrict__ src, float* __restrict__ dst, WeffRecipe r, int Cout, int Cin, int K,
+                            int transposed) {
+  const size_t n = (size_t)r.nphase * r.ntaps * Cout * Cin;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int ci = idx % Cin;
+    const int co = (idx / Cin) % Cout;
+    const int tp = (idx / ((size_t)Cin * Cout)) % r.ntaps;
+    const int ph = idx / ((size_t)Cin * Cout * r.ntaps);
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = r.src_k[ph][tp][u];
+      if (k >= 0) s += transposed ? src[((size_t)ci * Cout + co) * K + k] : src[((size_t)co * Cin + ci) * K + k];
+    }
+    dst[idx] = s;
+  }
+}
+
+// Weff -> UMMA weight blobs [phase][n_tile][kb][tap][kc][NT][16B] (the smem image of a K-major,
+// no-swizzle B operand: LBO = NT*16, SBO = 128).  One thread per 16-byte unit.
+template <int E>
+__global__ void pack_w_kernel(const float* __restrict__ weff, void* __restrict__ dst, int nphase, int ntaps, int Cout, int Cin,
+                              int NT, int n_tiles, int kblk, int nkb) {
+  const size_t units = (size_t)nphase * n_tiles * nkb * ntaps * kblk * NT;
+  for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
+    size_t r = u;
+    const int n = r % NT; r /= NT;
+    const int kc = r % kblk; r /= kblk;
+    const int tp = r % ntaps; r /= ntaps;
+    const int kb = r % nkb; r /= nkb;
+    const int nt = r % n_tiles; r /= n_tiles;
+    const int ph = (int)r;
+    const int co = nt * NT + n;
+    float v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int ci = (kb * kblk + kc) * E + e;
+      v[e] = (co < Cout && ci < Cin) ? weff[(((size_t)ph * ntaps + tp) * Cout + co) * Cin + ci] : 0.f;
+    }
+    uint8_t* d = reinterpret_cast<uint8_t*>(dst) + u * 16;
+    if (E == 4) {
+      *reinterpret_cast<float4*>(d) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
+    } else {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
+      *reinterpret_cast<uint4*>(d) = o;
+    }
+  }
+}
+
+// SnakeBeta parameters (activations.py:113-118, logscale): ea = exp(alpha), ib = 1/(exp(beta)+1e-9)
+__global__ void snake_params_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, float* __restrict__ ea,
+                                    float* __restrict__ ib, int C, int Cpad) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cpad) return;
+  ea[c] = (c < C) ? expf(alpha[c]) : 1.f;
+  ib[c] = (c < C) ? 1.0f / (expf(beta[c]) + 1e-9f) : 1.f;
+}
+
+// ------------------------------------------------------------------------------- conv_post + tanh
+// models.py:199-201: Conv1d(C -> 1, k=7, p=3) + tanh on fp32 planes; w is [7][Cpad] (tap-major).
+__global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg, const float* __restrict__ w, float bias,
+                                      float* __restrict__ wav, int T, int ktaps) {
+  extern __shared__ float sw[];
+  const int nw = ktaps * xg.nchunk * 4;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= T) return;
+  float acc = bias;
+  const int half = ktaps / 2;
+  for (int ch = 0; ch < xg.nchunk; ++ch) {
+    const float4* xp = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, ch, 0));
+    for (int j = 0; j < ktaps; ++j) {
+      const float4 v = xp[t + j - half];  // zero rows of the plane supply the conv padding
+      const float* wj = sw + (j * xg.nchunk + ch) * 4;
+      acc = fmaf(v.x, wj[0], acc); acc = fmaf(v.y, wj[1], acc); acc = fmaf(v.z, wj[2], acc); acc = fmaf(v.w, wj[3], acc);
+    }
+  }
+  wav[(size_t)b * T + t] = tanhf(acc);
+}
+
+// ------------------------------------------------------------------------------- GroupNorm
+// Normalize = GroupNorm(32, C, eps 1e-6, affine) (autoencoder1d.py:169-170); biased variance over
+// (C/32 channels x T).  stats[b][g] = {mean, rstd}.  One block per (group, b).
+__global__ void gn_stats_kernel(const float* __restrict__ x, PlaneGeom xg, int C, int T, int groups, float eps,
+                                float2* __restrict__ stats) {
+  __shared__ double rs[256], rq[256];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / groups;
+  const size_t n = (size_t)cpg * T;
+  float s = 0.f, q = 0.f;
+  double ds = 0.0, dq = 0.0;
+  int cnt = 0;
+  for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = g * cpg + (int)(i / T);
+    const int t = (int)(i % T);
+    const float v = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, c >> 2, t) + (c & 3) * 4);
+    s += v; q += v * v;
+    if (++cnt == 64) { ds += s; dq += q; s = q = 0.f; cnt = 0; }
+  }
+  rs[threadIdx.x] = ds + s;
+  rq[threadIdx.x] = dq + q;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rq[threadIdx.x] += rq[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = rs[0] / (double)n;
+    const double var = rq[0] / (double)n - mean * mean;
+    stats[b * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps)));
+  }
+}
+
+// y = (x-mean)*rstd*gamma + beta, optional swish (x*sigmoid(x), autoencoder1d.py:172-174), written
+// as operand planes (E=4 fp32/tf32 or E=8 bf16).
+template <int E>
+__global__ void gn_apply_kernel(const float* __restrict__ x, PlaneGeom xg, void* __restrict__ out, PlaneGeom og, int C, int T,
+                                int groups, const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, int swish, int rtf32) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oc = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const int cpg = C / groups;
+  float v[E];
+#pragma unroll
+  for (int h = 0; h < E / 4; ++h) {
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, oc * (E / 4) + h, t));
+    v[4 * h] = a.x; v[4 * h + 1] = a.y; v[4 * h + 2] = a.z; v[4 * h + 3] = a.w;
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int c = oc * E + e;
+    float y = 0.f;
+    if (c < C) {
+      const float2 st = stats[b * groups + c / cpg];
+      y = (v[e] - st.x) * st.y * gamma[c] + beta[c];
+      if (swish) y = y / (1.f + __expf(-y));
+    }
+    v[e] = y;
+  }
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out) + plane_row_off(og, b, oc, t);
+  if (E == 4) {
+    if (rtf32) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = round_tf32(v[e]);
+    }
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
+    *reinterpret_cast<uint4*>(dst) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------- attention (AttnBlock1D)
+// autoencoder1d.py:257-278: S[i][j] = scale * sum_c q[c][i] k[c][j]; P = softmax_j S;
+// h[c][i] = sum_j v[c][j] P[i][j].  q,k,v fp32 planes; S row-major [B][T][T] fp32.
+__device__ __forceinline__ float plane_elem(const float* x, const PlaneGeom& g, int b, int c, int t) {
+  return *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(g, b, c >> 2, t) + (c & 3) * 4);
+}
+
+__global__ void __launch_bounds__(256) attn_scores_kernel(const float* __restrict__ q, const float* __restrict__ k, PlaneGeom g,
+                                                            int C, int T, float scale, float* __restrict__ S) {
+  __shared__ float Qs[32][33], Ks[32][33];
+  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty 0..7
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {  // r = channel within tile, tx = time
+      const int c = c0 + r;
+      Qs[r][tx] = (c < C && i0 + tx < T) ? plane_elem(q, g, b, c, i0 + tx) : 0.f;
+      Ks[r][tx] = (c < C && j0 + tx < T) ? plane_elem(k, g, b, c, j0 + tx) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const float kv = Ks[c][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(Qs[c][ty * 4 + r], kv, acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty * 4 + r, j = j0 + tx;
+    if (i < T && j < T) S[((size_t)b * T + i) * T + j] = acc[r] * scale;
+  }
+}
+
+__global__ void softmax_rows_kernel(float* __restrict__ S, int T) {
+  const int row = blockIdx.x;  // b*T + i
+  float* p = S + (size_t)row * T;
+  __shared__ float red[32];
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) m = fmaxf(m, p[j]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) {
+    const float e = expf(p[j] - m);
+    p[j] = e;
+    s += e;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+  const float inv = 1.f / s;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) p[j] *= inv;
+}
+
+__global__ void __launch_bounds__(256) attn_pv_kernel(const float* __restrict__ v, PlaneGeom g, const float* __restrict__ P, int C,
+                                                        int T, float* __restrict__ h, PlaneGeom hg) {
+  __shared__ float Vs[32][33], Ps[32][33];
+  const int c0 = blockIdx.y * 32, i0 = blockIdx.x * 32, b = blockIdx.z;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j0 = 0; j0 < T; j0 += 32) {
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+      Vs[r][tx] = (c0 + r < C && j0 + tx < T) ? plane_elem(v, g, b, c0 + r, j0 + tx) : 0.f;       // Vs[c][j]
+      Ps[r][tx] = (i0 + r < T && j0 + tx < T) ? P[((size_t)b * T + i0 + r) * T + j0 + tx] : 0.f;   // Ps[i][j]
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float pv = Ps[tx][j];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(Vs[ty * 4 + r][j], pv, acc[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int c = c0 + ty * 4 + r, i = i0 + tx;
+    if (c < C && i < T)
+      *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h) + plane_row_off(hg, b, c >> 2, i) + (c & 3) * 4) = acc[r];
+  }
+}
+
+}  // namespace alcm

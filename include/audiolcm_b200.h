@@ -1,0 +1,159 @@
+/* audiolcm_b200 - C-ABI of the B200-native latent->waveform decode path of AudioLCM.
+ *
+ * The reference (Text-to-Audio/AudioLCM) is pure PyTorch and has no FFI; these entry points are
+ * what a binding for its two decode call sites would bind:
+ *
+ *   alcm_vocoder_create / alcm_vocode      <- VocoderBigVGAN.__init__ / .vocode
+ *                                             /root/reference/vocoder/bigvgan/models.py:393-414
+ *                                             (generator forward: models.py:181-203)
+ *   alcm_vae_create / alcm_vae_decode      <- AutoencoderKL.decode as called by
+ *                                             LCM_audio.decode_first_stage
+ *                                             /root/reference/ldm/models/autoencoder1d.py:59-62,484-517
+ *                                             /root/reference/ldm/models/diffusion/lcm_audio.py:392-406
+ *   alcm_decode_to_wav                     <- the caller loop that chains both
+ *                                             /root/reference/pythonscripts/InferAPI.py:87-96
+ *
+ * Conventions: plain pointers and sizes only.  All tensor pointers are DEVICE pointers to
+ * contiguous fp32 arrays in the reference's own layouts ([B,C,T], weights as in the state_dict).
+ * The caller owns inputs and outputs; the library owns packed weights and per-(B,T) workspaces
+ * (allocated on the first call for a shape, reused afterwards - no allocation on later calls).
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Functions return
+ * 0 on success or a negative code; alcm_last_error() gives the message.  Nothing aborts or
+ * throws across this boundary.  Handles are not thread-safe; use one ctx per host thread.
+ */
+#ifndef AUDIOLCM_B200_H
+#define AUDIOLCM_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct alcm_ctx alcm_ctx;
+typedef struct alcm_vocoder alcm_vocoder;
+typedef struct alcm_vae alcm_vae;
+
+/* arithmetic used by the conv GEMMs */
+enum {
+  ALCM_PREC_FP32 = 0, /* CUDA-core FFMA, fp32 end to end (exact mode; slow)                        */
+  ALCM_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 storage, fp32 accumulate  ("fp32 mode")          */
+  ALCM_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 residual stream and accumulators  */
+};
+
+enum {
+  ALCM_OK = 0,
+  ALCM_ERR_INVALID = -1, /* bad argument / unsupported configuration */
+  ALCM_ERR_CUDA = -2,    /* CUDA runtime error                      */
+  ALCM_ERR_INTERNAL = -3
+};
+
+int alcm_ctx_create(alcm_ctx** out, int device);
+void alcm_ctx_destroy(alcm_ctx* ctx);
+/* message of the last failing call on this thread (never NULL) */
+const char* alcm_last_error(void);
+
+/* ---- BigVGAN vocoder ------------------------------------------------------------------------
+ * cfg mirrors the generator keys of bigvgan_audioset16khz_80band.json (resblock "1", snakebeta,
+ * snake_logscale true are the only supported choices - models.py:146,60-70).
+ * `tensors` lists device fp32 pointers in this order (state_dict names in brackets):
+ *   conv_pre:   weight_g, weight_v, bias
+ *   for i in 0..num_upsamples-1:
+ *     ups.i.0:  weight_g, weight_v, bias
+ *     for j in 0..num_kernels-1   [resblocks.(i*num_kernels+j)]:
+ *       convs1.0..2: (weight_g, weight_v, bias) x3
+ *       convs2.0..2: (weight_g, weight_v, bias) x3
+ *       activations.0..5.act: (alpha, beta) x6
+ *   activation_post.act: alpha, beta
+ *   conv_post:  weight_g, weight_v, bias
+ */
+typedef struct {
+  int num_mels;
+  int upsample_initial_channel;
+  int num_upsamples;
+  int num_kernels;
+  int upsample_rates[8];
+  int upsample_kernel_sizes[8];
+  int resblock_kernel_sizes[4];
+  int resblock_dilation_sizes[4][3];
+} alcm_bigvgan_cfg;
+
+int alcm_vocoder_num_tensors(const alcm_bigvgan_cfg* cfg);
+int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float* const* tensors, int n_tensors,
+                        int precision, alcm_vocoder** out);
+void alcm_vocoder_destroy(alcm_vocoder* v);
+/* mel [B,num_mels,T] -> wav [B, T*prod(upsample_rates)] (conv_post + tanh applied) */
+int alcm_vocode(alcm_vocoder* v, const float* mel, int B, int T, float* wav, void* stream);
+
+/* ---- 1-D KL-VAE decoder -----------------------------------------------------------------------
+ * cfg mirrors ddconfig of configs/audiolcm.yaml:54-70.  upsample_levels[l] = 1 when level l ends
+ * with an Upsample1D (reference: l in [d+1 for d in down_layers]).
+ * `tensors` order (each conv = weight,bias; each norm = weight,bias; resblock = norm1, conv1,
+ * norm2, conv2, then nin_shortcut iff in!=out):
+ *   post_quant_conv, decoder.conv_in, mid.block_1, mid.attn_1 (norm, q, k, v, proj_out),
+ *   mid.block_2, then for level = n_levels-1 .. 0: block.0 .. block.num_res_blocks,
+ *   [upsample.conv], finally norm_out, conv_out.
+ */
+typedef struct {
+  int ch;
+  int out_ch;
+  int z_channels;
+  int embed_dim;
+  int kernel_size;
+  int num_res_blocks;
+  int n_levels;
+  int ch_mult[8];
+  int upsample_levels[8];
+} alcm_vae_cfg;
+
+int alcm_vae_num_tensors(const alcm_vae_cfg* cfg);
+int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* tensors, int n_tensors, int precision,
+                    alcm_vae** out);
+void alcm_vae_destroy(alcm_vae* v);
+/* z [B,embed_dim,T] -> mel [B,out_ch,T*2^n_up];  inv_scale = 1/scale_factor (lcm_audio.py:400) */
+int alcm_vae_decode(alcm_vae* v, const float* z, int B, int T, float inv_scale, float* mel, void* stream);
+
+/* latent -> waveform with the mel kept on the device (mel_out may be NULL) */
+int alcm_decode_to_wav(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, int T, float inv_scale, float* mel_out,
+                       float* wav, void* stream);
+
+/* ---- single-op entry points (tests / micro-benchmarks); tensors are [B,C,T] fp32 on device -----*/
+/* Activation1d(SnakeBeta logscale): act.py:23-28.  precision BF16 returns bf16-rounded values. */
+int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, const float* beta, float* y, int B, int C,
+                          int T, int precision, void* stream);
+/* Conv1d(Cin,Cout,K,dilation, padding=(K*d-d)/2) (+bias, +res if non-NULL); w [Cout,Cin,K] */
+int alcm_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, float* y, int B,
+                    int Cin, int Cout, int T, int K, int dilation, int precision, void* stream);
+/* ConvTranspose1d(Cin,Cout,K=2*stride,stride,padding=stride/2); w [Cin,Cout,K]; y [B,Cout,T*stride] */
+int alcm_conv_transpose1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int Cin,
+                              int Cout, int T, int stride, int precision, void* stream);
+/* nearest x2 + Conv1d(C,C,3,p=1): autoencoder1d.py:291-295; y [B,Cout,2T] */
+int alcm_upsample_conv3_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int Cin,
+                            int Cout, int T, int precision, void* stream);
+/* GroupNorm(groups, eps) [+ swish] */
+int alcm_groupnorm_swish_fwd(alcm_ctx* ctx, const float* x, const float* gamma, const float* beta, float* y, int B, int C,
+                             int T, int groups, float eps, int swish, void* stream);
+/* softmax_j(q^T k * C^-0.5) applied to v: autoencoder1d.py:264-275; q,k,v,out [B,C,T] */
+int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* v, float* out, int B, int C, int T,
+                    void* stream);
+
+/* ---- measurement ------------------------------------------------------------------------------
+ * Kernel classes for per-class device timing. */
+enum { ALCM_CLS_CONV = 0, ALCM_CLS_ACT = 1, ALCM_CLS_NORM = 2, ALCM_CLS_ATTN = 3, ALCM_CLS_MISC = 4, ALCM_NUM_CLS = 5 };
+typedef struct {
+  double ms[ALCM_NUM_CLS];       /* summed CUDA-event time per class over `iters` runs */
+  double flops[ALCM_NUM_CLS];    /* algorithmic FLOPs per run (conv: 2*Cin*Cout*k*T)     */
+  double bytes[ALCM_NUM_CLS];    /* algorithmic HBM bytes per run (one read + one write) */
+  int launches[ALCM_NUM_CLS];    /* kernel launches per run                              */
+} alcm_profile;
+/* runs the vocoder (vae may be NULL) / vae+vocoder op lists eagerly with an event pair around every
+ * kernel; the normal path replays a CUDA graph and has no events inside. */
+int alcm_profile_decode(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iters, alcm_profile* out, void* stream);
+/* kernels launched by one alcm_vocode / alcm_vae_decode call for this shape (after planning) */
+int alcm_vocoder_launches(alcm_vocoder* v, int B, int T);
+int alcm_vae_launches(alcm_vae* v, int B, int T);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOLCM_B200_H */

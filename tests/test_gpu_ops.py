@@ -1,0 +1,166 @@
+"""GPU parity tests of the single kernels, called through the C-ABI (audiolcm_b200.ops).
+
+fp32 : CUDA-core path, compared with torch fp32/fp64 ops at ~1e-5.
+tf32 / bf16 : tcgen05 path; operands are rounded exactly as the device does (tests/util.py) and the
+reference is evaluated in float64, so what is left is accumulation order: tolerance 2e-5 relative
+to the output scale.  A wrong descriptor/stride/tap shift shows up as O(1) error.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import round_operand
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from audiolcm_b200 import ops as _ops
+    return _ops
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).float()
+
+
+# ----------------------------------------------------------------------------------- Activation1d
+@pytest.mark.parametrize("case", ["a", "b", "c", "d", "e"])
+def test_activation1d_golden_fp32(ops, golden_dir, case):
+    g = np.load(os.path.join(golden_dir, "activation1d.npz"))
+    x, al, be = (torch.from_numpy(g[f"{case}_{n}"]).to(DEV) for n in ("x", "alpha", "beta"))
+    y = ops.activation1d(x, al, be, "fp32").cpu().numpy()
+    np.testing.assert_allclose(y, g[f"{case}_y64"], atol=1e-5, rtol=1e-5)   # reference module output (float64 run)
+    np.testing.assert_allclose(y, g[f"{case}_y"], atol=2e-5, rtol=1e-5)     # and its fp32 run
+
+
+@pytest.mark.parametrize("shape", [(1, 768, 2500), (2, 24, 4099), (1, 17, 511), (1, 16, 513), (3, 40, 1030)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_activation1d_vs_oracle(ops, shape, precision):
+    from oracle import decode_oracle as O
+    B, C, T = shape
+    x = _rand(B, C, T, seed=1, scale=1.5)
+    al, be = _rand(C, seed=2, scale=0.5), _rand(C, seed=3, scale=0.5)
+    ref = O.activation1d(x.double(), al.double(), be.double(), O.kaiser_sinc_filter().double())
+    y = ops.activation1d(x.to(DEV), al.to(DEV), be.to(DEV), precision).cpu()
+    tol = {"fp32": 1e-5, "tf32": 2.0 ** -11, "bf16": 2.0 ** -8}[precision]
+    err = (y.double() - ref).abs()
+    assert float((err / (ref.abs() + 1.0)).max()) < tol * 1.01 + 1e-5, float(err.max())
+    if precision != "fp32":  # output must be exactly representable in the operand type
+        assert torch.equal(round_operand(y, precision), y)
+
+
+# ----------------------------------------------------------------------------------- Conv1d
+CONV_CASES = [
+    # B, Cin, Cout, T, K, d
+    (1, 16, 16, 128, 3, 1),
+    (2, 24, 24, 300, 11, 5),
+    (1, 80, 192, 625, 7, 1),
+    (1, 192, 192, 1000, 7, 3),
+    (2, 384, 384, 257, 3, 5),
+    (1, 768, 768, 250, 11, 1),
+    (1, 20, 1536, 312, 5, 1),
+    (1, 1536, 768, 100, 1, 1),
+    (1, 48, 48, 1, 3, 1),
+    (1, 5, 3, 9, 3, 1),
+    (1, 96, 80, 129, 5, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_conv1d(ops, case, precision):
+    B, Cin, Cout, T, K, d = case
+    x = _rand(B, Cin, T, seed=4)
+    w = _rand(Cout, Cin, K, seed=5, scale=1.0 / np.sqrt(Cin * K))
+    b = _rand(Cout, seed=6, scale=0.1)
+    res = _rand(B, Cout, T, seed=7)
+    xr, wr = round_operand(x, precision), round_operand(w, precision)
+    ref = F.conv1d(xr.double(), wr.double(), b.double(), dilation=d, padding=(K * d - d) // 2) + res.double()
+    y = ops.conv1d(x.to(DEV), w.to(DEV), b.to(DEV), res.to(DEV), dilation=d, precision=precision).cpu()
+    err = float((y.double() - ref).abs().max())
+    assert err < 3e-5 * max(1.0, float(ref.abs().max())), err
+    y2 = ops.conv1d(x.to(DEV), w.to(DEV), None, None, dilation=d, precision=precision).cpu()
+    ref2 = F.conv1d(xr.double(), wr.double(), None, dilation=d, padding=(K * d - d) // 2)
+    assert float((y2.double() - ref2).abs().max()) < 3e-5 * max(1.0, float(ref2.abs().max()))
+
+
+@pytest.mark.parametrize("case", [(1, 1536, 768, 625, 4), (2, 96, 48, 333, 2), (1, 48, 24, 1000, 2), (1, 8, 4, 5, 4), (1, 4, 2, 1, 2)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_conv_transpose1d(ops, case, precision):
+    B, Cin, Cout, T, u = case
+    x = _rand(B, Cin, T, seed=8)
+    w = _rand(Cin, Cout, 2 * u, seed=9, scale=1.0 / np.sqrt(Cin * 2))
+    b = _rand(Cout, seed=10, scale=0.1)
+    xr, wr = round_operand(x, precision), round_operand(w, precision)
+    ref = F.conv_transpose1d(xr.double(), wr.double(), b.double(), stride=u, padding=u // 2)
+    y = ops.conv_transpose1d(x.to(DEV), w.to(DEV), b.to(DEV), stride=u, precision=precision).cpu()
+    assert y.shape == ref.shape
+    assert float((y.double() - ref).abs().max()) < 3e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("case", [(1, 768, 768, 312), (2, 64, 64, 17), (1, 32, 32, 1)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_upsample_conv3(ops, case, precision):
+    B, Cin, Cout, T = case
+    x = _rand(B, Cin, T, seed=11)
+    w = _rand(Cout, Cin, 3, seed=12, scale=1.0 / np.sqrt(Cin * 3))
+    b = _rand(Cout, seed=13, scale=0.1)
+    xr = round_operand(x, precision)
+    # the device sums taps in fp32 BEFORE rounding to the operand type (polyphase form)
+    w0, w1, w2 = w[..., 0], w[..., 1], w[..., 2]
+    r = lambda t: round_operand(t.contiguous(), precision).double()
+    xp = F.pad(xr.double(), (1, 1))
+    e = lambda off, ww: torch.einsum("bit,oi->bot", xp[..., 1 + off:1 + off + T], ww)
+    ref = torch.zeros(B, Cout, 2 * T, dtype=torch.float64)
+    ref[..., 0::2] = e(-1, r(w0)) + e(0, r(w1 + w2))
+    ref[..., 1::2] = e(0, r(w0 + w1)) + e(1, r(w2))
+    ref += b.double().view(1, -1, 1)
+    y = ops.upsample_conv3(x.to(DEV), w.to(DEV), b.to(DEV), precision=precision).cpu()
+    assert float((y.double() - ref).abs().max()) < 3e-5 * max(1.0, float(ref.abs().max()))
+    if precision == "fp32":  # and against the reference formulation itself
+        ref0 = F.conv1d(F.interpolate(x.double(), scale_factor=2.0, mode="nearest"), w.double(), b.double(), padding=1)
+        assert float((y.double() - ref0).abs().max()) < 3e-5 * max(1.0, float(ref0.abs().max()))
+
+
+# ----------------------------------------------------------------------------------- GroupNorm / attention
+@pytest.mark.parametrize("shape", [(1, 1536, 312), (2, 384, 624), (1, 32, 5), (2, 64, 1), (1, 128, 48)])
+@pytest.mark.parametrize("swish", [True, False])
+def test_groupnorm_swish(ops, shape, swish):
+    B, C, T = shape
+    x = _rand(B, C, T, seed=14, scale=2.0) + 0.5
+    gm, bt = 1 + _rand(C, seed=15, scale=0.2), _rand(C, seed=16, scale=0.1)
+    ref = F.group_norm(x.double(), 32, gm.double(), bt.double(), eps=1e-6)
+    if swish:
+        ref = ref * torch.sigmoid(ref)
+    y = ops.groupnorm_swish(x.to(DEV), gm.to(DEV), bt.to(DEV), swish=swish).cpu()
+    assert float((y.double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(1, 1536, 312), (2, 128, 24), (1, 32, 1), (1, 64, 33)])
+def test_attn1d(ops, shape):
+    B, C, T = shape
+    q, k, v = _rand(B, C, T, seed=17), _rand(B, C, T, seed=18), _rand(B, C, T, seed=19)
+    w = torch.softmax(torch.bmm(q.double().permute(0, 2, 1), k.double()) * (C ** -0.5), dim=2)
+    ref = torch.bmm(v.double(), w.permute(0, 2, 1))
+    y = ops.attn1d(q.to(DEV), k.to(DEV), v.to(DEV)).cpu()
+    assert float((y.double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_bad_arguments_raise(ops):
+    from audiolcm_b200 import AlcmError
+    x = torch.zeros(1, 4, 8, device=DEV)
+    with pytest.raises(AlcmError):
+        ops.conv1d(x, torch.zeros(4, 4, 4, device=DEV))          # even kernel
+    with pytest.raises(AlcmError):
+        ops.conv1d(x, torch.zeros(4, 4, 11, device=DEV), dilation=9)  # halo too large
+    with pytest.raises(AlcmError):
+        ops.groupnorm_swish(torch.zeros(1, 20, 8, device=DEV), torch.ones(20, device=DEV), torch.zeros(20, device=DEV))
+    with pytest.raises(AlcmError):
+        ops.activation1d(torch.zeros(1, 4, 8), torch.zeros(4), torch.zeros(4))  # CPU tensor: no fallback
