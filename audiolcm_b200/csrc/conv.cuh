@@ -40,7 +40,6 @@ struct ConvArgs {
   unsigned long long w_phase_stride;  // bytes between phases in w
   float scale;
   int accum;
-  int desc_swap;  // debug: swap LBO/SBO fields of the smem descriptors (ALCM_DESC_SWAP)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -134,10 +133,8 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
           const uint32_t a_base = sA + as * L.a_stage + (uint32_t)(a.tap_off[ph][j] - a.min_off[ph]) * 16;
           const uint32_t w_base = sW + ws * L.w_stage;
           for (int i = 0; i < a.kblk; i += 2) {
-            const uint64_t ad = a.desc_swap ? umma_desc_kmajor(a_base + i * rowsA * 16, 128, rowsA * 16)
-                                            : umma_desc_kmajor(a_base + i * rowsA * 16, rowsA * 16, 128);
-            const uint64_t bd = a.desc_swap ? umma_desc_kmajor(w_base + i * a.NT * 16, 128, a.NT * 16)
-                                            : umma_desc_kmajor(w_base + i * a.NT * 16, a.NT * 16, 128);
+            const uint64_t ad = umma_desc_kmajor(a_base + i * rowsA * 16, rowsA * 16, 128);
+            const uint64_t bd = umma_desc_kmajor(w_base + i * a.NT * 16, a.NT * 16, 128);
             umma_ss<KIND>(tmem_base, ad, bd, a.idesc, acc);
             acc = 1;
           }

@@ -248,7 +248,6 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
   a.span = L.span;
   a.Cin = L.Cin; a.Cout = L.Cout;
   a.scale = scale; a.accum = accum;
-  a.desc_swap = env_int("ALCM_DESC_SWAP", 0);
   const int B = x.B;
   if (L.prec == ALCM_PREC_FP32) {
     a.w = reinterpret_cast<const uint8_t*>(L.weff);

@@ -205,31 +205,36 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg,
 // (C/32 channels x T).  stats[b][g] = {mean, rstd}.  One block per (group, b).
 __global__ void gn_stats_kernel(const float* __restrict__ x, PlaneGeom xg, int C, int T, int groups, float eps,
                                 float2* __restrict__ stats) {
-  __shared__ double rs[256], rq[256];
+  __shared__ double red[256];
+  __shared__ double s_mean;
   const int g = blockIdx.x, b = blockIdx.y;
   const int cpg = C / groups;
   const size_t n = (size_t)cpg * T;
-  float s = 0.f, q = 0.f;
-  double ds = 0.0, dq = 0.0;
-  int cnt = 0;
-  for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const int c = g * cpg + (int)(i / T);
-    const int t = (int)(i % T);
-    const float v = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, c >> 2, t) + (c & 3) * 4);
-    s += v; q += v * v;
-    if (++cnt == 64) { ds += s; dq += q; s = q = 0.f; cnt = 0; }
-  }
-  rs[threadIdx.x] = ds + s;
-  rq[threadIdx.x] = dq + q;
-  __syncthreads();
-  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rq[threadIdx.x] += rq[threadIdx.x + o]; }
+  // two passes (mean, then centred sum of squares): E[x^2]-mean^2 cancels badly for small groups
+  for (int pass = 0; pass < 2; ++pass) {
+    const float mean = pass ? (float)s_mean : 0.f;
+    float s = 0.f;
+    double ds = 0.0;
+    int cnt = 0;
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const int c = g * cpg + (int)(i / T);
+      const int t = (int)(i % T);
+      const float v = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, c >> 2, t) + (c & 3) * 4);
+      const float d = v - mean;
+      s += pass ? d * d : v;
+      if (++cnt == 64) { ds += s; s = 0.f; cnt = 0; }
+    }
+    red[threadIdx.x] = ds + s;
     __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const double mean = rs[0] / (double)n;
-    const double var = rq[0] / (double)n - mean * mean;
-    stats[b * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt((var > 0 ? var : 0) + (double)eps)));
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      if (pass == 0) s_mean = red[0] / (double)n;
+      else stats[b * groups + g] = make_float2((float)s_mean, (float)(1.0 / sqrt(red[0] / (double)n + (double)eps)));
+    }
+    __syncthreads();
   }
 }
 

@@ -113,3 +113,16 @@ class LatentToWaveform(object):
 
     def launches(self, B, T):
         return self.vae.launches(B, T) + self.voc.launches(B, T * self.vae.up_factor) - 1  # mel stays packed
+
+    def profile(self, B, T, iters=3):
+        """Per-kernel-class device time (CUDA events around every kernel, eager launches) plus the
+        algorithmic FLOPs / bytes of each class for one decode of shape (B, T)."""
+        import ctypes as C
+        prof = _lib.Profile()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.load().alcm_profile_decode(self.vae._h, self.voc._h, B, T, iters, C.byref(prof), stream))
+        out = {}
+        for i, name in enumerate(_lib.CLASSES):
+            out[name] = dict(ms=prof.ms[i] / iters, flops=prof.flops[i], bytes=prof.bytes[i], launches=prof.launches[i])
+        return out

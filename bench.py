@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds per second of latent->waveform decode (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|tf32|fp32] [--batch B]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+
+Workload (BASELINE.json configs[1]): full latent->waveform decode - autoencoder1d VAE decoder +
+BigVGAN-16k - of one 10 s clip (z [B,20,312] -> wav [B,159744]), batch 1 per GPU, random-init
+weights of the shipped architectures (oracle/synth.py), synthetic latents.  A step = one decode.
+N>1 (torchrun): every rank decodes its own clip, no data-path collective (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA events around each step on
+the launching stream, L2 flushed between steps, max over ranks.  `e2e`: the public API
+(`LatentToWaveform.decode`) with a pinned host latent in and a host waveform out every step.
+`roofline`: dominant kernel class (tcgen05 conv GEMMs) - algorithmic FLOPs / CUDA-event time per
+launch measured in this process (eager launches with an event pair per kernel), against the
+measured peaks in MEASURED_PEAKS.json.  `cpu_baseline`: the oracle port of the reference's CPU path
+on this box's host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T_LAT = 312                      # configs/audiolcm.yaml:13 mel_length -> 10 s clip
+SR, HOP, VAE_UP = 16000, 256, 2
+METRIC = "audio_seconds_per_second_latent_to_waveform_decode"
+
+
+def audio_seconds(B, t_lat):
+    return B * t_lat * VAE_UP * HOP / SR
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_decode_fn(threads):
+    import torch
+    from oracle import decode_oracle as O
+    from oracle import synth
+    torch.set_num_threads(threads)
+    dd, h = synth.vae_config(), synth.bigvgan_config()
+    vsd = {k: torch.from_numpy(v) for k, v in synth.vae_decoder_state_dict(dd, seed=3).items()}
+    gsd = {k: torch.from_numpy(v) for k, v in synth.bigvgan_state_dict(h, seed=0).items()}
+
+    def run(z):
+        with torch.no_grad():
+            mel = O.decode_first_stage(vsd, dd, z)
+            return O.bigvgan_forward(gsd, h, mel)
+    return run
+
+
+def cpu_baseline(budget_s=25.0):
+    """Oracle port of the reference CPU decode on all host cores: full 10 s clip, best of <=2 runs
+    (bounded to ~budget_s of CPU work)."""
+    from oracle import synth
+    import torch
+    cores = os.cpu_count() or 1
+    run = cpu_decode_fn(cores)
+    run(torch.from_numpy(synth.synth_latent(1, 8, seed=1)))      # touch the code paths / thread pool
+    z = torch.from_numpy(synth.synth_latent(1, T_LAT, seed=0))
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(2):
+        t0 = time.perf_counter()
+        run(z)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start + times[-1] > budget_s:
+            break
+    return dict(value=round(audio_seconds(1, T_LAT) / min(times), 4), unit="audio-s/s", cores=cores, kind="port",
+                sample=f"{len(times)} full decode(s) of the same 10 s clip (VAE+BigVGAN-16k, fp32, batch 1), best; "
+                       f"oracle/decode_oracle.py = same ATen CPU ops as the reference modules")
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is pure
+    Python/PyTorch under /root/reference (absent on the GPU box, nothing to compile into
+    oracle/_ref), so this times the oracle port (same torch CPU ops, pinned to the reference by
+    tests/golden) with all host threads.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import synth
+    cores = os.cpu_count() or 1
+    run = cpu_decode_fn(cores)
+    # bound the whole run to a few minutes: calibrate on a 1 s clip, then pick the clip length
+    zc = torch.from_numpy(synth.synth_latent(1, 32, seed=1))
+    run(zc)
+    t0 = time.perf_counter()
+    run(zc)
+    per_lat = (time.perf_counter() - t0) / 32
+    n_runs = args.steps + args.warmup
+    t_lat = T_LAT
+    while t_lat > 32 and per_lat * t_lat * n_runs > 200.0:
+        t_lat //= 2
+    z = torch.from_numpy(synth.synth_latent(1, t_lat, seed=0))
+    for _ in range(args.warmup):
+        run(z)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(z)
+    dt = time.perf_counter() - t0
+    val = audio_seconds(1, t_lat) * args.steps / dt
+    sample = (f"each step = full decode of a {audio_seconds(1, t_lat):.2f} s clip (z [1,20,{t_lat}]), fp32, batch 1, "
+              f"{cores} host threads; oracle port of the reference modules (reference is Python, cannot travel)")
+    line = dict(metric=METRIC, value=round(val, 4), unit="audio-s/s", impl="reference", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=round(1e3 * dt / args.steps, 3), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"latent->waveform decode (VAE decoder + BigVGAN-16k), batch 1, "
+                                     f"{audio_seconds(1, t_lat):.2f} s clip, CPU"),
+                cpu_baseline=dict(value=round(val, 4), unit="audio-s/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=round(val, 4), unit="audio-s/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        hi = sorted(sm)[len(sm) // 2:]  # upper half = samples taken under load
+        return dict(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def build_pipe(precision, device):
+    from audiolcm_b200 import AutoencoderKLDecoder, LatentToWaveform, VocoderBigVGAN
+    from oracle import synth  # seeded synthetic weights/inputs only (data generator, not the checker)
+    dd, h = synth.vae_config(), synth.bigvgan_config()
+    vae = AutoencoderKLDecoder(synth.vae_decoder_state_dict(dd, seed=3), dd, synth.VAE_EMBED_DIM, device, precision)
+    voc = VocoderBigVGAN.from_state_dict(synth.bigvgan_state_dict(h, seed=0), h, device, precision)
+    return LatentToWaveform(vae, voc)
+
+
+def time_steps(pipe, z_dev, steps, warmup, flush):
+    import torch
+    for _ in range(warmup):
+        pipe.decode_tensor(z_dev)
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
+        flush.zero_()                       # > L2 (126 MB): every step starts cold in L2
+        e0.record()
+        pipe.decode_tensor(z_dev)
+        e1.record()
+    torch.cuda.synchronize()
+    return sum(e0.elapsed_time(e1) for e0, e1 in evs) / 1e3  # seconds of device time over `steps`
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: audiolcm_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    B = args.batch
+    pipe = build_pipe(args.precision, device)
+    z_host = torch.from_numpy(synth.synth_latent(B, T_LAT, seed=rank)).pin_memory()
+    z_dev = z_host.to(device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    pipe.decode_tensor(z_dev)               # plan + CUDA graph
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    dev_s = time_steps(pipe, z_dev, args.steps, args.warmup, flush)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    # end to end through the public API: pinned host latent in, host waveform out, every step
+    barrier()
+    for _ in range(max(1, args.warmup)):
+        pipe.decode(z_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        wav = pipe.decode(z_host)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if world > 1:
+        t = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        peaks = measured_peaks()
+        asec = audio_seconds(B, T_LAT)
+        value = world * asec * args.steps / dev_s
+        prof = pipe.profile(B, T_LAT, iters=3)
+        conv, act = prof["conv"], prof["act"]
+        tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+        act_gbs = act["bytes"] / (act["ms"] * 1e-3) / 1e9
+        total_ms = sum(c["ms"] for c in prof.values())
+        launches = pipe.launches(B, T_LAT)
+        line = dict(
+            metric=METRIC, value=round(value, 2), unit="audio-s/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=round(1e3 * dev_s / args.steps, 4), higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype={"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}[args.precision], data="synthetic",
+            config=dict(workload=f"configs[1]: full latent->waveform decode (autoencoder1d VAE decoder + BigVGAN-16k), batch {B} "
+                                 f"per GPU, 10 s clip (z [{B},20,{T_LAT}] -> wav [{B},{T_LAT * VAE_UP * HOP}])",
+                        precision=args.precision, l2="flushed between timed steps (256 MiB write)", graph=True,
+                        weights="random-init (seeded), shipped architectures"),
+            e2e=dict(value=round(world * asec * args.steps / e2e_s, 2), unit="audio-s/s", h2d_bytes_per_step=int(z_host.numel() * 4),
+                     d2h_bytes_per_step=int(wav.size * 4), api="LatentToWaveform.decode(pinned host latent) -> host ndarray"),
+            gpu_launches=launches * args.steps,
+            clocks=clocks,
+            roofline=dict(bound="tensor", achieved=round(tf, 2), peak=peaks["tf_sustained"], unit="TFLOP/s",
+                          frac=round(tf / peaks["tf_sustained"], 4), traffic=None, kernel="conv_umma_kernel (all conv GEMM launches)",
+                          peak_source=f"{peaks['source']} bf16 sustained", flops_per_step=conv["flops"],
+                          ms_per_step=round(conv["ms"], 4), launches=conv["launches"]),
+            roofline_act=dict(bound="hbm", achieved=round(act_gbs, 1), peak=peaks["hbm"], unit="GB/s",
+                              frac=round(act_gbs / peaks["hbm"], 4), kernel="act1d_kernel (all Activation1d launches)",
+                              bytes_per_step=act["bytes"], ms_per_step=round(act["ms"], 4), launches=act["launches"],
+                              note="batch-1 tensors (<=15 MB) are L2-resident; see DESIGN.md for the HBM-sized run"),
+            class_ms={k: round(v["ms"], 4) for k, v in prof.items()},
+            class_ms_total_eager=round(total_ms, 4),
+        )
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("ALCM_BENCH_PRECISION", "bf16"), choices=["bf16", "tf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
