@@ -40,6 +40,7 @@ struct ConvArgs {
   unsigned long long w_phase_stride;  // bytes between phases in w
   float scale;
   int accum;
+  int dbg;  // micro-benchmark only: bit0 skip weight copies, bit1 skip activation copies (results are garbage)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -96,54 +97,85 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   const int q0 = mt * kTileM;
 
+  // Both asynchronous roles keep their warp CONVERGENT and predicate the async instructions with
+  // elect.sync: UBLKCP / UTCHMMA / UTCBAR take warp-uniform operands, and issuing them from a
+  // divergent `if (lane == 0)` makes the compiler wrap each one in an ELECT/R2UR/BRA serialisation
+  // loop, which left the tensor pipe waiting on the issuing thread.
   if (warp == 0) {
-    if (lane == 0) {
-      const int row0 = q0 + a.min_off[ph] + a.xg.pad;  // >= 0 because |min_off| <= pad
-      const int nrows = min(rowsA, a.xg.Tp - row0);
-      const uint8_t* xb = a.x + (size_t)b * a.xg.nchunk * a.xg.Tp * 16;
-      const uint8_t* wb = a.w + (size_t)ph * a.w_phase_stride + (size_t)nt * a.nkb * a.ntaps * L.w_stage;
-      int wit = 0;
-      for (int kb = 0; kb < a.nkb; ++kb) {
-        const int as = kb & 1;
-        mbar_wait(a_empty + 8 * as, ((kb >> 1) & 1) ^ 1);
-        mbar_expect_tx(a_full + 8 * as, (uint32_t)a.kblk * nrows * 16);
-        for (int c = 0; c < a.kblk; ++c)
-          bulk_g2s(sA + as * L.a_stage + c * rowsA * 16, xb + ((size_t)(kb * a.kblk + c) * a.xg.Tp + row0) * 16,
-                   (uint32_t)nrows * 16, a_full + 8 * as);
-        for (int j = 0; j < a.ntaps; ++j, ++wit) {
-          const int ws = wit % S;
-          mbar_wait(w_empty + 8 * ws, ((wit / S) & 1) ^ 1);
-          mbar_expect_tx(w_full + 8 * ws, L.w_stage);
-          bulk_g2s(sW + ws * L.w_stage, wb + (size_t)(kb * a.ntaps + j) * L.w_stage, L.w_stage, w_full + 8 * ws);
+    const bool leader = elect_one();
+    const int row0 = q0 + a.min_off[ph] + a.xg.pad;  // >= 0 because |min_off| <= pad
+    const int nrows = min(rowsA, a.xg.Tp - row0);
+    const uint8_t* wsrc = a.w + (size_t)ph * a.w_phase_stride + (size_t)nt * a.nkb * a.ntaps * L.w_stage;
+    const size_t plane_bytes = (size_t)a.xg.Tp * 16;
+    const uint8_t* xsrc = a.x + ((size_t)b * a.xg.nchunk * a.xg.Tp + row0) * 16;
+    const uint32_t a_bytes = (uint32_t)nrows * 16, a_pitch = (uint32_t)rowsA * 16;
+    int ws = 0;
+    uint32_t wpar = 1;  // producer waits on the "previous" phase of the empty barriers first
+    for (int kb = 0; kb < a.nkb; ++kb) {
+      const int as = kb & 1;
+      mbar_wait(a_empty + 8 * as, ((kb >> 1) & 1) ^ 1);
+      if (a.dbg & 2) {
+        if (leader) mbar_arrive(a_full + 8 * as);
+        xsrc += plane_bytes * a.kblk;
+      } else {
+        if (leader) mbar_expect_tx(a_full + 8 * as, (uint32_t)a.kblk * a_bytes);
+        uint32_t dst = sA + as * L.a_stage;
+        for (int c = 0; c < a.kblk; ++c, dst += a_pitch, xsrc += plane_bytes)
+          if (leader) bulk_g2s(dst, xsrc, a_bytes, a_full + 8 * as);
+      }
+      for (int j = 0; j < a.ntaps; ++j) {
+        mbar_wait(w_empty + 8 * ws, wpar);
+        if (leader) {
+          if (a.dbg & 1) {
+            mbar_arrive(w_full + 8 * ws);
+          } else {
+            mbar_expect_tx(w_full + 8 * ws, L.w_stage);
+            bulk_g2s(sW + ws * L.w_stage, wsrc, L.w_stage, w_full + 8 * ws);
+          }
         }
+        wsrc += L.w_stage;
+        if (++ws == S) { ws = 0; wpar ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      int wit = 0;
-      uint32_t acc = 0;
-      for (int kb = 0; kb < a.nkb; ++kb) {
-        const int as = kb & 1;
-        mbar_wait(a_full + 8 * as, (kb >> 1) & 1);
+    const bool leader = elect_one();
+    // Descriptors differ only in their 14-bit start-address field: build the constant part once
+    // and add (byte offset >> 4) per MMA.
+    const uint64_t a_desc0 = umma_desc_kmajor(sA, rowsA * 16, 128);
+    const uint64_t w_desc0 = umma_desc_kmajor(sW, a.NT * 16, 128);
+    const uint32_t a_step = (uint32_t)(2 * rowsA), w_step = (uint32_t)(2 * a.NT);  // two K chunks, in 16 B units
+    const uint32_t a_stage16 = L.a_stage >> 4, w_stage16 = L.w_stage >> 4;
+    // every parameter the loop needs lives in a register: the asm memory clobbers would otherwise
+    // make the compiler re-read the constant bank on each iteration of the single issuing warp.
+    // The tap shift (row offset of tap j inside the A slab) is linear in j for every conv form here.
+    const int nkb = a.nkb, ntaps = a.ntaps, nk2 = a.kblk >> 1;
+    const uint32_t idesc = a.idesc;
+    const uint32_t shift0 = (uint32_t)(a.tap_off[ph][0] - a.min_off[ph]);
+    const int dshift = ntaps > 1 ? a.tap_off[ph][1] - a.tap_off[ph][0] : 0;
+    int ws = 0;
+    uint32_t wpar = 0, acc = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int as = kb & 1;
+      mbar_wait(a_full + 8 * as, (kb >> 1) & 1);
+      uint64_t a_tap = a_desc0 + (uint64_t)(as * a_stage16 + shift0);
+      for (int j = 0; j < ntaps; ++j, a_tap += (uint64_t)(int64_t)dshift) {
+        mbar_wait(w_full + 8 * ws, wpar);
         tc_fence_after();
-        for (int j = 0; j < a.ntaps; ++j, ++wit) {
-          const int ws = wit % S;
-          mbar_wait(w_full + 8 * ws, (wit / S) & 1);
-          tc_fence_after();
-          const uint32_t a_base = sA + as * L.a_stage + (uint32_t)(a.tap_off[ph][j] - a.min_off[ph]) * 16;
-          const uint32_t w_base = sW + ws * L.w_stage;
-          for (int i = 0; i < a.kblk; i += 2) {
-            const uint64_t ad = umma_desc_kmajor(a_base + i * rowsA * 16, rowsA * 16, 128);
-            const uint64_t bd = umma_desc_kmajor(w_base + i * a.NT * 16, a.NT * 16, 128);
-            umma_ss<KIND>(tmem_base, ad, bd, a.idesc, acc);
+        if (leader) {
+          uint64_t ad = a_tap, bd = w_desc0 + (uint64_t)(ws * w_stage16);
+#pragma unroll 4
+          for (int i = 0; i < nk2; ++i, ad += a_step, bd += w_step) {
+            umma_ss<KIND>(tmem_base, ad, bd, idesc, acc);
             acc = 1;
           }
           tc_commit(w_empty + 8 * ws);  // frees the weight slot when these MMAs retire
+          if (j == ntaps - 1) tc_commit(a_empty + 8 * as);
         }
-        tc_commit(a_empty + 8 * as);
+        if (++ws == S) { ws = 0; wpar ^= 1; }
       }
-      tc_commit(acc_full);
     }
+    if (leader) tc_commit(acc_full);
     __syncwarp();
   } else {
     mbar_wait(acc_full, 0);

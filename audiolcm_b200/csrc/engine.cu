@@ -188,22 +188,16 @@ static ConvLayer prepare_conv(Arena& ar, int prec, ConvKind kind, const float* w
   REQUIRE(L.NT % 16 == 0 && L.NT >= 16 && L.NT <= 256, "bad N tile");
   L.n_tiles = (cout_pad + L.NT - 1) / L.NT;
   L.tmem_cols = 32;
-  while (L.tmem_cols < L.NT) L.tmem_cols *= 2;
+  while (L.tmem_cols < L.NT * (env_int("ALCM_TMEM2", 0) ? 2 : 1)) L.tmem_cols *= 2;
   L.kchunks = round_up(Cin, 16) / E;
   L.kblk = 0;
   if (L.kchunks <= 12) L.kblk = L.kchunks;
-  else for (int d = 8; d >= 2; d -= 2) if (L.kchunks % d == 0) { L.kblk = d; break; }
+  else for (int d = env_int("ALCM_KBLK_MAX", 8); d >= 2; d -= 2) if (L.kchunks % d == 0) { L.kblk = d; break; }
   REQUIRE(L.kblk >= 2 && L.kblk % 2 == 0, "bad k-block");
   L.nkb = L.kchunks / L.kblk;
   L.idesc = umma_idesc(prec == ALCM_PREC_BF16 ? 1 : 2, L.NT);
-  const uint32_t budget = (uint32_t)env_int("ALCM_SMEM_BUDGET", 100 * 1024);
-  const uint32_t a2 = 2u * L.kblk * (kTileM + L.span) * 16, ws = (uint32_t)L.kblk * L.NT * 16;
-  int S = (budget > a2 + 256) ? (int)((budget - a2 - 256) / ws) : 0;
-  S = std::max(2, std::min(8, S));
-  S = std::min(S, std::max(2, L.nkb * L.ntaps));
-  L.w_stages = S;
-  L.smem = conv_smem_layout(L.kblk, L.span, L.NT, S).total;
-  REQUIRE(L.smem <= 227 * 1024, "conv tile does not fit shared memory");
+  L.w_stages = 0;  // chosen per launch (pick_stages)
+  L.smem = 0;
   L.phase_stride = (size_t)L.n_tiles * L.nkb * L.ntaps * L.kblk * L.NT * 16;
   L.wpack = static_cast<uint8_t*>(ar.alloc(L.phase_stride * L.nphase, false));
   const size_t units = L.phase_stride * L.nphase / 16;
@@ -227,12 +221,31 @@ static float* fold_wn(Arena& tmp, const float* g, const float* v, int dim0, int 
 }
 
 // ------------------------------------------------------------------------------------------ ops
+enum { OP_FORK = -1, OP_JOIN = -2 };  // markers: ops between them carry a lane (independent chains)
+constexpr int kMaxLanes = 4;
 struct Op {
   int cls;
   double flops, bytes;
   std::function<void(cudaStream_t)> fn;
+  int lane = 0;
 };
 
+static int g_sm_count = 148;
+
+// Weight-ring depth for one launch: with at most one CTA per SM use most of the 227 KB (more bytes
+// in flight hide the L2/HBM latency of the 16-32 KB weight blobs); otherwise leave room for 2 CTAs/SM.
+static void pick_stages(const ConvLayer& L, long ctas, int* stages, uint32_t* smem) {
+  const uint32_t budget = (uint32_t)env_int("ALCM_SMEM_BUDGET", ctas <= (long)g_sm_count ? 200 * 1024 : 100 * 1024);
+  const uint32_t a2 = 2u * L.kblk * (kTileM + L.span) * 16, ws = (uint32_t)L.kblk * L.NT * 16;
+  int S = (budget > a2 + 256) ? (int)((budget - a2 - 256) / ws) : 0;
+  S = std::max(2, std::min(12, S));
+  S = std::min(S, std::max(2, L.nkb * L.ntaps));
+  *stages = S;
+  *smem = conv_smem_layout(L.kblk, L.span, L.NT, S).total;
+  REQUIRE(*smem <= 227 * 1024, "conv tile does not fit shared memory");
+}
+
+static int g_conv_dbg = 0;
 static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const float* res, int M, float scale, int accum,
                         cudaStream_t st) {
   ConvArgs a;
@@ -248,6 +261,7 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
   a.span = L.span;
   a.Cin = L.Cin; a.Cout = L.Cout;
   a.scale = scale; a.accum = accum;
+  a.dbg = g_conv_dbg;
   const int B = x.B;
   if (L.prec == ALCM_PREC_FP32) {
     a.w = reinterpret_cast<const uint8_t*>(L.weff);
@@ -256,11 +270,13 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
   } else {
     a.w = L.wpack;
     a.kchunks = L.kchunks; a.kblk = L.kblk; a.nkb = L.nkb;
-    a.NT = L.NT; a.n_tiles = L.n_tiles; a.tmem_cols = L.tmem_cols; a.w_stages = L.w_stages;
+    a.NT = L.NT; a.n_tiles = L.n_tiles; a.tmem_cols = L.tmem_cols;
     a.idesc = L.idesc; a.w_phase_stride = L.phase_stride;
     dim3 grid((M + kTileM - 1) / kTileM, L.n_tiles, B * L.nphase);
-    if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0><<<grid, 192, L.smem, st>>>(a);
-    else conv_umma_kernel<1><<<grid, 192, L.smem, st>>>(a);
+    uint32_t smem = 0;
+    pick_stages(L, (long)grid.x * grid.y * grid.z, &a.w_stages, &smem);
+    if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0><<<grid, 192, smem, st>>>(a);
+    else conv_umma_kernel<1><<<grid, 192, smem, st>>>(a);
   }
 }
 
@@ -279,7 +295,7 @@ struct OpList {
     ConvLayer Lc = L;
     PlaneT xc = x, oc = out;
     op.fn = [=](cudaStream_t st) { launch_conv(Lc, xc, oc, rp, M, scale, accum, st); };
-    ops.push_back(op);
+    push(op);
   }
   void act(const PlaneT& x, const PlaneT& out, const float* ea, const float* ib, int round_tf32) {
     REQUIRE(x.esz == 4 && x.T == out.T && x.B == out.B, "act: bad planes");
@@ -295,7 +311,7 @@ struct OpList {
       if (oesz == 4) act1d_kernel<1, 512><<<dim3((T + 511) / 512, nch, B), kActThreads, 0, st>>>(a);
       else act1d_kernel<2, 256><<<dim3((T + 255) / 256, nch, B), kActThreads, 0, st>>>(a);
     };
-    ops.push_back(op);
+    push(op);
   }
   // fp32 planes -> operand planes (bf16 / tf32-rounded)
   void cast(const PlaneT& x, const PlaneT& out) {
@@ -309,10 +325,72 @@ struct OpList {
       if (oesz == 2) cast_planes_kernel<8><<<grid, 256, 0, st>>>(xc.f(), xc.g, oc.p, oc.g, T);
       else cast_planes_kernel<4><<<grid, 256, 0, st>>>(xc.f(), xc.g, oc.p, oc.g, T);
     };
-    ops.push_back(op);
+    push(op);
   }
+  // n-way sum of fp32 planes (block mean of the AMP blocks, models.py:190-196, when the blocks ran as
+  // parallel lanes); writes fp32 planes and/or operand planes for the next conv
+  void sum(const std::vector<PlaneT>& in, const PlaneT* out32, const PlaneT* out_op, int round_tf) {
+    REQUIRE(in.size() >= 2 && in.size() <= 4 && (out32 || out_op), "sum: bad arguments");
+    SumArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = (int)in.size();
+    for (int i = 0; i < a.n; ++i) a.in[i] = in[i].f();
+    a.g = in[0].g;
+    a.T = in[0].T;
+    a.out32 = out32 ? out32->f() : nullptr;
+    a.out_op = out_op ? out_op->p : nullptr;
+    a.og = out_op ? out_op->g : in[0].g;
+    a.op_bf16 = out_op ? (out_op->esz == 2) : 0;
+    a.round_tf32 = round_tf;
+    const int B = in[0].B, T = in[0].T, nch = in[0].g.nchunk;
+    Op op;
+    op.cls = ALCM_CLS_MISC; op.flops = 0;
+    op.bytes = (double)B * T * nch * 4 * (4.0 * a.n + (out32 ? 4 : 0) + (out_op ? out_op->esz : 0));
+    op.fn = [=](cudaStream_t st) { sum_planes_kernel<<<dim3((T + 255) / 256, nch / 2, B), 256, 0, st>>>(a); };
+    push(op);
+  }
+  void fork() { Op m; m.cls = OP_FORK; m.flops = m.bytes = 0; ops.push_back(m); }
+  void join() { Op m; m.cls = OP_JOIN; m.flops = m.bytes = 0; cur_lane = 0; ops.push_back(m); }
+  void lane(int l) { cur_lane = l; }
+  void push(Op& op) { op.lane = cur_lane; ops.push_back(op); }
+  int cur_lane = 0;
+  int launches() const {
+    int n = 0;
+    for (const Op& o : ops) n += o.cls >= 0;
+    return n;
+  }
+  // serial execution on one stream (eager mode / profiling): lanes simply run one after another
   void run(cudaStream_t st) const {
-    for (const Op& o : ops) o.fn(st);
+    for (const Op& o : ops) if (o.cls >= 0) o.fn(st);
+  }
+  // execution with fork/join across side streams (used under stream capture -> parallel graph branches)
+  void run_lanes(cudaStream_t st, cudaStream_t* side, std::vector<cudaEvent_t>& evs) const {
+    size_t ei = 0;
+    auto next_ev = [&]() {
+      if (ei == evs.size()) {
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        evs.push_back(e);
+      }
+      return evs[ei++];
+    };
+    bool used[kMaxLanes] = {false, false, false, false};
+    for (const Op& o : ops) {
+      if (o.cls == OP_FORK) {
+        cudaEvent_t e = next_ev();
+        CUDA_CHECK(cudaEventRecord(e, st));
+        for (int l = 1; l < kMaxLanes; ++l) { CUDA_CHECK(cudaStreamWaitEvent(side[l - 1], e, 0)); used[l] = false; }
+      } else if (o.cls == OP_JOIN) {
+        for (int l = 1; l < kMaxLanes; ++l) {
+          cudaEvent_t e = next_ev();
+          CUDA_CHECK(cudaEventRecord(e, side[l - 1]));
+          CUDA_CHECK(cudaStreamWaitEvent(st, e, 0));
+        }
+      } else {
+        o.fn(o.lane == 0 ? st : side[o.lane - 1]);
+      }
+    }
+    (void)used;
   }
 };
 
@@ -334,16 +412,25 @@ struct GraphExec {
 static bool use_graph() { return env_int("ALCM_GRAPH", 1) != 0; }
 
 static void capture_graph(const OpList& ol, GraphExec& ge) {
-  cudaStream_t cs;
+  cudaStream_t cs, side[kMaxLanes - 1];
   CUDA_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  for (auto& sd : side) CUDA_CHECK(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+  std::vector<cudaEvent_t> evs;
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
   if (e == cudaSuccess) {
-    ol.run(cs);
-    e = cudaStreamEndCapture(cs, &graph);
+    try {
+      ol.run_lanes(cs, side, evs);
+      e = cudaStreamEndCapture(cs, &graph);
+    } catch (...) {
+      cudaStreamEndCapture(cs, &graph);
+      e = cudaErrorUnknown;
+    }
   }
   if (e == cudaSuccess) e = cudaGraphInstantiate(&ge.exec, graph, 0);
   if (graph) cudaGraphDestroy(graph);
+  for (auto ev : evs) cudaEventDestroy(ev);
+  for (auto sd : side) cudaStreamDestroy(sd);
   cudaStreamDestroy(cs);
   if (e != cudaSuccess) {
     ge.exec = nullptr;
@@ -411,19 +498,36 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
   int C = v->cfg.upsample_initial_channel, Tc = T;
   PlaneT xprev = make_planes(P.ar, B, C, Tc, 4);
   P.ol.conv(v->conv_pre, P.mel_in, xprev, nullptr);
+  PlaneT next_up_in;
+  bool have_next_up_in = false;
   for (size_t i = 0; i < v->stages.size(); ++i) {
     const VocStage& S = v->stages[i];
     PlaneT up_in = xprev;
-    if (prec == ALCM_PREC_BF16) {
+    if (have_next_up_in) {
+      up_in = next_up_in;
+      have_next_up_in = false;
+    } else if (prec == ALCM_PREC_BF16) {
       up_in = make_planes(P.ar, B, C, Tc, 2);
       P.ol.cast(xprev, up_in);
     }
     C = S.C; Tc *= S.u;
-    PlaneT X = make_planes(P.ar, B, C, Tc, 4), R = make_planes(P.ar, B, C, Tc, 4), Y = make_planes(P.ar, B, C, Tc, 4);
-    PlaneT XS = make_planes(P.ar, B, C, Tc, 4), A = make_planes(P.ar, B, C, Tc, oe);
+    PlaneT X = make_planes(P.ar, B, C, Tc, 4);
     P.ol.conv(S.up, up_in, X, nullptr);
+    // The nk AMP blocks of a stage are independent chains.  When one conv launch cannot fill the
+    // machine (few time tiles: batch-1 clips) they run as parallel graph lanes with private buffers;
+    // otherwise they run back to back, share buffers and accumulate straight into XS.
+    const long conv_ctas = (long)((Tc + kTileM - 1) / kTileM) * std::max(1, round_up(C, 16) / 128) * B;
+    const bool parallel = nk > 1 && nk <= kMaxLanes && env_int("ALCM_LANES", 1) && conv_ctas < 3L * g_sm_count;
+    PlaneT XS = make_planes(P.ar, B, C, Tc, 4);
+    std::vector<PlaneT> Z;
+    PlaneT R, Y, A;
+    if (parallel) P.ol.fork();
     for (int j = 0; j < nk; ++j) {
       const AmpBlock& bk = S.blocks[j];
+      if (parallel || j == 0) {
+        R = make_planes(P.ar, B, C, Tc, 4); Y = make_planes(P.ar, B, C, Tc, 4); A = make_planes(P.ar, B, C, Tc, oe);
+      }
+      if (parallel) P.ol.lane(j);
       const PlaneT* cur = &X;
       for (int l = 0; l < 3; ++l) {  // models.py:72-81
         P.ol.act(*cur, A, bk.a[2 * l].ea, bk.a[2 * l].ib, rtf);
@@ -432,9 +536,23 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
         if (l < 2) {
           P.ol.conv(bk.c2[l], A, R, cur);
           cur = &R;
+        } else if (parallel) {  // block output in place of its residual stream (same thread reads then writes)
+          P.ol.conv(bk.c2[l], A, R, cur, 1.0f / nk, 0);
+          Z.push_back(R);
         } else {  // x = xs / num_kernels, models.py:190-196, folded into the last conv of each block
           P.ol.conv(bk.c2[l], A, XS, cur, 1.0f / nk, j > 0);
         }
+      }
+    }
+    if (parallel) {
+      P.ol.join();
+      const bool last = (i + 1 == v->stages.size());
+      if (prec == ALCM_PREC_BF16 && !last) {  // the only consumer is the next upsampler: emit its bf16 operand directly
+        next_up_in = make_planes(P.ar, B, C, Tc, 2);
+        P.ol.sum(Z, nullptr, &next_up_in, 0);
+        have_next_up_in = true;
+      } else {
+        P.ol.sum(Z, &XS, nullptr, 0);
       }
     }
     xprev = XS;
@@ -503,7 +621,7 @@ static void op_gn(OpList& ol, Arena& ar, const PlaneT& x, const PlaneT& out, con
   GnP nn = n;
   Op a;
   a.cls = ALCM_CLS_NORM; a.flops = 0; a.bytes = (double)B * C * T * 4;
-  a.fn = [=](cudaStream_t st) { gn_stats_kernel<<<dim3(groups, B), 256, 0, st>>>(xc.f(), xc.g, C, T, groups, 1e-6f, stats); };
+  a.fn = [=](cudaStream_t st) { gn_stats_kernel<<<dim3(groups, B), 512, 0, st>>>(xc.f(), xc.g, C, T, groups, 1e-6f, stats); };
   ol.ops.push_back(a);
   Op b;
   b.cls = ALCM_CLS_NORM; b.flops = 0; b.bytes = (double)B * C * T * (4.0 + out.esz);
@@ -641,6 +759,7 @@ int alcm_ctx_create(alcm_ctx** out, int device) {
     alcm_ctx* c = new alcm_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
+    g_sm_count = c->sm_count;
     *out = c;
   });
 }
@@ -1000,17 +1119,18 @@ static void profile_ops(const OpList& ol, int iters, alcm_profile* out, cudaStre
   for (int it = 0; it < iters; ++it) {
     CUDA_CHECK(cudaEventRecord(ev[0], st));
     for (size_t i = 0; i < ol.ops.size(); ++i) {
-      ol.ops[i].fn(st);
+      if (ol.ops[i].cls >= 0) ol.ops[i].fn(st);
       CUDA_CHECK(cudaEventRecord(ev[i + 1], st));
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
     for (size_t i = 0; i < ol.ops.size(); ++i) {
       float ms = 0.f;
       CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-      out->ms[ol.ops[i].cls] += ms;
+      if (ol.ops[i].cls >= 0) out->ms[ol.ops[i].cls] += ms;
     }
   }
   for (const Op& o : ol.ops) {
+    if (o.cls < 0) continue;
     out->flops[o.cls] += o.flops;
     out->bytes[o.cls] += o.bytes;
     out->launches[o.cls] += 1;
@@ -1035,11 +1155,42 @@ int alcm_profile_decode(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iter
   });
 }
 
+int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int dilation, int precision, int iters, int dbg,
+                    float* ms_per_launch) {
+  return guarded([&] {
+    REQUIRE(ctx && ms_per_launch && iters >= 1, "bench_conv: bad argument");
+    REQUIRE(precision == ALCM_PREC_TF32 || precision == ALCM_PREC_BF16 || dbg == 0, "bench_conv: dbg flags need a tcgen05 mode");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    Arena ar;
+    float* w = static_cast<float*>(ar.alloc((size_t)Cout * Cin * K * 4, true));
+    ConvLayer L = prepare_conv(ar, precision, KIND_CONV, w, nullptr, Cout, Cin, K, dilation);
+    PlaneT x = make_planes(ar, B, Cin, T, opnd_esz(precision)), out = make_planes(ar, B, Cout, T, 4);
+    OpList ol;
+    ol.conv(L, x, out, nullptr);
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    g_conv_dbg = dbg;
+    for (int i = 0; i < 3; ++i) ol.run(0);
+    CUDA_CHECK(cudaEventRecord(e0, 0));
+    for (int i = 0; i < iters; ++i) ol.run(0);
+    CUDA_CHECK(cudaEventRecord(e1, 0));
+    cudaError_t err = cudaEventSynchronize(e1);
+    g_conv_dbg = 0;
+    CUDA_CHECK(err);
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  });
+}
+
 int alcm_vocoder_launches(alcm_vocoder* v, int B, int T) {
   int n = -1;
   guarded([&] {
     REQUIRE(v, "NULL vocoder");
-    n = (int)voc_plan(v, B, T)->ol.ops.size() + 2;  // + mel pack + conv_post
+    n = voc_plan(v, B, T)->ol.launches() + 2;  // + mel pack + conv_post
   });
   return n;
 }
@@ -1047,7 +1198,7 @@ int alcm_vae_launches(alcm_vae* v, int B, int T) {
   int n = -1;
   guarded([&] {
     REQUIRE(v, "NULL vae");
-    n = (int)vae_plan(v, B, T)->ol.ops.size() + 2;  // + latent pack + mel unpack
+    n = vae_plan(v, B, T)->ol.launches() + 2;  // + latent pack + mel unpack
   });
   return n;
 }

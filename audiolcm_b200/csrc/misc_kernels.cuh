@@ -89,6 +89,50 @@ __global__ void cast_planes_kernel(const float* __restrict__ in, PlaneGeom ig, v
   }
 }
 
+// n-way sum of fp32 planes -> fp32 planes and/or operand planes (bf16 E=8 or tf32-rounded fp32).
+// One thread handles two adjacent fp32 chunks (= one bf16 chunk) of one time step.
+struct SumArgs {
+  const float* in[4];
+  int n;
+  PlaneGeom g;       // geometry of the fp32 inputs and of out32
+  float* out32;      // may be null
+  void* out_op;      // may be null
+  PlaneGeom og;      // geometry of out_op
+  int op_bf16, round_tf32, T;
+};
+__global__ void sum_planes_kernel(SumArgs a) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pc = blockIdx.y, b = blockIdx.z;  // pair of fp32 chunks 2*pc, 2*pc+1
+  if (t >= a.T) return;
+  float4 s[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const size_t off = plane_row_off(a.g, b, 2 * pc + h, t);
+    float4 acc = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(a.in[0]) + off);
+    for (int i = 1; i < a.n; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(a.in[i]) + off);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    s[h] = acc;
+    if (a.out32) *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a.out32) + off) = acc;
+  }
+  if (a.out_op) {
+    if (a.op_bf16) {
+      uint4 o;
+      o.x = pack_bf16x2(s[0].x, s[0].y); o.y = pack_bf16x2(s[0].z, s[0].w);
+      o.z = pack_bf16x2(s[1].x, s[1].y); o.w = pack_bf16x2(s[1].z, s[1].w);
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out_op) + plane_row_off(a.og, b, pc, t)) = o;
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float4 v = s[h];
+        if (a.round_tf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+        *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(a.out_op) + plane_row_off(a.og, b, 2 * pc + h, t)) = v;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- weights
 // weight_norm fold (torch.nn.utils.weight_norm dim=0; models.py:36-51,143,152,174):
 // w[i,:,:] = g[i] * v[i,:,:] / ||v[i,:,:]||.  One block per dim-0 slice.
@@ -203,26 +247,43 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg,
 // ------------------------------------------------------------------------------- GroupNorm
 // Normalize = GroupNorm(32, C, eps 1e-6, affine) (autoencoder1d.py:169-170); biased variance over
 // (C/32 channels x T).  stats[b][g] = {mean, rstd}.  One block per (group, b).
-__global__ void gn_stats_kernel(const float* __restrict__ x, PlaneGeom xg, int C, int T, int groups, float eps,
-                                float2* __restrict__ stats) {
-  __shared__ double red[256];
+__global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__ x, PlaneGeom xg, int C, int T, int groups,
+                                                         float eps, float2* __restrict__ stats) {
+  __shared__ double red[512];
   __shared__ double s_mean;
   const int g = blockIdx.x, b = blockIdx.y;
   const int cpg = C / groups;
   const size_t n = (size_t)cpg * T;
+  const bool vec = (cpg & 3) == 0;  // the group is a whole number of 4-channel planes -> float4 loads
   // two passes (mean, then centred sum of squares): E[x^2]-mean^2 cancels badly for small groups
   for (int pass = 0; pass < 2; ++pass) {
     const float mean = pass ? (float)s_mean : 0.f;
     float s = 0.f;
     double ds = 0.0;
     int cnt = 0;
-    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
-      const int c = g * cpg + (int)(i / T);
-      const int t = (int)(i % T);
-      const float v = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, c >> 2, t) + (c & 3) * 4);
-      const float d = v - mean;
-      s += pass ? d * d : v;
-      if (++cnt == 64) { ds += s; s = 0.f; cnt = 0; }
+    if (vec) {
+      const size_t nv = n >> 2;
+      for (size_t i = threadIdx.x; i < nv; i += blockDim.x) {
+        const int pl = (g * cpg >> 2) + (int)(i / T);
+        const int t = (int)(i % T);
+        const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, pl, t));
+        if (pass) {
+          const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+          s += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        } else {
+          s += (v.x + v.y) + (v.z + v.w);
+        }
+        if (++cnt == 16) { ds += s; s = 0.f; cnt = 0; }
+      }
+    } else {
+      for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = g * cpg + (int)(i / T);
+        const int t = (int)(i % T);
+        const float v = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, c >> 2, t) + (c & 3) * 4);
+        const float d = v - mean;
+        s += pass ? d * d : v;
+        if (++cnt == 64) { ds += s; s = 0.f; cnt = 0; }
+      }
     }
     red[threadIdx.x] = ds + s;
     __syncthreads();

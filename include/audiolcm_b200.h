@@ -149,6 +149,10 @@ typedef struct {
 /* runs the vocoder (vae may be NULL) / vae+vocoder op lists eagerly with an event pair around every
  * kernel; the normal path replays a CUDA graph and has no events inside. */
 int alcm_profile_decode(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iters, alcm_profile* out, void* stream);
+/* times `iters` back-to-back launches of one Conv1d(Cin,Cout,K,dilation) on synthetic (zero) data of
+ * shape [B,Cin,T]; dbg is for kernel bring-up (bit0/bit1 skip the weight/activation copies) */
+int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int dilation, int precision, int iters, int dbg,
+                    float* ms_per_launch);
 /* kernels launched by one alcm_vocode / alcm_vae_decode call for this shape (after planning) */
 int alcm_vocoder_launches(alcm_vocoder* v, int B, int T);
 int alcm_vae_launches(alcm_vae* v, int B, int T);
