@@ -77,6 +77,7 @@ SYMBOLS = {
     "alcm_attn1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_profile_decode": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Profile), _P]),
     "alcm_bench_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "alcm_bench_act": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "alcm_vocoder_launches": (C.c_int, [_P, C.c_int, C.c_int]),
     "alcm_vae_launches": (C.c_int, [_P, C.c_int, C.c_int]),
 }

@@ -6,18 +6,28 @@
 //   down : out[m]  = sum_{k<12} y[clamp(2m+k-5, 0, 2T-1)] f[k]
 // c() clamps to [0,T-1] (replicate padding on both FIRs).  Input: fp32 planes (E=4).  Output:
 // fp32 planes (optionally RNE-rounded to tf32 for the tf32 MMA) or bf16 planes (E=8, two input
-// planes per output plane).  One thread = one time step x one 16-byte output unit: all global
-// accesses are 128-bit and a warp touches 512 contiguous bytes per plane.
+// planes per output plane).
+//
+// Structure: a block stages a halo'd time tile of x in shared memory (coalesced 128-bit loads, a
+// one-slot pad every 8 rows makes the strided register-blocking reads conflict-free); every thread
+// then produces 4 consecutive outputs entirely in registers: 18 up-sampled values (9 even, 9 odd, both
+// from the same 6-row window), snake, scatter into the 4 accumulators.  FIR arithmetic is packed
+// FFMA2 (two channels per instruction).  No intermediate (2T-long) signal ever reaches memory.
 #pragma once
 #include "common.cuh"
 
 namespace alcm {
 
-// kaiser_sinc_filter1d(cutoff=0.25, half_width=0.3, kernel_size=12) - filter.py:28-57; symmetric.
+// kaiser_sinc_filter1d(cutoff=0.25, half_width=0.3, kernel_size=12) - filter.py:28-57; symmetric:
+// f[k] = f[11-k]; only f[0..5] are stored.
 __constant__ float c_fir[12] = {0.0020289647f, 0.0093894657f,  -0.0255434588f, -0.0576573834f, 0.1285725832f, 0.4432097971f,
                                 0.4432097971f, 0.1285725832f, -0.0576573834f, -0.0255434588f, 0.0093894657f, 0.0020289647f};
 
-constexpr int kActThreads = 256;
+constexpr int kActThreads = 128;
+constexpr int kActR = 4;                              // outputs per thread
+constexpr int kActTile = kActThreads * kActR;         // 512 outputs per block
+constexpr int kActRows = kActTile + 10;               // x[t0-5 .. t0+tile+4]
+constexpr int kActSlots = kActRows + (kActRows >> 3) + 1;
 
 struct ActArgs {
   const float* x;   // fp32 planes
@@ -30,8 +40,8 @@ struct ActArgs {
   int round_tf32;
 };
 
-__device__ __forceinline__ float snake1(float v, float ea, float ib) {
-  // sin^2 has period pi: reduce a*v to [-pi/2, pi/2] (2-term Cody-Waite) then MUFU.SIN
+// accurate snake: sin^2 has period pi -> reduce a*v to [-pi/2, pi/2] (2-term Cody-Waite), MUFU.SIN
+__device__ __forceinline__ float snake_acc(float v, float ea, float ib) {
   const float t = v * ea;
   const float k = rintf(t * 0.31830988618379067f);
   float r = fmaf(-k, 3.14159274101257324f, t);
@@ -39,92 +49,149 @@ __device__ __forceinline__ float snake1(float v, float ea, float ib) {
   const float s = __sinf(r);
   return fmaf(ib * s, s, v);
 }
+// fast snake: v + ib*sin^2(ea v) = (v + ib/2) - (ib/2) cos(2 ea v); ea2 = 2 ea, hb = ib/2
+__device__ __forceinline__ float snake_fast(float v, float ea2, float hb) { return fmaf(-hb, __cosf(v * ea2), v + hb); }
 
-template <int NPL, int kActTT>  // NPL input planes per thread: 1 -> fp32 out, 2 -> bf16 out; kActTT steps per block
-__global__ void __launch_bounds__(kActThreads) act1d_kernel(const __grid_constant__ ActArgs a) {
-  __shared__ float4 sx[NPL][kActTT + 12];
-  __shared__ float4 se[NPL][kActTT + 6];
-  __shared__ float4 so[NPL][kActTT + 6];
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+// One up-sampled value at (clamped) up-sampled index j, read from the staged tile (edge path only).
+__device__ __forceinline__ float4 act_y_at(const float4* sx, int j, int t0, int T, float4 ea, float4 ib) {
+  const int n = j >> 1, odd = j & 1;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const int t = min(max(n - 3 + odd + q, 0), T - 1);
+    const int lr = t - (t0 - 5);
+    const float4 xv = sx[lr + (lr >> 3)];
+    const float w = 2.f * c_fir[11 - odd - 2 * q];
+    s.x = fmaf(xv.x, w, s.x); s.y = fmaf(xv.y, w, s.y); s.z = fmaf(xv.z, w, s.z); s.w = fmaf(xv.w, w, s.w);
+  }
+  return make_float4(snake_acc(s.x, ea.x, ib.x), snake_acc(s.y, ea.y, ib.y), snake_acc(s.z, ea.z, ib.z), snake_acc(s.w, ea.w, ib.w));
+}
+
+// Four consecutive outputs of one 4-channel plane, entirely in registers (see header comment).
+// EDGE is warp-uniform: only warps holding the first / last outputs of a plane pay for the y fix-ups.
+template <bool FAST, bool EDGE>
+__device__ __forceinline__ void act_plane(const float4* sx, int tid, int m0, int t0, int T, float4 ea, float4 ib,
+                                          float4 (&out)[kActR]) {
+    // window xl[k] = x[m0-5+k], k = 0..13 ; local row of x[m0-5] is 4*tid
+    float2 xlo[14], xhi[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      const int lr = kActR * tid + k;
+      const float4 v = sx[lr + (lr >> 3)];
+      xlo[k] = make_float2(v.x, v.y);
+      xhi[k] = make_float2(v.z, v.w);
+    }
+    float2 f2[6], g2[6];  // broadcast taps: f[k] (down) and 2 f[k] (up), k = 0..5 (symmetric filter)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      f2[k] = make_float2(c_fir[k], c_fir[k]);
+      g2[k] = make_float2(2.f * c_fir[k], 2.f * c_fir[k]);
+    }
+    const float2 ea_lo = FAST ? make_float2(2.f * ea.x, 2.f * ea.y) : make_float2(ea.x, ea.y);
+    const float2 ea_hi = FAST ? make_float2(2.f * ea.z, 2.f * ea.w) : make_float2(ea.z, ea.w);
+    const float2 ib_lo = FAST ? make_float2(0.5f * ib.x, 0.5f * ib.y) : make_float2(ib.x, ib.y);
+    const float2 ib_hi = FAST ? make_float2(0.5f * ib.z, 0.5f * ib.w) : make_float2(ib.z, ib.w);
+    float4 y_first = make_float4(0.f, 0.f, 0.f, 0.f), y_last = y_first;
+    if (EDGE && m0 < 3) y_first = act_y_at(sx, 0, t0, T, ea, ib);                    // x[0..] is in this (first) tile
+    if (EDGE && m0 + 6 > T - 1) y_last = act_y_at(sx, 2 * T - 1, t0, T, ea, ib);     // x[..T-1] is in this (last) tile
+    float2 alo[kActR], ahi[kActR];
+#pragma unroll
+    for (int r = 0; r < kActR; ++r) alo[r] = ahi[r] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < 9; ++s) {
+      // odd value  y[2(m0-3+s)+1] = sum_q xl[s+q] * 2f[10-2q] ; even value y[2(m0-2+s)] = sum_q xl[s+q] * 2f[11-2q]
+      float2 olo = make_float2(0.f, 0.f), ohi = olo, elo = olo, ehi = olo;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const int ko = 10 - 2 * q, ke = 11 - 2 * q;
+        const float2 wo = g2[ko < 6 ? ko : 11 - ko], we = g2[ke < 6 ? ke : 11 - ke];
+        olo = ffma2(xlo[s + q], wo, olo); ohi = ffma2(xhi[s + q], wo, ohi);
+        elo = ffma2(xlo[s + q], we, elo); ehi = ffma2(xhi[s + q], we, ehi);
+      }
+      if (FAST) {
+        olo.x = snake_fast(olo.x, ea_lo.x, ib_lo.x); olo.y = snake_fast(olo.y, ea_lo.y, ib_lo.y);
+        ohi.x = snake_fast(ohi.x, ea_hi.x, ib_hi.x); ohi.y = snake_fast(ohi.y, ea_hi.y, ib_hi.y);
+        elo.x = snake_fast(elo.x, ea_lo.x, ib_lo.x); elo.y = snake_fast(elo.y, ea_lo.y, ib_lo.y);
+        ehi.x = snake_fast(ehi.x, ea_hi.x, ib_hi.x); ehi.y = snake_fast(ehi.y, ea_hi.y, ib_hi.y);
+      } else {
+        olo.x = snake_acc(olo.x, ea_lo.x, ib_lo.x); olo.y = snake_acc(olo.y, ea_lo.y, ib_lo.y);
+        ohi.x = snake_acc(ohi.x, ea_hi.x, ib_hi.x); ohi.y = snake_acc(ohi.y, ea_hi.y, ib_hi.y);
+        elo.x = snake_acc(elo.x, ea_lo.x, ib_lo.x); elo.y = snake_acc(elo.y, ea_lo.y, ib_lo.y);
+        ehi.x = snake_acc(ehi.x, ea_hi.x, ib_hi.x); ehi.y = snake_acc(ehi.y, ea_hi.y, ib_hi.y);
+      }
+      if (EDGE) {  // replicate padding of the down filter acts on y: y[j<0] = y[0], y[j>=2T] = y[2T-1]
+        const int no = m0 - 3 + s, ne = m0 - 2 + s;
+        if (no < 0) { olo = make_float2(y_first.x, y_first.y); ohi = make_float2(y_first.z, y_first.w); }
+        if (ne < 0) { elo = make_float2(y_first.x, y_first.y); ehi = make_float2(y_first.z, y_first.w); }
+        if (no >= T) { olo = make_float2(y_last.x, y_last.y); ohi = make_float2(y_last.z, y_last.w); }
+        if (ne >= T) { elo = make_float2(y_last.x, y_last.y); ehi = make_float2(y_last.z, y_last.w); }
+      }
+      // scatter: out[m0+r] += yo*f[2d] + ye*f[2d+1], d = s-r in [0,5]
+#pragma unroll
+      for (int r = 0; r < kActR; ++r) {
+        const int d = s - r;
+        if (d >= 0 && d <= 5) {
+          const int k0 = 2 * d, k1 = 2 * d + 1;
+          const float2 w0 = f2[k0 < 6 ? k0 : 11 - k0], w1 = f2[k1 < 6 ? k1 : 11 - k1];
+          alo[r] = ffma2(olo, w0, alo[r]); ahi[r] = ffma2(ohi, w0, ahi[r]);
+          alo[r] = ffma2(elo, w1, alo[r]); ahi[r] = ffma2(ehi, w1, ahi[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < kActR; ++r) out[r] = make_float4(alo[r].x, alo[r].y, ahi[r].x, ahi[r].y);
+}
+
+template <int NPL, bool FAST>  // NPL input planes per output unit: 1 -> fp32 out, 2 -> bf16 out
+__global__ void __launch_bounds__(kActThreads, 6) act1d_kernel(const __grid_constant__ ActArgs a) {
+  __shared__ float4 sx[NPL][kActSlots];
   const int tid = threadIdx.x;
-  const int t0 = blockIdx.x * kActTT;
+  const int t0 = blockIdx.x * kActTile;
   const int oc = blockIdx.y, b = blockIdx.z;
   const int T = a.T;
-  float f[12];
-#pragma unroll
-  for (int i = 0; i < 12; ++i) f[i] = c_fir[i];
 
+  // ---- stage x[t0-5 .. t0+tile+4] (replicate-clamped) -----------------------------------------
 #pragma unroll
   for (int p = 0; p < NPL; ++p) {
-    const int chunk = oc * NPL + p;
-    const float4* xp = reinterpret_cast<const float4*>(a.x) + ((size_t)b * a.xg.nchunk + chunk) * a.xg.Tp + a.xg.pad;
-    for (int i = tid; i < kActTT + 12; i += kActThreads) {
-      const int t = min(max(t0 - 6 + i, 0), T - 1);
-      sx[p][i] = xp[t];
+    const float4* xp = reinterpret_cast<const float4*>(a.x) + ((size_t)b * a.xg.nchunk + (oc * NPL + p)) * a.xg.Tp + a.xg.pad;
+    for (int lr = tid; lr < kActRows; lr += kActThreads) {
+      const int t = min(max(t0 - 5 + lr, 0), T - 1);
+      sx[p][lr + (lr >> 3)] = xp[t];
     }
   }
   __syncthreads();
 
+  const int m0 = t0 + kActR * tid;
+  if (m0 >= T) return;
+  // up-sampled pairs n in [m0-3, m0+6]: where n falls outside [0,T-1] the down filter's replicate
+  // padding wants y[0] / y[2T-1] instead (only the first / last one or two threads of a plane)
+  const bool edge = (m0 < 3) || (m0 + 6 > T - 1);
+
+  float4 res[NPL][kActR];
 #pragma unroll
   for (int p = 0; p < NPL; ++p) {
     const int chunk = oc * NPL + p;
     const float4 ea = *reinterpret_cast<const float4*>(a.ea + chunk * 4);
     const float4 ib = *reinterpret_cast<const float4*>(a.ib + chunk * 4);
-    for (int i = tid; i < kActTT + 6; i += kActThreads) {
-      const int n = t0 - 3 + i;           // up-sampled pair index (unclamped)
-      const int nc = min(max(n, 0), T - 1);
-      // sx index of x[nc + d] with clamp: position of time t is (t - (t0-6))
-      float4 ev = make_float4(0.f, 0.f, 0.f, 0.f), ov = ev;
-#pragma unroll
-      for (int q = 0; q < 7; ++q) {
-        const int t = min(max(nc - 3 + q, 0), T - 1);
-        const float4 xv = sx[p][t - (t0 - 6)];
-        if (q < 6) {  // even: x[c(n-3+q)] * f[11-2q]
-          const float w = f[11 - 2 * q];
-          ev.x = fmaf(xv.x, w, ev.x); ev.y = fmaf(xv.y, w, ev.y); ev.z = fmaf(xv.z, w, ev.z); ev.w = fmaf(xv.w, w, ev.w);
-        }
-        if (q > 0) {  // odd: x[c(n-2+q')] * f[10-2q'], q' = q-1
-          const float w = f[12 - 2 * q];
-          ov.x = fmaf(xv.x, w, ov.x); ov.y = fmaf(xv.y, w, ov.y); ov.z = fmaf(xv.z, w, ov.z); ov.w = fmaf(xv.w, w, ov.w);
-        }
-      }
-      ev.x = snake1(2.f * ev.x, ea.x, ib.x); ev.y = snake1(2.f * ev.y, ea.y, ib.y);
-      ev.z = snake1(2.f * ev.z, ea.z, ib.z); ev.w = snake1(2.f * ev.w, ea.w, ib.w);
-      ov.x = snake1(2.f * ov.x, ea.x, ib.x); ov.y = snake1(2.f * ov.y, ea.y, ib.y);
-      ov.z = snake1(2.f * ov.z, ea.z, ib.z); ov.w = snake1(2.f * ov.w, ea.w, ib.w);
-      // replicate padding of the down filter acts on y: y[j<0] = y[0], y[j>=2T] = y[2T-1]
-      if (n < 0) ov = ev;       // both slots = y[0]   (nc == 0)
-      if (n >= T) ev = ov;      // both slots = y[2T-1] (nc == T-1)
-      se[p][i] = ev;
-      so[p][i] = ov;
-    }
+    if (__any_sync(0xffffffffu, edge)) act_plane<FAST, true>(sx[p], tid, m0, t0, T, ea, ib, res[p]);
+    else act_plane<FAST, false>(sx[p], tid, m0, t0, T, ea, ib, res[p]);
   }
-  __syncthreads();
 
-  for (int i = tid; i < kActTT; i += kActThreads) {
-    const int m = t0 + i;
+#pragma unroll
+  for (int r = 0; r < kActR; ++r) {
+    const int m = m0 + r;
     if (m >= T) break;
-    float4 r[NPL];
-#pragma unroll
-    for (int p = 0; p < NPL; ++p) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      // k odd  -> even slot of n = m + (k-5)/2 ; k even -> odd slot of n = m + (k-6)/2 ; slot idx = n - (t0-3)
-#pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        const int n_rel = (k & 1) ? (i + 3 + (k - 5) / 2) : (i + 3 + (k - 6) / 2);
-        const float4 yv = (k & 1) ? se[p][n_rel] : so[p][n_rel];
-        const float w = f[k];
-        acc.x = fmaf(yv.x, w, acc.x); acc.y = fmaf(yv.y, w, acc.y); acc.z = fmaf(yv.z, w, acc.z); acc.w = fmaf(yv.w, w, acc.w);
-      }
-      r[p] = acc;
-    }
     if (NPL == 1) {
-      float4 o = r[0];
+      float4 o = res[0][r];
       if (a.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
       float4* op = reinterpret_cast<float4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
       op[m] = o;
     } else {
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(r[0].x, r[0].y), h1 = __floats2bfloat162_rn(r[0].z, r[0].w);
-      __nv_bfloat162 h2 = __floats2bfloat162_rn(r[NPL - 1].x, r[NPL - 1].y), h3 = __floats2bfloat162_rn(r[NPL - 1].z, r[NPL - 1].w);
+      const float4 u = res[0][r], v = res[NPL - 1][r];
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(u.x, u.y), h1 = __floats2bfloat162_rn(u.z, u.w);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(v.x, v.y), h3 = __floats2bfloat162_rn(v.z, v.w);
       uint4 o;
       o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
       o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);

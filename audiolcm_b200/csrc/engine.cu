@@ -297,7 +297,7 @@ struct OpList {
     op.fn = [=](cudaStream_t st) { launch_conv(Lc, xc, oc, rp, M, scale, accum, st); };
     push(op);
   }
-  void act(const PlaneT& x, const PlaneT& out, const float* ea, const float* ib, int round_tf32) {
+  void act(const PlaneT& x, const PlaneT& out, const float* ea, const float* ib, int round_tf32, bool fast) {
     REQUIRE(x.esz == 4 && x.T == out.T && x.B == out.B, "act: bad planes");
     ActArgs a;
     a.x = x.f(); a.xg = x.g; a.out = out.p; a.og = out.g; a.ea = ea; a.ib = ib; a.T = x.T; a.round_tf32 = round_tf32;
@@ -308,8 +308,13 @@ struct OpList {
     op.flops = 0;
     op.bytes = (double)B * T * round_up(x.C, 16) * (4.0 + oesz);
     op.fn = [=](cudaStream_t st) {
-      if (oesz == 4) act1d_kernel<1, 512><<<dim3((T + 511) / 512, nch, B), kActThreads, 0, st>>>(a);
-      else act1d_kernel<2, 256><<<dim3((T + 255) / 256, nch, B), kActThreads, 0, st>>>(a);
+      const dim3 grid((T + kActTile - 1) / kActTile, nch, B);
+      if (oesz == 4) {
+        if (fast) act1d_kernel<1, true><<<grid, kActThreads, 0, st>>>(a);
+        else act1d_kernel<1, false><<<grid, kActThreads, 0, st>>>(a);
+      } else {
+        act1d_kernel<2, true><<<grid, kActThreads, 0, st>>>(a);
+      }
     };
     push(op);
   }
@@ -493,6 +498,7 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
   P.B = B; P.T = T;
   const int prec = v->prec, oe = opnd_esz(prec);
   const int rtf = (prec == ALCM_PREC_TF32);
+  const bool fast = (prec != ALCM_PREC_FP32);  // MUFU.COS snake; the exact-fp32 mode keeps the range-reduced sin
   const int nk = v->cfg.num_kernels;
   P.mel_in = make_planes(P.ar, B, v->cfg.num_mels, T, oe);
   int C = v->cfg.upsample_initial_channel, Tc = T;
@@ -530,9 +536,9 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
       if (parallel) P.ol.lane(j);
       const PlaneT* cur = &X;
       for (int l = 0; l < 3; ++l) {  // models.py:72-81
-        P.ol.act(*cur, A, bk.a[2 * l].ea, bk.a[2 * l].ib, rtf);
+        P.ol.act(*cur, A, bk.a[2 * l].ea, bk.a[2 * l].ib, rtf, fast);
         P.ol.conv(bk.c1[l], A, Y, nullptr);
-        P.ol.act(Y, A, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, rtf);
+        P.ol.act(Y, A, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, rtf, fast);
         if (l < 2) {
           P.ol.conv(bk.c2[l], A, R, cur);
           cur = &R;
@@ -558,7 +564,7 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
     xprev = XS;
   }
   P.post_in = make_planes(P.ar, B, C, Tc, 4);
-  P.ol.act(xprev, P.post_in, v->act_post.ea, v->act_post.ib, 0);
+  P.ol.act(xprev, P.post_in, v->act_post.ea, v->act_post.ib, 0, fast);
   P.Tout = Tc;
   CUDA_CHECK(cudaDeviceSynchronize());
   if (use_graph()) capture_graph(P.ol, P.ge);
@@ -1010,7 +1016,7 @@ int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, con
     CUDA_CHECK(cudaDeviceSynchronize());
     launch_pack(x, xin, C, T, 1.f, ALCM_PREC_FP32, st);
     OpList ol;
-    ol.act(xin, out, sp.ea, sp.ib, precision == ALCM_PREC_TF32);
+    ol.act(xin, out, sp.ea, sp.ib, precision == ALCM_PREC_TF32, precision != ALCM_PREC_FP32);
     ol.run(st);
     if (precision == ALCM_PREC_BF16) {
       dim3 grid((T + 255) / 256, out.g.nchunk, B);
@@ -1177,6 +1183,33 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     CUDA_CHECK(cudaEventRecord(e1, 0));
     cudaError_t err = cudaEventSynchronize(e1);
     g_conv_dbg = 0;
+    CUDA_CHECK(err);
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+  });
+}
+
+int alcm_bench_act(alcm_ctx* ctx, int B, int C, int T, int precision, int iters, float* ms_per_launch) {
+  return guarded([&] {
+    REQUIRE(ctx && ms_per_launch && iters >= 1, "bench_act: bad argument");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    Arena ar;
+    PlaneT x = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, opnd_esz(precision));
+    float* ab = static_cast<float*>(ar.alloc((size_t)round_up(C, 16) * 4, true));
+    SnakeP sp = make_snake(ar, ab, ab, C);
+    OpList ol;
+    ol.act(x, out, sp.ea, sp.ib, precision == ALCM_PREC_TF32, precision != ALCM_PREC_FP32);
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) ol.run(0);
+    CUDA_CHECK(cudaEventRecord(e0, 0));
+    for (int i = 0; i < iters; ++i) ol.run(0);
+    CUDA_CHECK(cudaEventRecord(e1, 0));
+    cudaError_t err = cudaEventSynchronize(e1);
     CUDA_CHECK(err);
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));

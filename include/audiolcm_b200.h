@@ -153,6 +153,8 @@ int alcm_profile_decode(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iter
  * shape [B,Cin,T]; dbg is for kernel bring-up (bit0/bit1 skip the weight/activation copies) */
 int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int dilation, int precision, int iters, int dbg,
                     float* ms_per_launch);
+/* same for one Activation1d launch on [B,C,T] */
+int alcm_bench_act(alcm_ctx* ctx, int B, int C, int T, int precision, int iters, float* ms_per_launch);
 /* kernels launched by one alcm_vocode / alcm_vae_decode call for this shape (after planning) */
 int alcm_vocoder_launches(alcm_vocoder* v, int B, int T);
 int alcm_vae_launches(alcm_vae* v, int B, int T);

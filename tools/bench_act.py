@@ -1,0 +1,19 @@
+"""Activation1d micro-benchmark: algorithmic GB/s (fp32 in + operand out) of single launches."""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from audiolcm_b200 import _lib  # noqa: E402
+
+lib = _lib.load()
+ctx = _lib.ctx(0)
+SHAPES = [(1, 768, 2500), (1, 192, 20000), (1, 24, 160000), (8, 768, 2500), (8, 192, 20000), (8, 24, 160000), (64, 768, 2500), (64, 24, 160000)]
+for prec in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["bf16", "tf32"]):
+    osz = 2 if prec == "bf16" else 4
+    for (B, Cc, T) in SHAPES:
+        cpad = (Cc + 15) // 16 * 16
+        byt = B * cpad * T * (4 + osz)
+        ms = C.c_float()
+        _lib.check(lib.alcm_bench_act(ctx, B, Cc, T, _lib.PREC[prec], 20, C.byref(ms)))
+        print(f"{prec} B={B} C={Cc} T={T} ({byt / 1e6:.0f} MB): {ms.value * 1e3:8.1f} us {byt / ms.value / 1e6:7.0f} GB/s", flush=True)
