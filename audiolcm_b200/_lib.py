@@ -83,7 +83,7 @@ SYMBOLS = {
 }
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()  # re-entrant: check() calls load() while ctx() holds the lock
 _ctxs: dict[int, int] = {}
 
 

@@ -77,11 +77,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Bounded wait: a pipeline bug must surface as a trapped launch, never as a hung GPU.
+// Bounded wait: a pipeline bug must surface as a trapped launch, never as a hung GPU.  try_wait
+// itself suspends for a hardware-defined time, so the bound is wall time (2 s), not a spin count.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) __trap();
+    if ((++spins & 255u) == 0 && global_timer_ns() - t0 > 2000000000ull) __trap();
   }
 }
 

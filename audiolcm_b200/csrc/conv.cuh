@@ -35,55 +35,135 @@ struct ConvArgs {
   int span;           // max over phases of (max_off - min_off)
   int Cin, Cout;      // logical channels (SIMT) ; Cin padded to planes
   int kchunks, kblk, nkb;  // 16-byte K chunks: total, per k-block (even), number of k-blocks
-  int NT, n_tiles, tmem_cols, w_stages;
+  int NT, n_tiles, tmem_cols;
+  int w_stages;       // weight ring depth
+  int tpg;            // taps per weight stage (one bulk copy + one mbarrier round trip per `tpg` taps)
   uint32_t idesc;
   unsigned long long w_phase_stride;  // bytes between phases in w
   float scale;
   int accum;
   int dbg;  // micro-benchmark only: bit0 skip weight copies, bit1 skip activation copies (results are garbage)
+  // split-K (launches with too few output tiles to fill the GPU): blockIdx.z = (b*nphase+ph)*ksplit + s,
+  // split s reduces k-blocks [s*nkb/ksplit, (s+1)*nkb/ksplit); raw partial tiles go to `ws`, the last CTA
+  // to arrive at a tile (counter in `tile_ctr`, self-resetting) sums them in split order and runs the
+  // epilogue, so the result does not depend on arrival order.
+  int ksplit;
+  float* ws;               // [tile][ksplit][NT/4][128] float4
+  unsigned int* tile_ctr;  // [tile]
+  long long* trace;        // micro-benchmark only: 8 timestamps per CTA (tools/bench_conv.py with ALCM_TRACE=1)
 };
 
 // ---------------------------------------------------------------------------------------------
-// tcgen05 kernel.  grid = (ceil(M/128), n_tiles, B*nphase), block = 192 threads.
+// tcgen05 kernel.  grid = (ceil(M/128), n_tiles, B*nphase*ksplit), block = 192 threads.
 //   warp 0   : producer - per k-block one A slab per K chunk ([128+span rows] x 16 B, contiguous in
-//              the plane) and per tap one pre-packed weight blob, all cp.async.bulk + mbarrier tx.
+//              the plane) and per group of `tpg` taps one bulk copy of their (contiguous) pre-packed
+//              weight blobs, all cp.async.bulk + mbarrier tx.
 //   warp 1   : allocates TMEM, one lane issues tcgen05.mma; the tap shift is a 16 B*offset bump of
 //              the A descriptor's start address (no im2col copy is ever materialised).
 //   warps 2-5: epilogue - tcgen05.ld 32x32b (thread = time row), bias/residual/scale/accumulate,
 //              float4 stores: each warp-level store is 512 contiguous bytes of one output plane.
+// Measured on B200 (tools/mma_probe2.cu, ALCM_TRACE): one M=128,K=16 MMA costs max(N/2, 32+N/4)
+// cycles (tensor floor vs. 128 B/clk shared-memory operand reads); the MMA queue behind the issuing
+// thread is only ~2 deep, so every mbarrier round trip (~200 cycles of wait/fence/commit/loop code)
+// must be amortised over >= ~512 tensor cycles of MMAs - hence several taps per weight stage.
 // ---------------------------------------------------------------------------------------------
 struct ConvSmemLayout {
-  uint32_t a_stage, w_stage, a_off, w_off, bar_off, total;
+  uint32_t a_stage, w_blob, w_stage, a_off, w_off, bias_off, bar_off, total;
 };
-__host__ __device__ inline ConvSmemLayout conv_smem_layout(int kblk, int span, int NT, int w_stages) {
+__host__ __device__ inline ConvSmemLayout conv_smem_layout(int kblk, int span, int NT, int w_stages, int tpg) {
   ConvSmemLayout L;
   L.a_stage = (uint32_t)kblk * (kTileM + span) * 16;
-  L.w_stage = (uint32_t)kblk * NT * 16;
+  L.w_blob = (uint32_t)kblk * NT * 16;
+  L.w_stage = L.w_blob * tpg;
   L.a_off = 0;
   L.w_off = 2 * L.a_stage;
-  L.bar_off = L.w_off + w_stages * L.w_stage;
+  L.bias_off = L.w_off + w_stages * L.w_stage;
+  L.bar_off = L.bias_off + NT * 4;
   L.total = L.bar_off + 8 * (5 + 2 * w_stages) + 16;
   return L;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
+// MMA-issuing warp.  NK2 = MMAs per (k-block, tap) (two 16-byte K chunks per MMA); static so that
+// the burst is straight-line code (a rolled loop re-writes the uniform descriptor registers of
+// in-flight UTCHMMAs and stalls ~300 cycles per trip).
+template <int KIND, int NK2>
+__device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, int ph, uint32_t sA, uint32_t sW, const ConvSmemLayout& L, int rowsA,
+                                              uint32_t tmem_base, uint32_t a_full, uint32_t a_empty, uint32_t w_full,
+                                              uint32_t w_empty, uint32_t acc_full, int kb0, int kb1, long long* trace) {
+  const bool leader = elect_one();
+  // Descriptors differ only in their 14-bit start-address field: build the constant part once
+  // and add (byte offset >> 4) per MMA.
+  const uint64_t a_desc0 = umma_desc_kmajor(sA, rowsA * 16, 128);
+  const uint64_t w_desc0 = umma_desc_kmajor(sW, a.NT * 16, 128);
+  const uint32_t a_step = (uint32_t)(2 * rowsA), w_step = (uint32_t)(2 * a.NT);  // two K chunks, in 16 B units
+  const uint32_t a_stage16 = L.a_stage >> 4, w_stage16 = L.w_stage >> 4, w_blob16 = L.w_blob >> 4;
+  // every parameter the loop needs lives in a register: the asm memory clobbers would otherwise
+  // make the compiler re-read the constant bank on each iteration of the single issuing warp.
+  // The tap shift (row offset of tap j inside the A slab) is linear in j for every conv form here.
+  const int ntaps = a.ntaps, S = a.w_stages, tpg = a.tpg;
+  const uint32_t idesc = a.idesc;
+  const uint32_t shift0 = (uint32_t)(a.tap_off[ph][0] - a.min_off[ph]);
+  const uint64_t dshift = (uint64_t)(int64_t)(ntaps > 1 ? a.tap_off[ph][1] - a.tap_off[ph][0] : 0);
+  int ws = 0;
+  uint32_t wpar = 0, acc = 0;
+  for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
+    const int as = it & 1;
+    mbar_wait(a_full + 8 * as, (it >> 1) & 1);
+    uint64_t a_tap = a_desc0 + (uint64_t)(as * a_stage16 + shift0);
+    for (int j0 = 0; j0 < ntaps; j0 += tpg) {
+      const int g = min(tpg, ntaps - j0);
+      mbar_wait(w_full + 8 * ws, wpar);
+      tc_fence_after();
+      if (trace && acc == 0 && leader) trace[3] = clock64();
+      // descriptor arithmetic stays warp-uniform (all lanes); only the async instructions are elected -
+      // a lane-private descriptor makes ptxas wrap every UTCHMMA in an ELECT/R2UR.BROADCAST/BRA.U.ANY loop
+      uint64_t bd = w_desc0 + (uint64_t)(ws * w_stage16);
+      for (int t = 0; t < g; ++t, a_tap += dshift, bd += w_blob16) {
+        if (leader) {
+#pragma unroll
+          for (int i = 0; i < NK2; ++i)
+            umma_ss<KIND>(tmem_base, a_tap + (uint64_t)(i * a_step), bd + (uint64_t)(i * w_step), idesc, (i > 0) ? 1u : acc);
+        }
+        acc = 1;
+      }
+      if (leader) {
+        tc_commit(w_empty + 8 * ws);  // frees the weight slot when these MMAs retire
+        if (j0 + g == ntaps) tc_commit(a_empty + 8 * as);
+      }
+      acc = 1;
+      if (++ws == S) { ws = 0; wpar ^= 1; }
+    }
+  }
+  if (leader) tc_commit(acc_full);
+  if (trace && leader) trace[4] = clock64();
+  __syncwarp();
+}
+
+template <int KIND, int MINB>
+__global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
-  const int b = blockIdx.z / a.nphase, ph = blockIdx.z % a.nphase;
+  const int ksplit = a.ksplit;
+  const int zs = blockIdx.z % ksplit, zb = blockIdx.z / ksplit;
+  const int b = zb / a.nphase, ph = zb % a.nphase;
+  const int kb0 = (int)((long)zs * a.nkb / ksplit), kb1 = (int)((long)(zs + 1) * a.nkb / ksplit);
   const int S = a.w_stages;
   const int rowsA = kTileM + a.span;
-  const ConvSmemLayout L = conv_smem_layout(a.kblk, a.span, a.NT, S);
+  const ConvSmemLayout L = conv_smem_layout(a.kblk, a.span, a.NT, S, a.tpg);
   const uint32_t sA = smem_u32(smem) + L.a_off;
   const uint32_t sW = smem_u32(smem) + L.w_off;
   const uint32_t bars = smem_u32(smem) + L.bar_off;
+  float* s_bias = reinterpret_cast<float*>(smem + L.bias_off);
   // barrier slots: [0,1] a_full, [2,3] a_empty, [4..4+S) w_full, [4+S..4+2S) w_empty, [4+2S] acc_full
   const uint32_t a_full = bars, a_empty = bars + 16, w_full = bars + 32, w_empty = bars + 32 + 8 * S;
   const uint32_t acc_full = bars + 32 + 16 * S;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * (5 + 2 * S));
+  volatile uint32_t* s_last = tmem_slot + 1;  // split-K: "this CTA arrived last at its tile"
 
+  long long* trace = a.trace ? a.trace + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
   if (threadIdx.x == 0) {
+    if (trace) { trace[0] = (long long)global_timer_ns(); trace[1] = clock64(); }
     for (int i = 0; i < 5 + 2 * S; ++i) mbar_init(bars + 8 * i, 1);
     fence_mbar_init();
   }
@@ -96,6 +176,7 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int q0 = mt * kTileM;
+  if (trace && threadIdx.x == 0) trace[2] = clock64();
 
   // Both asynchronous roles keep their warp CONVERGENT and predicate the async instructions with
   // elect.sync: UBLKCP / UTCHMMA / UTCBAR take warp-uniform operands, and issuing them from a
@@ -105,15 +186,16 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
     const bool leader = elect_one();
     const int row0 = q0 + a.min_off[ph] + a.xg.pad;  // >= 0 because |min_off| <= pad
     const int nrows = min(rowsA, a.xg.Tp - row0);
-    const uint8_t* wsrc = a.w + (size_t)ph * a.w_phase_stride + (size_t)nt * a.nkb * a.ntaps * L.w_stage;
+    const uint8_t* wsrc = a.w + (size_t)ph * a.w_phase_stride + ((size_t)nt * a.nkb + kb0) * a.ntaps * L.w_blob;
     const size_t plane_bytes = (size_t)a.xg.Tp * 16;
-    const uint8_t* xsrc = a.x + ((size_t)b * a.xg.nchunk * a.xg.Tp + row0) * 16;
+    const uint8_t* xsrc = a.x + (((size_t)b * a.xg.nchunk + (size_t)kb0 * a.kblk) * a.xg.Tp + row0) * 16;
     const uint32_t a_bytes = (uint32_t)nrows * 16, a_pitch = (uint32_t)rowsA * 16;
+    const int ntaps = a.ntaps, tpg = a.tpg;
     int ws = 0;
     uint32_t wpar = 1;  // producer waits on the "previous" phase of the empty barriers first
-    for (int kb = 0; kb < a.nkb; ++kb) {
-      const int as = kb & 1;
-      mbar_wait(a_empty + 8 * as, ((kb >> 1) & 1) ^ 1);
+    for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
+      const int as = it & 1;
+      mbar_wait(a_empty + 8 * as, ((it >> 1) & 1) ^ 1);
       if (a.dbg & 2) {
         if (leader) mbar_arrive(a_full + 8 * as);
         xsrc += plane_bytes * a.kblk;
@@ -123,99 +205,136 @@ __global__ void __launch_bounds__(192) conv_umma_kernel(const __grid_constant__ 
         for (int c = 0; c < a.kblk; ++c, dst += a_pitch, xsrc += plane_bytes)
           if (leader) bulk_g2s(dst, xsrc, a_bytes, a_full + 8 * as);
       }
-      for (int j = 0; j < a.ntaps; ++j) {
+      for (int j0 = 0; j0 < ntaps; j0 += tpg) {
+        const uint32_t bytes = (uint32_t)min(tpg, ntaps - j0) * L.w_blob;
         mbar_wait(w_empty + 8 * ws, wpar);
         if (leader) {
           if (a.dbg & 1) {
             mbar_arrive(w_full + 8 * ws);
           } else {
-            mbar_expect_tx(w_full + 8 * ws, L.w_stage);
-            bulk_g2s(sW + ws * L.w_stage, wsrc, L.w_stage, w_full + 8 * ws);
+            mbar_expect_tx(w_full + 8 * ws, bytes);
+            bulk_g2s(sW + ws * L.w_stage, wsrc, bytes, w_full + 8 * ws);
           }
         }
-        wsrc += L.w_stage;
+        wsrc += bytes;
         if (++ws == S) { ws = 0; wpar ^= 1; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    const bool leader = elect_one();
-    // Descriptors differ only in their 14-bit start-address field: build the constant part once
-    // and add (byte offset >> 4) per MMA.
-    const uint64_t a_desc0 = umma_desc_kmajor(sA, rowsA * 16, 128);
-    const uint64_t w_desc0 = umma_desc_kmajor(sW, a.NT * 16, 128);
-    const uint32_t a_step = (uint32_t)(2 * rowsA), w_step = (uint32_t)(2 * a.NT);  // two K chunks, in 16 B units
-    const uint32_t a_stage16 = L.a_stage >> 4, w_stage16 = L.w_stage >> 4;
-    // every parameter the loop needs lives in a register: the asm memory clobbers would otherwise
-    // make the compiler re-read the constant bank on each iteration of the single issuing warp.
-    // The tap shift (row offset of tap j inside the A slab) is linear in j for every conv form here.
-    const int nkb = a.nkb, ntaps = a.ntaps, nk2 = a.kblk >> 1;
-    const uint32_t idesc = a.idesc;
-    const uint32_t shift0 = (uint32_t)(a.tap_off[ph][0] - a.min_off[ph]);
-    const int dshift = ntaps > 1 ? a.tap_off[ph][1] - a.tap_off[ph][0] : 0;
-    int ws = 0;
-    uint32_t wpar = 0, acc = 0;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int as = kb & 1;
-      mbar_wait(a_full + 8 * as, (kb >> 1) & 1);
-      uint64_t a_tap = a_desc0 + (uint64_t)(as * a_stage16 + shift0);
-      for (int j = 0; j < ntaps; ++j, a_tap += (uint64_t)(int64_t)dshift) {
-        mbar_wait(w_full + 8 * ws, wpar);
-        tc_fence_after();
-        if (leader) {
-          uint64_t ad = a_tap, bd = w_desc0 + (uint64_t)(ws * w_stage16);
-#pragma unroll 4
-          for (int i = 0; i < nk2; ++i, ad += a_step, bd += w_step) {
-            umma_ss<KIND>(tmem_base, ad, bd, idesc, acc);
-            acc = 1;
-          }
-          tc_commit(w_empty + 8 * ws);  // frees the weight slot when these MMAs retire
-          if (j == ntaps - 1) tc_commit(a_empty + 8 * as);
-        }
-        if (++ws == S) { ws = 0; wpar ^= 1; }
-      }
+    switch (a.kblk >> 1) {
+      case 1: conv_mma_loop<KIND, 1>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
+      case 2: conv_mma_loop<KIND, 2>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
+      case 3: conv_mma_loop<KIND, 3>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
+      case 4: conv_mma_loop<KIND, 4>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
+      case 5: conv_mma_loop<KIND, 5>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
+      default: conv_mma_loop<KIND, 6>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
     }
-    if (leader) tc_commit(acc_full);
-    __syncwarp();
   } else {
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
+    // while the main loop runs: stage this N tile's bias in shared memory (the epilogue reads it as broadcasts)
+    const int et = threadIdx.x - 64;
+    for (int i = et; i < a.NT; i += 128) s_bias[i] = a.bias ? __ldg(a.bias + nt * a.NT + i) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
     const int qd = warp & 3;  // TMEM lane quarter this warp may access
-    const int q = q0 + qd * 32 + lane;
+    const int row = qd * 32 + lane;
+    const int q = q0 + row;
     const bool valid = q < a.M;
     const size_t orow = (size_t)q * a.ostride + ph;
     const float scale = a.scale;
-    for (int c0 = 0; c0 < a.NT; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld_x16(tmem_base + ((uint32_t)(qd * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      if (valid) {
+    const int nq = a.NT >> 2;                              // float4 column groups in this tile
+    const int nq_valid = min(nq, a.og.nchunk - nt * nq);   // those that exist in the output planes
+    const size_t plane4 = (size_t)a.og.Tp;                 // float4 units between consecutive chunks
+    const size_t off0 = ((size_t)b * a.og.nchunk + (size_t)nt * nq) * a.og.Tp + a.og.pad + orow;  // float4 units
+    const float4* res4 = reinterpret_cast<const float4*>(a.res);
+    float4* out4 = reinterpret_cast<float4*>(a.out);
+    const bool has_res = (a.res != nullptr) && valid, accum = (a.accum != 0) && valid;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    if (trace && threadIdx.x == 64) trace[5] = clock64();
+    // bias / residual / scale / accumulate + store of 16 consecutive output channels of this thread's row
+    auto emit = [&](int c0, const float (&v)[16], const float4 (&rr)[4], const float4 (&oo)[4]) {
+      if (!valid) return;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = nt * a.NT + c0 + 4 * g;
-          const int chunk = col >> 2;
-          if (chunk < a.og.nchunk) {
-            float4 r = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]),
-                                   __uint_as_float(v[4 * g + 3]));
-            if (a.bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + col));
-              r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+      for (int g = 0; g < 4; ++g) {
+        const int cq = (c0 >> 2) + g;
+        if (cq < nq_valid) {
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
+          float4 r = make_float4(v[4 * g] + bb.x, v[4 * g + 1] + bb.y, v[4 * g + 2] + bb.z, v[4 * g + 3] + bb.w);
+          r.x = (r.x + rr[g].x) * scale + oo[g].x; r.y = (r.y + rr[g].y) * scale + oo[g].y;
+          r.z = (r.z + rr[g].z) * scale + oo[g].z; r.w = (r.w + rr[g].w) * scale + oo[g].w;
+          out4[off0 + (size_t)cq * plane4] = r;
+        }
+      }
+    };
+    // residual / accumulate operands of 16 channels (issued before the TMEM load they are combined with)
+    auto fetch = [&](int c0, float4 (&rr)[4], float4 (&oo)[4]) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int cq = (c0 >> 2) + g;
+        rr[g] = oo[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cq < nq_valid) {
+          if (has_res) rr[g] = res4[off0 + (size_t)cq * plane4];
+          if (accum) oo[g] = out4[off0 + (size_t)cq * plane4];
+        }
+      }
+    };
+    if (ksplit == 1) {
+      for (int c0 = 0; c0 < a.NT; c0 += 16) {
+        float4 rr[4], oo[4];
+        fetch(c0, rr, oo);
+        uint32_t u[16];
+        tmem_ld_x16(tmem_base + ((uint32_t)(qd * 32) << 16) + c0, u);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
+        emit(c0, v, rr, oo);
+      }
+    } else {
+      // partial tile -> workspace, [col/4][row] float4 so that a warp writes 512 contiguous bytes
+      const size_t tile = ((size_t)zb * gridDim.y + nt) * gridDim.x + mt;
+      float4* wst = reinterpret_cast<float4*>(a.ws) + (tile * ksplit) * (size_t)(nq * kTileM);
+      float4* mine = wst + (size_t)zs * (nq * kTileM);
+      for (int c0 = 0; c0 < a.NT; c0 += 16) {
+        uint32_t u[16];
+        tmem_ld_x16(tmem_base + ((uint32_t)(qd * 32) << 16) + c0, u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          mine[(size_t)((c0 >> 2) + g) * kTileM + row] =
+              make_float4(__uint_as_float(u[4 * g]), __uint_as_float(u[4 * g + 1]), __uint_as_float(u[4 * g + 2]),
+                          __uint_as_float(u[4 * g + 3]));
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const unsigned int old = atomicAdd(a.tile_ctr + tile, 1u);
+        const unsigned int last = (old == (unsigned int)(ksplit - 1));
+        if (last) a.tile_ctr[tile] = 0;  // every split has arrived: safe to re-arm for the next launch
+        *s_last = last;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*s_last) {
+        __threadfence();
+        for (int c0 = 0; c0 < a.NT; c0 += 16) {
+          float4 rr[4], oo[4];
+          fetch(c0, rr, oo);
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          for (int s = 0; s < ksplit; ++s) {
+            const float4* src = wst + (size_t)s * (nq * kTileM);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float4 p = __ldcg(src + (size_t)((c0 >> 2) + g) * kTileM + row);
+              v[4 * g] += p.x; v[4 * g + 1] += p.y; v[4 * g + 2] += p.z; v[4 * g + 3] += p.w;
             }
-            const size_t off = (((size_t)b * a.og.nchunk + chunk) * a.og.Tp + a.og.pad + orow) * 4;
-            if (a.res) {
-              const float4 rr = *reinterpret_cast<const float4*>(a.res + off);
-              r.x += rr.x; r.y += rr.y; r.z += rr.z; r.w += rr.w;
-            }
-            r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
-            if (a.accum) {
-              const float4 oo = *reinterpret_cast<const float4*>(a.out + off);
-              r.x += oo.x; r.y += oo.y; r.z += oo.z; r.w += oo.w;
-            }
-            *reinterpret_cast<float4*>(a.out + off) = r;
           }
+          emit(c0, v, rr, oo);
         }
       }
     }
+    if (trace && threadIdx.x == 64) { trace[6] = clock64(); trace[7] = (long long)global_timer_ns(); }
   }
   tc_fence_before();
   __syncthreads();

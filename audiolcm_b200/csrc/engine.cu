@@ -192,8 +192,8 @@ static ConvLayer prepare_conv(Arena& ar, int prec, ConvKind kind, const float* w
   L.kchunks = round_up(Cin, 16) / E;
   L.kblk = 0;
   if (L.kchunks <= 12) L.kblk = L.kchunks;
-  else for (int d = env_int("ALCM_KBLK_MAX", 8); d >= 2; d -= 2) if (L.kchunks % d == 0) { L.kblk = d; break; }
-  REQUIRE(L.kblk >= 2 && L.kblk % 2 == 0, "bad k-block");
+  else for (int d = std::min(12, env_int("ALCM_KBLK_MAX", 8)); d >= 2; d -= 2) if (L.kchunks % d == 0) { L.kblk = d; break; }
+  REQUIRE(L.kblk >= 2 && L.kblk % 2 == 0 && L.kblk <= 12, "bad k-block");
   L.nkb = L.kchunks / L.kblk;
   L.idesc = umma_idesc(prec == ALCM_PREC_BF16 ? 1 : 2, L.NT);
   L.w_stages = 0;  // chosen per launch (pick_stages)
@@ -232,22 +232,48 @@ struct Op {
 
 static int g_sm_count = 148;
 
-// Weight-ring depth for one launch: with at most one CTA per SM use most of the 227 KB (more bytes
-// in flight hide the L2/HBM latency of the 16-32 KB weight blobs); otherwise leave room for 2 CTAs/SM.
-static void pick_stages(const ConvLayer& L, long ctas, int* stages, uint32_t* smem) {
+// Pipeline shape of one launch.  Taps per weight stage: enough MMAs per mbarrier round trip to cover
+// ~512 tensor cycles (see conv.cuh).  Ring depth: with at most one CTA per SM use most of the 227 KB
+// (more bytes in flight hide the L2/HBM latency of the weight stream); otherwise leave room for 2 CTAs/SM.
+static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, int* stages, int* tpg, uint32_t* smem) {
   const uint32_t budget = (uint32_t)env_int("ALCM_SMEM_BUDGET", ctas <= (long)g_sm_count ? 200 * 1024 : 100 * 1024);
-  const uint32_t a2 = 2u * L.kblk * (kTileM + L.span) * 16, ws = (uint32_t)L.kblk * L.NT * 16;
-  int S = (budget > a2 + 256) ? (int)((budget - a2 - 256) / ws) : 0;
+  const double cyc_mma = std::max(L.NT / 2.0, 32.0 + L.NT / 4.0);
+  const double cyc_tap = (L.kblk / 2) * cyc_mma;
+  int tmin = std::max(1, std::min(L.ntaps, (int)std::ceil(512.0 / cyc_tap)));
+  const int ngrp = (L.ntaps + tmin - 1) / tmin;
+  int t = (L.ntaps + ngrp - 1) / ngrp;
+  if (env_int("ALCM_TPG", 0) > 0) t = std::min(L.ntaps, env_int("ALCM_TPG", 0));
+  const uint32_t a2 = 2u * L.kblk * (kTileM + L.span) * 16, blob = (uint32_t)L.kblk * L.NT * 16, fixed = a2 + L.NT * 4 + 512;
+  while (t > 1 && fixed + 2u * t * blob > budget) --t;
+  int S = (budget > fixed) ? (int)((budget - fixed) / (t * blob)) : 0;
   S = std::max(2, std::min(12, S));
-  S = std::min(S, std::max(2, L.nkb * L.ntaps));
+  const int nkb_local = (L.nkb + ksplit - 1) / ksplit;
+  S = std::min(S, std::max(2, nkb_local * ((L.ntaps + t - 1) / t)));
   *stages = S;
-  *smem = conv_smem_layout(L.kblk, L.span, L.NT, S).total;
+  *tpg = t;
+  *smem = conv_smem_layout(L.kblk, L.span, L.NT, S, t).total;
   REQUIRE(*smem <= 227 * 1024, "conv tile does not fit shared memory");
 }
 
 static int g_conv_dbg = 0;
+static long long* g_conv_trace = nullptr;  // micro-benchmark only
+
+struct SplitK {  // per-launch split-K resources (see ConvArgs::ksplit)
+  int ksplit = 1;
+  float* ws = nullptr;
+  unsigned int* ctr = nullptr;
+};
+
+// How many K splits a conv launch gets: only launches whose output tiles cannot fill the GPU are split.
+static int pick_ksplit(const ConvLayer& L, int M, int B) {
+  if (L.prec == ALCM_PREC_FP32 || !env_int("ALCM_SPLITK", 1) || L.nkb < 2) return 1;
+  const long ctas = (long)((M + kTileM - 1) / kTileM) * L.n_tiles * B * L.nphase;
+  if (ctas * 2 > (long)g_sm_count) return 1;
+  return (int)std::max<long>(1, std::min<long>(std::min<long>(L.nkb, g_sm_count / ctas), 8));
+}
+
 static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const float* res, int M, float scale, int accum,
-                        cudaStream_t st) {
+                        const SplitK& sk, cudaStream_t st) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x.p; a.xg = x.g;
@@ -262,6 +288,7 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
   a.Cin = L.Cin; a.Cout = L.Cout;
   a.scale = scale; a.accum = accum;
   a.dbg = g_conv_dbg;
+  a.ksplit = 1;
   const int B = x.B;
   if (L.prec == ALCM_PREC_FP32) {
     a.w = reinterpret_cast<const uint8_t*>(L.weff);
@@ -272,16 +299,27 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
     a.kchunks = L.kchunks; a.kblk = L.kblk; a.nkb = L.nkb;
     a.NT = L.NT; a.n_tiles = L.n_tiles; a.tmem_cols = L.tmem_cols;
     a.idesc = L.idesc; a.w_phase_stride = L.phase_stride;
-    dim3 grid((M + kTileM - 1) / kTileM, L.n_tiles, B * L.nphase);
+    a.ksplit = sk.ksplit; a.ws = sk.ws; a.tile_ctr = sk.ctr;
+    a.trace = g_conv_trace;
+    dim3 grid((M + kTileM - 1) / kTileM, L.n_tiles, B * L.nphase * sk.ksplit);
     uint32_t smem = 0;
-    pick_stages(L, (long)grid.x * grid.y * grid.z, &a.w_stages, &smem);
-    if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0><<<grid, 192, smem, st>>>(a);
-    else conv_umma_kernel<1><<<grid, 192, smem, st>>>(a);
+    pick_pipeline(L, (long)grid.x * grid.y * grid.z, sk.ksplit, &a.w_stages, &a.tpg, &smem);
+    // wide tiles are limited to 2 CTAs/SM by shared memory anyway and get the registers; narrow ones want occupancy
+    if (L.NT >= 128) {
+      if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0, 2><<<grid, 192, smem, st>>>(a);
+      else conv_umma_kernel<1, 2><<<grid, 192, smem, st>>>(a);
+    } else {
+      if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0, 4><<<grid, 192, smem, st>>>(a);
+      else conv_umma_kernel<1, 4><<<grid, 192, smem, st>>>(a);
+    }
   }
 }
 
 struct OpList {
   std::vector<Op> ops;
+  Arena* ar = nullptr;  // where split-K workspaces come from (null: never split)
+  float* ws[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  size_t ws_bytes[kMaxLanes] = {0, 0, 0, 0};
   void conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const PlaneT* res, float scale = 1.f, int accum = 0) {
     const int M = x.T;  // rows per batch item are input time steps (== output steps / nphase)
     REQUIRE(x.esz == opnd_esz(L.prec), "conv: operand dtype mismatch");
@@ -294,7 +332,19 @@ struct OpList {
     const float* rp = res ? res->f() : nullptr;
     ConvLayer Lc = L;
     PlaneT xc = x, oc = out;
-    op.fn = [=](cudaStream_t st) { launch_conv(Lc, xc, oc, rp, M, scale, accum, st); };
+    SplitK sk;
+    if (ar) sk.ksplit = pick_ksplit(L, M, x.B);
+    if (sk.ksplit > 1) {
+      const size_t tiles = (size_t)((M + kTileM - 1) / kTileM) * L.n_tiles * x.B * L.nphase;
+      const size_t need = tiles * sk.ksplit * (size_t)L.NT * kTileM * 4;
+      if (need > ws_bytes[cur_lane]) {  // ops of one lane run in stream order and can share the partial-tile workspace
+        ws_bytes[cur_lane] = std::max<size_t>(need, (size_t)16 << 20);
+        ws[cur_lane] = static_cast<float*>(ar->alloc(ws_bytes[cur_lane], false));
+      }
+      sk.ws = ws[cur_lane];
+      sk.ctr = static_cast<unsigned int*>(ar->alloc(tiles * sizeof(unsigned int), true));
+    }
+    op.fn = [=](cudaStream_t st) { launch_conv(Lc, xc, oc, rp, M, scale, accum, sk, st); };
     push(op);
   }
   void act(const PlaneT& x, const PlaneT& out, const float* ea, const float* ib, int round_tf32, bool fast) {
@@ -496,6 +546,7 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
   std::unique_ptr<VocPlan> pl(new VocPlan());
   VocPlan& P = *pl;
   P.B = B; P.T = T;
+  P.ol.ar = &P.ar;
   const int prec = v->prec, oe = opnd_esz(prec);
   const int rtf = (prec == ALCM_PREC_TF32);
   const bool fast = (prec != ALCM_PREC_FP32);  // MUFU.COS snake; the exact-fp32 mode keeps the range-reduced sin
@@ -705,6 +756,7 @@ static VaePlan* vae_plan(alcm_vae* v, int B, int T) {
   std::unique_ptr<VaePlan> pl(new VaePlan());
   VaePlan& P = *pl;
   P.B = B; P.T = T;
+  P.ol.ar = &P.ar;
   const int prec = v->prec, oe = opnd_esz(prec);
   P.z_in = make_planes(P.ar, B, v->cfg.embed_dim, T, oe);
   PlaneT h0 = make_planes(P.ar, B, v->cfg.z_channels, T, 4);
@@ -743,8 +795,10 @@ static void vae_run(alcm_vae* v, VaePlan* P, const float* z, float inv_scale, cu
 
 // ------------------------------------------------------------------------------------------ C-ABI
 static void set_kernel_attrs() {
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 
 extern "C" {
@@ -1045,7 +1099,9 @@ static void run_conv_test(alcm_ctx* ctx, ConvKind kind, const float* x, const fl
   launch_pack(x, xin, Cin, T, 1.f, precision, st);
   if (res) launch_pack(res, rp, Cout, T * L.nphase, 1.f, ALCM_PREC_FP32, st);
   OpList ol;
+  ol.ar = &ar;
   ol.conv(L, xin, out, res ? &rp : nullptr);
+  CUDA_CHECK(cudaDeviceSynchronize());  // workspace memsets
   ol.run(st);
   launch_unpack(out, y, Cout, T * L.nphase, st);
   CUDA_CHECK(cudaGetLastError());
@@ -1172,6 +1228,7 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     ConvLayer L = prepare_conv(ar, precision, KIND_CONV, w, nullptr, Cout, Cin, K, dilation);
     PlaneT x = make_planes(ar, B, Cin, T, opnd_esz(precision)), out = make_planes(ar, B, Cout, T, 4);
     OpList ol;
+    ol.ar = &ar;
     ol.conv(L, x, out, nullptr);
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0));
@@ -1184,6 +1241,30 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     cudaError_t err = cudaEventSynchronize(e1);
     g_conv_dbg = 0;
     CUDA_CHECK(err);
+    if (env_int("ALCM_TRACE", 0) && precision != ALCM_PREC_FP32) {  // one more launch with per-CTA timestamps
+      const int ks = pick_ksplit(L, T, B);
+      const size_t nctas = (size_t)((T + kTileM - 1) / kTileM) * L.n_tiles * B * L.nphase * ks;
+      long long* tr = static_cast<long long*>(ar.alloc(nctas * 8 * sizeof(long long), true));
+      CUDA_CHECK(cudaDeviceSynchronize());
+      g_conv_trace = tr;
+      ol.run(0);
+      g_conv_trace = nullptr;
+      CUDA_CHECK(cudaDeviceSynchronize());
+      std::vector<long long> h(nctas * 8);
+      CUDA_CHECK(cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost));
+      long long t_min = h[0], t_max = h[7], s_max = h[0];
+      double d[5] = {0, 0, 0, 0, 0}, life = 0;
+      for (size_t c = 0; c < nctas; ++c) {
+        const long long* t = &h[c * 8];
+        t_min = std::min(t_min, t[0]); t_max = std::max(t_max, t[7]); s_max = std::max(s_max, t[0]);
+        for (int i = 0; i < 5; ++i) d[i] += (double)(t[i + 2] - t[i + 1]);
+        life += (double)(t[7] - t[0]);
+      }
+      fprintf(stderr, "  trace: %zu CTAs (ksplit %d, NT %d, kblk %d, stages ~), span %.1f us, last start +%.1f us, mean CTA life %.1f us; "
+              "mean cycles: setup %.0f, first-operands %.0f, mma-issue %.0f, drain %.0f, epilogue %.0f\n",
+              nctas, ks, L.NT, L.kblk, (t_max - t_min) / 1e3, (s_max - t_min) / 1e3, life / nctas / 1e3, d[0] / nctas, d[1] / nctas,
+              d[2] / nctas, d[3] / nctas, d[4] / nctas);
+    }
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
     *ms_per_launch = ms / iters;

@@ -247,55 +247,65 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg,
 // ------------------------------------------------------------------------------- GroupNorm
 // Normalize = GroupNorm(32, C, eps 1e-6, affine) (autoencoder1d.py:169-170); biased variance over
 // (C/32 channels x T).  stats[b][g] = {mean, rstd}.  One block per (group, b).
+__device__ __forceinline__ double gn_block_sum(float s, double* red) {
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __syncthreads();  // red[] may still be read from the previous pass
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = (double)s;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
 __global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__ x, PlaneGeom xg, int C, int T, int groups,
                                                          float eps, float2* __restrict__ stats) {
-  __shared__ double red[512];
-  __shared__ double s_mean;
+  __shared__ double red[16];
   const int g = blockIdx.x, b = blockIdx.y;
   const int cpg = C / groups;
-  const size_t n = (size_t)cpg * T;
+  const double n = (double)cpg * (double)T;
   const bool vec = (cpg & 3) == 0;  // the group is a whole number of 4-channel planes -> float4 loads
-  // two passes (mean, then centred sum of squares): E[x^2]-mean^2 cancels badly for small groups
+  // two passes (mean, then centred sum of squares): E[x^2]-mean^2 cancels badly for small groups.
+  // Per-thread partial sums stay short (n / 512 terms), the cross-thread combination is in double.
+  float mean = 0.f;
+  double dmean = 0.0;
   for (int pass = 0; pass < 2; ++pass) {
-    const float mean = pass ? (float)s_mean : 0.f;
     float s = 0.f;
-    double ds = 0.0;
-    int cnt = 0;
     if (vec) {
-      const size_t nv = n >> 2;
-      for (size_t i = threadIdx.x; i < nv; i += blockDim.x) {
-        const int pl = (g * cpg >> 2) + (int)(i / T);
-        const int t = (int)(i % T);
-        const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, pl, t));
-        if (pass) {
-          const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-          s += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-        } else {
-          s += (v.x + v.y) + (v.z + v.w);
+      const int npl = cpg >> 2;
+      for (int pl = 0; pl < npl; ++pl) {
+        const float4* xp = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, (g * cpg >> 2) + pl, 0));
+        float sp = 0.f;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+          const float4 v = xp[t];
+          if (pass) {
+            const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+            sp += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+          } else {
+            sp += (v.x + v.y) + (v.z + v.w);
+          }
         }
-        if (++cnt == 16) { ds += s; s = 0.f; cnt = 0; }
+        s += sp;
       }
     } else {
-      for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const int c = g * cpg + (int)(i / T);
-        const int t = (int)(i % T);
-        const float v = *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, c >> 2, t) + (c & 3) * 4);
-        const float d = v - mean;
-        s += pass ? d * d : v;
-        if (++cnt == 64) { ds += s; s = 0.f; cnt = 0; }
+      for (int cc = 0; cc < cpg; ++cc) {
+        const int c = g * cpg + cc;
+        const float* xp = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, c >> 2, 0)) + (c & 3);
+        float sp = 0.f;
+        for (int t = threadIdx.x; t < T; t += blockDim.x) {
+          const float d = xp[(size_t)t * 4] - mean;
+          sp += pass ? d * d : d;
+        }
+        s += sp;
       }
     }
-    red[threadIdx.x] = ds + s;
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
-      if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-      __syncthreads();
+    const double tot = gn_block_sum(s, red);
+    if (pass == 0) {
+      dmean = tot / n;
+      mean = (float)dmean;
+    } else if (threadIdx.x == 0) {
+      // the second pass centred on the rounded mean: var = E[(x-m)^2] - (mean-m)^2, the correction is ~1e-16
+      stats[b * groups + g] = make_float2(mean, (float)(1.0 / sqrt(tot / n + (double)eps)));
     }
-    if (threadIdx.x == 0) {
-      if (pass == 0) s_mean = red[0] / (double)n;
-      else stats[b * groups + g] = make_float2((float)s_mean, (float)(1.0 / sqrt(red[0] / (double)n + (double)eps)));
-    }
-    __syncthreads();
   }
 }
 

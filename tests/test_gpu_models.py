@@ -111,23 +111,28 @@ def test_full_path_vs_reference(golden_dir, precision):
     assert pipe.decode(z).shape == (1, 24 * 512)
 
 
-def test_batch_and_time_shard_properties():
-    """Size-independent properties at a mid-size config: batching is per-sample exact and the
-    34-frame-halo time sharding (config 4) reproduces the un-sharded result in the interior."""
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_batch_and_time_shard_properties(precision):
+    """Size-independent properties at a mid-size config: batching does not mix samples and the
+    34-frame-halo time sharding (config 4) reproduces the un-sharded result in the interior.
+    fp32 (CUDA-core convs, fixed summation order): equal to 2e-6.  tf32: the split-K factor of small
+    launches depends on the launch geometry, and a 1-ulp fp32 difference can flip the tf32 rounding of
+    an operand, so the bound is the path's parity gate (1e-3) - mixing samples would be O(0.1)."""
+    tol = {"fp32": 2e-6, "tf32": 1e-3}[precision]
     h = synth.bigvgan_config(256)
     sd = synth.bigvgan_state_dict(h, seed=2)
-    voc = _voc(h, sd, "tf32")
+    voc = _voc(h, sd, precision)
     mel = torch.from_numpy(synth.synth_mel(3, 200, seed=3)).to(DEV)
     full = voc.vocode_tensor(mel)
     for b in range(3):
         one = voc.vocode_tensor(mel[b:b + 1])
-        assert torch.equal(one[0], full[b])
+        assert float((one[0] - full[b]).abs().max()) < tol
     halo, hop = 34, voc.hop
     left = voc.vocode_tensor(mel[..., :100 + halo])[..., :100 * hop]
     right = voc.vocode_tensor(mel[..., 100 - halo:])[..., halo * hop:]
     stitched = torch.cat([left, right], dim=-1)
     assert stitched.shape == full.shape
-    assert float((stitched - full).abs().max()) < 2e-6
+    assert float((stitched - full).abs().max()) < tol
 
 
 def test_shape_errors():
