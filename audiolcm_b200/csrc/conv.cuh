@@ -91,6 +91,7 @@ __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, int ph, uint32_
                                               uint32_t tmem_base, uint32_t a_full, uint32_t a_empty, uint32_t w_full,
                                               uint32_t w_empty, uint32_t acc_full, int kb0, int kb1, long long* trace) {
   const bool leader = elect_one();
+  const uint32_t lead = leader ? 1u : 0u;
   // Descriptors differ only in their 14-bit start-address field: build the constant part once
   // and add (byte offset >> 4) per MMA.
   const uint64_t a_desc0 = umma_desc_kmajor(sA, rowsA * 16, 128);
@@ -115,21 +116,18 @@ __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, int ph, uint32_
       mbar_wait(w_full + 8 * ws, wpar);
       tc_fence_after();
       if (trace && acc == 0 && leader) trace[3] = clock64();
-      // descriptor arithmetic stays warp-uniform (all lanes); only the async instructions are elected -
-      // a lane-private descriptor makes ptxas wrap every UTCHMMA in an ELECT/R2UR.BROADCAST/BRA.U.ANY loop
+      // branch-free, warp-uniform issue: the election is the predicate of the async instructions themselves
+      // (a lane-private descriptor or a divergent region makes ptxas wrap every UTCHMMA in an
+      // ELECT/R2UR.BROADCAST/BRA.U.ANY loop or shuttle descriptors through R2UR)
       uint64_t bd = w_desc0 + (uint64_t)(ws * w_stage16);
       for (int t = 0; t < g; ++t, a_tap += dshift, bd += w_blob16) {
-        if (leader) {
 #pragma unroll
-          for (int i = 0; i < NK2; ++i)
-            umma_ss<KIND>(tmem_base, a_tap + (uint64_t)(i * a_step), bd + (uint64_t)(i * w_step), idesc, (i > 0) ? 1u : acc);
-        }
+        for (int i = 0; i < NK2; ++i)
+          umma_ss_pred<KIND>(tmem_base, a_tap + (uint64_t)(i * a_step), bd + (uint64_t)(i * w_step), idesc, (i > 0) ? 1u : acc, lead);
         acc = 1;
       }
-      if (leader) {
-        tc_commit(w_empty + 8 * ws);  // frees the weight slot when these MMAs retire
-        if (j0 + g == ntaps) tc_commit(a_empty + 8 * as);
-      }
+      tc_commit_pred(w_empty + 8 * ws, lead);  // frees the weight slot when these MMAs retire
+      if (j0 + g == ntaps) tc_commit_pred(a_empty + 8 * as, lead);
       acc = 1;
       if (++ws == S) { ws = 0; wpar ^= 1; }
     }
