@@ -52,7 +52,7 @@ def measured_peaks():
 def cpu_decode_fn(threads):
     import torch
     from oracle import decode_oracle as O
-    from oracle import synth
+    from audiolcm_b200 import synth
     torch.set_num_threads(threads)
     dd, h = synth.vae_config(), synth.bigvgan_config()
     vsd = {k: torch.from_numpy(v) for k, v in synth.vae_decoder_state_dict(dd, seed=3).items()}
@@ -68,7 +68,7 @@ def cpu_decode_fn(threads):
 def cpu_baseline(budget_s=25.0):
     """Oracle port of the reference CPU decode on all host cores: full 10 s clip, best of <=2 runs
     (bounded to ~budget_s of CPU work)."""
-    from oracle import synth
+    from audiolcm_b200 import synth
     import torch
     cores = os.cpu_count() or 1
     run = cpu_decode_fn(cores)
@@ -96,7 +96,7 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    from oracle import synth
+    from audiolcm_b200 import synth
     cores = os.cpu_count() or 1
     run = cpu_decode_fn(cores)
     # bound the whole run to a few minutes: calibrate on a 1 s clip, then pick the clip length
@@ -173,7 +173,7 @@ class ClockSampler:
 
 def build_pipe(precision, device):
     from audiolcm_b200 import AutoencoderKLDecoder, LatentToWaveform, VocoderBigVGAN
-    from oracle import synth  # seeded synthetic weights/inputs only (data generator, not the checker)
+    from audiolcm_b200 import synth  # seeded synthetic weights/inputs only (data generator, not the checker)
     dd, h = synth.vae_config(), synth.bigvgan_config()
     vae = AutoencoderKLDecoder(synth.vae_decoder_state_dict(dd, seed=3), dd, synth.VAE_EMBED_DIM, device, precision)
     voc = VocoderBigVGAN.from_state_dict(synth.bigvgan_state_dict(h, seed=0), h, device, precision)
@@ -198,7 +198,7 @@ def time_steps(pipe, z_dev, steps, warmup, flush):
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from oracle import synth
+    from audiolcm_b200 import synth
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

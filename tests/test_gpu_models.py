@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from oracle import decode_oracle as O
-from oracle import synth
+from audiolcm_b200 import synth
 from tests.util import snr_db
 
 pytestmark = pytest.mark.gpu

@@ -12,7 +12,7 @@ from audiolcm_b200 import _lib
 from audiolcm_b200.autoencoder import vae_tensor_names
 from audiolcm_b200.pipeline import shard_range, halo_frames
 from audiolcm_b200.vocoder import bigvgan_tensor_names
-from oracle import synth
+from audiolcm_b200 import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

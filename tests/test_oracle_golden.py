@@ -8,7 +8,7 @@ import torch
 
 from oracle import decode_oracle as O
 from oracle import np_closed_form as NP
-from oracle import synth
+from audiolcm_b200 import synth
 
 
 def _load(golden_dir, name):

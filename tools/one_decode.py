@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import build_pipe, T_LAT  # noqa: E402
-from oracle import synth  # noqa: E402
+from audiolcm_b200 import synth  # noqa: E402
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
