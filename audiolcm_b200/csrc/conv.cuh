@@ -13,11 +13,17 @@
 // ldm/models/autoencoder1d.py:186-213,291-295 (Conv1d, Upsample1D); bias / residual add
 // (models.py:79) / block mean (models.py:193-196) are fused in the epilogue.
 #pragma once
+#include "act1d.cuh"
 #include "common.cuh"
 
 namespace alcm {
 
 constexpr int kTileM = 128;
+// Fused Activation1d epilogue: a tile of 128 conv rows yields the 116 activation outputs whose +-5-row
+// FIR support lies inside the tile (rows 5..120 of the tile = 29 threads x 4 outputs); tiles overlap by 12 rows.
+constexpr int kFuseOwn = 116, kFuseHalo = 5;
+constexpr int kFuseVT = kFuseOwn / kActR;                       // 29 four-output work items per plane
+constexpr int kFuseSlots = kTileM + (kTileM >> 3) + 1;           // staged rows incl. the anti-conflict pad slots
 
 struct ConvArgs {
   const uint8_t* x;   // input planes (operand dtype)
@@ -51,6 +57,16 @@ struct ConvArgs {
   float* ws;               // [tile][ksplit][NT/4][128] float4
   unsigned int* tile_ctr;  // [tile]
   long long* trace;        // micro-benchmark only: 8 timestamps per CTA (tools/bench_conv.py with ALCM_TRACE=1)
+  // Fused Activation1d epilogue (models.py:72-81: the SnakeBeta between c1/c2 and between AMP layers):
+  // act_out != null -> the tile is staged in shared memory, run through UpSample1d -> SnakeBeta ->
+  // DownSample1d and written as operand planes for the next conv.  `out` (fp32, the residual stream) is
+  // then optional.  Tiles advance by kFuseOwn rows; nphase = 1, scale = 1, accum = 0, res must not alias out.
+  void* act_out;
+  PlaneGeom ag;
+  const float* ea;         // exp(alpha)          [n_tiles*NT]
+  const float* ib;         // 1/(exp(beta)+1e-9)  [n_tiles*NT]
+  int act_bf16;            // operand planes are bf16 (E=8) / fp32 (E=4)
+  int act_round_tf32;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -137,8 +153,53 @@ __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, int ph, uint32_
   __syncwarp();
 }
 
-template <int KIND, int MINB>
-__global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
+// Activation1d on the staged tile (all warps of the CTA): work item = (output unit, 4 consecutive rows).
+template <int NPL>  // fp32 planes per output unit: 1 -> fp32/tf32 operand planes, 2 -> bf16
+__device__ __forceinline__ void conv_fused_act(const ConvArgs& a, const float4* ys, int b, int nt, int q0) {
+  const int T = a.M;
+  const int units = (a.NT >> 2) / NPL;
+  const int units_valid = min(units, a.ag.nchunk - nt * units);
+  const int t0 = q0 + kFuseHalo;  // first activation output of this tile; staged row lr <-> time t0 - 5 + lr
+  for (int item = threadIdx.x; item < units * kFuseVT; item += blockDim.x) {
+    const int u = item / kFuseVT, vt = item - u * kFuseVT;
+    const int m0 = t0 + kActR * vt;
+    const bool live = (u < units_valid) && (m0 < T);
+    const bool edge = live && ((m0 < 3) || (m0 + 6 > T - 1));
+    const bool any_edge = __any_sync(__activemask(), edge);
+    if (!live) continue;
+    float4 res[NPL][kActR];
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) {
+      const int pl = u * NPL + p;  // plane within the tile
+      const float4 ea = *reinterpret_cast<const float4*>(a.ea + nt * a.NT + pl * 4);
+      const float4 ib = *reinterpret_cast<const float4*>(a.ib + nt * a.NT + pl * 4);
+      if (any_edge) act_plane<true, true>(ys + pl * kFuseSlots, vt, m0, t0, T, ea, ib, res[p]);
+      else act_plane<true, false>(ys + pl * kFuseSlots, vt, m0, t0, T, ea, ib, res[p]);
+    }
+    const size_t base = ((size_t)b * a.ag.nchunk + (size_t)nt * units + u) * a.ag.Tp + a.ag.pad;
+#pragma unroll
+    for (int r = 0; r < kActR; ++r) {
+      const int m = m0 + r;
+      if (m >= T) break;
+      if (NPL == 1) {
+        float4 o = res[0][r];
+        if (a.act_round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        reinterpret_cast<float4*>(a.act_out)[base + m] = o;
+      } else {
+        const float4 lo = res[0][r], hi = res[NPL - 1][r];
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(lo.x, lo.y), h1 = __floats2bfloat162_rn(lo.z, lo.w);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(hi.x, hi.y), h3 = __floats2bfloat162_rn(hi.z, hi.w);
+        uint4 o;
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        reinterpret_cast<uint4*>(a.act_out)[base + m] = o;
+      }
+    }
+  }
+}
+
+template <int KIND, int MINB, bool FUSED>
+__global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = blockIdx.x, nt = blockIdx.y;
@@ -148,6 +209,7 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
   const int kb0 = (int)((long)zs * a.nkb / ksplit), kb1 = (int)((long)(zs + 1) * a.nkb / ksplit);
   const int S = a.w_stages;
   const int rowsA = kTileM + a.span;
+  constexpr bool fused = FUSED;  // Activation1d epilogue compiled in (launches with a.act_out != nullptr)
   const ConvSmemLayout L = conv_smem_layout(a.kblk, a.span, a.NT, S, a.tpg);
   const uint32_t sA = smem_u32(smem) + L.a_off;
   const uint32_t sW = smem_u32(smem) + L.w_off;
@@ -164,6 +226,7 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
     if (trace) { trace[0] = (long long)global_timer_ns(); trace[1] = clock64(); }
     for (int i = 0; i < 5 + 2 * S; ++i) mbar_init(bars + 8 * i, 1);
     fence_mbar_init();
+    *s_last = 1;
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(tmem_slot), a.tmem_cols);
@@ -173,7 +236,8 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int q0 = mt * kTileM;
+  // fused tiles overlap: tile mt owns activation outputs [mt*116, mt*116+116) and computes conv rows from 5 earlier
+  const int q0 = fused ? mt * kFuseOwn - kFuseHalo : mt * kTileM;
   if (trace && threadIdx.x == 0) trace[2] = clock64();
 
   // Both asynchronous roles keep their warp CONVERGENT and predicate the async instructions with
@@ -182,7 +246,7 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
   // loop, which left the tensor pipe waiting on the issuing thread.
   if (warp == 0) {
     const bool leader = elect_one();
-    const int row0 = q0 + a.min_off[ph] + a.xg.pad;  // >= 0 because |min_off| <= pad
+    const int row0 = q0 + a.min_off[ph] + a.xg.pad;  // >= 0: |min_off| + kFuseHalo <= pad
     const int nrows = min(rowsA, a.xg.Tp - row0);
     const uint8_t* wsrc = a.w + (size_t)ph * a.w_phase_stride + ((size_t)nt * a.nkb + kb0) * a.ntaps * L.w_blob;
     const size_t plane_bytes = (size_t)a.xg.Tp * 16;
@@ -228,7 +292,7 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
       case 5: conv_mma_loop<KIND, 5>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
       default: conv_mma_loop<KIND, 6>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
     }
-  } else {
+  } else if (warp < 6) {
     // while the main loop runs: stage this N tile's bias in shared memory (the epilogue reads it as broadcasts)
     const int et = threadIdx.x - 64;
     for (int i = et; i < a.NT; i += 128) s_bias[i] = a.bias ? __ldg(a.bias + nt * a.NT + i) : 0.f;
@@ -236,7 +300,9 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
     const int qd = warp & 3;  // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
     const int q = q0 + row;
-    const bool valid = q < a.M;
+    const bool in_seq = q >= 0 && q < a.M;
+    // rows whose fp32 result this tile stores: all of them, or only the ones it owns when tiles overlap
+    const bool valid = in_seq && (!fused || (row >= kFuseHalo && row < kFuseHalo + kFuseOwn));
     const size_t orow = (size_t)q * a.ostride + ph;
     const float scale = a.scale;
     const int nq = a.NT >> 2;                              // float4 column groups in this tile
@@ -245,23 +311,23 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
     const size_t off0 = ((size_t)b * a.og.nchunk + (size_t)nt * nq) * a.og.Tp + a.og.pad + orow;  // float4 units
     const float4* res4 = reinterpret_cast<const float4*>(a.res);
     float4* out4 = reinterpret_cast<float4*>(a.out);
-    const bool has_res = (a.res != nullptr) && valid, accum = (a.accum != 0) && valid;
+    const bool has_res = (a.res != nullptr) && in_seq, accum = (a.accum != 0) && valid, store = (a.out != nullptr) && valid;
+    float4* ys = reinterpret_cast<float4*>(smem);  // fused: staged tile [plane][kFuseSlots] float4, over the drained pipeline buffers
+    const int yrow = row + (row >> 3);
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (trace && threadIdx.x == 64) trace[5] = clock64();
-    // bias / residual / scale / accumulate + store of 16 consecutive output channels of this thread's row
+    // bias / residual / scale / accumulate of 16 consecutive output channels of this thread's row; fp32 store and/or staging
     auto emit = [&](int c0, const float (&v)[16], const float4 (&rr)[4], const float4 (&oo)[4]) {
-      if (!valid) return;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int cq = (c0 >> 2) + g;
-        if (cq < nq_valid) {
-          const float4 bb = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
-          float4 r = make_float4(v[4 * g] + bb.x, v[4 * g + 1] + bb.y, v[4 * g + 2] + bb.z, v[4 * g + 3] + bb.w);
-          r.x = (r.x + rr[g].x) * scale + oo[g].x; r.y = (r.y + rr[g].y) * scale + oo[g].y;
-          r.z = (r.z + rr[g].z) * scale + oo[g].z; r.w = (r.w + rr[g].w) * scale + oo[g].w;
-          out4[off0 + (size_t)cq * plane4] = r;
-        }
+        const float4 bb = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
+        float4 r = make_float4(v[4 * g] + bb.x, v[4 * g + 1] + bb.y, v[4 * g + 2] + bb.z, v[4 * g + 3] + bb.w);
+        r.x = (r.x + rr[g].x) * scale + oo[g].x; r.y = (r.y + rr[g].y) * scale + oo[g].y;
+        r.z = (r.z + rr[g].z) * scale + oo[g].z; r.w = (r.w + rr[g].w) * scale + oo[g].w;
+        if (store && cq < nq_valid) out4[off0 + (size_t)cq * plane4] = r;
+        if (fused) ys[cq * kFuseSlots + yrow] = r;
       }
     };
     // residual / accumulate operands of 16 channels (issued before the TMEM load they are combined with)
@@ -332,8 +398,29 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
         }
       }
     }
-    if (trace && threadIdx.x == 64) { trace[6] = clock64(); trace[7] = (long long)global_timer_ns(); }
+    if (trace && threadIdx.x == 64) trace[6] = clock64();
   }
+  if constexpr (FUSED) {
+    // ---- Activation1d on the staged tile, by every warp of the CTA (the async warps are done by now) ----
+    __syncthreads();  // tile staged (and, for split-K, s_last decided)
+    if (*s_last) {
+      float4* ys = reinterpret_cast<float4*>(smem);
+      const int T = a.M, npl = a.NT >> 2;
+      // replicate padding of the up-sampling FIR (resample.py:28): rows before t=0 / after t=T-1 take the edge sample
+      const int lo = -q0, hi = T - q0;  // staged rows [lo, hi) are inside the sequence
+      if (lo > 0 || hi < kTileM) {
+        for (int i = threadIdx.x; i < npl * kTileM; i += blockDim.x) {
+          const int pl = i / kTileM, r = i - pl * kTileM;
+          const int src = r < lo ? lo : (r >= hi ? hi - 1 : r);
+          if (src != r && src >= 0 && src < kTileM) ys[pl * kFuseSlots + r + (r >> 3)] = ys[pl * kFuseSlots + src + (src >> 3)];
+        }
+        __syncthreads();
+      }
+      if (a.act_bf16) conv_fused_act<2>(a, ys, b, nt, q0);
+      else conv_fused_act<1>(a, ys, b, nt, q0);
+    }
+  }
+  if (trace && threadIdx.x == 64) trace[7] = (long long)global_timer_ns();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {

@@ -235,7 +235,7 @@ static int g_sm_count = 148;
 // Pipeline shape of one launch.  Taps per weight stage: enough MMAs per mbarrier round trip to cover
 // ~512 tensor cycles (see conv.cuh).  Ring depth: with at most one CTA per SM use most of the 227 KB
 // (more bytes in flight hide the L2/HBM latency of the weight stream); otherwise leave room for 2 CTAs/SM.
-static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, int* stages, int* tpg, uint32_t* smem) {
+static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused, int* stages, int* tpg, uint32_t* smem) {
   const uint32_t budget = (uint32_t)env_int("ALCM_SMEM_BUDGET", ctas <= (long)g_sm_count ? 200 * 1024 : 100 * 1024);
   const double cyc_mma = std::max(L.NT / 2.0, 32.0 + L.NT / 4.0);
   const double cyc_tap = (L.kblk / 2) * cyc_mma;
@@ -249,6 +249,11 @@ static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, int* stages
   S = std::max(2, std::min(12, S));
   const int nkb_local = (L.nkb + ksplit - 1) / ksplit;
   S = std::min(S, std::max(2, nkb_local * ((L.ntaps + t - 1) / t)));
+  if (fused) {  // the staged output tile overlays the (drained) A and W buffers
+    const uint32_t staging = (uint32_t)(L.NT / 4) * kFuseSlots * 16;
+    while (a2 + (uint32_t)S * t * blob < staging && S < 12) ++S;
+    REQUIRE(a2 + (uint32_t)S * t * blob >= staging, "fused activation: staging tile does not fit under the pipeline buffers");
+  }
   *stages = S;
   *tpg = t;
   *smem = conv_smem_layout(L.kblk, L.span, L.NT, S, t).total;
@@ -264,16 +269,27 @@ struct SplitK {  // per-launch split-K resources (see ConvArgs::ksplit)
   unsigned int* ctr = nullptr;
 };
 
+// Fused Activation1d epilogue of a conv launch (ConvArgs::act_out)
+struct FusedAct {
+  PlaneT out;          // operand planes written by the epilogue (p == nullptr: not fused)
+  const float* ea = nullptr;
+  const float* ib = nullptr;
+  int round_tf32 = 0;
+};
+
+static inline int conv_m_tiles(int M, bool fused) { return fused ? (M + kFuseOwn - 1) / kFuseOwn : (M + kTileM - 1) / kTileM; }
+
 // How many K splits a conv launch gets: only launches whose output tiles cannot fill the GPU are split.
-static int pick_ksplit(const ConvLayer& L, int M, int B) {
+static int pick_ksplit(const ConvLayer& L, int M, int B, bool fused = false) {
   if (L.prec == ALCM_PREC_FP32 || !env_int("ALCM_SPLITK", 1) || L.nkb < 2) return 1;
-  const long ctas = (long)((M + kTileM - 1) / kTileM) * L.n_tiles * B * L.nphase;
+  const long ctas = (long)conv_m_tiles(M, fused) * L.n_tiles * B * L.nphase;
   if (ctas * 2 > (long)g_sm_count) return 1;
   return (int)std::max<long>(1, std::min<long>(std::min<long>(L.nkb, g_sm_count / ctas), 8));
 }
 
+// `out` may be empty (p == nullptr) for a fused launch that only produces the activated operand planes.
 static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const float* res, int M, float scale, int accum,
-                        const SplitK& sk, cudaStream_t st) {
+                        const SplitK& sk, const FusedAct& fa, cudaStream_t st) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x.p; a.xg = x.g;
@@ -290,7 +306,9 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
   a.dbg = g_conv_dbg;
   a.ksplit = 1;
   const int B = x.B;
+  const bool fused = fa.out.p != nullptr;
   if (L.prec == ALCM_PREC_FP32) {
+    REQUIRE(!fused, "conv: the fp32 (CUDA-core) path has no fused activation");
     a.w = reinterpret_cast<const uint8_t*>(L.weff);
     dim3 grid((M + kSimtTM - 1) / kSimtTM, (L.Cout + kSimtTN - 1) / kSimtTN, B * L.nphase);
     conv_simt_kernel<<<grid, 256, 0, st>>>(a);
@@ -301,16 +319,24 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
     a.idesc = L.idesc; a.w_phase_stride = L.phase_stride;
     a.ksplit = sk.ksplit; a.ws = sk.ws; a.tile_ctr = sk.ctr;
     a.trace = g_conv_trace;
-    dim3 grid((M + kTileM - 1) / kTileM, L.n_tiles, B * L.nphase * sk.ksplit);
+    if (fused) {
+      a.act_out = fa.out.p; a.ag = fa.out.g; a.ea = fa.ea; a.ib = fa.ib;
+      a.act_bf16 = fa.out.esz == 2; a.act_round_tf32 = fa.round_tf32;
+    }
+    dim3 grid(conv_m_tiles(M, fused), L.n_tiles, B * L.nphase * sk.ksplit);
     uint32_t smem = 0;
-    pick_pipeline(L, (long)grid.x * grid.y * grid.z, sk.ksplit, &a.w_stages, &a.tpg, &smem);
-    // wide tiles are limited to 2 CTAs/SM by shared memory anyway and get the registers; narrow ones want occupancy
-    if (L.NT >= 128) {
-      if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0, 2><<<grid, 192, smem, st>>>(a);
-      else conv_umma_kernel<1, 2><<<grid, 192, smem, st>>>(a);
+    pick_pipeline(L, (long)grid.x * grid.y * grid.z, sk.ksplit, fused, &a.w_stages, &a.tpg, &smem);
+    // wide tiles are limited to 2 CTAs/SM by shared memory anyway and get the registers; narrow ones want
+    // occupancy; the fused epilogue runs the (register-hungry) activation on 8 warps
+    if (fused) {
+      if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0, 2, true><<<grid, 256, smem, st>>>(a);
+      else conv_umma_kernel<1, 2, true><<<grid, 256, smem, st>>>(a);
+    } else if (L.NT >= 128) {
+      if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0, 2, false><<<grid, 192, smem, st>>>(a);
+      else conv_umma_kernel<1, 2, false><<<grid, 192, smem, st>>>(a);
     } else {
-      if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0, 4><<<grid, 192, smem, st>>>(a);
-      else conv_umma_kernel<1, 4><<<grid, 192, smem, st>>>(a);
+      if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0, 3, false><<<grid, 192, smem, st>>>(a);
+      else conv_umma_kernel<1, 3, false><<<grid, 192, smem, st>>>(a);
     }
   }
 }
@@ -318,24 +344,48 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
 struct OpList {
   std::vector<Op> ops;
   Arena* ar = nullptr;  // where split-K workspaces come from (null: never split)
+  double fused_act_bytes = 0;  // Activation1d work absorbed by conv epilogues
+  int fused_acts = 0;
   float* ws[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   size_t ws_bytes[kMaxLanes] = {0, 0, 0, 0};
   void conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const PlaneT* res, float scale = 1.f, int accum = 0) {
+    conv_act(L, x, &out, res, scale, accum, nullptr, nullptr, nullptr, 0);
+  }
+  // conv (+bias, +residual) with the following Activation1d fused into the epilogue: `out` (fp32, optional)
+  // receives the conv result, `aout` (operand planes) the activated one.  aout == nullptr: plain conv.
+  void conv_act(const ConvLayer& L, const PlaneT& x, const PlaneT* out, const PlaneT* res, float scale, int accum,
+                const PlaneT* aout, const float* ea, const float* ib, int round_tf32) {
     const int M = x.T;  // rows per batch item are input time steps (== output steps / nphase)
+    const bool fused = aout != nullptr;
+    REQUIRE(out || fused, "conv: no output");
     REQUIRE(x.esz == opnd_esz(L.prec), "conv: operand dtype mismatch");
-    REQUIRE(out.esz == 4 && out.T == x.T * L.nphase, "conv: bad output planes");
-    REQUIRE(x.g.nchunk * (16 / x.esz) >= L.Cin && out.g.nchunk * 4 >= L.Cout, "conv: channel mismatch");
+    if (out) {
+      REQUIRE(out->esz == 4 && out->T == x.T * L.nphase, "conv: bad output planes");
+      REQUIRE(out->g.nchunk * 4 >= L.Cout, "conv: channel mismatch");
+    }
+    REQUIRE(x.g.nchunk * (16 / x.esz) >= L.Cin, "conv: channel mismatch");
+    if (fused) {
+      REQUIRE(L.prec != ALCM_PREC_FP32 && L.nphase == 1 && scale == 1.f && accum == 0, "fused activation: plain Conv1d launches only");
+      REQUIRE(aout->esz == opnd_esz(L.prec) && aout->T == x.T && aout->B == x.B && aout->g.nchunk * (16 / aout->esz) >= L.Cout,
+              "fused activation: bad operand planes");
+      REQUIRE(!(res && out && res->p == out->p), "fused activation: the residual is read with a halo and must not alias the output");
+      REQUIRE(L.n_tiles * L.NT == round_up(L.Cout, 16), "fused activation: N tiles must cover the padded channels exactly");
+      REQUIRE(-L.min_off[0] + kFuseHalo <= kPad, "fused activation: conv halo + FIR halo exceed the plane padding");
+    }
     Op op;
     op.cls = ALCM_CLS_CONV;
     op.flops = 2.0 * L.Cin * L.Cout * L.ntaps * L.nphase * (double)M * x.B;
-    op.bytes = (double)x.B * x.T * ((double)L.Cin * x.esz + (double)L.Cout * L.nphase * 4 * (res ? 2 : 1));
+    op.bytes = (double)x.B * x.T * ((double)L.Cin * x.esz + (out ? (double)L.Cout * L.nphase * 4 : 0.0) +
+                                    (res ? (double)L.Cout * 4 : 0.0) + (fused ? (double)L.Cout * aout->esz : 0.0));
     const float* rp = res ? res->f() : nullptr;
     ConvLayer Lc = L;
-    PlaneT xc = x, oc = out;
+    PlaneT xc = x, oc = out ? *out : PlaneT();
+    FusedAct fa;
+    if (fused) { fa.out = *aout; fa.ea = ea; fa.ib = ib; fa.round_tf32 = round_tf32; }
     SplitK sk;
-    if (ar) sk.ksplit = pick_ksplit(L, M, x.B);
+    if (ar) sk.ksplit = pick_ksplit(L, M, x.B, fused);
     if (sk.ksplit > 1) {
-      const size_t tiles = (size_t)((M + kTileM - 1) / kTileM) * L.n_tiles * x.B * L.nphase;
+      const size_t tiles = (size_t)conv_m_tiles(M, fused) * L.n_tiles * x.B * L.nphase;
       const size_t need = tiles * sk.ksplit * (size_t)L.NT * kTileM * 4;
       if (need > ws_bytes[cur_lane]) {  // ops of one lane run in stream order and can share the partial-tile workspace
         ws_bytes[cur_lane] = std::max<size_t>(need, (size_t)16 << 20);
@@ -344,8 +394,12 @@ struct OpList {
       sk.ws = ws[cur_lane];
       sk.ctr = static_cast<unsigned int*>(ar->alloc(tiles * sizeof(unsigned int), true));
     }
-    op.fn = [=](cudaStream_t st) { launch_conv(Lc, xc, oc, rp, M, scale, accum, sk, st); };
+    op.fn = [=](cudaStream_t st) { launch_conv(Lc, xc, oc, rp, M, scale, accum, sk, fa, st); };
     push(op);
+    if (fused) {  // count the activation the launch absorbs in the act class' algorithmic bytes (bench roofline_act)
+      fused_act_bytes += (double)x.B * x.T * round_up(L.Cout, 16) * (4.0 + aout->esz);
+      ++fused_acts;
+    }
   }
   void act(const PlaneT& x, const PlaneT& out, const float* ea, const float* ib, int round_tf32, bool fast) {
     REQUIRE(x.esz == 4 && x.T == out.T && x.B == out.B, "act: bad planes");
@@ -530,7 +584,7 @@ struct alcm_vocoder {
 };
 
 static SnakeP make_snake(Arena& ar, const float* alpha, const float* beta, int C) {
-  const int Cpad = round_up(C, 16);
+  const int Cpad = round_up(C, 16) + 256;  // the fused conv epilogue indexes by (N tile, column)
   SnakeP s;
   s.ea = static_cast<float*>(ar.alloc((size_t)Cpad * 4, false));
   s.ib = static_cast<float*>(ar.alloc((size_t)Cpad * 4, false));
@@ -577,15 +631,42 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
     const bool parallel = nk > 1 && nk <= kMaxLanes && env_int("ALCM_LANES", 1) && conv_ctas < 3L * g_sm_count;
     PlaneT XS = make_planes(P.ar, B, C, Tc, 4);
     std::vector<PlaneT> Z;
-    PlaneT R, Y, A;
+    PlaneT R, R2, Y, A, A2;
+    // Measured on B200 (round 1): with the current register-blocked activation code the fused epilogue leaves the
+    // tensor pipe idle for longer than a separate launch costs (batch-1 decode 4.53 ms fused vs 4.05 ms unfused), so
+    // the fused chain is opt-in until the activation phase overlaps the next tile's main loop.
+    const bool fuse = (prec != ALCM_PREC_FP32) && env_int("ALCM_FUSE_ACT", 0);
     if (parallel) P.ol.fork();
     for (int j = 0; j < nk; ++j) {
       const AmpBlock& bk = S.blocks[j];
       if (parallel || j == 0) {
-        R = make_planes(P.ar, B, C, Tc, 4); Y = make_planes(P.ar, B, C, Tc, 4); A = make_planes(P.ar, B, C, Tc, oe);
+        R = make_planes(P.ar, B, C, Tc, 4); A = make_planes(P.ar, B, C, Tc, oe);
+        if (fuse) { R2 = make_planes(P.ar, B, C, Tc, 4); A2 = make_planes(P.ar, B, C, Tc, oe); }
+        else Y = make_planes(P.ar, B, C, Tc, 4);
       }
       if (parallel) P.ol.lane(j);
       const PlaneT* cur = &X;
+      if (fuse) {
+        // models.py:72-81 with every Activation1d but the first of the block running in the epilogue of the
+        // conv that produces its input: c1 emits only the activated operand (its fp32 output is never
+        // needed), c2 emits the new residual stream (fp32, ping-pong R/R2) and its activation.
+        P.ol.act(X, A, bk.a[0].ea, bk.a[0].ib, rtf, fast);
+        PlaneT* rnext = &R;
+        for (int l = 0; l < 3; ++l) {
+          P.ol.conv_act(bk.c1[l], A, nullptr, nullptr, 1.f, 0, &A2, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, rtf);
+          if (l < 2) {
+            P.ol.conv_act(bk.c2[l], A2, rnext, cur, 1.f, 0, &A, bk.a[2 * l + 2].ea, bk.a[2 * l + 2].ib, rtf);
+            cur = rnext;
+            rnext = (rnext == &R) ? &R2 : &R;
+          } else if (parallel) {
+            P.ol.conv(bk.c2[l], A2, *rnext, cur, 1.0f / nk, 0);
+            Z.push_back(*rnext);
+          } else {
+            P.ol.conv(bk.c2[l], A2, XS, cur, 1.0f / nk, j > 0);
+          }
+        }
+        continue;
+      }
       for (int l = 0; l < 3; ++l) {  // models.py:72-81
         P.ol.act(*cur, A, bk.a[2 * l].ea, bk.a[2 * l].ib, rtf, fast);
         P.ol.conv(bk.c1[l], A, Y, nullptr);
@@ -795,10 +876,13 @@ static void vae_run(alcm_vae* v, VaePlan* P, const float* z, float inv_scale, cu
 
 // ------------------------------------------------------------------------------------------ C-ABI
 static void set_kernel_attrs() {
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  const int mx = 227 * 1024;
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
 }
 
 extern "C" {
@@ -1115,6 +1199,41 @@ int alcm_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* 
     run_conv_test(ctx, KIND_CONV, x, w, bias, res, y, B, Cin, Cout, T, K, dilation, precision, static_cast<cudaStream_t>(stream));
   });
 }
+int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, const float* alpha,
+                        const float* beta, float* y_conv, float* y_act, int B, int Cin, int Cout, int T, int K, int dilation,
+                        int precision, void* stream) {
+  return guarded([&] {
+    REQUIRE(ctx && x && w && alpha && beta && y_act, "conv1d_act: NULL argument");
+    REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T >= 1 && dilation >= 1, "conv1d_act: bad shape");
+    REQUIRE(precision == ALCM_PREC_TF32 || precision == ALCM_PREC_BF16, "conv1d_act: tf32 / bf16 only");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar;
+    ConvLayer L = prepare_conv(ar, precision, KIND_CONV, w, bias, Cout, Cin, K, dilation);
+    PlaneT xin = make_planes(ar, B, Cin, T, opnd_esz(precision));
+    PlaneT out = make_planes(ar, B, Cout, T, 4), aout = make_planes(ar, B, Cout, T, opnd_esz(precision));
+    PlaneT rp;
+    if (res) rp = make_planes(ar, B, Cout, T, 4);
+    SnakeP sp = make_snake(ar, alpha, beta, Cout);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    launch_pack(x, xin, Cin, T, 1.f, precision, st);
+    if (res) launch_pack(res, rp, Cout, T, 1.f, ALCM_PREC_FP32, st);
+    OpList ol;
+    ol.ar = &ar;
+    ol.conv_act(L, xin, y_conv ? &out : nullptr, res ? &rp : nullptr, 1.f, 0, &aout, sp.ea, sp.ib, precision == ALCM_PREC_TF32);
+    CUDA_CHECK(cudaDeviceSynchronize());  // workspace memsets
+    ol.run(st);
+    if (y_conv) launch_unpack(out, y_conv, Cout, T, st);
+    if (precision == ALCM_PREC_BF16) {
+      dim3 grid((T + 255) / 256, aout.g.nchunk, B);
+      unpack_cf_bf16_kernel<<<grid, 256, 0, st>>>(aout.p, aout.g, y_act, Cout, T);
+    } else {
+      launch_unpack(aout, y_act, Cout, T, st);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    sync_free(st);
+  });
+}
 int alcm_conv_transpose1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
                               int T, int stride, int precision, void* stream) {
   return guarded([&] {
@@ -1229,7 +1348,15 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     PlaneT x = make_planes(ar, B, Cin, T, opnd_esz(precision)), out = make_planes(ar, B, Cout, T, 4);
     OpList ol;
     ol.ar = &ar;
-    ol.conv(L, x, out, nullptr);
+    const bool bench_fused = env_int("ALCM_BENCH_FUSED", 0) && precision != ALCM_PREC_FP32;
+    if (bench_fused) {  // conv + fused Activation1d, operand planes only (the c1 launches of the AMP blocks)
+      PlaneT aout = make_planes(ar, B, Cout, T, opnd_esz(precision));
+      float* ab = static_cast<float*>(ar.alloc((size_t)(round_up(Cout, 16) + 256) * 4, true));
+      SnakeP sp = make_snake(ar, ab, ab, Cout);
+      ol.conv_act(L, x, nullptr, nullptr, 1.f, 0, &aout, sp.ea, sp.ib, precision == ALCM_PREC_TF32);
+    } else {
+      ol.conv(L, x, out, nullptr);
+    }
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0));
     CUDA_CHECK(cudaEventCreate(&e1));
@@ -1242,8 +1369,8 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     g_conv_dbg = 0;
     CUDA_CHECK(err);
     if (env_int("ALCM_TRACE", 0) && precision != ALCM_PREC_FP32) {  // one more launch with per-CTA timestamps
-      const int ks = pick_ksplit(L, T, B);
-      const size_t nctas = (size_t)((T + kTileM - 1) / kTileM) * L.n_tiles * B * L.nphase * ks;
+      const int ks = pick_ksplit(L, T, B, bench_fused);
+      const size_t nctas = (size_t)conv_m_tiles(T, bench_fused) * L.n_tiles * B * L.nphase * ks;
       long long* tr = static_cast<long long*>(ar.alloc(nctas * 8 * sizeof(long long), true));
       CUDA_CHECK(cudaDeviceSynchronize());
       g_conv_trace = tr;

@@ -49,6 +49,23 @@ def conv1d(x, w, bias=None, res=None, dilation=1, precision="fp32"):
     return y
 
 
+def conv1d_act(x, w, bias, res, alpha, beta, dilation=1, precision="bf16", want_conv=True):
+    """Conv1d (+bias, +residual) and the Activation1d that follows it, one launch - models.py:72-81.
+
+    Returns (conv result or None, activated result)."""
+    (x, w, bias, res, alpha, beta), dev = _prep(x, w, bias, res, alpha, beta)
+    B, Cin, T = x.shape
+    Cout, Cin2, K = w.shape
+    assert Cin2 == Cin
+    yc = torch.empty((B, Cout, T), dtype=torch.float32, device=dev) if want_conv else None
+    ya = torch.empty((B, Cout, T), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().alcm_conv1d_act_fwd(_lib.ctx(dev.index), _p(x), _p(w), _p(bias), _p(res), _p(alpha), _p(beta),
+                                                   _p(yc), _p(ya), B, Cin, Cout, T, K, int(dilation), _lib.PREC[precision],
+                                                   _stream()))
+    return yc, ya
+
+
 def conv_transpose1d(x, w, bias=None, stride=2, precision="fp32"):
     """ConvTranspose1d(k=2*stride, stride, padding=stride/2) - vocoder/bigvgan/models.py:150-155."""
     (x, w, bias), dev = _prep(x, w, bias)

@@ -121,6 +121,12 @@ int alcm_decode_to_wav(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, 
 /* Activation1d(SnakeBeta logscale): act.py:23-28.  precision BF16 returns bf16-rounded values. */
 int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, const float* beta, float* y, int B, int C,
                           int T, int precision, void* stream);
+/* Conv1d (+bias, +res) followed by Activation1d(SnakeBeta) in ONE launch - the c1->act and c2(+x)->act steps of
+ * AMPBlock1.forward (models.py:72-81).  y_conv (may be NULL) receives the conv result, y_act its activation
+ * (rounded to the operand type of `precision`).  TF32 / BF16 only (the fp32 CUDA-core path is not fused). */
+int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, const float* alpha,
+                        const float* beta, float* y_conv, float* y_act, int B, int Cin, int Cout, int T, int K, int dilation,
+                        int precision, void* stream);
 /* Conv1d(Cin,Cout,K,dilation, padding=(K*d-d)/2) (+bias, +res if non-NULL); w [Cout,Cin,K] */
 int alcm_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, float* y, int B,
                     int Cin, int Cout, int T, int K, int dilation, int precision, void* stream);

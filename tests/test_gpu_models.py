@@ -135,6 +135,21 @@ def test_batch_and_time_shard_properties(precision):
     assert float((stitched - full).abs().max()) < tol
 
 
+def test_fused_activation_chain_matches_reference(golden_dir, monkeypatch):
+    """The opt-in plan that runs Activation1d inside the conv epilogues (ALCM_FUSE_ACT=1) meets the same gates."""
+    monkeypatch.setenv("ALCM_FUSE_ACT", "1")
+    g = np.load(os.path.join(golden_dir, "bigvgan_c256.npz"))
+    h = synth.bigvgan_config(int(g["c0"]))
+    mel = synth.synth_mel(int(g["B"]), int(g["T"]), seed=int(g["xseed"]))
+    for precision in ("tf32", "bf16"):
+        voc = _voc(h, synth.bigvgan_state_dict(h, seed=int(g["wseed"])), precision)
+        wav = voc.vocode(torch.from_numpy(mel))
+        ref = g["wav"].reshape(wav.shape)
+        err = np.abs(wav - ref).max()
+        print(f"\n[fused {precision}] max-abs {err:.3e} SNR {snr_db(ref, wav):.1f} dB")
+        assert err <= WAV_TOL[precision]
+
+
 def test_shape_errors():
     h = synth.bigvgan_config(64)
     voc = _voc(h, synth.bigvgan_state_dict(h, seed=0), "tf32")

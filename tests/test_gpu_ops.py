@@ -91,6 +91,50 @@ def test_conv1d(ops, case, precision):
     assert float((y2.double() - ref2).abs().max()) < 3e-5 * max(1.0, float(ref2.abs().max()))
 
 
+# ----------------------------------------------------------------------------------- Conv1d + fused Activation1d
+FUSED_CASES = [
+    # B, Cin, Cout, T, K, d
+    (1, 768, 768, 250, 3, 1),     # several N tiles, split-K
+    (2, 192, 192, 1000, 7, 3),    # NT = 192, 9 overlapping M tiles
+    (1, 24, 24, 4099, 11, 5),     # padded channels, widest conv halo (25) + FIR halo (5)
+    (1, 96, 96, 116, 3, 1),       # exactly one tile
+    (1, 96, 96, 117, 3, 5),       # one row spills into a second tile
+    (2, 48, 48, 232, 7, 1),       # exactly two tiles
+    (1, 48, 48, 1, 3, 1),         # T = 1: every row is replicate padding
+    (1, 32, 32, 7, 11, 1),
+    (1, 384, 384, 123, 7, 5),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("with_res", [True, False])
+def test_conv1d_fused_activation(ops, case, precision, with_res):
+    """conv (+bias, +residual) -> Activation1d in one launch (models.py:72-81) against the float64 oracle
+    evaluated on the operands exactly as the device rounds them."""
+    from oracle import decode_oracle as O
+    B, Cin, Cout, T, K, d = case
+    x = _rand(B, Cin, T, seed=20)
+    w = _rand(Cout, Cin, K, seed=21, scale=1.0 / np.sqrt(Cin * K))
+    b = _rand(Cout, seed=22, scale=0.1)
+    res = _rand(B, Cout, T, seed=23) if with_res else None
+    al, be = _rand(Cout, seed=24, scale=0.5), _rand(Cout, seed=25, scale=0.5)
+    xr, wr = round_operand(x, precision), round_operand(w, precision)
+    conv_ref = F.conv1d(xr.double(), wr.double(), b.double(), dilation=d, padding=(K * d - d) // 2)
+    if with_res:
+        conv_ref = conv_ref + res.double()
+    act_ref = O.activation1d(conv_ref, al.double(), be.double(), O.kaiser_sinc_filter().double())
+    yc, ya = ops.conv1d_act(x.to(DEV), w.to(DEV), b.to(DEV), None if res is None else res.to(DEV), al.to(DEV), be.to(DEV),
+                            dilation=d, precision=precision, want_conv=with_res)
+    if with_res:  # the fp32 conv result (residual stream) is also produced, only for the rows each tile owns
+        assert float((yc.cpu().double() - conv_ref).abs().max()) < 3e-5 * max(1.0, float(conv_ref.abs().max()))
+    ya = ya.cpu()
+    tol = {"tf32": 2.0 ** -11, "bf16": 2.0 ** -8}[precision]
+    err = (ya.double() - act_ref).abs()
+    assert float((err / (act_ref.abs() + 1.0)).max()) < tol * 1.01 + 3e-5, float(err.max())
+    assert torch.equal(round_operand(ya, precision), ya)
+
+
 @pytest.mark.parametrize("case", [(1, 1536, 768, 625, 4), (2, 96, 48, 333, 2), (1, 48, 24, 1000, 2), (1, 8, 4, 5, 4), (1, 4, 2, 1, 2)])
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_conv_transpose1d(ops, case, precision):
