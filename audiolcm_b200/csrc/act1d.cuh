@@ -146,6 +146,8 @@ __device__ __forceinline__ void act_plane(const float4* sx, int tid, int m0, int
 
 template <int NPL, bool FAST>  // NPL input planes per output unit: 1 -> fp32 out, 2 -> bf16 out
 __global__ void __launch_bounds__(kActThreads, 6) act1d_kernel(const __grid_constant__ ActArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float4 sx[NPL][kActSlots];
   const int tid = threadIdx.x;
   const int t0 = blockIdx.x * kActTile;
@@ -221,6 +223,91 @@ __global__ void __launch_bounds__(kActThreads, 6) act1d_kernel(const __grid_cons
           if (m0 + r >= T) break;
           op[m0 + r] = make_uint4(held[r].x, held[r].y, pk[r].x, pk[r].y);
         }
+      }
+    }
+  }
+}
+
+// Latency-oriented variant: a block of 128 threads works on TWO fp32 planes at once (64 threads x 4 outputs
+// each, tile = 256 outputs), so the two planes of a bf16 unit run side by side instead of back to back in one
+// thread; the halves meet through shared memory for the 16-byte store.  Twice the blocks, half the serial
+// instruction chain per block - what the small (batch-1) launches need.  fp32 / tf32 output: the two planes
+// are simply two independent output planes.
+constexpr int kPairThreads = 128, kPairHalf = 64;
+constexpr int kPairTile = kPairHalf * kActR;               // 256 outputs per block
+constexpr int kPairRows = kPairTile + 10;
+constexpr int kPairSlots = kPairRows + (kPairRows >> 3) + 1;
+
+template <bool BF16OUT, bool FAST>
+__global__ void __launch_bounds__(kPairThreads, 6) act1d_pair_kernel(const __grid_constant__ ActArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float4 sx[2][kPairSlots];
+  __shared__ uint2 xch[kPairHalf][kActR];
+  const int tid = threadIdx.x;
+  const int p = tid >> 6, ht = tid & (kPairHalf - 1);  // plane of the pair, thread within the plane
+  const int t0 = blockIdx.x * kPairTile;
+  const int pc = blockIdx.y, b = blockIdx.z;          // pair of fp32 planes 2*pc, 2*pc+1
+  const int T = a.T;
+
+  constexpr int kLd = (2 * kPairRows + kPairThreads - 1) / kPairThreads;
+  float4 stg[kLd];
+#pragma unroll
+  for (int k = 0; k < kLd; ++k) {
+    const int i = tid + k * kPairThreads;
+    const int pl = i >= kPairRows ? 1 : 0, lr = i - pl * kPairRows;
+    const float4* xp = reinterpret_cast<const float4*>(a.x) + ((size_t)b * a.xg.nchunk + (2 * pc + pl)) * a.xg.Tp + a.xg.pad;
+    const int t = min(max(t0 - 5 + min(lr, kPairRows - 1), 0), T - 1);
+    stg[k] = xp[t];
+  }
+#pragma unroll
+  for (int k = 0; k < kLd; ++k) {
+    const int i = tid + k * kPairThreads;
+    const int pl = i >= kPairRows ? 1 : 0, lr = i - pl * kPairRows;
+    if (i < 2 * kPairRows) sx[pl][lr + (lr >> 3)] = stg[k];
+  }
+  __syncthreads();
+
+  const int m0 = t0 + kActR * ht;
+  const bool live = m0 < T;
+  const bool edge = live && ((m0 < 3) || (m0 + 6 > T - 1));
+  float4 res[kActR];
+  if (live) {
+    const int chunk = 2 * pc + p;
+    const float4 ea = *reinterpret_cast<const float4*>(a.ea + chunk * 4);
+    const float4 ib = *reinterpret_cast<const float4*>(a.ib + chunk * 4);
+    if (__any_sync(__activemask(), edge)) act_plane<FAST, true>(sx[p], ht, m0, t0, T, ea, ib, res);
+    else act_plane<FAST, false>(sx[p], ht, m0, t0, T, ea, ib, res);
+  }
+  if (!BF16OUT) {
+    if (!live) return;
+    float4* op = reinterpret_cast<float4*>(a.out) + ((size_t)b * a.og.nchunk + (2 * pc + p)) * a.og.Tp + a.og.pad;
+#pragma unroll
+    for (int r = 0; r < kActR; ++r) {
+      if (m0 + r >= T) break;
+      float4 o = res[r];
+      if (a.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+      op[m0 + r] = o;
+    }
+  } else {
+    uint2 pk[kActR];
+#pragma unroll
+    for (int r = 0; r < kActR; ++r) {
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(res[r].x, res[r].y), h1 = __floats2bfloat162_rn(res[r].z, res[r].w);
+      pk[r] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    }
+    if (p == 0 && live) {
+#pragma unroll
+      for (int r = 0; r < kActR; ++r) xch[ht][r] = pk[r];
+    }
+    __syncthreads();
+    if (p == 1 && live) {
+      uint4* op = reinterpret_cast<uint4*>(a.out) + ((size_t)b * a.og.nchunk + pc) * a.og.Tp + a.og.pad;
+#pragma unroll
+      for (int r = 0; r < kActR; ++r) {
+        if (m0 + r >= T) break;
+        const uint2 lo = xch[ht][r];
+        op[m0 + r] = make_uint4(lo.x, lo.y, pk[r].x, pk[r].y);
       }
     }
   }

@@ -100,6 +100,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor drains; pdl_wait() blocks until the predecessor grid has
+// completed and its writes are visible.  Everything before it (barrier init, TMEM allocation, weight
+// prefetch) overlaps the predecessor's tail.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- tcgen05 / TMEM ----------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");

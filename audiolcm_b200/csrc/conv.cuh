@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
   // fused tiles overlap: tile mt owns activation outputs [mt*116, mt*116+116) and computes conv rows from 5 earlier
   const int q0 = fused ? mt * kFuseOwn - kFuseHalo : mt * kTileM;
   if (trace && threadIdx.x == 0) trace[2] = clock64();
+  pdl_launch_dependents();  // the next kernel may start its own setup / weight prefetch now
 
   // Both asynchronous roles keep their warp CONVERGENT and predicate the async instructions with
   // elect.sync: UBLKCP / UTCHMMA / UTCBAR take warp-uniform operands, and issuing them from a
@@ -255,6 +256,27 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
     const int ntaps = a.ntaps, tpg = a.tpg;
     int ws = 0;
     uint32_t wpar = 1;  // producer waits on the "previous" phase of the empty barriers first
+    // one weight stage (a group of taps): wait for the slot, arm the barrier, one bulk copy
+    auto load_w = [&](int j0) {
+      const uint32_t bytes = (uint32_t)min(tpg, ntaps - j0) * L.w_blob;
+      mbar_wait(w_empty + 8 * ws, wpar);
+      if (leader) {
+        if (a.dbg & 1) {
+          mbar_arrive(w_full + 8 * ws);
+        } else {
+          mbar_expect_tx(w_full + 8 * ws, bytes);
+          bulk_g2s(sW + ws * L.w_stage, wsrc, bytes, w_full + 8 * ws);
+        }
+      }
+      wsrc += bytes;
+      if (++ws == S) { ws = 0; wpar ^= 1; }
+    };
+    // weights do not depend on the previous kernel: fill the ring before waiting for it (PDL overlap)
+    const int ngrp = (ntaps + tpg - 1) / tpg;
+    const int pre = min(S, (kb1 - kb0) * ngrp);
+    for (int i = 0; i < pre; ++i) load_w((i % ngrp) * tpg);
+    pdl_wait();
+    int gi = 0;  // weight groups issued so far are [0, pre)
     for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
       const int as = it & 1;
       mbar_wait(a_empty + 8 * as, ((it >> 1) & 1) ^ 1);
@@ -267,20 +289,8 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
         for (int c = 0; c < a.kblk; ++c, dst += a_pitch, xsrc += plane_bytes)
           if (leader) bulk_g2s(dst, xsrc, a_bytes, a_full + 8 * as);
       }
-      for (int j0 = 0; j0 < ntaps; j0 += tpg) {
-        const uint32_t bytes = (uint32_t)min(tpg, ntaps - j0) * L.w_blob;
-        mbar_wait(w_empty + 8 * ws, wpar);
-        if (leader) {
-          if (a.dbg & 1) {
-            mbar_arrive(w_full + 8 * ws);
-          } else {
-            mbar_expect_tx(w_full + 8 * ws, bytes);
-            bulk_g2s(sW + ws * L.w_stage, wsrc, bytes, w_full + 8 * ws);
-          }
-        }
-        wsrc += bytes;
-        if (++ws == S) { ws = 0; wpar ^= 1; }
-      }
+      for (int j0 = 0; j0 < ntaps; j0 += tpg, ++gi)
+        if (gi >= pre) load_w(j0);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -297,6 +307,7 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
     const int et = threadIdx.x - 64;
     for (int i = et; i < a.NT; i += 128) s_bias[i] = a.bias ? __ldg(a.bias + nt * a.NT + i) : 0.f;
     asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+    pdl_wait();  // residual / accumulate reads, output and split-K workspace writes come after the previous kernel
     const int qd = warp & 3;  // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
     const int q = q0 + row;
@@ -401,6 +412,7 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
     if (trace && threadIdx.x == 64) trace[6] = clock64();
   }
   if constexpr (FUSED) {
+    pdl_wait();
     // ---- Activation1d on the staged tile, by every warp of the CTA (the async warps are done by now) ----
     __syncthreads();  // tile staged (and, for split-K, s_last decided)
     if (*s_last) {
@@ -437,6 +449,8 @@ constexpr int kSimtTM = 64, kSimtTN = 64, kSimtKC = 16;
 constexpr int kSimtRows = kSimtTM + 52;  // tile rows + largest span (50), padded
 
 __global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ ConvArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float Xs[kSimtKC][kSimtRows];
   __shared__ float Ws[kSimtKC][kSimtTN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;

@@ -102,6 +102,31 @@ static PlaneT make_planes(Arena& ar, int B, int C, int T, int esz) {
 
 static inline int opnd_esz(int prec) { return prec == ALCM_PREC_BF16 ? 2 : 4; }
 
+// ------------------------------------------------------------------------------------------ launches
+// Every kernel of a plan is launched with the programmatic-stream-serialization attribute (PDL): it may be
+// scheduled while its stream predecessor drains and synchronises itself with griddepcontrol.wait (pdl_wait()).
+// Under stream capture these become programmatic edges of the CUDA graph.  ALCM_PDL=0 turns it off.
+// Measured (round 1, batch-1 decode, CUDA-graph replay): 4.00 ms with PDL on every kernel, 3.97 ms with PDL on
+// the VAE chain only, 3.89 ms without - graph kernel->kernel edges are already cheap, and early-resident
+// dependents (up to 200 KB of shared memory each, idle in griddepcontrol.wait) keep other lanes' CTAs off
+// the SMs.  So it is off by default and a per-plan choice (OpList::pdl, or ALCM_PDL=1 to force it).
+static int g_pdl = -1;          // ALCM_PDL: -1 unset (per-plan default), 0 never, 1 always
+static thread_local int t_pdl = 0;  // set by OpList::run / run_lanes around the launches of a plan
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const int env_pdl = [] { const char* e = getenv("ALCM_PDL"); return e ? atoi(e) : -1; }();
+  g_pdl = env_pdl < 0 ? t_pdl : env_pdl;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+}
+
 // ------------------------------------------------------------------------------------------ conv layers
 enum ConvKind { KIND_CONV = 0, KIND_CONVT = 1, KIND_UPCONV3 = 2 };
 
@@ -311,7 +336,7 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
     REQUIRE(!fused, "conv: the fp32 (CUDA-core) path has no fused activation");
     a.w = reinterpret_cast<const uint8_t*>(L.weff);
     dim3 grid((M + kSimtTM - 1) / kSimtTM, (L.Cout + kSimtTN - 1) / kSimtTN, B * L.nphase);
-    conv_simt_kernel<<<grid, 256, 0, st>>>(a);
+    launch_k(conv_simt_kernel, dim3(grid), dim3(256), 0, st, a);
   } else {
     a.w = L.wpack;
     a.kchunks = L.kchunks; a.kblk = L.kblk; a.nkb = L.nkb;
@@ -329,14 +354,14 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
     // wide tiles are limited to 2 CTAs/SM by shared memory anyway and get the registers; narrow ones want
     // occupancy; the fused epilogue runs the (register-hungry) activation on 8 warps
     if (fused) {
-      if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0, 2, true><<<grid, 256, smem, st>>>(a);
-      else conv_umma_kernel<1, 2, true><<<grid, 256, smem, st>>>(a);
+      if (L.prec == ALCM_PREC_BF16) launch_k(conv_umma_kernel<0, 2, true>, dim3(grid), dim3(256), smem, st, a);
+      else launch_k(conv_umma_kernel<1, 2, true>, dim3(grid), dim3(256), smem, st, a);
     } else if (L.NT >= 128) {
-      if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0, 2, false><<<grid, 192, smem, st>>>(a);
-      else conv_umma_kernel<1, 2, false><<<grid, 192, smem, st>>>(a);
+      if (L.prec == ALCM_PREC_BF16) launch_k(conv_umma_kernel<0, 2, false>, dim3(grid), dim3(192), smem, st, a);
+      else launch_k(conv_umma_kernel<1, 2, false>, dim3(grid), dim3(192), smem, st, a);
     } else {
-      if (L.prec == ALCM_PREC_BF16) conv_umma_kernel<0, 3, false><<<grid, 192, smem, st>>>(a);
-      else conv_umma_kernel<1, 3, false><<<grid, 192, smem, st>>>(a);
+      if (L.prec == ALCM_PREC_BF16) launch_k(conv_umma_kernel<0, 3, false>, dim3(grid), dim3(192), smem, st, a);
+      else launch_k(conv_umma_kernel<1, 3, false>, dim3(grid), dim3(192), smem, st, a);
     }
   }
 }
@@ -344,6 +369,7 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
 struct OpList {
   std::vector<Op> ops;
   Arena* ar = nullptr;  // where split-K workspaces come from (null: never split)
+  int pdl = 0;          // launch this plan's kernels with programmatic dependent launch
   double fused_act_bytes = 0;  // Activation1d work absorbed by conv epilogues
   int fused_acts = 0;
   float* ws[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
@@ -411,13 +437,28 @@ struct OpList {
     op.cls = ALCM_CLS_ACT;
     op.flops = 0;
     op.bytes = (double)B * T * round_up(x.C, 16) * (4.0 + oesz);
+    const int nch32 = x.g.nchunk;
+    // two kernels, same arithmetic: the "pair" form (2 planes side by side, 256-output tiles) has half the serial
+    // work per block and twice the blocks - better while a launch cannot fill the GPU several times over
+    const long blocks_wide = (long)((T + kActTile - 1) / kActTile) * nch * B;
+    const int variant = env_int("ALCM_ACT_VARIANT", (oesz == 2 && blocks_wide < 24L * g_sm_count) ? 1 : 0);
     op.fn = [=](cudaStream_t st) {
+      if (variant == 1) {
+        const dim3 grid((T + kPairTile - 1) / kPairTile, nch32 / 2, B);
+        if (oesz == 4) {
+          if (fast) launch_k(act1d_pair_kernel<false, true>, dim3(grid), dim3(kPairThreads), 0, st, a);
+          else launch_k(act1d_pair_kernel<false, false>, dim3(grid), dim3(kPairThreads), 0, st, a);
+        } else {
+          launch_k(act1d_pair_kernel<true, true>, dim3(grid), dim3(kPairThreads), 0, st, a);
+        }
+        return;
+      }
       const dim3 grid((T + kActTile - 1) / kActTile, nch, B);
       if (oesz == 4) {
-        if (fast) act1d_kernel<1, true><<<grid, kActThreads, 0, st>>>(a);
-        else act1d_kernel<1, false><<<grid, kActThreads, 0, st>>>(a);
+        if (fast) launch_k(act1d_kernel<1, true>, dim3(grid), dim3(kActThreads), 0, st, a);
+        else launch_k(act1d_kernel<1, false>, dim3(grid), dim3(kActThreads), 0, st, a);
       } else {
-        act1d_kernel<2, true><<<grid, kActThreads, 0, st>>>(a);
+        launch_k(act1d_kernel<2, true>, dim3(grid), dim3(kActThreads), 0, st, a);
       }
     };
     push(op);
@@ -431,8 +472,8 @@ struct OpList {
     op.cls = ALCM_CLS_MISC; op.flops = 0; op.bytes = (double)B * T * round_up(x.C, 16) * (4.0 + oesz);
     op.fn = [=](cudaStream_t st) {
       dim3 grid((T + 255) / 256, nch, B);
-      if (oesz == 2) cast_planes_kernel<8><<<grid, 256, 0, st>>>(xc.f(), xc.g, oc.p, oc.g, T);
-      else cast_planes_kernel<4><<<grid, 256, 0, st>>>(xc.f(), xc.g, oc.p, oc.g, T);
+      if (oesz == 2) launch_k(cast_planes_kernel<8>, dim3(grid), dim3(256), 0, st, xc.f(), xc.g, oc.p, oc.g, T);
+      else launch_k(cast_planes_kernel<4>, dim3(grid), dim3(256), 0, st, xc.f(), xc.g, oc.p, oc.g, T);
     };
     push(op);
   }
@@ -455,7 +496,7 @@ struct OpList {
     Op op;
     op.cls = ALCM_CLS_MISC; op.flops = 0;
     op.bytes = (double)B * T * nch * 4 * (4.0 * a.n + (out32 ? 4 : 0) + (out_op ? out_op->esz : 0));
-    op.fn = [=](cudaStream_t st) { sum_planes_kernel<<<dim3((T + 255) / 256, nch / 2, B), 256, 0, st>>>(a); };
+    op.fn = [=](cudaStream_t st) { launch_k(sum_planes_kernel, dim3(dim3((T + 255) / 256, nch / 2, B)), dim3(256), 0, st, a); };
     push(op);
   }
   void fork() { Op m; m.cls = OP_FORK; m.flops = m.bytes = 0; ops.push_back(m); }
@@ -470,7 +511,9 @@ struct OpList {
   }
   // serial execution on one stream (eager mode / profiling): lanes simply run one after another
   void run(cudaStream_t st) const {
+    t_pdl = pdl;
     for (const Op& o : ops) if (o.cls >= 0) o.fn(st);
+    t_pdl = 0;
   }
   // execution with fork/join across side streams (used under stream capture -> parallel graph branches)
   void run_lanes(cudaStream_t st, cudaStream_t* side, std::vector<cudaEvent_t>& evs) const {
@@ -484,6 +527,7 @@ struct OpList {
       return evs[ei++];
     };
     bool used[kMaxLanes] = {false, false, false, false};
+    t_pdl = pdl;
     for (const Op& o : ops) {
       if (o.cls == OP_FORK) {
         cudaEvent_t e = next_ev();
@@ -500,17 +544,18 @@ struct OpList {
       }
     }
     (void)used;
+    t_pdl = 0;
   }
 };
 
 static void launch_pack(const float* in, const PlaneT& out, int C, int T, float mul, int prec, cudaStream_t st) {
   dim3 grid((T + 255) / 256, out.g.nchunk, out.B);
-  if (out.esz == 2) pack_cf_kernel<8><<<grid, 256, 0, st>>>(in, out.p, out.g, C, T, mul, 0);
-  else pack_cf_kernel<4><<<grid, 256, 0, st>>>(in, out.p, out.g, C, T, mul, prec == ALCM_PREC_TF32);
+  if (out.esz == 2) launch_k(pack_cf_kernel<8>, dim3(grid), dim3(256), 0, st, in, out.p, out.g, C, T, mul, 0);
+  else launch_k(pack_cf_kernel<4>, dim3(grid), dim3(256), 0, st, in, out.p, out.g, C, T, mul, prec == ALCM_PREC_TF32);
 }
 static void launch_unpack(const PlaneT& in, float* out, int C, int T, cudaStream_t st) {
   dim3 grid((T + 255) / 256, (C + 3) / 4, in.B);
-  unpack_cf_kernel<<<grid, 256, 0, st>>>(in.f(), in.g, out, C, T);
+  launch_k(unpack_cf_kernel, dim3(grid), dim3(256), 0, st, in.f(), in.g, out, C, T);
 }
 
 struct GraphExec {
@@ -714,7 +759,7 @@ static void voc_run(alcm_vocoder* v, VocPlan* P, const float* mel, const PlaneT*
   const int threads = 256;
   dim3 grid((P->Tout + threads - 1) / threads, P->B);
   const size_t sm = (size_t)7 * P->post_in.g.nchunk * 4 * sizeof(float);
-  conv_post_tanh_kernel<<<grid, threads, sm, st>>>(P->post_in.f(), P->post_in.g, v->post_w, v->post_bias, wav, P->Tout, 7);
+  launch_k(conv_post_tanh_kernel, dim3(grid), dim3(threads), sm, st, P->post_in.f(), P->post_in.g, v->post_w, v->post_bias, wav, P->Tout, 7);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -759,15 +804,15 @@ static void op_gn(OpList& ol, Arena& ar, const PlaneT& x, const PlaneT& out, con
   GnP nn = n;
   Op a;
   a.cls = ALCM_CLS_NORM; a.flops = 0; a.bytes = (double)B * C * T * 4;
-  a.fn = [=](cudaStream_t st) { gn_stats_kernel<<<dim3(groups, B), 512, 0, st>>>(xc.f(), xc.g, C, T, groups, 1e-6f, stats); };
+  a.fn = [=](cudaStream_t st) { launch_k(gn_stats_kernel, dim3(dim3(groups, B)), dim3(512), 0, st, xc.f(), xc.g, C, T, groups, 1e-6f, stats); };
   ol.ops.push_back(a);
   Op b;
   b.cls = ALCM_CLS_NORM; b.flops = 0; b.bytes = (double)B * C * T * (4.0 + out.esz);
   const int oesz = out.esz, nch = out.g.nchunk, rtf = (prec == ALCM_PREC_TF32);
   b.fn = [=](cudaStream_t st) {
     dim3 grid((T + 127) / 128, nch, B);
-    if (oesz == 2) gn_apply_kernel<8><<<grid, 128, 0, st>>>(xc.f(), xc.g, oc.p, oc.g, C, T, groups, stats, nn.gamma, nn.beta, swish, 0);
-    else gn_apply_kernel<4><<<grid, 128, 0, st>>>(xc.f(), xc.g, oc.p, oc.g, C, T, groups, stats, nn.gamma, nn.beta, swish, rtf);
+    if (oesz == 2) launch_k(gn_apply_kernel<8>, dim3(grid), dim3(128), 0, st, xc.f(), xc.g, oc.p, oc.g, C, T, groups, stats, nn.gamma, nn.beta, swish, 0);
+    else launch_k(gn_apply_kernel<4>, dim3(grid), dim3(128), 0, st, xc.f(), xc.g, oc.p, oc.g, C, T, groups, stats, nn.gamma, nn.beta, swish, rtf);
   };
   ol.ops.push_back(b);
 }
@@ -812,17 +857,17 @@ static PlaneT op_attn(OpList& ol, Arena& ar, const AttnBlk& at, const PlaneT& x,
   Op s1;
   s1.cls = ALCM_CLS_ATTN; s1.flops = 2.0 * B * (double)T * T * C; s1.bytes = (double)B * (2.0 * C * T + (double)T * T) * 4;
   s1.fn = [=](cudaStream_t st) {
-    attn_scores_kernel<<<dim3((T + 31) / 32, (T + 31) / 32, B), 256, 0, st>>>(q.f(), k.f(), q.g, C, T, scale, S);
+    launch_k(attn_scores_kernel, dim3(dim3((T + 31) / 32, (T + 31) / 32, B)), dim3(256), 0, st, q.f(), k.f(), q.g, C, T, scale, S);
   };
   ol.ops.push_back(s1);
   Op s2;
   s2.cls = ALCM_CLS_ATTN; s2.flops = 0; s2.bytes = 2.0 * B * (double)T * T * 4;
-  s2.fn = [=](cudaStream_t st) { softmax_rows_kernel<<<B * T, 128, 0, st>>>(S, T); };
+  s2.fn = [=](cudaStream_t st) { launch_k(softmax_rows_kernel, dim3(B * T), dim3(128), 0, st, S, T); };
   ol.ops.push_back(s2);
   Op s3;
   s3.cls = ALCM_CLS_ATTN; s3.flops = 2.0 * B * (double)T * T * C; s3.bytes = (double)B * (2.0 * C * T + (double)T * T) * 4;
   s3.fn = [=](cudaStream_t st) {
-    attn_pv_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), 256, 0, st>>>(v.f(), v.g, S, C, T, h.f(), h.g);
+    launch_k(attn_pv_kernel, dim3(dim3((T + 31) / 32, (C + 31) / 32, B)), dim3(256), 0, st, v.f(), v.g, S, C, T, h.f(), h.g);
   };
   ol.ops.push_back(s3);
   PlaneT out = make_planes(ar, B, C, T, 4);
@@ -1129,8 +1174,8 @@ int alcm_decode_to_wav(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, 
       const PlaneT& src = PV->mel_out;
       const PlaneT& dst = PW->mel_in;
       dim3 grid((src.T + 255) / 256, dst.g.nchunk, B);
-      if (dst.esz == 2) cast_planes_kernel<8><<<grid, 256, 0, st>>>(src.f(), src.g, dst.p, dst.g, src.T);
-      else if (voc->prec == ALCM_PREC_TF32) cast_planes_kernel<4><<<grid, 256, 0, st>>>(src.f(), src.g, dst.p, dst.g, src.T);
+      if (dst.esz == 2) launch_k(cast_planes_kernel<8>, dim3(grid), dim3(256), 0, st, src.f(), src.g, dst.p, dst.g, src.T);
+      else if (voc->prec == ALCM_PREC_TF32) launch_k(cast_planes_kernel<4>, dim3(grid), dim3(256), 0, st, src.f(), src.g, dst.p, dst.g, src.T);
       else CUDA_CHECK(cudaMemcpyAsync(dst.p, src.p, src.bytes, cudaMemcpyDeviceToDevice, st));
     }
     voc_run(voc, PW, nullptr, nullptr, wav, st);
@@ -1158,7 +1203,7 @@ int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, con
     ol.run(st);
     if (precision == ALCM_PREC_BF16) {
       dim3 grid((T + 255) / 256, out.g.nchunk, B);
-      unpack_cf_bf16_kernel<<<grid, 256, 0, st>>>(out.p, out.g, y, C, T);
+      launch_k(unpack_cf_bf16_kernel, dim3(grid), dim3(256), 0, st, out.p, out.g, y, C, T);
     } else {
       launch_unpack(out, y, C, T, st);
     }
@@ -1226,7 +1271,7 @@ int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const flo
     if (y_conv) launch_unpack(out, y_conv, Cout, T, st);
     if (precision == ALCM_PREC_BF16) {
       dim3 grid((T + 255) / 256, aout.g.nchunk, B);
-      unpack_cf_bf16_kernel<<<grid, 256, 0, st>>>(aout.p, aout.g, y_act, Cout, T);
+      launch_k(unpack_cf_bf16_kernel, dim3(grid), dim3(256), 0, st, aout.p, aout.g, y_act, Cout, T);
     } else {
       launch_unpack(aout, y_act, Cout, T, st);
     }
@@ -1284,9 +1329,9 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
     launch_pack(q, pq, C, T, 1.f, ALCM_PREC_FP32, st);
     launch_pack(k, pk, C, T, 1.f, ALCM_PREC_FP32, st);
     launch_pack(v, pv, C, T, 1.f, ALCM_PREC_FP32, st);
-    attn_scores_kernel<<<dim3((T + 31) / 32, (T + 31) / 32, B), 256, 0, st>>>(pq.f(), pk.f(), pq.g, C, T, 1.0f / sqrtf((float)C), S);
-    softmax_rows_kernel<<<B * T, 128, 0, st>>>(S, T);
-    attn_pv_kernel<<<dim3((T + 31) / 32, (C + 31) / 32, B), 256, 0, st>>>(pv.f(), pv.g, S, C, T, ph.f(), ph.g);
+    launch_k(attn_scores_kernel, dim3(dim3((T + 31) / 32, (T + 31) / 32, B)), dim3(256), 0, st, pq.f(), pk.f(), pq.g, C, T, 1.0f / sqrtf((float)C), S);
+    launch_k(softmax_rows_kernel, dim3(B * T), dim3(128), 0, st, S, T);
+    launch_k(attn_pv_kernel, dim3(dim3((T + 31) / 32, (C + 31) / 32, B)), dim3(256), 0, st, pv.f(), pv.g, S, C, T, ph.f(), ph.g);
     launch_unpack(ph, out, C, T, st);
     CUDA_CHECK(cudaGetLastError());
     sync_free(st);
@@ -1298,6 +1343,7 @@ static void profile_ops(const OpList& ol, int iters, alcm_profile* out, cudaStre
   std::vector<cudaEvent_t> ev(ol.ops.size() + 1);
   for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
   for (int it = 0; it < iters; ++it) {
+    t_pdl = 0;  // per-kernel timing: no overlap between neighbours
     CUDA_CHECK(cudaEventRecord(ev[0], st));
     for (size_t i = 0; i < ol.ops.size(); ++i) {
       if (ol.ops[i].cls >= 0) ol.ops[i].fn(st);

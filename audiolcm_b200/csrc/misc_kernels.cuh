@@ -16,6 +16,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 template <int E>
 __global__ void pack_cf_kernel(const float* __restrict__ in, void* __restrict__ out, PlaneGeom og, int C, int T, float mul,
                                int rtf32) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int chunk = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;
@@ -42,6 +44,8 @@ __global__ void pack_cf_kernel(const float* __restrict__ in, void* __restrict__ 
 
 // fp32 planes -> [B][C][T] fp32 channel-first
 __global__ void unpack_cf_kernel(const float* __restrict__ in, PlaneGeom ig, float* __restrict__ out, int C, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int chunk = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;
@@ -56,6 +60,8 @@ __global__ void unpack_cf_kernel(const float* __restrict__ in, PlaneGeom ig, flo
 
 // bf16 planes (E=8) -> [B][C][T] fp32 channel-first (test entry points only)
 __global__ void unpack_cf_bf16_kernel(const uint8_t* __restrict__ in, PlaneGeom ig, float* __restrict__ out, int C, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int chunk = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;
@@ -72,6 +78,8 @@ __global__ void unpack_cf_bf16_kernel(const uint8_t* __restrict__ in, PlaneGeom 
 // fp32 planes -> operand planes: bf16 (E=8, two in-planes per out-plane) or tf32-rounded fp32 copy
 template <int E>
 __global__ void cast_planes_kernel(const float* __restrict__ in, PlaneGeom ig, void* __restrict__ out, PlaneGeom og, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int oc = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;
@@ -101,6 +109,8 @@ struct SumArgs {
   int op_bf16, round_tf32, T;
 };
 __global__ void sum_planes_kernel(SumArgs a) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int pc = blockIdx.y, b = blockIdx.z;  // pair of fp32 chunks 2*pc, 2*pc+1
   if (t >= a.T) return;
@@ -224,6 +234,8 @@ __global__ void snake_params_kernel(const float* __restrict__ alpha, const float
 // models.py:199-201: Conv1d(C -> 1, k=7, p=3) + tanh on fp32 planes; w is [7][Cpad] (tap-major).
 __global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg, const float* __restrict__ w, float bias,
                                       float* __restrict__ wav, int T, int ktaps) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sw[];
   const int nw = ktaps * xg.nchunk * 4;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
@@ -259,6 +271,8 @@ __device__ __forceinline__ double gn_block_sum(float s, double* red) {
 
 __global__ void __launch_bounds__(512) gn_stats_kernel(const float* __restrict__ x, PlaneGeom xg, int C, int T, int groups,
                                                          float eps, float2* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double red[16];
   const int g = blockIdx.x, b = blockIdx.y;
   const int cpg = C / groups;
@@ -315,6 +329,8 @@ template <int E>
 __global__ void gn_apply_kernel(const float* __restrict__ x, PlaneGeom xg, void* __restrict__ out, PlaneGeom og, int C, int T,
                                 int groups, const float2* __restrict__ stats, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, int swish, int rtf32) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int oc = blockIdx.y, b = blockIdx.z;
   if (t >= T) return;
@@ -360,6 +376,8 @@ __device__ __forceinline__ float plane_elem(const float* x, const PlaneGeom& g, 
 
 __global__ void __launch_bounds__(256) attn_scores_kernel(const float* __restrict__ q, const float* __restrict__ k, PlaneGeom g,
                                                             int C, int T, float scale, float* __restrict__ S) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float Qs[32][33], Ks[32][33];
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32, b = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty 0..7
@@ -387,6 +405,8 @@ __global__ void __launch_bounds__(256) attn_scores_kernel(const float* __restric
 }
 
 __global__ void softmax_rows_kernel(float* __restrict__ S, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;  // b*T + i
   float* p = S + (size_t)row * T;
   __shared__ float red[32];
@@ -415,6 +435,8 @@ __global__ void softmax_rows_kernel(float* __restrict__ S, int T) {
 
 __global__ void __launch_bounds__(256) attn_pv_kernel(const float* __restrict__ v, PlaneGeom g, const float* __restrict__ P, int C,
                                                         int T, float* __restrict__ h, PlaneGeom hg) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float Vs[32][33], Ps[32][33];
   const int c0 = blockIdx.y * 32, i0 = blockIdx.x * 32, b = blockIdx.z;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
