@@ -237,6 +237,56 @@ static ConvLayer prepare_conv(Arena& ar, int prec, ConvKind kind, const float* w
   return L;
 }
 
+static int g_sm_count = 148;
+
+// ---- per-launch N tile -----------------------------------------------------------------------------------
+// Weights are packed for N = 128 (or the whole padded Cout when smaller).  A launch with few time tiles
+// (the VAE at T = 312/624, conv_pre) fills the GPU better with narrower N tiles: more CTAs per launch and a
+// split-K factor of at most 2, so the last-arriver fix-up reads 2 small partial tiles instead of 4-8 big ones.
+static int pick_nt(const ConvLayer& L, int M, int B) {
+  if (L.prec == ALCM_PREC_FP32 || !env_int("ALCM_RETILE", 1)) return L.NT;
+  const int cout_pad = round_up(L.Cout, 16);
+  const long m = (long)((M + kTileM - 1) / kTileM) * B * L.nphase;
+  const long want = (long)(0.6 * g_sm_count);
+  int best = L.NT;
+  for (int nt : {L.NT, 64, 32}) {
+    if (nt > L.NT || cout_pad % nt != 0) continue;
+    best = nt;
+    const long ctas = m * (cout_pad / nt);
+    if (ctas >= want || (L.nkb >= 2 && 2 * ctas >= want)) break;
+  }
+  return best;
+}
+
+struct RetileCache {  // owned by a model: re-tiled copies of its layers, keyed by (packed weights, N tile)
+  std::map<std::pair<const void*, int>, ConvLayer> m;
+};
+
+static const ConvLayer& retile(Arena& ar, RetileCache& cache, const ConvLayer& L, int NT2) {
+  if (NT2 == L.NT) return L;
+  auto key = std::make_pair((const void*)L.wpack, NT2);
+  auto it = cache.m.find(key);
+  if (it != cache.m.end()) return it->second;
+  ConvLayer R = L;
+  const int cout_pad = round_up(L.Cout, 16);
+  R.NT = NT2;
+  R.n_tiles = (cout_pad + NT2 - 1) / NT2;
+  R.tmem_cols = 32;
+  while (R.tmem_cols < NT2) R.tmem_cols *= 2;
+  R.idesc = umma_idesc(L.prec == ALCM_PREC_BF16 ? 1 : 2, NT2);
+  R.phase_stride = (size_t)R.n_tiles * L.nkb * L.ntaps * L.kblk * NT2 * 16;
+  R.wpack = static_cast<uint8_t*>(ar.alloc(R.phase_stride * L.nphase, false));
+  const size_t units = R.phase_stride * L.nphase / 16;
+  repack_nt_kernel<<<(unsigned)std::min<size_t>((units + 255) / 256, 8192), 256>>>(
+      reinterpret_cast<const uint4*>(L.wpack), reinterpret_cast<uint4*>(R.wpack), L.nphase, L.ntaps, L.kblk, L.nkb, L.NT, L.n_tiles,
+      NT2, R.n_tiles);
+  CUDA_CHECK(cudaGetLastError());
+  R.bias = static_cast<float*>(ar.alloc((size_t)R.n_tiles * NT2 * 4, true));
+  CUDA_CHECK(cudaMemcpy(R.bias, L.bias, (size_t)std::min(L.n_tiles * L.NT, R.n_tiles * NT2) * 4, cudaMemcpyDeviceToDevice));
+  CUDA_CHECK(cudaDeviceSynchronize());
+  return cache.m.emplace(key, R).first->second;
+}
+
 // weight_norm fold into a temp buffer (dim0 x inner)
 static float* fold_wn(Arena& tmp, const float* g, const float* v, int dim0, int inner) {
   float* w = static_cast<float*>(tmp.alloc((size_t)dim0 * inner * 4, false));
@@ -255,7 +305,6 @@ struct Op {
   int lane = 0;
 };
 
-static int g_sm_count = 148;
 
 // Pipeline shape of one launch.  Taps per weight stage: enough MMAs per mbarrier round trip to cover
 // ~512 tensor cycles (see conv.cuh).  Ring depth: with at most one CTA per SM use most of the 227 KB
@@ -370,6 +419,8 @@ struct OpList {
   std::vector<Op> ops;
   Arena* ar = nullptr;  // where split-K workspaces come from (null: never split)
   int pdl = 0;          // launch this plan's kernels with programmatic dependent launch
+  Arena* war = nullptr;          // model-owned arena + cache for re-tiled weights (null: keep the packed N tile)
+  RetileCache* cache = nullptr;
   double fused_act_bytes = 0;  // Activation1d work absorbed by conv epilogues
   int fused_acts = 0;
   float* ws[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
@@ -379,9 +430,10 @@ struct OpList {
   }
   // conv (+bias, +residual) with the following Activation1d fused into the epilogue: `out` (fp32, optional)
   // receives the conv result, `aout` (operand planes) the activated one.  aout == nullptr: plain conv.
-  void conv_act(const ConvLayer& L, const PlaneT& x, const PlaneT* out, const PlaneT* res, float scale, int accum,
+  void conv_act(const ConvLayer& L0, const PlaneT& x, const PlaneT* out, const PlaneT* res, float scale, int accum,
                 const PlaneT* aout, const float* ea, const float* ib, int round_tf32) {
     const int M = x.T;  // rows per batch item are input time steps (== output steps / nphase)
+    const ConvLayer& L = (war && cache) ? retile(*war, *cache, L0, pick_nt(L0, M, x.B)) : L0;
     const bool fused = aout != nullptr;
     REQUIRE(out || fused, "conv: no output");
     REQUIRE(x.esz == opnd_esz(L.prec), "conv: operand dtype mismatch");
@@ -625,6 +677,7 @@ struct alcm_vocoder {
   float* post_w = nullptr;  // [7][Cpad] tap-major fp32
   float post_bias = 0.f;
   int post_C = 0, hop = 1;
+  RetileCache retiled;
   std::map<std::pair<int, int>, std::unique_ptr<VocPlan>> plans;
 };
 
@@ -646,6 +699,7 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
   VocPlan& P = *pl;
   P.B = B; P.T = T;
   P.ol.ar = &P.ar;
+  P.ol.war = &v->war; P.ol.cache = &v->retiled;
   const int prec = v->prec, oe = opnd_esz(prec);
   const int rtf = (prec == ALCM_PREC_TF32);
   const bool fast = (prec != ALCM_PREC_FP32);  // MUFU.COS snake; the exact-fp32 mode keeps the range-reduced sin
@@ -793,15 +847,34 @@ struct alcm_vae {
   std::vector<VaeLevel> levels;  // in execution order (highest level first)
   GnP norm_out;
   int up_factor = 1;
+  RetileCache retiled;
   std::map<std::pair<int, int>, std::unique_ptr<VaePlan>> plans;
 };
 
 static void op_gn(OpList& ol, Arena& ar, const PlaneT& x, const PlaneT& out, const GnP& n, int swish, int prec) {
   const int B = x.B, C = x.C, T = x.T, groups = 32;
   REQUIRE(C % groups == 0, "GroupNorm: C must be a multiple of 32");
-  float2* stats = static_cast<float2*>(ar.alloc((size_t)B * groups * sizeof(float2), false));
   PlaneT xc = x, oc = out;
   GnP nn = n;
+  {  // one launch when a block's groups fit in shared memory (gn_fused_kernel)
+    const int cpg = C / groups, E = 16 / out.esz;
+    int gpb = 1;
+    while (gpb <= 4 && (gpb * cpg) % E != 0) ++gpb;
+    const size_t smem = (size_t)gpb * (cpg / 4) * T * 16;
+    if ((cpg % 4) == 0 && gpb <= 4 && groups % gpb == 0 && smem <= 200 * 1024 && env_int("ALCM_GN_FUSED", 1)) {
+      Op f;
+      f.cls = ALCM_CLS_NORM; f.flops = 0; f.bytes = (double)B * C * T * (4.0 + out.esz);
+      const int oesz = out.esz, rtf = (prec == ALCM_PREC_TF32);
+      f.fn = [=](cudaStream_t st) {
+        dim3 grid(groups / gpb, B);
+        if (oesz == 2) launch_k(gn_fused_kernel<8>, grid, dim3(512), smem, st, xc.f(), xc.g, oc.p, oc.g, C, T, groups, 1e-6f, nn.gamma, nn.beta, swish, 0, gpb);
+        else launch_k(gn_fused_kernel<4>, grid, dim3(512), smem, st, xc.f(), xc.g, oc.p, oc.g, C, T, groups, 1e-6f, nn.gamma, nn.beta, swish, rtf, gpb);
+      };
+      ol.ops.push_back(f);
+      return;
+    }
+  }
+  float2* stats = static_cast<float2*>(ar.alloc((size_t)B * groups * sizeof(float2), false));
   Op a;
   a.cls = ALCM_CLS_NORM; a.flops = 0; a.bytes = (double)B * C * T * 4;
   a.fn = [=](cudaStream_t st) { launch_k(gn_stats_kernel, dim3(dim3(groups, B)), dim3(512), 0, st, xc.f(), xc.g, C, T, groups, 1e-6f, stats); };
@@ -883,6 +956,7 @@ static VaePlan* vae_plan(alcm_vae* v, int B, int T) {
   VaePlan& P = *pl;
   P.B = B; P.T = T;
   P.ol.ar = &P.ar;
+  P.ol.war = &v->war; P.ol.cache = &v->retiled;
   const int prec = v->prec, oe = opnd_esz(prec);
   P.z_in = make_planes(P.ar, B, v->cfg.embed_dim, T, oe);
   PlaneT h0 = make_planes(P.ar, B, v->cfg.z_channels, T, 4);
@@ -922,6 +996,8 @@ static void vae_run(alcm_vae* v, VaePlan* P, const float* z, float inv_scale, cu
 // ------------------------------------------------------------------------------------------ C-ABI
 static void set_kernel_attrs() {
   const int mx = 227 * 1024;
+  CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));

@@ -221,6 +221,28 @@ __global__ void pack_w_kernel(const float* __restrict__ weff, void* __restrict__
   }
 }
 
+// Re-tile packed weight blobs to another N tile (pure permutation of 16-byte units): launches whose output
+// has few time tiles get narrower N tiles (more CTAs, smaller split-K fix-up) without keeping the fp32 weights.
+// Units of output channels >= n_tiles1*NT1 are zero.
+__global__ void repack_nt_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int nphase, int ntaps, int kblk, int nkb,
+                                 int NT1, int n_tiles1, int NT2, int n_tiles2) {
+  const size_t units = (size_t)nphase * n_tiles2 * nkb * ntaps * kblk * NT2;
+  for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
+    size_t r = u;
+    const int n = r % NT2; r /= NT2;
+    const int kc = r % kblk; r /= kblk;
+    const int tp = r % ntaps; r /= ntaps;
+    const int kb = r % nkb; r /= nkb;
+    const int nt = r % n_tiles2; r /= n_tiles2;
+    const int ph = (int)r;
+    const int co = nt * NT2 + n;
+    const int nt1 = co / NT1, n1 = co - nt1 * NT1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (nt1 < n_tiles1) v = src[(((((size_t)ph * n_tiles1 + nt1) * nkb + kb) * ntaps + tp) * kblk + kc) * NT1 + n1];
+    dst[u] = v;
+  }
+}
+
 // SnakeBeta parameters (activations.py:113-118, logscale): ea = exp(alpha), ib = 1/(exp(beta)+1e-9)
 __global__ void snake_params_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, float* __restrict__ ea,
                                     float* __restrict__ ib, int C, int Cpad) {
@@ -364,6 +386,97 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, PlaneGeom xg, void*
     o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
     o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
     *reinterpret_cast<uint4*>(dst) = o;
+  }
+}
+
+// Single-launch GroupNorm(+swish) for activations that fit in shared memory (every GroupNorm of the 10 s
+// clip does): one block owns `gpb` consecutive groups (gpb*cpg channels = a whole number of output units),
+// stages them once (npl fp32 planes x T rows), takes mean and centred variance from shared memory and writes
+// the normalised operand planes.  Same arithmetic as gn_stats_kernel + gn_apply_kernel, one HBM/L2 read
+// instead of three and one launch instead of two.  dynamic smem = gpb*(cpg/4)*T*16 bytes.
+template <int E>
+__global__ void __launch_bounds__(512) gn_fused_kernel(const float* __restrict__ x, PlaneGeom xg, void* __restrict__ out, PlaneGeom og,
+                                                         int C, int T, int groups, float eps, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int swish, int rtf32, int gpb) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float4 sg[];
+  __shared__ double red[16];
+  __shared__ float s_mean[4], s_rstd[4];
+  const int gb = blockIdx.x, b = blockIdx.y;
+  const int cpg = C / groups, nplg = cpg >> 2, npl = gpb * nplg;
+  const int plane0 = gb * gpb * nplg;
+  {  // stage the block's planes: 8 independent loads in flight per thread before the first shared-memory store
+    const float4* xp0 = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(xg, b, plane0, 0));
+    const int total = npl * T;
+    for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * blockDim.x;
+        if (i < total) {
+          const int pl = i / T, t = i - pl * T;
+          v[k] = xp0[(size_t)pl * xg.Tp + t];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = i0 + k * blockDim.x;
+        if (i < total) sg[i] = v[k];
+      }
+    }
+  }
+  __syncthreads();
+  const double n = (double)cpg * (double)T;
+  for (int g = 0; g < gpb; ++g) {
+    const float4* gp = sg + g * nplg * T;
+    const int cnt = nplg * T;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) { const float4 v = gp[i]; s += (v.x + v.y) + (v.z + v.w); }
+    const float mean = (float)(gn_block_sum(s, red) / n);
+    s = 0.f;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const float4 v = gp[i];
+      const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+      s += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
+    const double var = gn_block_sum(s, red) / n;
+    if (threadIdx.x == 0) { s_mean[g] = mean; s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps)); }
+  }
+  __syncthreads();
+  constexpr int PPU = E / 4;  // fp32 planes per output unit
+  const int units = npl / PPU;
+  for (int i = threadIdx.x; i < units * T; i += blockDim.x) {
+    const int u = i / T, t = i - u * T;
+    float v[E];
+#pragma unroll
+    for (int h = 0; h < PPU; ++h) {
+      const int pl = u * PPU + h;
+      const float4 a = sg[pl * T + t];
+      const int g = pl / nplg;
+      const float mean = s_mean[g], rstd = s_rstd[g];
+      const int c0 = (plane0 + pl) * 4;
+      const float4 gm = *reinterpret_cast<const float4*>(gamma + c0), bt = *reinterpret_cast<const float4*>(beta + c0);
+      v[4 * h] = (a.x - mean) * rstd * gm.x + bt.x; v[4 * h + 1] = (a.y - mean) * rstd * gm.y + bt.y;
+      v[4 * h + 2] = (a.z - mean) * rstd * gm.z + bt.z; v[4 * h + 3] = (a.w - mean) * rstd * gm.w + bt.w;
+    }
+    if (swish) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = v[e] / (1.f + __expf(-v[e]));
+    }
+    uint8_t* dst = reinterpret_cast<uint8_t*>(out) + plane_row_off(og, b, plane0 / PPU + u, t);
+    if (E == 4) {
+      if (rtf32) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e] = round_tf32(v[e]);
+      }
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
+      *reinterpret_cast<uint4*>(dst) = o;
+    }
   }
 }
 
