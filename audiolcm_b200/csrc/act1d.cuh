@@ -69,16 +69,28 @@ __device__ __forceinline__ float4 act_y_at(const float4* sx, int j, int t0, int 
   return make_float4(snake_acc(s.x, ea.x, ib.x), snake_acc(s.y, ea.y, ib.y), snake_acc(s.z, ea.z, ib.z), snake_acc(s.w, ea.w, ib.w));
 }
 
-// Four consecutive outputs of one 4-channel plane, entirely in registers (see header comment).
-// EDGE is warp-uniform: only warps holding the first / last outputs of a plane pay for the y fix-ups.
-template <bool FAST, bool EDGE>
-__device__ __forceinline__ void act_plane(const float4* sx, int tid, int m0, int t0, int T, float4 ea, float4 ib,
-                                          float4 (&out)[kActR]) {
-    // window xl[k] = x[m0-5+k], k = 0..13 ; local row of x[m0-5] is 4*tid
-    float2 xlo[14], xhi[14];
+// sum of the 12 taps (the filter is normalised to 1 up to rounding): the constant part of the fast snake,
+// v + ib/2, is added once per OUTPUT (scaled by this sum) instead of once per up-sampled value.
+__device__ __forceinline__ float fir_sum() {
+  float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 14; ++k) {
-      const int lr = kActR * tid + k;
+  for (int k = 0; k < 12; ++k) s += c_fir[k];
+  return s;
+}
+
+// R consecutive outputs of one 4-channel plane, entirely in registers (see header comment): window of R+10
+// staged rows, R+5 (odd, even) up-sampled pairs, snake, scatter into R accumulators.
+// EDGE is warp-uniform: only warps holding the first / last outputs of a plane pay for the y fix-ups.
+// FAST: y = v + (ib/2) - (ib/2) cos(2 ea v); the "+ ib/2" term commutes with the (linear, sum-1) down filter
+// and is added to the outputs, and the multiply / fma run packed over channel pairs (FMUL2 / FFMA2).
+template <bool FAST, bool EDGE, int R = kActR>
+__device__ __forceinline__ void act_plane(const float4* sx, int tid, int m0, int t0, int T, float4 ea, float4 ib,
+                                          float4 (&out)[R]) {
+    // window xl[k] = x[m0-5+k], k = 0..R+9 ; local row of x[m0-5] is R*tid
+    float2 xlo[R + 10], xhi[R + 10];
+#pragma unroll
+    for (int k = 0; k < R + 10; ++k) {
+      const int lr = R * tid + k;
       const float4 v = sx[lr + (lr >> 3)];
       xlo[k] = make_float2(v.x, v.y);
       xhi[k] = make_float2(v.z, v.w);
@@ -93,14 +105,19 @@ __device__ __forceinline__ void act_plane(const float4* sx, int tid, int m0, int
     const float2 ea_hi = FAST ? make_float2(2.f * ea.z, 2.f * ea.w) : make_float2(ea.z, ea.w);
     const float2 ib_lo = FAST ? make_float2(0.5f * ib.x, 0.5f * ib.y) : make_float2(ib.x, ib.y);
     const float2 ib_hi = FAST ? make_float2(0.5f * ib.z, 0.5f * ib.w) : make_float2(ib.z, ib.w);
+    const float2 nhb_lo = make_float2(-ib_lo.x, -ib_lo.y), nhb_hi = make_float2(-ib_hi.x, -ib_hi.y);
     float4 y_first = make_float4(0.f, 0.f, 0.f, 0.f), y_last = y_first;
-    if (EDGE && m0 < 3) y_first = act_y_at(sx, 0, t0, T, ea, ib);                    // x[0..] is in this (first) tile
-    if (EDGE && m0 + 6 > T - 1) y_last = act_y_at(sx, 2 * T - 1, t0, T, ea, ib);     // x[..T-1] is in this (last) tile
-    float2 alo[kActR], ahi[kActR];
+    if (EDGE && m0 < 3) y_first = act_y_at(sx, 0, t0, T, ea, ib);                        // x[0..] is in this (first) tile
+    if (EDGE && m0 + R + 2 > T - 1) y_last = act_y_at(sx, 2 * T - 1, t0, T, ea, ib);     // x[..T-1] is in this (last) tile
+    if (FAST && EDGE) {  // same representation as the in-register values: without the "+ ib/2" term
+      y_first.x -= ib_lo.x; y_first.y -= ib_lo.y; y_first.z -= ib_hi.x; y_first.w -= ib_hi.y;
+      y_last.x -= ib_lo.x; y_last.y -= ib_lo.y; y_last.z -= ib_hi.x; y_last.w -= ib_hi.y;
+    }
+    float2 alo[R], ahi[R];
 #pragma unroll
-    for (int r = 0; r < kActR; ++r) alo[r] = ahi[r] = make_float2(0.f, 0.f);
+    for (int r = 0; r < R; ++r) alo[r] = ahi[r] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int s = 0; s < 9; ++s) {
+    for (int s = 0; s < R + 5; ++s) {
       // odd value  y[2(m0-3+s)+1] = sum_q xl[s+q] * 2f[10-2q] ; even value y[2(m0-2+s)] = sum_q xl[s+q] * 2f[11-2q]
       float2 olo = make_float2(0.f, 0.f), ohi = olo, elo = olo, ehi = olo;
 #pragma unroll
@@ -111,10 +128,11 @@ __device__ __forceinline__ void act_plane(const float4* sx, int tid, int m0, int
         elo = ffma2(xlo[s + q], we, elo); ehi = ffma2(xhi[s + q], we, ehi);
       }
       if (FAST) {
-        olo.x = snake_fast(olo.x, ea_lo.x, ib_lo.x); olo.y = snake_fast(olo.y, ea_lo.y, ib_lo.y);
-        ohi.x = snake_fast(ohi.x, ea_hi.x, ib_hi.x); ohi.y = snake_fast(ohi.y, ea_hi.y, ib_hi.y);
-        elo.x = snake_fast(elo.x, ea_lo.x, ib_lo.x); elo.y = snake_fast(elo.y, ea_lo.y, ib_lo.y);
-        ehi.x = snake_fast(ehi.x, ea_hi.x, ib_hi.x); ehi.y = snake_fast(ehi.y, ea_hi.y, ib_hi.y);
+        float2 t, c;
+        t = __fmul2_rn(olo, ea_lo); c = make_float2(__cosf(t.x), __cosf(t.y)); olo = ffma2(nhb_lo, c, olo);
+        t = __fmul2_rn(ohi, ea_hi); c = make_float2(__cosf(t.x), __cosf(t.y)); ohi = ffma2(nhb_hi, c, ohi);
+        t = __fmul2_rn(elo, ea_lo); c = make_float2(__cosf(t.x), __cosf(t.y)); elo = ffma2(nhb_lo, c, elo);
+        t = __fmul2_rn(ehi, ea_hi); c = make_float2(__cosf(t.x), __cosf(t.y)); ehi = ffma2(nhb_hi, c, ehi);
       } else {
         olo.x = snake_acc(olo.x, ea_lo.x, ib_lo.x); olo.y = snake_acc(olo.y, ea_lo.y, ib_lo.y);
         ohi.x = snake_acc(ohi.x, ea_hi.x, ib_hi.x); ohi.y = snake_acc(ohi.y, ea_hi.y, ib_hi.y);
@@ -130,7 +148,7 @@ __device__ __forceinline__ void act_plane(const float4* sx, int tid, int m0, int
       }
       // scatter: out[m0+r] += yo*f[2d] + ye*f[2d+1], d = s-r in [0,5]
 #pragma unroll
-      for (int r = 0; r < kActR; ++r) {
+      for (int r = 0; r < R; ++r) {
         const int d = s - r;
         if (d >= 0 && d <= 5) {
           const int k0 = 2 * d, k1 = 2 * d + 1;
@@ -140,24 +158,34 @@ __device__ __forceinline__ void act_plane(const float4* sx, int tid, int m0, int
         }
       }
     }
+    if (FAST) {
+      const float fs = fir_sum();
+      const float2 add_lo = make_float2(ib_lo.x * fs, ib_lo.y * fs), add_hi = make_float2(ib_hi.x * fs, ib_hi.y * fs);
 #pragma unroll
-    for (int r = 0; r < kActR; ++r) out[r] = make_float4(alo[r].x, alo[r].y, ahi[r].x, ahi[r].y);
+      for (int r = 0; r < R; ++r) out[r] = make_float4(alo[r].x + add_lo.x, alo[r].y + add_lo.y, ahi[r].x + add_hi.x, ahi[r].y + add_hi.y);
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) out[r] = make_float4(alo[r].x, alo[r].y, ahi[r].x, ahi[r].y);
+    }
 }
 
-template <int NPL, bool FAST>  // NPL input planes per output unit: 1 -> fp32 out, 2 -> bf16 out
-__global__ void __launch_bounds__(kActThreads, 6) act1d_kernel(const __grid_constant__ ActArgs a) {
+// R outputs per thread: 4 (80 registers, 6 blocks/SM) or 8 (1.7x fewer instructions per element - the up-sampled
+// halo is shared by twice as many outputs - for launches big enough to fill the GPU with 4 blocks/SM).
+template <int NPL, bool FAST, int R>  // NPL input planes per output unit: 1 -> fp32 out, 2 -> bf16 out
+__global__ void __launch_bounds__(kActThreads, (R == 4 ? 6 : 4)) act1d_kernel(const __grid_constant__ ActArgs a) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float4 sx[NPL][kActSlots];
+  constexpr int kTile = kActThreads * R, kRows = kTile + 10, kSlots = kRows + (kRows >> 3) + 1;
+  __shared__ float4 sx[NPL][kSlots];
   const int tid = threadIdx.x;
-  const int t0 = blockIdx.x * kActTile;
+  const int t0 = blockIdx.x * kTile;
   const int oc = blockIdx.y, b = blockIdx.z;
   const int T = a.T;
 
   // ---- stage x[t0-5 .. t0+tile+4] (replicate-clamped) -----------------------------------------
   // all global loads of the thread are issued before the first shared-memory store: a rolled
   // load->store loop exposed one HBM round trip per row group (39 % of the warp stalls, ncu round 1)
-  constexpr int kLd = (kActRows + kActThreads - 1) / kActThreads;
+  constexpr int kLd = (kRows + kActThreads - 1) / kActThreads;
   float4 stg[NPL][kLd];
 #pragma unroll
   for (int p = 0; p < NPL; ++p) {
@@ -174,52 +202,52 @@ __global__ void __launch_bounds__(kActThreads, 6) act1d_kernel(const __grid_cons
 #pragma unroll
     for (int k = 0; k < kLd; ++k) {
       const int lr = tid + k * kActThreads;
-      if (lr < kActRows) sx[p][lr + (lr >> 3)] = stg[p][k];
+      if (lr < kRows) sx[p][lr + (lr >> 3)] = stg[p][k];
     }
   }
   __syncthreads();
 
-  const int m0 = t0 + kActR * tid;
+  const int m0 = t0 + R * tid;
   if (m0 >= T) return;
   // up-sampled pairs n in [m0-3, m0+6]: where n falls outside [0,T-1] the down filter's replicate
   // padding wants y[0] / y[2T-1] instead (only the first / last one or two threads of a plane)
-  const bool edge = (m0 < 3) || (m0 + 6 > T - 1);
+  const bool edge = (m0 < 3) || (m0 + R + 2 > T - 1);
 
   // One copy of the (fully unrolled, ~1k instruction) plane body: the kernel was instruction-fetch bound with
   // one copy per plane.  bf16 output packs two fp32 planes into one 16-byte unit: the first plane's four results
   // wait in registers (as packed bf16 pairs) for the second.
-  uint2 held[kActR];
+  uint2 held[R];
 #pragma unroll 1
   for (int p = 0; p < NPL; ++p) {
     const int chunk = oc * NPL + p;
     const float4 ea = *reinterpret_cast<const float4*>(a.ea + chunk * 4);
     const float4 ib = *reinterpret_cast<const float4*>(a.ib + chunk * 4);
-    float4 res[kActR];
-    if (__any_sync(0xffffffffu, edge)) act_plane<FAST, true>(sx[p], tid, m0, t0, T, ea, ib, res);
-    else act_plane<FAST, false>(sx[p], tid, m0, t0, T, ea, ib, res);
+    float4 res[R];
+    if (__any_sync(0xffffffffu, edge)) act_plane<FAST, true, R>(sx[p], tid, m0, t0, T, ea, ib, res);
+    else act_plane<FAST, false, R>(sx[p], tid, m0, t0, T, ea, ib, res);
     if (NPL == 1) {
       float4* op = reinterpret_cast<float4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
 #pragma unroll
-      for (int r = 0; r < kActR; ++r) {
+      for (int r = 0; r < R; ++r) {
         if (m0 + r >= T) break;
         float4 o = res[r];
         if (a.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
         op[m0 + r] = o;
       }
     } else {
-      uint2 pk[kActR];
+      uint2 pk[R];
 #pragma unroll
-      for (int r = 0; r < kActR; ++r) {
+      for (int r = 0; r < R; ++r) {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(res[r].x, res[r].y), h1 = __floats2bfloat162_rn(res[r].z, res[r].w);
         pk[r] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
       }
       if (p == 0) {
 #pragma unroll
-        for (int r = 0; r < kActR; ++r) held[r] = pk[r];
+        for (int r = 0; r < R; ++r) held[r] = pk[r];
       } else {
         uint4* op = reinterpret_cast<uint4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
 #pragma unroll
-        for (int r = 0; r < kActR; ++r) {
+        for (int r = 0; r < R; ++r) {
           if (m0 + r >= T) break;
           op[m0 + r] = make_uint4(held[r].x, held[r].y, pk[r].x, pk[r].y);
         }

@@ -493,7 +493,13 @@ struct OpList {
     // two kernels, same arithmetic: the "pair" form (2 planes side by side, 256-output tiles) has half the serial
     // work per block and twice the blocks - better while a launch cannot fill the GPU several times over
     const long blocks_wide = (long)((T + kActTile - 1) / kActTile) * nch * B;
-    const int variant = env_int("ALCM_ACT_VARIANT", (oesz == 2 && blocks_wide < 24L * g_sm_count) ? 1 : 0);
+    // variant 0: 4 outputs/thread, 512-output tiles; 1: "pair" form (small bf16 launches); 2: 8 outputs/thread
+    // (fewest instructions per element; needs enough blocks to fill 4 blocks/SM several times)
+    const long blocks_r8 = (long)((T + 2 * kActTile - 1) / (2 * kActTile)) * nch * B;
+    int variant = 0;
+    if (oesz == 2 && blocks_wide < 24L * g_sm_count) variant = 1;
+    else if (oesz == 2 && T >= 8 * kActTile && blocks_r8 >= 16L * g_sm_count) variant = 2;  // measured: +19 % on long planes, -10 % on T = 2500
+    variant = env_int("ALCM_ACT_VARIANT", variant);
     op.fn = [=](cudaStream_t st) {
       if (variant == 1) {
         const dim3 grid((T + kPairTile - 1) / kPairTile, nch32 / 2, B);
@@ -505,12 +511,22 @@ struct OpList {
         }
         return;
       }
+      if (variant == 2) {  // 8 outputs per thread
+        const dim3 grid((T + 2 * kActTile - 1) / (2 * kActTile), nch, B);
+        if (oesz == 4) {
+          if (fast) launch_k(act1d_kernel<1, true, 8>, grid, dim3(kActThreads), 0, st, a);
+          else launch_k(act1d_kernel<1, false, 8>, grid, dim3(kActThreads), 0, st, a);
+        } else {
+          launch_k(act1d_kernel<2, true, 8>, grid, dim3(kActThreads), 0, st, a);
+        }
+        return;
+      }
       const dim3 grid((T + kActTile - 1) / kActTile, nch, B);
       if (oesz == 4) {
-        if (fast) launch_k(act1d_kernel<1, true>, dim3(grid), dim3(kActThreads), 0, st, a);
-        else launch_k(act1d_kernel<1, false>, dim3(grid), dim3(kActThreads), 0, st, a);
+        if (fast) launch_k(act1d_kernel<1, true, 4>, grid, dim3(kActThreads), 0, st, a);
+        else launch_k(act1d_kernel<1, false, 4>, grid, dim3(kActThreads), 0, st, a);
       } else {
-        launch_k(act1d_kernel<2, true>, dim3(grid), dim3(kActThreads), 0, st, a);
+        launch_k(act1d_kernel<2, true, 4>, grid, dim3(kActThreads), 0, st, a);
       }
     };
     push(op);
