@@ -6,7 +6,7 @@
 
 Workload (BASELINE.json configs[1]): full latent->waveform decode - autoencoder1d VAE decoder +
 BigVGAN-16k - of one 10 s clip (z [B,20,312] -> wav [B,159744]), batch 1 per GPU, random-init
-weights of the shipped architectures (oracle/synth.py), synthetic latents.  A step = one decode.
+weights of the shipped architectures (audiolcm_b200/synth.py), synthetic latents.  A step = one decode.
 N>1 (torchrun): every rank decodes its own clip, no data-path collective (weak scaling).
 
 Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM, CUDA events around each step on
@@ -126,7 +126,7 @@ def run_reference(args):
                                      f"{audio_seconds(1, t_lat):.2f} s clip, CPU"),
                 cpu_baseline=dict(value=round(val, 4), unit="audio-s/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=round(val, 4), unit="audio-s/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -169,6 +169,38 @@ class ClockSampler:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
         hi = sorted(sm)[len(sm) // 2:]  # upper half = samples taken under load
         return dict(sm_mhz=statistics.median(hi), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+def kernel_rooflines(precision, peaks):
+    """The two kernel classes at sizes that fill the GPU (the batch-1 decode cannot): CUDA-event time of
+    back-to-back launches inside the library (alcm_bench_conv / alcm_bench_act), algorithmic work / time."""
+    import ctypes as C
+    from audiolcm_b200 import _lib
+    lib, ctx, prec = _lib.load(), _lib.ctx(0), _lib.PREC[precision]
+    out = {}
+    ms = C.c_float()
+    B, Cc, T, K = 8, 768, 2500, 11          # stage-1 AMP conv of the 10 s clip, batch 8
+    _lib.check(lib.alcm_bench_conv(ctx, B, Cc, Cc, T, K, 1, prec, 20, 0, C.byref(ms)))
+    tf = 2.0 * B * Cc * Cc * K * T / (ms.value * 1e-3) / 1e12
+    out["conv_gemm"] = dict(kernel="conv_umma_kernel", shape=f"Conv1d {Cc}->{Cc} k{K}, T={T}, batch {B}", bound="tensor",
+                            achieved=round(tf, 1), peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(tf / peaks["tf_sustained"], 4),
+                            us_per_launch=round(ms.value * 1e3, 1))
+    B, Cc, T = 64, 24, 160000               # last-stage Activation1d, batch 64: 2-2.6 GB, far beyond L2
+    _lib.check(lib.alcm_bench_act(ctx, B, Cc, T, prec, 10, C.byref(ms)))
+    byt = B * ((Cc + 15) // 16 * 16) * T * (4 + (2 if precision == "bf16" else 4))
+    gbs = byt / (ms.value * 1e-3) / 1e9
+    out["activation1d"] = dict(kernel="act1d_kernel", shape=f"C={Cc} T={T} batch {B} ({byt / 1e6:.0f} MB algorithmic)", bound="hbm",
+                               achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s", frac=round(gbs / peaks["hbm"], 4),
+                               us_per_launch=round(ms.value * 1e3, 1))
+    return out
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def build_pipe(precision, device):
@@ -263,22 +295,48 @@ def run_gpu(args):
             gpu_launches=launches * args.steps,
             clocks=clocks,
             roofline=dict(bound="tensor", achieved=round(tf, 2), peak=peaks["tf_sustained"], unit="TFLOP/s",
-                          frac=round(tf / peaks["tf_sustained"], 4), traffic=None, kernel="conv_umma_kernel (all conv GEMM launches)",
+                          frac=round(tf / peaks["tf_sustained"], 4), traffic=ncu_traffic(), kernel="conv_umma_kernel (all conv GEMM launches)",
                           peak_source=f"{peaks['source']} bf16 sustained", flops_per_step=conv["flops"],
-                          ms_per_step=round(conv["ms"], 4), launches=conv["launches"]),
+                          ms_per_step=round(conv["ms"], 4), launches=conv["launches"],
+                          flops_per_launch=round(conv["flops"] / max(conv["launches"], 1)),
+                          us_per_launch=round(1e3 * conv["ms"] / max(conv["launches"], 1), 2),
+                          note="per-launch averages over the conv GEMM launches of one batch-1 decode; `traffic` = ncu DRAM bytes per "
+                               "launch (profiles/r1_traffic.json); the same kernel at a GPU-filling size is in kernel_rooflines"),
             roofline_act=dict(bound="hbm", achieved=round(act_gbs, 1), peak=peaks["hbm"], unit="GB/s",
                               frac=round(act_gbs / peaks["hbm"], 4), kernel="act1d_kernel (all Activation1d launches)",
                               bytes_per_step=act["bytes"], ms_per_step=round(act["ms"], 4), launches=act["launches"],
                               note="batch-1 tensors (<=15 MB) are L2-resident; see DESIGN.md for the HBM-sized run"),
+            kernel_rooflines=kernel_rooflines(args.precision, peaks) if args.precision != "fp32" else None,
             class_ms={k: round(v["ms"], 4) for k, v in prof.items()},
             class_ms_total_eager=round(total_ms, 4),
         )
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_JSON_FD = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout: libraries that print to fd 1 (NCCL's version banner under
+    torchrun) are sent to stderr; emit() writes the line to the real stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -292,6 +350,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
