@@ -841,7 +841,7 @@ struct ResBlock {
   bool has_nin = false;
   int Cin, Cout;
 };
-struct AttnBlk { GnP norm; ConvLayer q, k, v, proj; int C; };
+struct AttnBlk { GnP norm; ConvLayer qkv, proj; int C; };  // q, k, v 1x1 convs run as one launch (Cout = 3C)
 struct VaeLevel { std::vector<ResBlock> blocks; bool has_up = false; ConvLayer up; int C; };
 
 struct VaePlan {
@@ -932,33 +932,49 @@ static PlaneT op_resblock(OpList& ol, Arena& ar, const ResBlock& rb, const Plane
   return out;
 }
 
-static PlaneT op_attn(OpList& ol, Arena& ar, const AttnBlk& at, const PlaneT& x, int prec) {  // autoencoder1d.py:257-278
-  const int oe = opnd_esz(prec), B = x.B, C = at.C, T = x.T;
-  PlaneT hn = make_planes(ar, B, C, T, oe);
-  op_gn(ol, ar, x, hn, at.norm, 0, prec);
-  PlaneT q = make_planes(ar, B, C, T, 4), k = make_planes(ar, B, C, T, 4), v = make_planes(ar, B, C, T, 4);
-  ol.conv(at.q, hn, q, nullptr);
-  ol.conv(at.k, hn, k, nullptr);
-  ol.conv(at.v, hn, v, nullptr);
-  float* S = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
-  PlaneT h = make_planes(ar, B, C, T, 4);
+// scores (channel-split partials) -> softmax -> PV; q, k, v, h are fp32 planes, Sp/Pm workspaces
+static void push_attention(OpList& ol, const PlaneT& q, const PlaneT& k, const PlaneT& v, const PlaneT& h, float* Sp, float* Pm,
+                           int B, int C, int T) {
   const float scale = 1.0f / sqrtf((float)C);  // reference unpacks (b,c,t) as (b,t,c): scale = C^-0.5
+  const int nsplit = (C >= 256) ? kAttnSplit : 1;
   Op s1;
   s1.cls = ALCM_CLS_ATTN; s1.flops = 2.0 * B * (double)T * T * C; s1.bytes = (double)B * (2.0 * C * T + (double)T * T) * 4;
   s1.fn = [=](cudaStream_t st) {
-    launch_k(attn_scores_kernel, dim3(dim3((T + 31) / 32, (T + 31) / 32, B)), dim3(256), 0, st, q.f(), k.f(), q.g, C, T, scale, S);
+    launch_k(attn_scores2_kernel, dim3((T + 63) / 64, (T + 63) / 64, B * nsplit), dim3(256), 0, st, q.f(), k.f(), q.g, C, T, scale, Sp, nsplit, B);
   };
   ol.ops.push_back(s1);
   Op s2;
-  s2.cls = ALCM_CLS_ATTN; s2.flops = 0; s2.bytes = 2.0 * B * (double)T * T * 4;
-  s2.fn = [=](cudaStream_t st) { launch_k(softmax_rows_kernel, dim3(B * T), dim3(128), 0, st, S, T); };
+  s2.cls = ALCM_CLS_ATTN; s2.flops = 0; s2.bytes = (double)B * T * T * 4 * (nsplit + 1.0);
+  s2.fn = [=](cudaStream_t st) { launch_k(softmax_rows2_kernel, dim3(B * T), dim3(128), (size_t)T * 4, st, Sp, nsplit, B * T, T, Pm); };
   ol.ops.push_back(s2);
   Op s3;
   s3.cls = ALCM_CLS_ATTN; s3.flops = 2.0 * B * (double)T * T * C; s3.bytes = (double)B * (2.0 * C * T + (double)T * T) * 4;
   s3.fn = [=](cudaStream_t st) {
-    launch_k(attn_pv_kernel, dim3(dim3((T + 31) / 32, (C + 31) / 32, B)), dim3(256), 0, st, v.f(), v.g, S, C, T, h.f(), h.g);
+    launch_k(attn_pv2_kernel, dim3((T + 63) / 64, ((C + 3) / 4 + 31) / 32, B), dim3(256), 0, st, v.f(), v.g, Pm, C, T, h.f(), h.g);
   };
   ol.ops.push_back(s3);
+}
+
+// channel sub-range [c0, c0+C) of a plane tensor as a view (same batch stride)
+static PlaneT plane_view(const PlaneT& x, int c0, int C) {
+  PlaneT v = x;
+  v.C = C;
+  v.p = x.p + (size_t)(c0 / (16 / x.esz)) * x.g.Tp * 16;
+  return v;
+}
+
+static PlaneT op_attn(OpList& ol, Arena& ar, const AttnBlk& at, const PlaneT& x, int prec) {  // autoencoder1d.py:257-278
+  const int oe = opnd_esz(prec), B = x.B, C = at.C, T = x.T;
+  PlaneT hn = make_planes(ar, B, C, T, oe);
+  op_gn(ol, ar, x, hn, at.norm, 0, prec);
+  PlaneT qkv = make_planes(ar, B, 3 * C, T, 4);
+  ol.conv(at.qkv, hn, qkv, nullptr);
+  const PlaneT q = plane_view(qkv, 0, C), k = plane_view(qkv, C, C), v = plane_view(qkv, 2 * C, C);
+  REQUIRE((size_t)T * 4 <= 200 * 1024, "attention: sequence too long for the row-softmax kernel");
+  float* Sp = static_cast<float*>(ar.alloc((size_t)kAttnSplit * B * T * T * 4, false));
+  float* Pm = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
+  PlaneT h = make_planes(ar, B, C, T, 4);
+  push_attention(ol, q, k, v, h, Sp, Pm, B, C, T);
   PlaneT out = make_planes(ar, B, C, T, 4);
   ol.conv(at.proj, as_operand(ol, ar, h, prec), out, &x);
   return out;
@@ -1012,6 +1028,7 @@ static void vae_run(alcm_vae* v, VaePlan* P, const float* z, float inv_scale, cu
 // ------------------------------------------------------------------------------------------ C-ABI
 static void set_kernel_attrs() {
   const int mx = 227 * 1024;
+  CUDA_CHECK(cudaFuncSetAttribute(softmax_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -1205,9 +1222,18 @@ int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* 
     v->mid1 = resblock(block_in, block_in);
     v->attn.C = block_in;
     v->attn.norm = gn(block_in);
-    v->attn.q = conv(block_in, block_in, 1);
-    v->attn.k = conv(block_in, block_in, 1);
-    v->attn.v = conv(block_in, block_in, 1);
+    {  // q, k, v (autoencoder1d.py:246-248): concatenate the three [C,C,1] weights -> one conv with Cout = 3C
+      const size_t wn = (size_t)block_in * block_in, bn = (size_t)block_in;
+      Arena tmpq;
+      float* wcat = static_cast<float*>(tmpq.alloc(3 * wn * 4, false));
+      float* bcat = static_cast<float*>(tmpq.alloc(3 * bn * 4, false));
+      for (int i = 0; i < 3; ++i) {
+        CUDA_CHECK(cudaMemcpy(wcat + i * wn, t[ti + 2 * i], wn * 4, cudaMemcpyDeviceToDevice));
+        CUDA_CHECK(cudaMemcpy(bcat + i * bn, t[ti + 2 * i + 1], bn * 4, cudaMemcpyDeviceToDevice));
+      }
+      v->attn.qkv = prepare_conv(v->war, precision, KIND_CONV, wcat, bcat, 3 * block_in, block_in, 1, 1);
+      ti += 6;
+    }
     v->attn.proj = conv(block_in, block_in, 1);
     v->mid2 = resblock(block_in, block_in);
     v->up_factor = 1;
@@ -1421,9 +1447,13 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
     launch_pack(q, pq, C, T, 1.f, ALCM_PREC_FP32, st);
     launch_pack(k, pk, C, T, 1.f, ALCM_PREC_FP32, st);
     launch_pack(v, pv, C, T, 1.f, ALCM_PREC_FP32, st);
-    launch_k(attn_scores_kernel, dim3(dim3((T + 31) / 32, (T + 31) / 32, B)), dim3(256), 0, st, pq.f(), pk.f(), pq.g, C, T, 1.0f / sqrtf((float)C), S);
-    launch_k(softmax_rows_kernel, dim3(B * T), dim3(128), 0, st, S, T);
-    launch_k(attn_pv_kernel, dim3(dim3((T + 31) / 32, (C + 31) / 32, B)), dim3(256), 0, st, pv.f(), pv.g, S, C, T, ph.f(), ph.g);
+    OpList ol;
+    float* Pm = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
+    float* Sp = static_cast<float*>(ar.alloc((size_t)kAttnSplit * B * T * T * 4, false));
+    (void)S;
+    push_attention(ol, pq, pk, pv, ph, Sp, Pm, B, C, T);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    ol.run(st);
     launch_unpack(ph, out, C, T, st);
     CUDA_CHECK(cudaGetLastError());
     sync_free(st);

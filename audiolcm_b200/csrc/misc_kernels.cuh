@@ -576,4 +576,142 @@ __global__ void __launch_bounds__(256) attn_pv_kernel(const float* __restrict__ 
   }
 }
 
+// ---- attention, second version: float4 plane loads, 64x64 / 64x128 register-blocked tiles, and a channel
+// split for the score GEMM (T = 312 gives only 25 output tiles; the partial score planes are summed - in split
+// order - by the softmax kernel).  Same arithmetic as the kernels above (fp32 FFMA), ~6x faster on the 10 s clip.
+constexpr int kAttnSplit = 8;
+
+__global__ void __launch_bounds__(256) attn_scores2_kernel(const float* __restrict__ q, const float* __restrict__ k, PlaneGeom g, int C,
+                                                             int T, float scale, float* __restrict__ Sp, int nsplit, int B) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float4 Qs[16][64], Ks[16][64];
+  const int j0 = blockIdx.x * 64, i0 = blockIdx.y * 64;
+  const int b = blockIdx.z / nsplit, z = blockIdx.z % nsplit;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int nch = (C + 3) >> 2, cps = (nch + nsplit - 1) / nsplit;
+  const int c_begin = z * cps, c_end = min(nch, c_begin + cps);
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int s = 0; s < 4; ++s) acc[r][s] = 0.f;
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2048; idx += 256) {
+      const int which = idx >> 10, kc = (idx >> 6) & 15, r = idx & 63;
+      const int chunk = c0 + kc, row = (which ? j0 : i0) + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (chunk < c_end && row < T)
+        v = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(which ? k : q) + plane_row_off(g, b, chunk, row));
+      if (which) Ks[kc][r] = v; else Qs[kc][r] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int kc = 0; kc < 16; ++kc) {
+      float4 qv[4], kv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { qv[r] = Qs[kc][ty * 4 + r]; kv[r] = Ks[kc][tx * 4 + r]; }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          acc[r][s] = fmaf(qv[r].x, kv[s].x, fmaf(qv[r].y, kv[s].y, fmaf(qv[r].z, kv[s].z, fmaf(qv[r].w, kv[s].w, acc[r][s]))));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty * 4 + r;
+    if (i >= T) continue;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int j = j0 + tx * 4 + s;
+      if (j < T) Sp[(((size_t)z * B + b) * T + i) * T + j] = acc[r][s] * scale;
+    }
+  }
+}
+
+// P[row][j] = softmax_j( sum_z Sp[z][row][j] ), row = b*T + i
+__global__ void softmax_rows2_kernel(const float* __restrict__ Sp, int nsplit, int BT, int T, float* __restrict__ P) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x;
+  __shared__ float red[32];
+  extern __shared__ float srow[];  // T floats
+  float m = -INFINITY;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) {
+    float v = 0.f;
+    for (int z = 0; z < nsplit; ++z) v += Sp[((size_t)z * BT + row) * T + j];
+    srow[j] = v;
+    m = fmaxf(m, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) {
+    const float e = expf(srow[j] - m);
+    srow[j] = e;
+    s += e;
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+  const float inv = 1.f / s;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) P[(size_t)row * T + j] = srow[j] * inv;
+}
+
+// h[c][i] = sum_j v[c][j] P[i][j]; block = 64 time steps i x 32 chunks (128 channels); thread = 4 i x 2 chunks
+__global__ void __launch_bounds__(256) attn_pv2_kernel(const float* __restrict__ v, PlaneGeom g, const float* __restrict__ P, int C,
+                                                         int T, float* __restrict__ h, PlaneGeom hg) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float4 Vs[32][32];   // [j][chunk]
+  __shared__ float Pt[32][65];    // [j][i]
+  const int i0 = blockIdx.x * 64, ch0 = blockIdx.y * 32, b = blockIdx.z;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int nch = (C + 3) >> 2;
+  float4 a0[4], a1[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) a0[r] = a1[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j0 = 0; j0 < T; j0 += 32) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 1024; idx += 256) {
+      const int cc = idx >> 5, jj = idx & 31;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ch0 + cc < nch && j0 + jj < T)
+        val = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(v) + plane_row_off(g, b, ch0 + cc, j0 + jj));
+      Vs[jj][cc] = val;
+    }
+    for (int idx = threadIdx.x; idx < 2048; idx += 256) {
+      const int ii = idx >> 5, jj = idx & 31;
+      Pt[jj][ii] = (i0 + ii < T && j0 + jj < T) ? P[((size_t)b * T + i0 + ii) * T + j0 + jj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int jj = 0; jj < 32; ++jj) {
+      const float4 v0 = Vs[jj][ty * 2], v1 = Vs[jj][ty * 2 + 1];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float p = Pt[jj][tx * 4 + r];
+        a0[r].x = fmaf(p, v0.x, a0[r].x); a0[r].y = fmaf(p, v0.y, a0[r].y); a0[r].z = fmaf(p, v0.z, a0[r].z); a0[r].w = fmaf(p, v0.w, a0[r].w);
+        a1[r].x = fmaf(p, v1.x, a1[r].x); a1[r].y = fmaf(p, v1.y, a1[r].y); a1[r].z = fmaf(p, v1.z, a1[r].z); a1[r].w = fmaf(p, v1.w, a1[r].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + tx * 4 + r;
+    if (i >= T) continue;
+    const int c0 = ch0 + ty * 2;
+    if (c0 < nch) *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(h) + plane_row_off(hg, b, c0, i)) = a0[r];
+    if (c0 + 1 < nch) *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(h) + plane_row_off(hg, b, c0 + 1, i)) = a1[r];
+  }
+}
+
 }  // namespace alcm
