@@ -43,6 +43,7 @@ struct ConvArgs {
   int kchunks, kblk, nkb;  // 16-byte K chunks: total, per k-block (even), number of k-blocks
   int NT, n_tiles, tmem_cols;
   int w_stages;       // weight ring depth
+  int a_stages;       // A-slab ring depth (2..4): short k-blocks (few taps) are bound by the slab's load latency
   int tpg;            // taps per weight stage (one bulk copy + one mbarrier round trip per `tpg` taps)
   uint32_t idesc;
   unsigned long long w_phase_stride;  // bytes between phases in w
@@ -86,16 +87,16 @@ struct ConvArgs {
 struct ConvSmemLayout {
   uint32_t a_stage, w_blob, w_stage, a_off, w_off, bias_off, bar_off, total;
 };
-__host__ __device__ inline ConvSmemLayout conv_smem_layout(int kblk, int span, int NT, int w_stages, int tpg) {
+__host__ __device__ inline ConvSmemLayout conv_smem_layout(int kblk, int span, int NT, int w_stages, int tpg, int a_stages) {
   ConvSmemLayout L;
   L.a_stage = (uint32_t)kblk * (kTileM + span) * 16;
   L.w_blob = (uint32_t)kblk * NT * 16;
   L.w_stage = L.w_blob * tpg;
   L.a_off = 0;
-  L.w_off = 2 * L.a_stage;
+  L.w_off = a_stages * L.a_stage;
   L.bias_off = L.w_off + w_stages * L.w_stage;
   L.bar_off = L.bias_off + NT * 4;
-  L.total = L.bar_off + 8 * (5 + 2 * w_stages) + 16;
+  L.total = L.bar_off + 8 * (2 * a_stages + 2 * w_stages + 1) + 16;
   return L;
 }
 
@@ -117,15 +118,14 @@ __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, int ph, uint32_
   // every parameter the loop needs lives in a register: the asm memory clobbers would otherwise
   // make the compiler re-read the constant bank on each iteration of the single issuing warp.
   // The tap shift (row offset of tap j inside the A slab) is linear in j for every conv form here.
-  const int ntaps = a.ntaps, S = a.w_stages, tpg = a.tpg;
+  const int ntaps = a.ntaps, S = a.w_stages, tpg = a.tpg, AS = a.a_stages;
   const uint32_t idesc = a.idesc;
   const uint32_t shift0 = (uint32_t)(a.tap_off[ph][0] - a.min_off[ph]);
   const uint64_t dshift = (uint64_t)(int64_t)(ntaps > 1 ? a.tap_off[ph][1] - a.tap_off[ph][0] : 0);
-  int ws = 0;
-  uint32_t wpar = 0, acc = 0;
-  for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
-    const int as = it & 1;
-    mbar_wait(a_full + 8 * as, (it >> 1) & 1);
+  int ws = 0, as = 0;
+  uint32_t wpar = 0, apar = 0, acc = 0;
+  for (int kb = kb0; kb < kb1; ++kb) {
+    mbar_wait(a_full + 8 * as, apar);
     uint64_t a_tap = a_desc0 + (uint64_t)(as * a_stage16 + shift0);
     for (int j0 = 0; j0 < ntaps; j0 += tpg) {
       const int g = min(tpg, ntaps - j0);
@@ -147,6 +147,7 @@ __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, int ph, uint32_
       acc = 1;
       if (++ws == S) { ws = 0; wpar ^= 1; }
     }
+    if (++as == AS) { as = 0; apar ^= 1; }
   }
   if (leader) tc_commit(acc_full);
   if (trace && leader) trace[4] = clock64();
@@ -210,21 +211,23 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
   const int S = a.w_stages;
   const int rowsA = kTileM + a.span;
   constexpr bool fused = FUSED;  // Activation1d epilogue compiled in (launches with a.act_out != nullptr)
-  const ConvSmemLayout L = conv_smem_layout(a.kblk, a.span, a.NT, S, a.tpg);
+  const int AS = a.a_stages;
+  const ConvSmemLayout L = conv_smem_layout(a.kblk, a.span, a.NT, S, a.tpg, AS);
   const uint32_t sA = smem_u32(smem) + L.a_off;
   const uint32_t sW = smem_u32(smem) + L.w_off;
   const uint32_t bars = smem_u32(smem) + L.bar_off;
   float* s_bias = reinterpret_cast<float*>(smem + L.bias_off);
-  // barrier slots: [0,1] a_full, [2,3] a_empty, [4..4+S) w_full, [4+S..4+2S) w_empty, [4+2S] acc_full
-  const uint32_t a_full = bars, a_empty = bars + 16, w_full = bars + 32, w_empty = bars + 32 + 8 * S;
-  const uint32_t acc_full = bars + 32 + 16 * S;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * (5 + 2 * S));
+  // barrier slots: a_full[AS], a_empty[AS], w_full[S], w_empty[S], acc_full
+  const uint32_t a_full = bars, a_empty = bars + 8 * AS, w_full = bars + 16 * AS, w_empty = w_full + 8 * S;
+  const uint32_t acc_full = w_empty + 8 * S;
+  const int nbars = 2 * AS + 2 * S + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * nbars);
   volatile uint32_t* s_last = tmem_slot + 1;  // split-K: "this CTA arrived last at its tile"
 
   long long* trace = a.trace ? a.trace + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
   if (threadIdx.x == 0) {
     if (trace) { trace[0] = (long long)global_timer_ns(); trace[1] = clock64(); }
-    for (int i = 0; i < 5 + 2 * S; ++i) mbar_init(bars + 8 * i, 1);
+    for (int i = 0; i < nbars; ++i) mbar_init(bars + 8 * i, 1);
     fence_mbar_init();
     *s_last = 1;
   }
@@ -271,15 +274,18 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
       wsrc += bytes;
       if (++ws == S) { ws = 0; wpar ^= 1; }
     };
-    // weights do not depend on the previous kernel: fill the ring before waiting for it (PDL overlap)
+    // Only the first weight group goes out before the first A slab: the first MMA needs exactly those two, and
+    // everything queued ahead of the slab delays it (12 prefetched groups cost ~1.3 us of first-MMA latency).
+    // (With programmatic dependent launch the weights could all be prefetched here; PDL is off by default.)
     const int ngrp = (ntaps + tpg - 1) / tpg;
-    const int pre = min(S, (kb1 - kb0) * ngrp);
-    for (int i = 0; i < pre; ++i) load_w((i % ngrp) * tpg);
+    const int pre = 1;
+    load_w(0);
     pdl_wait();
     int gi = 0;  // weight groups issued so far are [0, pre)
-    for (int kb = kb0, it = 0; kb < kb1; ++kb, ++it) {
-      const int as = it & 1;
-      mbar_wait(a_empty + 8 * as, ((it >> 1) & 1) ^ 1);
+    int as = 0;
+    uint32_t apar = 1;
+    for (int kb = kb0; kb < kb1; ++kb) {
+      mbar_wait(a_empty + 8 * as, apar);
       if (a.dbg & 2) {
         if (leader) mbar_arrive(a_full + 8 * as);
         xsrc += plane_bytes * a.kblk;
@@ -291,7 +297,9 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
       }
       for (int j0 = 0; j0 < ntaps; j0 += tpg, ++gi)
         if (gi >= pre) load_w(j0);
+      if (++as == AS) { as = 0; apar ^= 1; }
     }
+    (void)ngrp;
     __syncwarp();
   } else if (warp == 1) {
     switch (a.kblk >> 1) {

@@ -309,19 +309,26 @@ struct Op {
 // Pipeline shape of one launch.  Taps per weight stage: enough MMAs per mbarrier round trip to cover
 // ~512 tensor cycles (see conv.cuh).  Ring depth: with at most one CTA per SM use most of the 227 KB
 // (more bytes in flight hide the L2/HBM latency of the weight stream); otherwise leave room for 2 CTAs/SM.
-static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused, int* stages, int* tpg, uint32_t* smem) {
+static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused, int* stages, int* tpg, int* a_stages, uint32_t* smem) {
   const uint32_t budget = (uint32_t)env_int("ALCM_SMEM_BUDGET", ctas <= (long)g_sm_count ? 200 * 1024 : 100 * 1024);
   const double cyc_mma = std::max(L.NT / 2.0, 32.0 + L.NT / 4.0);
   const double cyc_tap = (L.kblk / 2) * cyc_mma;
-  int tmin = std::max(1, std::min(L.ntaps, (int)std::ceil(512.0 / cyc_tap)));
+  // ~1024 tensor cycles per weight stage (measured: stage-1 conv at batch 1, taps per stage 1/2/3/4 -> 802/978/1039/1046 TFLOP/s)
+  int tmin = std::max(1, std::min(L.ntaps, (int)std::ceil(1024.0 / cyc_tap)));
   const int ngrp = (L.ntaps + tmin - 1) / tmin;
   int t = (L.ntaps + ngrp - 1) / ngrp;
   if (env_int("ALCM_TPG", 0) > 0) t = std::min(L.ntaps, env_int("ALCM_TPG", 0));
-  const uint32_t a2 = 2u * L.kblk * (kTileM + L.span) * 16, blob = (uint32_t)L.kblk * L.NT * 16, fixed = a2 + L.NT * 4 + 512;
+  // A-slab ring: a k-block whose MMAs take less than the slab's load latency (~1300 cycles) needs more than 2 slabs in flight
+  const uint32_t a1 = (uint32_t)L.kblk * (kTileM + L.span) * 16, blob = (uint32_t)L.kblk * L.NT * 16;
+  int AS = (L.ntaps * cyc_tap < 1500.0) ? 4 : 2;
+  AS = std::max(2, std::min(4, env_int("ALCM_ASTAGES", AS)));
+  while (AS > 2 && AS * a1 > budget / 2) --AS;
+  const int nkb_local = (L.nkb + ksplit - 1) / ksplit;
+  AS = std::max(2, std::min(AS, nkb_local));
+  const uint32_t a2 = AS * a1, fixed = a2 + L.NT * 4 + 512;
   while (t > 1 && fixed + 2u * t * blob > budget) --t;
   int S = (budget > fixed) ? (int)((budget - fixed) / (t * blob)) : 0;
   S = std::max(2, std::min(12, S));
-  const int nkb_local = (L.nkb + ksplit - 1) / ksplit;
   S = std::min(S, std::max(2, nkb_local * ((L.ntaps + t - 1) / t)));
   if (fused) {  // the staged output tile overlays the (drained) A and W buffers
     const uint32_t staging = (uint32_t)(L.NT / 4) * kFuseSlots * 16;
@@ -330,7 +337,8 @@ static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused,
   }
   *stages = S;
   *tpg = t;
-  *smem = conv_smem_layout(L.kblk, L.span, L.NT, S, t).total;
+  *a_stages = AS;
+  *smem = conv_smem_layout(L.kblk, L.span, L.NT, S, t, AS).total;
   REQUIRE(*smem <= 227 * 1024, "conv tile does not fit shared memory");
 }
 
@@ -399,7 +407,7 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
     }
     dim3 grid(conv_m_tiles(M, fused), L.n_tiles, B * L.nphase * sk.ksplit);
     uint32_t smem = 0;
-    pick_pipeline(L, (long)grid.x * grid.y * grid.z, sk.ksplit, fused, &a.w_stages, &a.tpg, &smem);
+    pick_pipeline(L, (long)grid.x * grid.y * grid.z, sk.ksplit, fused, &a.w_stages, &a.tpg, &a.a_stages, &smem);
     // wide tiles are limited to 2 CTAs/SM by shared memory anyway and get the registers; narrow ones want
     // occupancy; the fused epilogue runs the (register-hungry) activation on 8 warps
     if (fused) {
@@ -1515,7 +1523,9 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     ConvLayer L = prepare_conv(ar, precision, KIND_CONV, w, nullptr, Cout, Cin, K, dilation);
     PlaneT x = make_planes(ar, B, Cin, T, opnd_esz(precision)), out = make_planes(ar, B, Cout, T, 4);
     OpList ol;
+    RetileCache rcache;
     ol.ar = &ar;
+    ol.war = &ar; ol.cache = &rcache;  // same per-launch N tile choice as the plans
     const bool bench_fused = env_int("ALCM_BENCH_FUSED", 0) && precision != ALCM_PREC_FP32;
     if (bench_fused) {  // conv + fused Activation1d, operand planes only (the c1 launches of the AMP blocks)
       PlaneT aout = make_planes(ar, B, Cout, T, opnd_esz(precision));
@@ -1537,8 +1547,9 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     g_conv_dbg = 0;
     CUDA_CHECK(err);
     if (env_int("ALCM_TRACE", 0) && precision != ALCM_PREC_FP32) {  // one more launch with per-CTA timestamps
-      const int ks = pick_ksplit(L, T, B, bench_fused);
-      const size_t nctas = (size_t)conv_m_tiles(T, bench_fused) * L.n_tiles * B * L.nphase * ks;
+      const ConvLayer& Lt = retile(ar, rcache, L, pick_nt(L, T, B));
+      const int ks = pick_ksplit(Lt, T, B, bench_fused);
+      const size_t nctas = (size_t)conv_m_tiles(T, bench_fused) * Lt.n_tiles * B * Lt.nphase * ks;
       long long* tr = static_cast<long long*>(ar.alloc(nctas * 8 * sizeof(long long), true));
       CUDA_CHECK(cudaDeviceSynchronize());
       g_conv_trace = tr;
@@ -1557,7 +1568,7 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
       }
       fprintf(stderr, "  trace: %zu CTAs (ksplit %d, NT %d, kblk %d, stages ~), span %.1f us, last start +%.1f us, mean CTA life %.1f us; "
               "mean cycles: setup %.0f, first-operands %.0f, mma-issue %.0f, drain %.0f, epilogue %.0f\n",
-              nctas, ks, L.NT, L.kblk, (t_max - t_min) / 1e3, (s_max - t_min) / 1e3, life / nctas / 1e3, d[0] / nctas, d[1] / nctas,
+              nctas, ks, Lt.NT, Lt.kblk, (t_max - t_min) / 1e3, (s_max - t_min) / 1e3, life / nctas / 1e3, d[0] / nctas, d[1] / nctas,
               d[2] / nctas, d[3] / nctas, d[4] / nctas);
     }
     float ms = 0.f;

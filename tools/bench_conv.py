@@ -13,6 +13,10 @@ SHAPES = [  # B, Cin, Cout, T, K, d
     (8, 768, 768, 2500, 11, 1),
     (8, 768, 768, 2500, 3, 1),
     (1, 1536, 1536, 312, 3, 1),
+    (1, 768, 768, 312, 3, 1),
+    (1, 768, 768, 624, 3, 1),
+    (1, 384, 384, 624, 3, 1),
+    (1, 1536, 1536, 312, 1, 1),
     (8, 384, 384, 10000, 7, 1),
     (8, 192, 192, 20000, 7, 1),
     (8, 96, 96, 40000, 7, 1),
