@@ -172,7 +172,7 @@ __device__ __forceinline__ void act_plane(const float4* sx, int tid, int m0, int
 // R outputs per thread: 4 (80 registers, 6 blocks/SM) or 8 (1.7x fewer instructions per element - the up-sampled
 // halo is shared by twice as many outputs - for launches big enough to fill the GPU with 4 blocks/SM).
 template <int NPL, bool FAST, int R>  // NPL input planes per output unit: 1 -> fp32 out, 2 -> bf16 out
-__global__ void __launch_bounds__(kActThreads, (R == 4 ? 6 : 4)) act1d_kernel(const __grid_constant__ ActArgs a) {
+__global__ void __launch_bounds__(kActThreads, (R == 4 ? 6 : (R == 6 ? 5 : 4))) act1d_kernel(const __grid_constant__ ActArgs a) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int kTile = kActThreads * R, kRows = kTile + 10, kSlots = kRows + (kRows >> 3) + 1;

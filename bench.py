@@ -186,12 +186,14 @@ def kernel_rooflines(precision, peaks):
                             achieved=round(tf, 1), peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(tf / peaks["tf_sustained"], 4),
                             us_per_launch=round(ms.value * 1e3, 1))
     B, Cc, T = 64, 24, 160000               # last-stage Activation1d, batch 64: 2-2.6 GB, far beyond L2
-    _lib.check(lib.alcm_bench_act(ctx, B, Cc, T, prec, 10, C.byref(ms)))
-    byt = B * ((Cc + 15) // 16 * 16) * T * (4 + (2 if precision == "bf16" else 4))
-    gbs = byt / (ms.value * 1e-3) / 1e9
-    out["activation1d"] = dict(kernel="act1d_kernel", shape=f"C={Cc} T={T} batch {B} ({byt / 1e6:.0f} MB algorithmic)", bound="hbm",
-                               achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s", frac=round(gbs / peaks["hbm"], 4),
-                               us_per_launch=round(ms.value * 1e3, 1))
+    for key, p, osz in (("activation1d", precision, 2 if precision == "bf16" else 4), ("activation1d_fp32_out", "tf32", 4)):
+        _lib.check(lib.alcm_bench_act(ctx, B, Cc, T, _lib.PREC[p], 10, C.byref(ms)))
+        byt = B * ((Cc + 15) // 16 * 16) * T * (4 + osz)
+        gbs = byt / (ms.value * 1e-3) / 1e9
+        out[key] = dict(kernel="act1d_kernel", shape=f"C={Cc} T={T} batch {B}, fp32 in / {'bf16' if osz == 2 else 'fp32'} out "
+                                                      f"({byt / 1e6:.0f} MB algorithmic)", bound="hbm",
+                        achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s", frac=round(gbs / peaks["hbm"], 4),
+                        us_per_launch=round(ms.value * 1e3, 1))
     return out
 
 

@@ -8,7 +8,7 @@ from audiolcm_b200 import _lib  # noqa: E402
 
 lib = _lib.load()
 ctx = _lib.ctx(0)
-SHAPES = [(1, 768, 2500), (1, 192, 20000), (1, 24, 160000), (8, 768, 2500), (8, 192, 20000), (8, 24, 160000), (64, 768, 2500), (64, 24, 160000)]
+SHAPES = [(1, 768, 2500), (1, 384, 10000), (1, 192, 20000), (1, 96, 40000), (1, 48, 80000), (1, 24, 160000), (8, 768, 2500), (8, 192, 20000), (8, 24, 160000), (64, 768, 2500), (64, 24, 160000)]
 for prec in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["bf16", "tf32"]):
     osz = 2 if prec == "bf16" else 4
     for (B, Cc, T) in SHAPES:
