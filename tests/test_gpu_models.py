@@ -167,3 +167,70 @@ def test_shape_errors():
     bad["activation"] = "snake"
     with pytest.raises(NotImplementedError):
         _voc(bad, synth.bigvgan_state_dict(h, seed=0), "tf32")
+
+
+# ----------------------------------------------------------------------------------- checkpoint ingestion
+def test_vocoder_checkpoint_dir_ingestion(tmp_path):
+    """``VocoderBigVGAN(ckpt_dir)`` reads ``best_netG.pt['generator']`` + ``args.yml`` like the reference
+    (vocoder/bigvgan/models.py:394-404), accepts torch>=2.1 parametrized weight-norm names, ignores the
+    (constant) ``filter`` buffers when they match and refuses a checkpoint whose filters differ."""
+    import json
+    import yaml
+    from audiolcm_b200 import VocoderBigVGAN
+    h = synth.bigvgan_config(64)
+    sd = {k: torch.from_numpy(v) for k, v in synth.bigvgan_state_dict(h, seed=4).items()}
+    taps = torch.tensor(O.kaiser_sinc_filter().reshape(1, 1, 12).numpy())
+    par = {}
+    for k, v in sd.items():  # the layout torch.nn.utils.parametrizations.weight_norm saves
+        if k.endswith(".weight_g"):
+            par[k[:-9] + ".parametrizations.weight.original0"] = v
+        elif k.endswith(".weight_v"):
+            par[k[:-9] + ".parametrizations.weight.original1"] = v
+        else:
+            par[k] = v
+    par["resblocks.0.activations.0.upsample.filter"] = taps
+    par["resblocks.0.activations.0.downsample.lowpass.filter"] = taps
+    ck = tmp_path / "bigv"
+    ck.mkdir()
+    torch.save({"generator": par}, ck / "best_netG.pt")
+    with open(ck / "args.yml", "w") as f:
+        yaml.safe_dump(json.loads(json.dumps(dict(h))), f)
+    mel = synth.synth_mel(1, 20, seed=9)
+    a = VocoderBigVGAN(str(ck), DEV, precision="tf32").vocode(mel[0])
+    b = _voc(h, synth.bigvgan_state_dict(h, seed=4), "tf32").vocode(mel[0])
+    np.testing.assert_array_equal(a, b)
+    par["resblocks.0.activations.0.upsample.filter"] = taps * 1.01
+    torch.save({"generator": par}, ck / "best_netG.pt")
+    with pytest.raises(ValueError):
+        VocoderBigVGAN(str(ck), DEV, precision="tf32")
+
+
+def test_vae_lightning_state_dict_and_install():
+    """The VAE decoder is cut out of a Lightning checkpoint's state_dict by prefix (``first_stage_model.*``,
+    pythonscripts/InferAPI.py:30-33), and ``install()`` rebinds ``model.first_stage_model.decode`` in place."""
+    import audiolcm_b200
+    dd = synth.vae_config(32)
+    sd = synth.vae_decoder_state_dict(dd, seed=6)
+    big = {"first_stage_model." + k: torch.from_numpy(v) for k, v in sd.items()}
+    big["model.diffusion_model.some.weight"] = torch.zeros(3)
+    big["scale_factor"] = torch.tensor(1.0)
+    z = torch.from_numpy(synth.synth_latent(2, 9, seed=2)).to(DEV)
+    ref = _vae(dd, sd, "tf32").decode(z)
+    got = audiolcm_b200.AutoencoderKLDecoder(big, dd, synth.VAE_EMBED_DIM, DEV, "tf32", prefix="first_stage_model.").decode(z)
+    assert torch.equal(ref, got)
+
+    class _FSM:  # the two things install() needs from the reference AutoencoderKL
+        embed_dim = synth.VAE_EMBED_DIM
+
+        def state_dict(self):
+            return {k: torch.from_numpy(v) for k, v in sd.items()}
+
+        def decode(self, z):
+            raise AssertionError("reference decode should have been replaced")
+
+    class _Model:
+        first_stage_model = _FSM()
+
+    m = _Model()
+    audiolcm_b200.install(m, dd, device=DEV, precision="tf32")
+    assert torch.equal(m.first_stage_model.decode(z), ref)
