@@ -312,6 +312,22 @@ def run_gpu(args):
             class_ms={k: round(v["ms"], 4) for k, v in prof.items()},
             class_ms_total_eager=round(total_ms, 4),
         )
+        if world == 1 and not args.no_batch64:
+            # BASELINE.json configs[2] on this GPU (64 x 10 s clips in one call) - context for the batch-1 headline
+            zb = torch.from_numpy(synth.synth_latent(64, T_LAT, seed=11)).to(device)
+            pipe.decode_tensor(zb)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_()
+            e0.record()
+            for _ in range(3):
+                pipe.decode_tensor(zb)
+            e1.record()
+            torch.cuda.synchronize()
+            ms64 = e0.elapsed_time(e1) / 3
+            line["configs2_batch64"] = dict(value=round(audio_seconds(64, T_LAT) / (ms64 * 1e-3), 1), unit="audio-s/s", ms_per_step=round(ms64, 2),
+                                            workload="configs[2]: 64 x 10 s clips in one call on one GPU (inputs in HBM, 3 steps)")
+            del zb
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
         emit(line)
@@ -350,6 +366,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("ALCM_BENCH_PRECISION", "bf16"), choices=["bf16", "tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-batch64", action="store_true", help="skip the configs[2] (batch 64) context measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     protect_stdout()
