@@ -58,6 +58,10 @@ struct ConvArgs {
   float* ws;               // [tile][ksplit][NT/4][128] float4
   unsigned int* tile_ctr;  // [tile]
   long long* trace;        // micro-benchmark only: 8 timestamps per CTA (tools/bench_conv.py with ALCM_TRACE=1)
+  // Tiles: linear index = (z * n_tiles + nt) * tiles_m + mt, z = (b * nphase + ph) * ksplit + split.  The grid is
+  // 1-D; a CTA processes tiles blockIdx.x, blockIdx.x + gridDim.x, ... (persistent launch when gridDim.x < tiles_total,
+  // with two TMEM accumulators so that the epilogue of one tile overlaps the main loop of the next).
+  int tiles_m, tiles_total, acc_stages;
   // Fused Activation1d epilogue (models.py:72-81: the SnakeBeta between c1/c2 and between AMP layers):
   // act_out != null -> the tile is staged in shared memory, run through UpSample1d -> SnakeBeta ->
   // DownSample1d and written as operand planes for the next conv.  `out` (fp32, the residual stream) is
@@ -96,17 +100,38 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int kblk, int span, i
   L.w_off = a_stages * L.a_stage;
   L.bias_off = L.w_off + w_stages * L.w_stage;
   L.bar_off = L.bias_off + NT * 4;
-  L.total = L.bar_off + 8 * (2 * a_stages + 2 * w_stages + 1) + 16;
+  L.total = L.bar_off + 8 * (2 * a_stages + 2 * w_stages + 4) + 16;
   return L;
+}
+
+struct ConvTile {
+  int mt, nt, zb, zs, b, ph, kb0, kb1, q0;
+};
+template <bool FUSED>
+__device__ __forceinline__ ConvTile conv_tile(const ConvArgs& a, int tile) {
+  ConvTile t;
+  t.mt = tile % a.tiles_m;
+  const int r = tile / a.tiles_m;
+  t.nt = r % a.n_tiles;
+  const int z = r / a.n_tiles;
+  t.zs = z % a.ksplit;
+  t.zb = z / a.ksplit;
+  t.b = t.zb / a.nphase;
+  t.ph = t.zb % a.nphase;
+  t.kb0 = (int)((long)t.zs * a.nkb / a.ksplit);
+  t.kb1 = (int)((long)(t.zs + 1) * a.nkb / a.ksplit);
+  // fused tiles overlap: tile mt owns activation outputs [mt*116, mt*116+116) and computes conv rows from 5 earlier
+  t.q0 = FUSED ? t.mt * kFuseOwn - kFuseHalo : t.mt * kTileM;
+  return t;
 }
 
 // MMA-issuing warp.  NK2 = MMAs per (k-block, tap) (two 16-byte K chunks per MMA); static so that
 // the burst is straight-line code (a rolled loop re-writes the uniform descriptor registers of
 // in-flight UTCHMMAs and stalls ~300 cycles per trip).
-template <int KIND, int NK2>
-__device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, int ph, uint32_t sA, uint32_t sW, const ConvSmemLayout& L, int rowsA,
+template <int KIND, int NK2, bool FUSED>
+__device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, uint32_t sA, uint32_t sW, const ConvSmemLayout& L, int rowsA,
                                               uint32_t tmem_base, uint32_t a_full, uint32_t a_empty, uint32_t w_full,
-                                              uint32_t w_empty, uint32_t acc_full, int kb0, int kb1, long long* trace) {
+                                              uint32_t w_empty, uint32_t acc_full, uint32_t acc_empty, long long* trace) {
   const bool leader = elect_one();
   const uint32_t lead = leader ? 1u : 0u;
   // Descriptors differ only in their 14-bit start-address field: build the constant part once
@@ -120,37 +145,47 @@ __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, int ph, uint32_
   // The tap shift (row offset of tap j inside the A slab) is linear in j for every conv form here.
   const int ntaps = a.ntaps, S = a.w_stages, tpg = a.tpg, AS = a.a_stages;
   const uint32_t idesc = a.idesc;
-  const uint32_t shift0 = (uint32_t)(a.tap_off[ph][0] - a.min_off[ph]);
-  const uint64_t dshift = (uint64_t)(int64_t)(ntaps > 1 ? a.tap_off[ph][1] - a.tap_off[ph][0] : 0);
   int ws = 0, as = 0;
-  uint32_t wpar = 0, apar = 0, acc = 0;
-  for (int kb = kb0; kb < kb1; ++kb) {
-    mbar_wait(a_full + 8 * as, apar);
-    uint64_t a_tap = a_desc0 + (uint64_t)(as * a_stage16 + shift0);
-    for (int j0 = 0; j0 < ntaps; j0 += tpg) {
-      const int g = min(tpg, ntaps - j0);
-      mbar_wait(w_full + 8 * ws, wpar);
+  uint32_t wpar = 0, apar = 0;
+  int it = 0;  // tiles done by this CTA
+  for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++it) {
+    const ConvTile T = conv_tile<FUSED>(a, tile);
+    const uint32_t shift0 = (uint32_t)(a.tap_off[T.ph][0] - a.min_off[T.ph]);
+    const uint64_t dshift = (uint64_t)(int64_t)(ntaps > 1 ? a.tap_off[T.ph][1] - a.tap_off[T.ph][0] : 0);
+    const int st = (a.acc_stages > 1) ? (it & 1) : 0;
+    const uint32_t tmem_d = tmem_base + (uint32_t)(st * a.NT);
+    if (a.acc_stages > 1) {  // the epilogue must have drained this accumulator (two tiles ago)
+      mbar_wait(acc_empty + 8 * st, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      if (trace && acc == 0 && leader) trace[3] = clock64();
-      // branch-free, warp-uniform issue: the election is the predicate of the async instructions themselves
-      // (a lane-private descriptor or a divergent region makes ptxas wrap every UTCHMMA in an
-      // ELECT/R2UR.BROADCAST/BRA.U.ANY loop or shuttle descriptors through R2UR)
-      uint64_t bd = w_desc0 + (uint64_t)(ws * w_stage16);
-      for (int t = 0; t < g; ++t, a_tap += dshift, bd += w_blob16) {
-#pragma unroll
-        for (int i = 0; i < NK2; ++i)
-          umma_ss_pred<KIND>(tmem_base, a_tap + (uint64_t)(i * a_step), bd + (uint64_t)(i * w_step), idesc, (i > 0) ? 1u : acc, lead);
-        acc = 1;
-      }
-      tc_commit_pred(w_empty + 8 * ws, lead);  // frees the weight slot when these MMAs retire
-      if (j0 + g == ntaps) tc_commit_pred(a_empty + 8 * as, lead);
-      acc = 1;
-      if (++ws == S) { ws = 0; wpar ^= 1; }
     }
-    if (++as == AS) { as = 0; apar ^= 1; }
+    uint32_t acc = 0;
+    for (int kb = T.kb0; kb < T.kb1; ++kb) {
+      mbar_wait(a_full + 8 * as, apar);
+      uint64_t a_tap = a_desc0 + (uint64_t)(as * a_stage16 + shift0);
+      for (int j0 = 0; j0 < ntaps; j0 += tpg) {
+        const int g = min(tpg, ntaps - j0);
+        mbar_wait(w_full + 8 * ws, wpar);
+        tc_fence_after();
+        if (trace && it == 0 && acc == 0 && leader) trace[3] = clock64();
+        // branch-free, warp-uniform issue: the election is the predicate of the async instructions themselves
+        // (a lane-private descriptor or a divergent region makes ptxas wrap every UTCHMMA in an
+        // ELECT/R2UR.BROADCAST/BRA.U.ANY loop or shuttle descriptors through R2UR)
+        uint64_t bd = w_desc0 + (uint64_t)(ws * w_stage16);
+        for (int t = 0; t < g; ++t, a_tap += dshift, bd += w_blob16) {
+#pragma unroll
+          for (int i = 0; i < NK2; ++i)
+            umma_ss_pred<KIND>(tmem_d, a_tap + (uint64_t)(i * a_step), bd + (uint64_t)(i * w_step), idesc, (i > 0) ? 1u : acc, lead);
+          acc = 1;
+        }
+        tc_commit_pred(w_empty + 8 * ws, lead);  // frees the weight slot when these MMAs retire
+        if (j0 + g == ntaps) tc_commit_pred(a_empty + 8 * as, lead);
+        if (++ws == S) { ws = 0; wpar ^= 1; }
+      }
+      if (++as == AS) { as = 0; apar ^= 1; }
+    }
+    tc_commit_pred(acc_full + 8 * st, lead);
+    if (trace && it == 0 && leader) trace[4] = clock64();
   }
-  if (leader) tc_commit(acc_full);
-  if (trace && leader) trace[4] = clock64();
   __syncwarp();
 }
 
@@ -203,31 +238,28 @@ template <int KIND, int MINB, bool FUSED>
 __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, nt = blockIdx.y;
   const int ksplit = a.ksplit;
-  const int zs = blockIdx.z % ksplit, zb = blockIdx.z / ksplit;
-  const int b = zb / a.nphase, ph = zb % a.nphase;
-  const int kb0 = (int)((long)zs * a.nkb / ksplit), kb1 = (int)((long)(zs + 1) * a.nkb / ksplit);
   const int S = a.w_stages;
   const int rowsA = kTileM + a.span;
-  constexpr bool fused = FUSED;  // Activation1d epilogue compiled in (launches with a.act_out != nullptr)
   const int AS = a.a_stages;
   const ConvSmemLayout L = conv_smem_layout(a.kblk, a.span, a.NT, S, a.tpg, AS);
   const uint32_t sA = smem_u32(smem) + L.a_off;
   const uint32_t sW = smem_u32(smem) + L.w_off;
   const uint32_t bars = smem_u32(smem) + L.bar_off;
   float* s_bias = reinterpret_cast<float*>(smem + L.bias_off);
-  // barrier slots: a_full[AS], a_empty[AS], w_full[S], w_empty[S], acc_full
+  // barrier slots: a_full[AS], a_empty[AS], w_full[S], w_empty[S], acc_full[2], acc_empty[2]
   const uint32_t a_full = bars, a_empty = bars + 8 * AS, w_full = bars + 16 * AS, w_empty = w_full + 8 * S;
-  const uint32_t acc_full = w_empty + 8 * S;
-  const int nbars = 2 * AS + 2 * S + 1;
+  const uint32_t acc_full = w_empty + 8 * S, acc_empty = acc_full + 16;
+  const int nbars = 2 * AS + 2 * S + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.bar_off + 8 * nbars);
   volatile uint32_t* s_last = tmem_slot + 1;  // split-K: "this CTA arrived last at its tile"
 
-  long long* trace = a.trace ? a.trace + 8 * ((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  long long* trace = a.trace ? a.trace + 8 * (size_t)blockIdx.x : nullptr;  // timestamps of the CTA's first tile
   if (threadIdx.x == 0) {
     if (trace) { trace[0] = (long long)global_timer_ns(); trace[1] = clock64(); }
-    for (int i = 0; i < nbars; ++i) mbar_init(bars + 8 * i, 1);
+    for (int i = 0; i < nbars - 2; ++i) mbar_init(bars + 8 * i, 1);
+    mbar_init(acc_empty, 4);       // one arrival per epilogue warp
+    mbar_init(acc_empty + 8, 4);
     fence_mbar_init();
     *s_last = 1;
   }
@@ -239,10 +271,10 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // fused tiles overlap: tile mt owns activation outputs [mt*116, mt*116+116) and computes conv rows from 5 earlier
-  const int q0 = fused ? mt * kFuseOwn - kFuseHalo : mt * kTileM;
   if (trace && threadIdx.x == 0) trace[2] = clock64();
   pdl_launch_dependents();  // the next kernel may start its own setup / weight prefetch now
+  // the (single) tile of a fused launch, for the activation phase after the role branches
+  const ConvTile T0 = conv_tile<FUSED>(a, blockIdx.x);
 
   // Both asynchronous roles keep their warp CONVERGENT and predicate the async instructions with
   // elect.sync: UBLKCP / UTCHMMA / UTCBAR take warp-uniform operands, and issuing them from a
@@ -250,174 +282,188 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
   // loop, which left the tensor pipe waiting on the issuing thread.
   if (warp == 0) {
     const bool leader = elect_one();
-    const int row0 = q0 + a.min_off[ph] + a.xg.pad;  // >= 0: |min_off| + kFuseHalo <= pad
-    const int nrows = min(rowsA, a.xg.Tp - row0);
-    const uint8_t* wsrc = a.w + (size_t)ph * a.w_phase_stride + ((size_t)nt * a.nkb + kb0) * a.ntaps * L.w_blob;
     const size_t plane_bytes = (size_t)a.xg.Tp * 16;
-    const uint8_t* xsrc = a.x + (((size_t)b * a.xg.nchunk + (size_t)kb0 * a.kblk) * a.xg.Tp + row0) * 16;
-    const uint32_t a_bytes = (uint32_t)nrows * 16, a_pitch = (uint32_t)rowsA * 16;
+    const uint32_t a_pitch = (uint32_t)rowsA * 16;
     const int ntaps = a.ntaps, tpg = a.tpg;
-    int ws = 0;
-    uint32_t wpar = 1;  // producer waits on the "previous" phase of the empty barriers first
-    // one weight stage (a group of taps): wait for the slot, arm the barrier, one bulk copy
-    auto load_w = [&](int j0) {
-      const uint32_t bytes = (uint32_t)min(tpg, ntaps - j0) * L.w_blob;
-      mbar_wait(w_empty + 8 * ws, wpar);
-      if (leader) {
-        if (a.dbg & 1) {
-          mbar_arrive(w_full + 8 * ws);
-        } else {
-          mbar_expect_tx(w_full + 8 * ws, bytes);
-          bulk_g2s(sW + ws * L.w_stage, wsrc, bytes, w_full + 8 * ws);
+    int ws = 0, as = 0;
+    uint32_t wpar = 1, apar = 1;  // producer waits on the "previous" phase of the empty barriers first
+    bool waited = false;
+    for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
+      const ConvTile T = conv_tile<FUSED>(a, tile);
+      const int row0 = T.q0 + a.min_off[T.ph] + a.xg.pad;  // >= 0: |min_off| + kFuseHalo <= pad
+      const int nrows = min(rowsA, a.xg.Tp - row0);
+      const uint8_t* wsrc = a.w + (size_t)T.ph * a.w_phase_stride + ((size_t)T.nt * a.nkb + T.kb0) * ntaps * L.w_blob;
+      const uint8_t* xsrc = a.x + (((size_t)T.b * a.xg.nchunk + (size_t)T.kb0 * a.kblk) * a.xg.Tp + row0) * 16;
+      const uint32_t a_bytes = (uint32_t)nrows * 16;
+      // one weight stage (a group of taps): wait for the slot, arm the barrier, one bulk copy
+      auto load_w = [&](int j0) {
+        const uint32_t bytes = (uint32_t)min(tpg, ntaps - j0) * L.w_blob;
+        mbar_wait(w_empty + 8 * ws, wpar);
+        if (leader) {
+          if (a.dbg & 1) {
+            mbar_arrive(w_full + 8 * ws);
+          } else {
+            mbar_expect_tx(w_full + 8 * ws, bytes);
+            bulk_g2s(sW + ws * L.w_stage, wsrc, bytes, w_full + 8 * ws);
+          }
         }
+        wsrc += bytes;
+        if (++ws == S) { ws = 0; wpar ^= 1; }
+      };
+      // Only the first weight group goes out before the first A slab: the first MMA needs exactly those two, and
+      // everything queued ahead of the slab delays it (12 prefetched groups cost ~1.3 us of first-MMA latency).
+      load_w(0);
+      if (!waited) { pdl_wait(); waited = true; }
+      int gi = 0;
+      for (int kb = T.kb0; kb < T.kb1; ++kb) {
+        mbar_wait(a_empty + 8 * as, apar);
+        if (a.dbg & 2) {
+          if (leader) mbar_arrive(a_full + 8 * as);
+          xsrc += plane_bytes * a.kblk;
+        } else {
+          if (leader) mbar_expect_tx(a_full + 8 * as, (uint32_t)a.kblk * a_bytes);
+          uint32_t dst = sA + as * L.a_stage;
+          for (int c = 0; c < a.kblk; ++c, dst += a_pitch, xsrc += plane_bytes)
+            if (leader) bulk_g2s(dst, xsrc, a_bytes, a_full + 8 * as);
+        }
+        for (int j0 = 0; j0 < ntaps; j0 += tpg, ++gi)
+          if (gi >= 1) load_w(j0);
+        if (++as == AS) { as = 0; apar ^= 1; }
       }
-      wsrc += bytes;
-      if (++ws == S) { ws = 0; wpar ^= 1; }
-    };
-    // Only the first weight group goes out before the first A slab: the first MMA needs exactly those two, and
-    // everything queued ahead of the slab delays it (12 prefetched groups cost ~1.3 us of first-MMA latency).
-    // (With programmatic dependent launch the weights could all be prefetched here; PDL is off by default.)
-    const int ngrp = (ntaps + tpg - 1) / tpg;
-    const int pre = 1;
-    load_w(0);
-    pdl_wait();
-    int gi = 0;  // weight groups issued so far are [0, pre)
-    int as = 0;
-    uint32_t apar = 1;
-    for (int kb = kb0; kb < kb1; ++kb) {
-      mbar_wait(a_empty + 8 * as, apar);
-      if (a.dbg & 2) {
-        if (leader) mbar_arrive(a_full + 8 * as);
-        xsrc += plane_bytes * a.kblk;
-      } else {
-        if (leader) mbar_expect_tx(a_full + 8 * as, (uint32_t)a.kblk * a_bytes);
-        uint32_t dst = sA + as * L.a_stage;
-        for (int c = 0; c < a.kblk; ++c, dst += a_pitch, xsrc += plane_bytes)
-          if (leader) bulk_g2s(dst, xsrc, a_bytes, a_full + 8 * as);
-      }
-      for (int j0 = 0; j0 < ntaps; j0 += tpg, ++gi)
-        if (gi >= pre) load_w(j0);
-      if (++as == AS) { as = 0; apar ^= 1; }
     }
-    (void)ngrp;
     __syncwarp();
   } else if (warp == 1) {
     switch (a.kblk >> 1) {
-      case 1: conv_mma_loop<KIND, 1>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
-      case 2: conv_mma_loop<KIND, 2>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
-      case 3: conv_mma_loop<KIND, 3>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
-      case 4: conv_mma_loop<KIND, 4>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
-      case 5: conv_mma_loop<KIND, 5>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
-      default: conv_mma_loop<KIND, 6>(a, ph, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, kb0, kb1, trace); break;
+      case 1: conv_mma_loop<KIND, 1, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      case 2: conv_mma_loop<KIND, 2, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      case 3: conv_mma_loop<KIND, 3, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      case 4: conv_mma_loop<KIND, 4, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      case 5: conv_mma_loop<KIND, 5, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      default: conv_mma_loop<KIND, 6, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
     }
   } else if (warp < 6) {
-    // while the main loop runs: stage this N tile's bias in shared memory (the epilogue reads it as broadcasts)
     const int et = threadIdx.x - 64;
-    for (int i = et; i < a.NT; i += 128) s_bias[i] = a.bias ? __ldg(a.bias + nt * a.NT + i) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-    pdl_wait();  // residual / accumulate reads, output and split-K workspace writes come after the previous kernel
     const int qd = warp & 3;  // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
-    const int q = q0 + row;
-    const bool in_seq = q >= 0 && q < a.M;
-    // rows whose fp32 result this tile stores: all of them, or only the ones it owns when tiles overlap
-    const bool valid = in_seq && (!fused || (row >= kFuseHalo && row < kFuseHalo + kFuseOwn));
-    const size_t orow = (size_t)q * a.ostride + ph;
     const float scale = a.scale;
-    const int nq = a.NT >> 2;                              // float4 column groups in this tile
-    const int nq_valid = min(nq, a.og.nchunk - nt * nq);   // those that exist in the output planes
+    const int nq = a.NT >> 2;                              // float4 column groups in a tile
     const size_t plane4 = (size_t)a.og.Tp;                 // float4 units between consecutive chunks
-    const size_t off0 = ((size_t)b * a.og.nchunk + (size_t)nt * nq) * a.og.Tp + a.og.pad + orow;  // float4 units
     const float4* res4 = reinterpret_cast<const float4*>(a.res);
     float4* out4 = reinterpret_cast<float4*>(a.out);
-    const bool has_res = (a.res != nullptr) && in_seq, accum = (a.accum != 0) && valid, store = (a.out != nullptr) && valid;
     float4* ys = reinterpret_cast<float4*>(smem);  // fused: staged tile [plane][kFuseSlots] float4, over the drained pipeline buffers
     const int yrow = row + (row >> 3);
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    if (trace && threadIdx.x == 64) trace[5] = clock64();
-    // bias / residual / scale / accumulate of 16 consecutive output channels of this thread's row; fp32 store and/or staging
-    auto emit = [&](int c0, const float (&v)[16], const float4 (&rr)[4], const float4 (&oo)[4]) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int cq = (c0 >> 2) + g;
-        const float4 bb = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
-        float4 r = make_float4(v[4 * g] + bb.x, v[4 * g + 1] + bb.y, v[4 * g + 2] + bb.z, v[4 * g + 3] + bb.w);
-        r.x = (r.x + rr[g].x) * scale + oo[g].x; r.y = (r.y + rr[g].y) * scale + oo[g].y;
-        r.z = (r.z + rr[g].z) * scale + oo[g].z; r.w = (r.w + rr[g].w) * scale + oo[g].w;
-        if (store && cq < nq_valid) out4[off0 + (size_t)cq * plane4] = r;
-        if (fused) ys[cq * kFuseSlots + yrow] = r;
+    int it = 0, nt_staged = -1;
+    for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++it) {
+      const ConvTile T = conv_tile<FUSED>(a, tile);
+      const int st = (a.acc_stages > 1) ? (it & 1) : 0;
+      const uint32_t tmem_d = tmem_base + (uint32_t)(st * a.NT);
+      // while the main loop runs: stage this N tile's bias in shared memory (the epilogue reads it as broadcasts)
+      if (T.nt != nt_staged) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only: nobody still reads the old bias
+        for (int i = et; i < a.NT; i += 128) s_bias[i] = a.bias ? __ldg(a.bias + T.nt * a.NT + i) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        nt_staged = T.nt;
       }
-    };
-    // residual / accumulate operands of 16 channels (issued before the TMEM load they are combined with)
-    auto fetch = [&](int c0, float4 (&rr)[4], float4 (&oo)[4]) {
+      if (it == 0) pdl_wait();  // residual / accumulate reads, output and split-K workspace writes come after the previous kernel
+      const int q = T.q0 + row;
+      const bool in_seq = q >= 0 && q < a.M;
+      // rows whose fp32 result this tile stores: all of them, or only the ones it owns when tiles overlap
+      const bool valid = in_seq && (!FUSED || (row >= kFuseHalo && row < kFuseHalo + kFuseOwn));
+      const size_t orow = (size_t)q * a.ostride + T.ph;
+      const int nq_valid = min(nq, a.og.nchunk - T.nt * nq);   // column groups that exist in the output planes
+      const size_t off0 = ((size_t)T.b * a.og.nchunk + (size_t)T.nt * nq) * a.og.Tp + a.og.pad + orow;  // float4 units
+      const bool has_res = (a.res != nullptr) && in_seq, accum = (a.accum != 0) && valid, store = (a.out != nullptr) && valid;
+      mbar_wait(acc_full + 8 * st, (it >> 1) & 1);
+      tc_fence_after();
+      if (trace && it == 0 && threadIdx.x == 64) trace[5] = clock64();
+      // bias / residual / scale / accumulate of 16 consecutive output channels of this thread's row; fp32 store and/or staging
+      auto emit = [&](int c0, const float (&v)[16], const float4 (&rr)[4], const float4 (&oo)[4]) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int cq = (c0 >> 2) + g;
-        rr[g] = oo[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (cq < nq_valid) {
-          if (has_res) rr[g] = res4[off0 + (size_t)cq * plane4];
-          if (accum) oo[g] = out4[off0 + (size_t)cq * plane4];
+        for (int g = 0; g < 4; ++g) {
+          const int cq = (c0 >> 2) + g;
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * g);
+          float4 r = make_float4(v[4 * g] + bb.x, v[4 * g + 1] + bb.y, v[4 * g + 2] + bb.z, v[4 * g + 3] + bb.w);
+          r.x = (r.x + rr[g].x) * scale + oo[g].x; r.y = (r.y + rr[g].y) * scale + oo[g].y;
+          r.z = (r.z + rr[g].z) * scale + oo[g].z; r.w = (r.w + rr[g].w) * scale + oo[g].w;
+          if (store && cq < nq_valid) out4[off0 + (size_t)cq * plane4] = r;
+          if (FUSED) ys[cq * kFuseSlots + yrow] = r;
         }
-      }
-    };
-    if (ksplit == 1) {
-      for (int c0 = 0; c0 < a.NT; c0 += 16) {
-        float4 rr[4], oo[4];
-        fetch(c0, rr, oo);
-        uint32_t u[16];
-        tmem_ld_x16(tmem_base + ((uint32_t)(qd * 32) << 16) + c0, u);
-        tmem_ld_wait();
-        float v[16];
+      };
+      // residual / accumulate operands of 16 channels (issued before the TMEM load they are combined with)
+      auto fetch = [&](int c0, float4 (&rr)[4], float4 (&oo)[4]) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
-        emit(c0, v, rr, oo);
-      }
-    } else {
-      // partial tile -> workspace, [col/4][row] float4 so that a warp writes 512 contiguous bytes
-      const size_t tile = ((size_t)zb * gridDim.y + nt) * gridDim.x + mt;
-      float4* wst = reinterpret_cast<float4*>(a.ws) + (tile * ksplit) * (size_t)(nq * kTileM);
-      float4* mine = wst + (size_t)zs * (nq * kTileM);
-      for (int c0 = 0; c0 < a.NT; c0 += 16) {
-        uint32_t u[16];
-        tmem_ld_x16(tmem_base + ((uint32_t)(qd * 32) << 16) + c0, u);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          mine[(size_t)((c0 >> 2) + g) * kTileM + row] =
-              make_float4(__uint_as_float(u[4 * g]), __uint_as_float(u[4 * g + 1]), __uint_as_float(u[4 * g + 2]),
-                          __uint_as_float(u[4 * g + 3]));
-      }
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        const unsigned int old = atomicAdd(a.tile_ctr + tile, 1u);
-        const unsigned int last = (old == (unsigned int)(ksplit - 1));
-        if (last) a.tile_ctr[tile] = 0;  // every split has arrived: safe to re-arm for the next launch
-        *s_last = last;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*s_last) {
-        __threadfence();
+        for (int g = 0; g < 4; ++g) {
+          const int cq = (c0 >> 2) + g;
+          rr[g] = oo[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cq < nq_valid) {
+            if (has_res) rr[g] = res4[off0 + (size_t)cq * plane4];
+            if (accum) oo[g] = out4[off0 + (size_t)cq * plane4];
+          }
+        }
+      };
+      if (ksplit == 1) {
         for (int c0 = 0; c0 < a.NT; c0 += 16) {
           float4 rr[4], oo[4];
           fetch(c0, rr, oo);
+          uint32_t u[16];
+          tmem_ld_x16(tmem_d + ((uint32_t)(qd * 32) << 16) + c0, u);
+          tmem_ld_wait();
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0.f;
-          for (int s = 0; s < ksplit; ++s) {
-            const float4* src = wst + (size_t)s * (nq * kTileM);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 p = __ldcg(src + (size_t)((c0 >> 2) + g) * kTileM + row);
-              v[4 * g] += p.x; v[4 * g + 1] += p.y; v[4 * g + 2] += p.z; v[4 * g + 3] += p.w;
-            }
-          }
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
           emit(c0, v, rr, oo);
         }
+      } else {
+        // partial tile -> workspace, [col/4][row] float4 so that a warp writes 512 contiguous bytes
+        const size_t wtile = ((size_t)T.zb * a.n_tiles + T.nt) * a.tiles_m + T.mt;
+        float4* wst = reinterpret_cast<float4*>(a.ws) + (wtile * ksplit) * (size_t)(nq * kTileM);
+        float4* mine = wst + (size_t)T.zs * (nq * kTileM);
+        for (int c0 = 0; c0 < a.NT; c0 += 16) {
+          uint32_t u[16];
+          tmem_ld_x16(tmem_d + ((uint32_t)(qd * 32) << 16) + c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            mine[(size_t)((c0 >> 2) + g) * kTileM + row] =
+                make_float4(__uint_as_float(u[4 * g]), __uint_as_float(u[4 * g + 1]), __uint_as_float(u[4 * g + 2]),
+                            __uint_as_float(u[4 * g + 3]));
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const unsigned int old = atomicAdd(a.tile_ctr + wtile, 1u);
+          const unsigned int last = (old == (unsigned int)(ksplit - 1));
+          if (last) a.tile_ctr[wtile] = 0;  // every split has arrived: safe to re-arm for the next launch
+          *s_last = last;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*s_last) {
+          __threadfence();
+          for (int c0 = 0; c0 < a.NT; c0 += 16) {
+            float4 rr[4], oo[4];
+            fetch(c0, rr, oo);
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            for (int s = 0; s < ksplit; ++s) {
+              const float4* src = wst + (size_t)s * (nq * kTileM);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const float4 p = __ldcg(src + (size_t)((c0 >> 2) + g) * kTileM + row);
+                v[4 * g] += p.x; v[4 * g + 1] += p.y; v[4 * g + 2] += p.z; v[4 * g + 3] += p.w;
+              }
+            }
+            emit(c0, v, rr, oo);
+          }
+        }
       }
+      if (a.acc_stages > 1) {  // hand the accumulator back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + 8 * st);
+      }
+      if (trace && it == 0 && threadIdx.x == 64) trace[6] = clock64();
     }
-    if (trace && threadIdx.x == 64) trace[6] = clock64();
   }
   if constexpr (FUSED) {
     pdl_wait();
@@ -425,7 +471,7 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
     __syncthreads();  // tile staged (and, for split-K, s_last decided)
     if (*s_last) {
       float4* ys = reinterpret_cast<float4*>(smem);
-      const int T = a.M, npl = a.NT >> 2;
+      const int T = a.M, npl = a.NT >> 2, q0 = T0.q0;
       // replicate padding of the up-sampling FIR (resample.py:28): rows before t=0 / after t=T-1 take the edge sample
       const int lo = -q0, hi = T - q0;  // staged rows [lo, hi) are inside the sequence
       if (lo > 0 || hi < kTileM) {
@@ -436,8 +482,8 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
         }
         __syncthreads();
       }
-      if (a.act_bf16) conv_fused_act<2>(a, ys, b, nt, q0);
-      else conv_fused_act<1>(a, ys, b, nt, q0);
+      if (a.act_bf16) conv_fused_act<2>(a, ys, T0.b, T0.nt, q0);
+      else conv_fused_act<1>(a, ys, T0.b, T0.nt, q0);
     }
   }
   if (trace && threadIdx.x == 64) trace[7] = (long long)global_timer_ns();

@@ -344,6 +344,7 @@ static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused,
 
 static int g_conv_dbg = 0;
 static long long* g_conv_trace = nullptr;  // micro-benchmark only
+static int g_conv_last_grid = 0;            // micro-benchmark only: CTAs of the last tcgen05 conv launch
 
 struct SplitK {  // per-launch split-K resources (see ConvArgs::ksplit)
   int ksplit = 1;
@@ -405,21 +406,38 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
       a.act_out = fa.out.p; a.ag = fa.out.g; a.ea = fa.ea; a.ib = fa.ib;
       a.act_bf16 = fa.out.esz == 2; a.act_round_tf32 = fa.round_tf32;
     }
-    dim3 grid(conv_m_tiles(M, fused), L.n_tiles, B * L.nphase * sk.ksplit);
+    a.tiles_m = conv_m_tiles(M, fused);
+    a.tiles_total = a.tiles_m * L.n_tiles * B * L.nphase * sk.ksplit;
+    a.acc_stages = 1;
     uint32_t smem = 0;
-    pick_pipeline(L, (long)grid.x * grid.y * grid.z, sk.ksplit, fused, &a.w_stages, &a.tpg, &a.a_stages, &smem);
+    pick_pipeline(L, (long)a.tiles_total, sk.ksplit, fused, &a.w_stages, &a.tpg, &a.a_stages, &smem);
     // wide tiles are limited to 2 CTAs/SM by shared memory anyway and get the registers; narrow ones want
     // occupancy; the fused epilogue runs the (register-hungry) activation on 8 warps
-    if (fused) {
-      if (L.prec == ALCM_PREC_BF16) launch_k(conv_umma_kernel<0, 2, true>, dim3(grid), dim3(256), smem, st, a);
-      else launch_k(conv_umma_kernel<1, 2, true>, dim3(grid), dim3(256), smem, st, a);
-    } else if (L.NT >= 128) {
-      if (L.prec == ALCM_PREC_BF16) launch_k(conv_umma_kernel<0, 2, false>, dim3(grid), dim3(192), smem, st, a);
-      else launch_k(conv_umma_kernel<1, 2, false>, dim3(grid), dim3(192), smem, st, a);
-    } else {
-      if (L.prec == ALCM_PREC_BF16) launch_k(conv_umma_kernel<0, 3, false>, dim3(grid), dim3(192), smem, st, a);
-      else launch_k(conv_umma_kernel<1, 3, false>, dim3(grid), dim3(192), smem, st, a);
+    void (*kern)(ConvArgs) = nullptr;
+    int threads = 192;
+    if (fused) { kern = (L.prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, true> : conv_umma_kernel<1, 2, true>; threads = 256; }
+    else if (L.NT >= 128) kern = (L.prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, false> : conv_umma_kernel<1, 2, false>;
+    else kern = (L.prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 3, false> : conv_umma_kernel<1, 3, false>;
+    // Persistent launch for multi-wave grids: one CTA per resident slot loops over tiles with two TMEM accumulators,
+    // so barrier/TMEM setup is paid once per CTA and the epilogue of tile i overlaps the main loop of tile i+1.
+    int grid = a.tiles_total;
+    if (!fused && sk.ksplit == 1 && 2 * L.NT <= 512 && env_int("ALCM_PERSIST", 1)) {
+      int tcols2 = 32;
+      while (tcols2 < 2 * L.NT) tcols2 *= 2;
+      // resident CTAs per SM: shared memory (1 KB reserved per CTA), registers (128/thread -> 2 CTAs of 192 threads for the
+      // wide variant, 80/thread -> 4 for the narrow one), TMEM columns.  Persistent only if doubling the TMEM columns does
+      // not cost a resident CTA (N = 192 would drop from 2 to 1 CTA/SM) and there is more than one wave of tiles.
+      int occ = (int)((227u * 1024u) / (smem + 1024u));
+      occ = std::min(occ, L.NT >= 128 ? 2 : 4);
+      const int occ_np = std::min(occ, 512 / L.tmem_cols), occ_p = std::min(occ, 512 / tcols2);
+      if (occ_p >= 1 && occ_p == occ_np && a.tiles_total > occ_p * g_sm_count) {
+        grid = occ_p * g_sm_count;
+        a.acc_stages = 2;
+        a.tmem_cols = tcols2;
+      }
     }
+    g_conv_last_grid = grid;
+    launch_k(kern, dim3(grid), dim3(threads), smem, st, a);
   }
 }
 
@@ -1571,9 +1589,10 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
       CUDA_CHECK(cudaDeviceSynchronize());
       std::vector<long long> h(nctas * 8);
       CUDA_CHECK(cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost));
+      const size_t launched = (size_t)g_conv_last_grid;
       long long t_min = h[0], t_max = h[7], s_max = h[0];
       double d[5] = {0, 0, 0, 0, 0}, life = 0;
-      for (size_t c = 0; c < nctas; ++c) {
+      for (size_t c = 0; c < launched; ++c) {
         const long long* t = &h[c * 8];
         t_min = std::min(t_min, t[0]); t_max = std::max(t_max, t[7]); s_max = std::max(s_max, t[0]);
         for (int i = 0; i < 5; ++i) d[i] += (double)(t[i + 2] - t[i + 1]);
@@ -1581,8 +1600,8 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
       }
       fprintf(stderr, "  trace: %zu CTAs (ksplit %d, NT %d, kblk %d, stages ~), span %.1f us, last start +%.1f us, mean CTA life %.1f us; "
               "mean cycles: setup %.0f, first-operands %.0f, mma-issue %.0f, drain %.0f, epilogue %.0f\n",
-              nctas, ks, Lt.NT, Lt.kblk, (t_max - t_min) / 1e3, (s_max - t_min) / 1e3, life / nctas / 1e3, d[0] / nctas, d[1] / nctas,
-              d[2] / nctas, d[3] / nctas, d[4] / nctas);
+              launched, ks, Lt.NT, Lt.kblk, (t_max - t_min) / 1e3, (s_max - t_min) / 1e3, life / launched / 1e3, d[0] / launched, d[1] / launched,
+              d[2] / launched, d[3] / launched, d[4] / launched);
     }
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));

@@ -17,6 +17,12 @@ SHAPES = [  # B, Cin, Cout, T, K, d
     (1, 768, 768, 624, 3, 1),
     (1, 384, 384, 624, 3, 1),
     (1, 1536, 1536, 312, 1, 1),
+    (1, 384, 384, 10000, 7, 1),
+    (1, 192, 192, 20000, 7, 1),
+    (1, 96, 96, 40000, 7, 1),
+    (1, 48, 48, 80000, 7, 1),
+    (1, 32, 32, 160000, 7, 1),
+    (1, 32, 32, 160000, 11, 1),
     (8, 384, 384, 10000, 7, 1),
     (8, 192, 192, 20000, 7, 1),
     (8, 96, 96, 40000, 7, 1),
