@@ -248,12 +248,17 @@ static int pick_nt(const ConvLayer& L, int M, int B) {
   const int cout_pad = round_up(L.Cout, 16);
   const long m = (long)((M + kTileM - 1) / kTileM) * B * L.nphase;
   const long want = (long)(0.6 * g_sm_count);
+  // Measured (ALCM_TRACE, dbg flags): these launches are bound by fixed per-CTA costs and the split-K fix-up, not by
+  // operand traffic - so first look for the widest tile that fills the GPU WITHOUT a K split, then with a split of 2.
   int best = L.NT;
-  for (int nt : {L.NT, 64, 32}) {
-    if (nt > L.NT || cout_pad % nt != 0) continue;
-    best = nt;
-    const long ctas = m * (cout_pad / nt);
-    if (ctas >= want || (L.nkb >= 2 && 2 * ctas >= want)) break;
+  const int mode = env_int("ALCM_RETILE_MODE", 1);
+  for (int pass = (mode ? 0 : 1); pass < 2; ++pass) {
+    for (int nt : {L.NT, 64, 32}) {
+      if (nt > L.NT || cout_pad % nt != 0) continue;
+      best = nt;
+      const long ctas = m * (cout_pad / nt);
+      if (ctas >= want || (pass == 1 && L.nkb >= 2 && 2 * ctas >= want)) return best;
+    }
   }
   return best;
 }

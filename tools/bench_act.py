@@ -15,5 +15,5 @@ for prec in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["bf16", "tf32"]):
         cpad = (Cc + 15) // 16 * 16
         byt = B * cpad * T * (4 + osz)
         ms = C.c_float()
-        _lib.check(lib.alcm_bench_act(ctx, B, Cc, T, _lib.PREC[prec], 20, C.byref(ms)))
+        _lib.check(lib.alcm_bench_act(ctx, B, Cc, T, _lib.PREC[prec], 100, C.byref(ms)))
         print(f"{prec} B={B} C={Cc} T={T} ({byt / 1e6:.0f} MB): {ms.value * 1e3:8.1f} us {byt / ms.value / 1e6:7.0f} GB/s", flush=True)

@@ -36,6 +36,6 @@ for prec in precs:
         out = []
         for dbg in dbgs:
             ms = C.c_float()
-            _lib.check(lib.alcm_bench_conv(ctx, B, Cin, Cout, T, K, d, _lib.PREC[prec], 10, dbg, C.byref(ms)))
+            _lib.check(lib.alcm_bench_conv(ctx, B, Cin, Cout, T, K, d, _lib.PREC[prec], 100, dbg, C.byref(ms)))
             out.append(f"dbg{dbg}: {ms.value * 1e3:8.1f} us {fl / ms.value / 1e9:7.1f} TF/s")
         print(f"{prec} B={B} C={Cin}->{Cout} T={T} K={K}: " + " | ".join(out), flush=True)
