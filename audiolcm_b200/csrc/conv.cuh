@@ -55,6 +55,8 @@ struct ConvArgs {
   // to arrive at a tile (counter in `tile_ctr`, self-resetting) sums them in split order and runs the
   // epilogue, so the result does not depend on arrival order.
   int ksplit;
+  int cluster_splitk;      // 1: the ksplit CTAs of a tile form a thread-block cluster and reduce through distributed shared
+                           //    memory (each CTA owns NT/ksplit columns); 0: global workspace + last-arriver fix-up
   float* ws;               // [tile][ksplit][NT/4][128] float4
   unsigned int* tile_ctr;  // [tile]
   long long* trace;        // micro-benchmark only: 8 timestamps per CTA (tools/bench_conv.py with ALCM_TRACE=1)
@@ -110,12 +112,13 @@ struct ConvTile {
 template <bool FUSED>
 __device__ __forceinline__ ConvTile conv_tile(const ConvArgs& a, int tile) {
   ConvTile t;
-  t.mt = tile % a.tiles_m;
-  const int r = tile / a.tiles_m;
+  // the K splits of one output tile are consecutive CTAs (= one cluster when the reduction goes through DSMEM)
+  t.zs = tile % a.ksplit;
+  const int tl = tile / a.ksplit;
+  t.mt = tl % a.tiles_m;
+  const int r = tl / a.tiles_m;
   t.nt = r % a.n_tiles;
-  const int z = r / a.n_tiles;
-  t.zs = z % a.ksplit;
-  t.zb = z / a.ksplit;
+  t.zb = r / a.n_tiles;
   t.b = t.zb / a.nphase;
   t.ph = t.zb % a.nphase;
   t.kb0 = (int)((long)t.zs * a.nkb / a.ksplit);
@@ -413,6 +416,49 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
           emit(c0, v, rr, oo);
         }
+      } else if (a.cluster_splitk) {
+        // K splits of this tile = the CTAs of this cluster.  Reduce-scatter through distributed shared memory: every CTA
+        // owns NT/ksplit columns and receives the other CTAs' partial sums for them in its own (drained) pipeline
+        // buffers: staging[source split][column group][row] float4.  Barrier A: all accumulators of the cluster are
+        // complete, so every CTA's pipeline buffers may be overwritten; barrier B (after the role branches): all
+        // pushes have landed.
+        cluster_arrive();
+        cluster_wait();
+        const int nqs = nq / ksplit;
+        const uint32_t stg = smem_u32(smem);
+        for (int c0 = 0; c0 < a.NT; c0 += 16) {
+          uint32_t u[16];
+          tmem_ld_x16(tmem_d + ((uint32_t)(qd * 32) << 16) + c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int cq = (c0 >> 2) + g, owner = cq / nqs, cql = cq - owner * nqs;
+            const uint32_t laddr = stg + (uint32_t)(((T.zs * nqs + cql) * kTileM + row) * 16);
+            st_shared_cluster_f4(map_shared_rank(laddr, (uint32_t)owner),
+                                 make_float4(__uint_as_float(u[4 * g]), __uint_as_float(u[4 * g + 1]), __uint_as_float(u[4 * g + 2]),
+                                             __uint_as_float(u[4 * g + 3])));
+          }
+        }
+        cluster_arrive();
+        cluster_wait();
+        // my column slice: sum the ksplit partials in split order (deterministic), then the usual epilogue
+        const float4* st4 = reinterpret_cast<const float4*>(smem);
+        for (int cql = 0; cql < nqs; ++cql) {
+          const int cq = T.zs * nqs + cql;
+          float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int s = 0; s < ksplit; ++s) {
+            const float4 p = st4[(s * nqs + cql) * kTileM + row];
+            r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
+          }
+          if (!(valid && cq < nq_valid)) continue;
+          const float4 bb = *reinterpret_cast<const float4*>(s_bias + cq * 4);
+          r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w;
+          const size_t off = off0 + (size_t)cq * plane4;
+          if (has_res) { const float4 rr = res4[off]; r.x += rr.x; r.y += rr.y; r.z += rr.z; r.w += rr.w; }
+          r.x *= scale; r.y *= scale; r.z *= scale; r.w *= scale;
+          if (accum) { const float4 oo = out4[off]; r.x += oo.x; r.y += oo.y; r.z += oo.z; r.w += oo.w; }
+          if (a.out != nullptr) out4[off] = r;
+        }
       } else {
         // partial tile -> workspace, [col/4][row] float4 so that a warp writes 512 contiguous bytes
         const size_t wtile = ((size_t)T.zb * a.n_tiles + T.nt) * a.tiles_m + T.mt;
@@ -464,6 +510,12 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
       }
       if (trace && it == 0 && threadIdx.x == 64) trace[6] = clock64();
     }
+  }
+  if (!FUSED && ksplit > 1 && a.cluster_splitk && !(warp >= 2 && warp < 6)) {
+    cluster_arrive();  // barrier A and B of the DSMEM split-K reduction (the epilogue warps arrive inside their branch)
+    cluster_wait();
+    cluster_arrive();
+    cluster_wait();
   }
   if constexpr (FUSED) {
     pdl_wait();

@@ -112,6 +112,7 @@ static inline int opnd_esz(int prec) { return prec == ALCM_PREC_BF16 ? 2 : 4; }
 // the SMs.  So it is off by default and a per-plan choice (OpList::pdl, or ALCM_PDL=1 to force it).
 static int g_pdl = -1;          // ALCM_PDL: -1 unset (per-plan default), 0 never, 1 always
 static thread_local int t_pdl = 0;  // set by OpList::run / run_lanes around the launches of a plan
+static thread_local int t_cluster_x = 1;  // >1: the next launch_k() launches thread-block clusters of this many CTAs (x)
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   static const int env_pdl = [] { const char* e = getenv("ALCM_PDL"); return e ? atoi(e) : -1; }();
@@ -119,11 +120,21 @@ static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (g_pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (t_cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)t_cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+    t_cluster_x = 1;
+  }
   cfg.attrs = at;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = n;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
 }
 
@@ -263,6 +274,61 @@ static int pick_nt(const ConvLayer& L, int M, int B) {
   return best;
 }
 
+// Tile shape of a launch whose output has few time tiles (the VAE at T = 312/624, conv_pre): N tile and K split
+// chosen together with a small cost model of one CTA - main loop (MMAs at max(N/2, 32+N/4) cycles, ~300 cycles per
+// mbarrier round trip) plus the cluster reduce-scatter (two cluster barriers, N/16 TMEM->DSMEM pushes) - among the
+// shapes that fit one wave.  Measured: at these sizes the launch is bound by per-CTA fixed costs, not by operand
+// traffic, so wide tiles (efficient MMAs) with a split of 4-8 reduced through DSMEM beat narrow un-split ones.
+static void conv_kernel_for(int prec, int NT, bool fused, void (**kern)(ConvArgs), int* threads);
+
+// CTAs that can be co-resident when launched as clusters of `ks` (GPC boundaries cost a few SMs): one big-smem CTA per SM
+static long cluster_capacity(int prec, int ks) {
+  static long cap[2][9] = {{0}};
+  const int pi = prec == ALCM_PREC_BF16 ? 0 : 1;
+  if (ks <= 1) return g_sm_count;
+  if (cap[pi][ks] == 0) {
+    void (*kern)(ConvArgs) = nullptr;
+    int threads = 192;
+    conv_kernel_for(prec, 128, false, &kern, &threads);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(ks * 64); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 200 * 1024;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ks; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_sm_count / ks * 3 / 4; }
+    cap[pi][ks] = (long)n * ks;
+  }
+  return cap[pi][ks];
+}
+
+static bool choose_cluster_tile(const ConvLayer& L, int M, int B, int* nt_out, int* ks_out) {
+  if (L.prec == ALCM_PREC_FP32 || !env_int("ALCM_CLUSTER_SPLITK", 1)) return false;
+  const int cout_pad = round_up(L.Cout, 16);
+  const long m = (long)((M + kTileM - 1) / kTileM) * B * L.nphase;
+  if (m * ((cout_pad + L.NT - 1) / L.NT) * 2 > (long)g_sm_count) return false;  // the default tiling already fills the GPU
+  double best = 1e30;
+  bool found = false;
+  for (int nt : {256, 128, 64, 32}) {
+    if (cout_pad % nt != 0) continue;
+    for (int ks : {1, 2, 4, 8}) {
+      if (ks > L.nkb || (nt / 4) % ks != 0) continue;
+      const long ctas = m * (cout_pad / nt) * ks;
+      if (ctas > cluster_capacity(L.prec, ks)) continue;
+      const double cyc_mma = std::max(nt / 2.0, 32.0 + nt / 4.0);
+      const int kbs = (L.nkb + ks - 1) / ks;
+      double cost = kbs * (L.ntaps * (L.kblk / 2) * cyc_mma + 300.0);
+      if (ks > 1) cost += 900.0 + (nt / 16) * 70.0 + (nt / 4 / ks) * ks * 8.0;
+      cost += (nt / 16) * 40.0 / (ks > 1 ? ks : 1);                                  // epilogue stores
+      cost *= std::max(1.0, 0.6 * g_sm_count / (double)ctas);                        // idle SMs
+      if (cost < best) { best = cost; *nt_out = nt; *ks_out = ks; found = true; }
+    }
+  }
+  return found;
+}
+
 struct RetileCache {  // owned by a model: re-tiled copies of its layers, keyed by (packed weights, N tile)
   std::map<std::pair<const void*, int>, ConvLayer> m;
 };
@@ -314,7 +380,7 @@ struct Op {
 // Pipeline shape of one launch.  Taps per weight stage: enough MMAs per mbarrier round trip to cover
 // ~512 tensor cycles (see conv.cuh).  Ring depth: with at most one CTA per SM use most of the 227 KB
 // (more bytes in flight hide the L2/HBM latency of the weight stream); otherwise leave room for 2 CTAs/SM.
-static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused, int* stages, int* tpg, int* a_stages, uint32_t* smem) {
+static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused, bool cluster, int* stages, int* tpg, int* a_stages, uint32_t* smem) {
   const uint32_t budget = (uint32_t)env_int("ALCM_SMEM_BUDGET", ctas <= (long)g_sm_count ? 200 * 1024 : 100 * 1024);
   const double cyc_mma = std::max(L.NT / 2.0, 32.0 + L.NT / 4.0);
   const double cyc_tap = (L.kblk / 2) * cyc_mma;
@@ -340,6 +406,11 @@ static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused,
     while (a2 + (uint32_t)S * t * blob < staging && S < 12) ++S;
     REQUIRE(a2 + (uint32_t)S * t * blob >= staging, "fused activation: staging tile does not fit under the pipeline buffers");
   }
+  if (cluster) {  // DSMEM split-K: the partial tiles pushed by the other CTAs overlay the (drained) A and W buffers
+    const uint32_t staging = (uint32_t)L.NT * 512u;
+    while (a2 + (uint32_t)S * t * blob < staging && S < 12 && fixed + (uint32_t)(S + 1) * t * blob <= 220u * 1024u) ++S;
+    REQUIRE(a2 + (uint32_t)S * t * blob >= staging, "cluster split-K: staging does not fit under the pipeline buffers");
+  }
   *stages = S;
   *tpg = t;
   *a_stages = AS;
@@ -353,6 +424,7 @@ static int g_conv_last_grid = 0;            // micro-benchmark only: CTAs of the
 
 struct SplitK {  // per-launch split-K resources (see ConvArgs::ksplit)
   int ksplit = 1;
+  int cluster = 0;  // reduce through a thread-block cluster's distributed shared memory instead of the global workspace
   float* ws = nullptr;
   unsigned int* ctr = nullptr;
 };
@@ -373,6 +445,13 @@ static int pick_ksplit(const ConvLayer& L, int M, int B, bool fused = false) {
   const long ctas = (long)conv_m_tiles(M, fused) * L.n_tiles * B * L.nphase;
   if (ctas * 2 > (long)g_sm_count) return 1;
   return (int)std::max<long>(1, std::min<long>(std::min<long>(L.nkb, g_sm_count / ctas), 8));
+}
+
+static void conv_kernel_for(int prec, int NT, bool fused, void (**kern)(ConvArgs), int* threads) {
+  *threads = 192;
+  if (fused) { *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, true> : conv_umma_kernel<1, 2, true>; *threads = 256; }
+  else if (NT >= 128) *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, false> : conv_umma_kernel<1, 2, false>;
+  else *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 3, false> : conv_umma_kernel<1, 3, false>;
 }
 
 // `out` may be empty (p == nullptr) for a fused launch that only produces the activated operand planes.
@@ -405,7 +484,7 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
     a.kchunks = L.kchunks; a.kblk = L.kblk; a.nkb = L.nkb;
     a.NT = L.NT; a.n_tiles = L.n_tiles; a.tmem_cols = L.tmem_cols;
     a.idesc = L.idesc; a.w_phase_stride = L.phase_stride;
-    a.ksplit = sk.ksplit; a.ws = sk.ws; a.tile_ctr = sk.ctr;
+    a.ksplit = sk.ksplit; a.ws = sk.ws; a.tile_ctr = sk.ctr; a.cluster_splitk = sk.cluster;
     a.trace = g_conv_trace;
     if (fused) {
       a.act_out = fa.out.p; a.ag = fa.out.g; a.ea = fa.ea; a.ib = fa.ib;
@@ -415,14 +494,12 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
     a.tiles_total = a.tiles_m * L.n_tiles * B * L.nphase * sk.ksplit;
     a.acc_stages = 1;
     uint32_t smem = 0;
-    pick_pipeline(L, (long)a.tiles_total, sk.ksplit, fused, &a.w_stages, &a.tpg, &a.a_stages, &smem);
+    pick_pipeline(L, (long)a.tiles_total, sk.ksplit, fused, sk.cluster != 0, &a.w_stages, &a.tpg, &a.a_stages, &smem);
     // wide tiles are limited to 2 CTAs/SM by shared memory anyway and get the registers; narrow ones want
     // occupancy; the fused epilogue runs the (register-hungry) activation on 8 warps
     void (*kern)(ConvArgs) = nullptr;
     int threads = 192;
-    if (fused) { kern = (L.prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, true> : conv_umma_kernel<1, 2, true>; threads = 256; }
-    else if (L.NT >= 128) kern = (L.prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, false> : conv_umma_kernel<1, 2, false>;
-    else kern = (L.prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 3, false> : conv_umma_kernel<1, 3, false>;
+    conv_kernel_for(L.prec, L.NT, fused, &kern, &threads);
     // Persistent launch for multi-wave grids: one CTA per resident slot loops over tiles with two TMEM accumulators,
     // so barrier/TMEM setup is paid once per CTA and the epilogue of tile i overlaps the main loop of tile i+1.
     int grid = a.tiles_total;
@@ -442,6 +519,7 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
       }
     }
     g_conv_last_grid = grid;
+    if (sk.cluster) t_cluster_x = sk.ksplit;
     launch_k(kern, dim3(grid), dim3(threads), smem, st, a);
   }
 }
@@ -464,7 +542,9 @@ struct OpList {
   void conv_act(const ConvLayer& L0, const PlaneT& x, const PlaneT* out, const PlaneT* res, float scale, int accum,
                 const PlaneT* aout, const float* ea, const float* ib, int round_tf32) {
     const int M = x.T;  // rows per batch item are input time steps (== output steps / nphase)
-    const ConvLayer& L = (war && cache) ? retile(*war, *cache, L0, pick_nt(L0, M, x.B)) : L0;
+    int nt_c = 0, ks_c = 1;
+    const bool clustered = war && cache && ar && aout == nullptr && choose_cluster_tile(L0, M, x.B, &nt_c, &ks_c);
+    const ConvLayer& L = (war && cache) ? retile(*war, *cache, L0, clustered ? nt_c : pick_nt(L0, M, x.B)) : L0;
     const bool fused = aout != nullptr;
     REQUIRE(out || fused, "conv: no output");
     REQUIRE(x.esz == opnd_esz(L.prec), "conv: operand dtype mismatch");
@@ -492,8 +572,9 @@ struct OpList {
     FusedAct fa;
     if (fused) { fa.out = *aout; fa.ea = ea; fa.ib = ib; fa.round_tf32 = round_tf32; }
     SplitK sk;
-    if (ar) sk.ksplit = pick_ksplit(L, M, x.B, fused);
-    if (sk.ksplit > 1) {
+    if (clustered) { sk.ksplit = ks_c; sk.cluster = ks_c > 1; }
+    else if (ar) sk.ksplit = pick_ksplit(L, M, x.B, fused);
+    if (sk.ksplit > 1 && !sk.cluster) {
       const size_t tiles = (size_t)conv_m_tiles(M, fused) * L.n_tiles * x.B * L.nphase;
       const size_t need = tiles * sk.ksplit * (size_t)L.NT * kTileM * 4;
       if (need > ws_bytes[cur_lane]) {  // ops of one lane run in stream order and can share the partial-tile workspace
@@ -1583,8 +1664,10 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     g_conv_dbg = 0;
     CUDA_CHECK(err);
     if (env_int("ALCM_TRACE", 0) && precision != ALCM_PREC_FP32) {  // one more launch with per-CTA timestamps
-      const ConvLayer& Lt = retile(ar, rcache, L, pick_nt(L, T, B));
-      const int ks = pick_ksplit(Lt, T, B, bench_fused);
+      int nt_c = 0, ks_c = 1;
+      const bool clustered = !bench_fused && choose_cluster_tile(L, T, B, &nt_c, &ks_c);
+      const ConvLayer& Lt = retile(ar, rcache, L, clustered ? nt_c : pick_nt(L, T, B));
+      const int ks = clustered ? ks_c : pick_ksplit(Lt, T, B, bench_fused);
       const size_t nctas = (size_t)conv_m_tiles(T, bench_fused) * Lt.n_tiles * B * Lt.nphase * ks;
       long long* tr = static_cast<long long*>(ar.alloc(nctas * 8 * sizeof(long long), true));
       CUDA_CHECK(cudaDeviceSynchronize());
