@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -143,3 +144,29 @@ def test_time_sharded_vocode_matches_unsharded_gloo():
     assert got.shape == ref.shape == (1, T * 256)
     assert np.abs(got - ref).max() < 1e-9
     assert halo_frames() == 34
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints exactly one JSON line with
+    the contract's keys; on a box without a GPU the product arm must refuse instead of falling back."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "audio-s/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    import torch
+    if not torch.cuda.is_available():
+        ours = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                              timeout=600, cwd=root)
+        assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)
