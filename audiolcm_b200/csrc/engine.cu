@@ -1471,7 +1471,9 @@ static void run_conv_test(alcm_ctx* ctx, ConvKind kind, const float* x, const fl
   launch_pack(x, xin, Cin, T, 1.f, precision, st);
   if (res) launch_pack(res, rp, Cout, T * L.nphase, 1.f, ALCM_PREC_FP32, st);
   OpList ol;
+  RetileCache rcache;
   ol.ar = &ar;
+  ol.war = &ar; ol.cache = &rcache;  // same per-launch tile choice (N tile, K split, cluster reduction) as the plans
   ol.conv(L, xin, out, res ? &rp : nullptr);
   CUDA_CHECK(cudaDeviceSynchronize());  // workspace memsets
   ol.run(st);

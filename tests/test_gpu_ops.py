@@ -70,6 +70,10 @@ CONV_CASES = [
     (1, 48, 48, 1, 3, 1),
     (1, 5, 3, 9, 3, 1),
     (1, 96, 80, 129, 5, 1),
+    (1, 1536, 1536, 312, 3, 1),   # VAE mid block: cluster split-K (DSMEM reduce-scatter), re-tiled N
+    (1, 768, 768, 624, 3, 1),
+    (2, 384, 384, 624, 3, 1),
+    (1, 1536, 4608, 312, 1, 1),   # merged q/k/v
 ]
 
 
