@@ -262,16 +262,13 @@ __global__ void __launch_bounds__(kActThreads, (R == 4 ? 6 : (R == 6 ? 5 : 4))) 
 // instruction chain per block - what the small (batch-1) launches need.  fp32 / tf32 output: the two planes
 // are simply two independent output planes.
 constexpr int kPairThreads = 128, kPairHalf = 64;
-constexpr int kPairTile = kPairHalf * kActR;               // 256 outputs per block
-constexpr int kPairRows = kPairTile + 10;
-constexpr int kPairSlots = kPairRows + (kPairRows >> 3) + 1;
-
-template <bool BF16OUT, bool FAST>
-__global__ void __launch_bounds__(kPairThreads, 6) act1d_pair_kernel(const __grid_constant__ ActArgs a) {
+template <bool BF16OUT, bool FAST, int R>  // R outputs per thread: tile = 64 * R outputs
+__global__ void __launch_bounds__(kPairThreads, (R == 4 ? 6 : (R == 6 ? 5 : 4))) act1d_pair_kernel(const __grid_constant__ ActArgs a) {
   pdl_launch_dependents();
   pdl_wait();
+  constexpr int kPairTile = kPairHalf * R, kPairRows = kPairTile + 10, kPairSlots = kPairRows + (kPairRows >> 3) + 1;
   __shared__ float4 sx[2][kPairSlots];
-  __shared__ uint2 xch[kPairHalf][kActR];
+  __shared__ uint2 xch[kPairHalf][R];
   const int tid = threadIdx.x;
   const int p = tid >> 6, ht = tid & (kPairHalf - 1);  // plane of the pair, thread within the plane
   const int t0 = blockIdx.x * kPairTile;
@@ -296,43 +293,43 @@ __global__ void __launch_bounds__(kPairThreads, 6) act1d_pair_kernel(const __gri
   }
   __syncthreads();
 
-  const int m0 = t0 + kActR * ht;
+  const int m0 = t0 + R * ht;
   const bool live = m0 < T;
-  const bool edge = live && ((m0 < 3) || (m0 + 6 > T - 1));
-  float4 res[kActR];
+  const bool edge = live && ((m0 < 3) || (m0 + R + 2 > T - 1));
+  float4 res[R];
   if (live) {
     const int chunk = 2 * pc + p;
     const float4 ea = *reinterpret_cast<const float4*>(a.ea + chunk * 4);
     const float4 ib = *reinterpret_cast<const float4*>(a.ib + chunk * 4);
-    if (__any_sync(__activemask(), edge)) act_plane<FAST, true>(sx[p], ht, m0, t0, T, ea, ib, res);
-    else act_plane<FAST, false>(sx[p], ht, m0, t0, T, ea, ib, res);
+    if (__any_sync(__activemask(), edge)) act_plane<FAST, true, R>(sx[p], ht, m0, t0, T, ea, ib, res);
+    else act_plane<FAST, false, R>(sx[p], ht, m0, t0, T, ea, ib, res);
   }
   if (!BF16OUT) {
     if (!live) return;
     float4* op = reinterpret_cast<float4*>(a.out) + ((size_t)b * a.og.nchunk + (2 * pc + p)) * a.og.Tp + a.og.pad;
 #pragma unroll
-    for (int r = 0; r < kActR; ++r) {
+    for (int r = 0; r < R; ++r) {
       if (m0 + r >= T) break;
       float4 o = res[r];
       if (a.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
       op[m0 + r] = o;
     }
   } else {
-    uint2 pk[kActR];
+    uint2 pk[R];
 #pragma unroll
-    for (int r = 0; r < kActR; ++r) {
+    for (int r = 0; r < R; ++r) {
       __nv_bfloat162 h0 = __floats2bfloat162_rn(res[r].x, res[r].y), h1 = __floats2bfloat162_rn(res[r].z, res[r].w);
       pk[r] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
     }
     if (p == 0 && live) {
 #pragma unroll
-      for (int r = 0; r < kActR; ++r) xch[ht][r] = pk[r];
+      for (int r = 0; r < R; ++r) xch[ht][r] = pk[r];
     }
     __syncthreads();
     if (p == 1 && live) {
       uint4* op = reinterpret_cast<uint4*>(a.out) + ((size_t)b * a.og.nchunk + pc) * a.og.Tp + a.og.pad;
 #pragma unroll
-      for (int r = 0; r < kActR; ++r) {
+      for (int r = 0; r < R; ++r) {
         if (m0 + r >= T) break;
         const uint2 lo = xch[ht][r];
         op[m0 + r] = make_uint4(lo.x, lo.y, pk[r].x, pk[r].y);

@@ -612,17 +612,22 @@ struct OpList {
     // (batch 64, last stage: 3.48 TB/s bf16 out, 4.63 TB/s = 72 % of the HBM peak fp32 out)
     const long blocks_r6 = (long)((T + 6 * kActThreads - 1) / (6 * kActThreads)) * nch * B;
     int variant = 0;
-    if (oesz == 2 && blocks_wide < 24L * g_sm_count) variant = 1;
+    if (oesz == 2 && blocks_wide < 24L * g_sm_count) variant = 5;  // pair form, 6 outputs/thread: batch-1 decode 3.53 -> 3.45 ms vs 4 outputs/thread
     else if (blocks_r6 >= 8L * g_sm_count) variant = 3;
     variant = env_int("ALCM_ACT_VARIANT", variant);
     op.fn = [=](cudaStream_t st) {
-      if (variant == 1) {
-        const dim3 grid((T + kPairTile - 1) / kPairTile, nch32 / 2, B);
+      if (variant == 1 || variant == 5 || variant == 6) {  // pair form, 4 / 6 / 8 outputs per thread
+        const int tile = kPairHalf * (variant == 1 ? 4 : (variant == 5 ? 6 : 8));
+        const dim3 grid((T + tile - 1) / tile, nch32 / 2, B);
         if (oesz == 4) {
-          if (fast) launch_k(act1d_pair_kernel<false, true>, dim3(grid), dim3(kPairThreads), 0, st, a);
-          else launch_k(act1d_pair_kernel<false, false>, dim3(grid), dim3(kPairThreads), 0, st, a);
+          if (fast) launch_k(act1d_pair_kernel<false, true, 4>, grid, dim3(kPairThreads), 0, st, a);
+          else launch_k(act1d_pair_kernel<false, false, 4>, grid, dim3(kPairThreads), 0, st, a);
+        } else if (variant == 1) {
+          launch_k(act1d_pair_kernel<true, true, 4>, grid, dim3(kPairThreads), 0, st, a);
+        } else if (variant == 5) {
+          launch_k(act1d_pair_kernel<true, true, 6>, grid, dim3(kPairThreads), 0, st, a);
         } else {
-          launch_k(act1d_pair_kernel<true, true>, dim3(grid), dim3(kPairThreads), 0, st, a);
+          launch_k(act1d_pair_kernel<true, true, 8>, grid, dim3(kPairThreads), 0, st, a);
         }
         return;
       }
