@@ -378,10 +378,12 @@ struct Op {
 
 
 // Pipeline shape of one launch.  Taps per weight stage: enough MMAs per mbarrier round trip to cover
-// ~512 tensor cycles (see conv.cuh).  Ring depth: with at most one CTA per SM use most of the 227 KB
-// (more bytes in flight hide the L2/HBM latency of the weight stream); otherwise leave room for 2 CTAs/SM.
+// ~1024 tensor cycles (see conv.cuh).  Ring depth: ~100 KB (2 CTAs/SM) for multi-wave grids; single-wave grids
+// get 120 KB - measured on the batch-1 decode (tools/sweep_env.sh): 200 KB 3.450 ms, 150 KB 3.496, 120 KB 3.424
+// (operand traffic is not the limiter at that size, and a smaller footprint leaves room for the other lanes' blocks).
 static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused, bool cluster, int* stages, int* tpg, int* a_stages, uint32_t* smem) {
-  const uint32_t budget = (uint32_t)env_int("ALCM_SMEM_BUDGET", ctas <= (long)g_sm_count ? 200 * 1024 : 100 * 1024);
+  const uint32_t budget = (uint32_t)env_int("ALCM_SMEM_BUDGET", ctas <= (long)g_sm_count ? env_int("ALCM_SMEM_BUDGET_1W", 120 * 1000)
+                                                                                          : env_int("ALCM_SMEM_BUDGET_MW", 100 * 1024));
   const double cyc_mma = std::max(L.NT / 2.0, 32.0 + L.NT / 4.0);
   const double cyc_tap = (L.kblk / 2) * cyc_mma;
   // ~1024 tensor cycles per weight stage (measured: stage-1 conv at batch 1, taps per stage 1/2/3/4 -> 802/978/1039/1046 TFLOP/s)
