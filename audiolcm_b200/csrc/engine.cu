@@ -871,11 +871,12 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
     C = S.C; Tc *= S.u;
     PlaneT X = make_planes(P.ar, B, C, Tc, 4);
     P.ol.conv(S.up, up_in, X, nullptr);
-    // The nk AMP blocks of a stage are independent chains.  When one conv launch cannot fill the
-    // machine (few time tiles: batch-1 clips) they run as parallel graph lanes with private buffers;
-    // otherwise they run back to back, share buffers and accumulate straight into XS.
+    // The nk AMP blocks of a stage are independent chains.  Up to ~20 waves of conv CTAs per launch they run as
+    // parallel graph lanes with private buffers (measured, tools/sweep_env.sh / sweep_lanes.sh: batch-1 decode 3.43 ms
+    // with a 3-wave threshold, 3.30 ms with every stage in lanes; batch 4: 10.84 -> 10.05 ms); beyond that (batch 64)
+    // they run back to back, share buffers and accumulate straight into XS.
     const long conv_ctas = (long)((Tc + kTileM - 1) / kTileM) * std::max(1, round_up(C, 16) / 128) * B;
-    const bool parallel = nk > 1 && nk <= kMaxLanes && env_int("ALCM_LANES", 1) && conv_ctas < 3L * g_sm_count;
+    const bool parallel = nk > 1 && nk <= kMaxLanes && env_int("ALCM_LANES", 1) && conv_ctas < (long)env_int("ALCM_LANE_WAVES", 20) * g_sm_count;
     PlaneT XS = make_planes(P.ar, B, C, Tc, 4);
     std::vector<PlaneT> Z;
     PlaneT R, R2, Y, A, A2;
