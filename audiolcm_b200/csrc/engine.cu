@@ -883,7 +883,7 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
     // Measured on B200 (round 1): with the current register-blocked activation code the fused epilogue leaves the
     // tensor pipe idle for longer than a separate launch costs (batch-1 decode 4.53 ms fused vs 4.05 ms unfused), so
     // the fused chain is opt-in until the activation phase overlaps the next tile's main loop.
-    const bool fuse = (prec != ALCM_PREC_FP32) && env_int("ALCM_FUSE_ACT", 0);
+    const bool fuse = (prec != ALCM_PREC_FP32) && (env_int("ALCM_FUSE_ACT", 0) || ((env_int("ALCM_FUSE_STAGES", 0) >> i) & 1));
     if (parallel) P.ol.fork();
     for (int j = 0; j < nk; ++j) {
       const AmpBlock& bk = S.blocks[j];
