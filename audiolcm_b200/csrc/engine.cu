@@ -1577,7 +1577,6 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
     Arena ar;
     PlaneT pq = make_planes(ar, B, C, T, 4), pk = make_planes(ar, B, C, T, 4), pv = make_planes(ar, B, C, T, 4);
     PlaneT ph = make_planes(ar, B, C, T, 4);
-    float* S = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
     CUDA_CHECK(cudaDeviceSynchronize());
     launch_pack(q, pq, C, T, 1.f, ALCM_PREC_FP32, st);
     launch_pack(k, pk, C, T, 1.f, ALCM_PREC_FP32, st);
@@ -1585,7 +1584,6 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
     OpList ol;
     float* Pm = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
     float* Sp = static_cast<float*>(ar.alloc((size_t)kAttnSplit * B * T * T * 4, false));
-    (void)S;
     push_attention(ol, pq, pk, pv, ph, Sp, Pm, B, C, T);
     CUDA_CHECK(cudaDeviceSynchronize());
     ol.run(st);

@@ -483,102 +483,9 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------- attention (AttnBlock1D)
 // autoencoder1d.py:257-278: S[i][j] = scale * sum_c q[c][i] k[c][j]; P = softmax_j S;
 // h[c][i] = sum_j v[c][j] P[i][j].  q,k,v fp32 planes; S row-major [B][T][T] fp32.
-__device__ __forceinline__ float plane_elem(const float* x, const PlaneGeom& g, int b, int c, int t) {
-  return *reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(x) + plane_row_off(g, b, c >> 2, t) + (c & 3) * 4);
-}
-
-__global__ void __launch_bounds__(256) attn_scores_kernel(const float* __restrict__ q, const float* __restrict__ k, PlaneGeom g,
-                                                            int C, int T, float scale, float* __restrict__ S) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ float Qs[32][33], Ks[32][33];
-  const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32, b = blockIdx.z;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty 0..7
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {  // r = channel within tile, tx = time
-      const int c = c0 + r;
-      Qs[r][tx] = (c < C && i0 + tx < T) ? plane_elem(q, g, b, c, i0 + tx) : 0.f;
-      Ks[r][tx] = (c < C && j0 + tx < T) ? plane_elem(k, g, b, c, j0 + tx) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int c = 0; c < 32; ++c) {
-      const float kv = Ks[c][tx];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] = fmaf(Qs[c][ty * 4 + r], kv, acc[r]);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int i = i0 + ty * 4 + r, j = j0 + tx;
-    if (i < T && j < T) S[((size_t)b * T + i) * T + j] = acc[r] * scale;
-  }
-}
-
-__global__ void softmax_rows_kernel(float* __restrict__ S, int T) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int row = blockIdx.x;  // b*T + i
-  float* p = S + (size_t)row * T;
-  __shared__ float red[32];
-  float m = -INFINITY;
-  for (int j = threadIdx.x; j < T; j += blockDim.x) m = fmaxf(m, p[j]);
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  m = red[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
-  __syncthreads();
-  float s = 0.f;
-  for (int j = threadIdx.x; j < T; j += blockDim.x) {
-    const float e = expf(p[j] - m);
-    p[j] = e;
-    s += e;
-  }
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  s = 0.f;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
-  const float inv = 1.f / s;
-  for (int j = threadIdx.x; j < T; j += blockDim.x) p[j] *= inv;
-}
-
-__global__ void __launch_bounds__(256) attn_pv_kernel(const float* __restrict__ v, PlaneGeom g, const float* __restrict__ P, int C,
-                                                        int T, float* __restrict__ h, PlaneGeom hg) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ float Vs[32][33], Ps[32][33];
-  const int c0 = blockIdx.y * 32, i0 = blockIdx.x * 32, b = blockIdx.z;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int j0 = 0; j0 < T; j0 += 32) {
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-      Vs[r][tx] = (c0 + r < C && j0 + tx < T) ? plane_elem(v, g, b, c0 + r, j0 + tx) : 0.f;       // Vs[c][j]
-      Ps[r][tx] = (i0 + r < T && j0 + tx < T) ? P[((size_t)b * T + i0 + r) * T + j0 + tx] : 0.f;   // Ps[i][j]
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) {
-      const float pv = Ps[tx][j];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) acc[r] = fmaf(Vs[ty * 4 + r][j], pv, acc[r]);
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int c = c0 + ty * 4 + r, i = i0 + tx;
-    if (c < C && i < T)
-      *reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(h) + plane_row_off(hg, b, c >> 2, i) + (c & 3) * 4) = acc[r];
-  }
-}
-
-// ---- attention, second version: float4 plane loads, 64x64 / 64x128 register-blocked tiles, and a channel
-// split for the score GEMM (T = 312 gives only 25 output tiles; the partial score planes are summed - in split
-// order - by the softmax kernel).  Same arithmetic as the kernels above (fp32 FFMA), ~6x faster on the 10 s clip.
+// float4 plane loads, 64x64 / 64x128 register-blocked tiles, and a channel split for the score GEMM (T = 312
+// gives only 25 output tiles; the partial score planes are summed - in split order - by the softmax kernel).
+// fp32 FFMA throughout (0.6 of the path's 1193 GFLOP).
 constexpr int kAttnSplit = 8;
 
 __global__ void __launch_bounds__(256) attn_scores2_kernel(const float* __restrict__ q, const float* __restrict__ k, PlaneGeom g, int C,
