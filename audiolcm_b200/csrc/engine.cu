@@ -793,6 +793,22 @@ static void capture_graph(const OpList& ol, GraphExec& ge) {
 }
 
 // ------------------------------------------------------------------------------------------ vocoder
+// Plans (buffers + CUDA graph per (B,T) shape) are cached per model; a caller that keeps changing the shape
+// (variable-length clips) must not grow the cache without bound: beyond ALCM_MAX_PLANS (default 16) the least
+// recently used plan is destroyed (cudaFree synchronises, so no kernel of it can still be in flight).
+static unsigned long long g_plan_clock = 0;
+template <class Map>
+static void evict_plans(Map& plans) {
+  const size_t cap = (size_t)std::max(1, env_int("ALCM_MAX_PLANS", 16));
+  while (plans.size() >= cap) {
+    auto victim = plans.begin();
+    for (auto it = plans.begin(); it != plans.end(); ++it)
+      if (it->second->stamp < victim->second->stamp) victim = it;
+    CUDA_CHECK(cudaDeviceSynchronize());
+    plans.erase(victim);
+  }
+}
+
 struct SnakeP { float* ea; float* ib; };
 
 struct AmpBlock {
@@ -807,6 +823,7 @@ struct VocStage {
 
 struct VocPlan {
   Arena ar;
+  unsigned long long stamp = 0;  // last use (plan cache eviction)
   int B, T, Tout;
   PlaneT mel_in;   // operand planes
   PlaneT post_in;  // fp32 planes feeding conv_post
@@ -842,8 +859,10 @@ static SnakeP make_snake(Arena& ar, const float* alpha, const float* beta, int C
 static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
   auto key = std::make_pair(B, T);
   auto it = v->plans.find(key);
-  if (it != v->plans.end()) return it->second.get();
+  if (it != v->plans.end()) { it->second->stamp = ++g_plan_clock; return it->second.get(); }
+  evict_plans(v->plans);
   std::unique_ptr<VocPlan> pl(new VocPlan());
+  pl->stamp = ++g_plan_clock;
   VocPlan& P = *pl;
   P.B = B; P.T = T;
   P.ol.ar = &P.ar;
@@ -979,6 +998,7 @@ struct VaeLevel { std::vector<ResBlock> blocks; bool has_up = false; ConvLayer u
 
 struct VaePlan {
   Arena ar;
+  unsigned long long stamp = 0;
   int B, T, Tout;
   PlaneT z_in, mel_out;
   OpList ol;
@@ -1116,8 +1136,10 @@ static PlaneT op_attn(OpList& ol, Arena& ar, const AttnBlk& at, const PlaneT& x,
 static VaePlan* vae_plan(alcm_vae* v, int B, int T) {
   auto key = std::make_pair(B, T);
   auto it = v->plans.find(key);
-  if (it != v->plans.end()) return it->second.get();
+  if (it != v->plans.end()) { it->second->stamp = ++g_plan_clock; return it->second.get(); }
+  evict_plans(v->plans);
   std::unique_ptr<VaePlan> pl(new VaePlan());
+  pl->stamp = ++g_plan_clock;
   VaePlan& P = *pl;
   P.B = B; P.T = T;
   P.ol.ar = &P.ar;

@@ -234,3 +234,15 @@ def test_vae_lightning_state_dict_and_install():
     m = _Model()
     audiolcm_b200.install(m, dd, device=DEV, precision="tf32")
     assert torch.equal(m.first_stage_model.decode(z), ref)
+
+
+def test_plan_cache_is_bounded(monkeypatch):
+    """Changing clip lengths must not grow the per-shape plan cache without bound: with ALCM_MAX_PLANS=2 the
+    least recently used plan is destroyed and rebuilt on demand, with identical results."""
+    monkeypatch.setenv("ALCM_MAX_PLANS", "2")
+    h = synth.bigvgan_config(64)
+    voc = _voc(h, synth.bigvgan_state_dict(h, seed=5), "tf32")
+    mels = {T: torch.from_numpy(synth.synth_mel(1, T, seed=T)).to(DEV) for T in (7, 12, 20, 33)}
+    first = {T: voc.vocode_tensor(m).clone() for T, m in mels.items()}      # 4 shapes through a 2-entry cache
+    for T in (7, 33, 12, 20, 7):
+        assert torch.equal(voc.vocode_tensor(mels[T]), first[T])
