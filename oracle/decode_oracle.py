@@ -119,8 +119,8 @@ def bigvgan_forward(sd, h, mel, dtype=torch.float32):
     """vocoder/bigvgan/models.py:181-203.  mel (B,num_mels,T) -> (B,1,T*prod(upsample_rates))."""
     if h["resblock"] != "1" or h["activation"] != "snakebeta" or not h["snake_logscale"]:
         raise NotImplementedError("oracle covers AMPBlock1 + snakebeta(logscale) only (the 16k config)")
-    filt = kaiser_sinc_filter(dtype=dtype)
     x = _t(mel, dtype)
+    filt = kaiser_sinc_filter(dtype=dtype).to(x.device)  # (the GPU tests also run this port as "ATen eager on the same B200")
     w, b = _wn(sd, "conv_pre", dtype)
     x = F.conv1d(x, w, b, padding=3)
     nk = len(h["resblock_kernel_sizes"])
