@@ -50,7 +50,7 @@ struct ConvArgs {
   float scale;
   int accum;
   int dbg;  // micro-benchmark only: bit0 skip weight copies, bit1 skip activation copies (results are garbage)
-  // split-K (launches with too few output tiles to fill the GPU): blockIdx.z = (b*nphase+ph)*ksplit + s,
+  // split-K (launches with too few output tiles to fill the GPU): tile index = (...)*ksplit + s (see tiles_total below),
   // split s reduces k-blocks [s*nkb/ksplit, (s+1)*nkb/ksplit); raw partial tiles go to `ws`, the last CTA
   // to arrive at a tile (counter in `tile_ctr`, self-resetting) sums them in split order and runs the
   // epilogue, so the result does not depend on arrival order.
@@ -77,7 +77,8 @@ struct ConvArgs {
 };
 
 // ---------------------------------------------------------------------------------------------
-// tcgen05 kernel.  grid = (ceil(M/128), n_tiles, B*nphase*ksplit), block = 192 threads.
+// tcgen05 kernel.  1-D grid over output tiles (or over resident CTA slots for a persistent launch), block = 192
+// threads (256 with the fused Activation1d epilogue).
 //   warp 0   : producer - per k-block one A slab per K chunk ([128+span rows] x 16 B, contiguous in
 //              the plane) and per group of `tpg` taps one bulk copy of their (contiguous) pre-packed
 //              weight blobs, all cp.async.bulk + mbarrier tx.
