@@ -452,8 +452,10 @@ static int pick_ksplit(const ConvLayer& L, int M, int B, bool fused = false) {
 static void conv_kernel_for(int prec, int NT, bool fused, void (**kern)(ConvArgs), int* threads) {
   *threads = 192;
   if (fused) { *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, true> : conv_umma_kernel<1, 2, true>; *threads = 256; }
-  else if (NT >= 128) *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, false> : conv_umma_kernel<1, 2, false>;
-  else *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 3, false> : conv_umma_kernel<1, 3, false>;
+  // one register budget for every tile width (128/thread, 2 CTAs of 192 threads per SM): a narrower, spilling
+  // 80-register build for N < 128 (4 CTAs/SM) measured slower at every batch size (batch 1: 3.31 -> 3.24 ms)
+  else *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, false> : conv_umma_kernel<1, 2, false>;
+  (void)NT;
 }
 
 // `out` may be empty (p == nullptr) for a fused launch that only produces the activated operand planes.
@@ -508,11 +510,11 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
     if (!fused && sk.ksplit == 1 && 2 * L.NT <= 512 && env_int("ALCM_PERSIST", 1)) {
       int tcols2 = 32;
       while (tcols2 < 2 * L.NT) tcols2 *= 2;
-      // resident CTAs per SM: shared memory (1 KB reserved per CTA), registers (128/thread -> 2 CTAs of 192 threads for the
-      // wide variant, 80/thread -> 4 for the narrow one), TMEM columns.  Persistent only if doubling the TMEM columns does
+      // resident CTAs per SM: shared memory (1 KB reserved per CTA), registers (128/thread -> 2 CTAs of 192 threads),
+      // TMEM columns.  Persistent only if doubling the TMEM columns does
       // not cost a resident CTA (N = 192 would drop from 2 to 1 CTA/SM) and there is more than one wave of tiles.
       int occ = (int)((227u * 1024u) / (smem + 1024u));
-      occ = std::min(occ, L.NT >= 128 ? 2 : 4);
+      occ = std::min(occ, 2);
       const int occ_np = std::min(occ, 512 / L.tmem_cols), occ_p = std::min(occ, 512 / tcols2);
       if (occ_p >= 1 && occ_p == occ_np && a.tiles_total > occ_p * g_sm_count) {
         grid = occ_p * g_sm_count;
@@ -1190,8 +1192,6 @@ static void set_kernel_attrs() {
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
 }
 
 extern "C" {
