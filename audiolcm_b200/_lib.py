@@ -64,11 +64,17 @@ SYMBOLS = {
     "alcm_vocoder_create": (C.c_int, [_P, C.POINTER(BigVGANCfg), C.POINTER(_FP), C.c_int, C.c_int, C.POINTER(_P)]),
     "alcm_vocoder_destroy": (None, [_P]),
     "alcm_vocode": (C.c_int, [_P, _FP, C.c_int, C.c_int, _FP, _P]),
+    "alcm_vocode_pcm16": (C.c_int, [_P, _FP, C.c_int, C.c_int, _FP, _P]),
+    "alcm_vocoder_plan": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "alcm_vocoder_workspace_bytes": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "alcm_vae_num_tensors": (C.c_int, [C.POINTER(VAECfg)]),
     "alcm_vae_create": (C.c_int, [_P, C.POINTER(VAECfg), C.POINTER(_FP), C.c_int, C.c_int, C.POINTER(_P)]),
     "alcm_vae_destroy": (None, [_P]),
     "alcm_vae_decode": (C.c_int, [_P, _FP, C.c_int, C.c_int, C.c_float, _FP, _P]),
+    "alcm_vae_plan": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "alcm_vae_workspace_bytes": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "alcm_decode_to_wav": (C.c_int, [_P, _P, _FP, C.c_int, C.c_int, C.c_float, _FP, _FP, _P]),
+    "alcm_decode_to_pcm16": (C.c_int, [_P, _P, _FP, C.c_int, C.c_int, C.c_float, _FP, _FP, _P]),
     "alcm_activation1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_conv1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_conv1d_act_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
@@ -77,6 +83,7 @@ SYMBOLS = {
     "alcm_groupnorm_swish_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
     "alcm_attn1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_profile_decode": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Profile), _P]),
+    "alcm_profile_stages": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Profile), C.c_int, _P]),
     "alcm_bench_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "alcm_bench_act": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "alcm_vocoder_launches": (C.c_int, [_P, C.c_int, C.c_int]),
@@ -85,7 +92,7 @@ SYMBOLS = {
 
 _lib = None
 _lock = threading.RLock()  # re-entrant: check() calls load() while ctx() holds the lock
-_ctxs: dict[int, int] = {}
+_ctxs: dict[tuple, int] = {}
 
 
 class AlcmError(RuntimeError):
@@ -118,14 +125,17 @@ def check(rc: int):
 
 
 def ctx(device_index: int) -> int:
-    """One alcm_ctx per CUDA device, created on first use."""
+    """One alcm_ctx per (CUDA device, Python thread), created on first use.  The library keeps no
+    process-global mutable state, so threads with their own ctx and their own model handles run
+    concurrently (ctypes releases the GIL for the duration of a call)."""
     lib = load()
+    key = (int(device_index), threading.get_ident())
     with _lock:
-        if device_index not in _ctxs:
+        if key not in _ctxs:
             h = _P()
             check(lib.alcm_ctx_create(C.byref(h), int(device_index)))
-            _ctxs[device_index] = h.value
-        return _ctxs[device_index]
+            _ctxs[key] = h.value
+        return _ctxs[key]
 
 
 def ptr_array(tensors):

@@ -124,6 +124,17 @@ class AutoencoderKLDecoder(object):
 
     __call__ = decode
 
+    def plan(self, B, T):
+        """Build the (B,T) plan now on the current stream (see ``VocoderBigVGAN.plan``); returns its bytes."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().alcm_vae_plan(self._h, int(B), int(T), torch.cuda.current_stream().cuda_stream))
+        return self.workspace_bytes(B, T)
+
+    def workspace_bytes(self, B, T):
+        n = C.c_size_t()
+        _lib.check(_lib.load().alcm_vae_workspace_bytes(self._h, int(B), int(T), C.byref(n)))
+        return int(n.value)
+
     def launches(self, B, T):
         return _lib.load().alcm_vae_launches(self._h, B, T)
 

@@ -338,4 +338,241 @@ __global__ void __launch_bounds__(kPairThreads, (R == 4 ? 6 : (R == 6 ? 5 : 4)))
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-phase form (round 2; the default for launches that fill the GPU).  The register-blocked kernels above
+// recompute the up-sampled halo in every thread ((R+5)/R = 1.8x of the up-FIR + snake work at R = 6) and were
+// issue-bound (ncu, round 1: issue slots 60-69 % busy at 41 % of the HBM peak).  Here every up-sampled value is
+// computed exactly once per block:
+//   stage : ONE bulk (TMA) copy per input plane brings x[t0-5 .. t0+TILE+4] into shared memory - the rows of a plane
+//           are contiguous, so there is no per-thread load / store code at all; replicate padding is patched in by
+//           the first / last block of a plane only.
+//   phase1: thread i computes U consecutive "shifted pairs" P_s = (y[2t0-5+2s], y[2t0-4+2s]) - both values come from
+//           the same 6-row window x[t0-5+s .. t0+s] - applies snake and stores them to shared memory (yo[s], ye[s]).
+//   phase2: thread i produces R consecutive outputs: out[t0+Ri+r] = sum_{d<6} yo[Ri+r+d] f[2d] + ye[Ri+r+d] f[2d+1].
+// U and R are ODD: a thread's rows are then an odd number of 16-byte units apart, which makes the 128-bit shared
+// accesses of each 8-thread phase hit 8 different bank groups without any padding slots (and keeps the x tile a
+// plain contiguous image of the plane, as the bulk copy needs).
+// Per (time step, 4-channel plane): 24 + 24 packed FMAs for the two FIRs, 24 instructions of snake, ~8 shared-memory
+// accesses - about 0.7x of the instruction count of the R = 6 register-blocked form.
+// ---------------------------------------------------------------------------------------------------------------
+template <int UR, int THREADS>
+struct ActV2Geom {
+  static constexpr int kTile = THREADS * UR;        // outputs per block
+  static constexpr int kRows = kTile + 10;          // staged x rows
+  static constexpr int kPairs = kTile + 5;          // shifted pairs
+  static constexpr int kXBytes = kRows * 16;
+  static constexpr int kYBytes = kPairs * 16;       // one of yo / ye
+  static constexpr size_t smem(int npl) { return (size_t)npl * kXBytes + 2 * (size_t)kYBytes + 16; }
+};
+
+// one shifted pair from a 6-row window -> (odd, even) snake'd values of a 4-channel plane
+template <bool FAST>
+__device__ __forceinline__ void act_pair(const float2 (&xlo)[6], const float2 (&xhi)[6], const float2 (&g2)[6], float2 ea_lo, float2 ea_hi,
+                                         float2 ib_lo, float2 ib_hi, float4& yo, float4& ye) {
+  float2 olo = make_float2(0.f, 0.f), ohi = olo, elo = olo, ehi = olo;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const int ko = 10 - 2 * q, ke = 11 - 2 * q;
+    const float2 wo = g2[ko < 6 ? ko : 11 - ko], we = g2[ke < 6 ? ke : 11 - ke];
+    olo = ffma2(xlo[q], wo, olo); ohi = ffma2(xhi[q], wo, ohi);
+    elo = ffma2(xlo[q], we, elo); ehi = ffma2(xhi[q], we, ehi);
+  }
+  if (FAST) {  // y = v - (ib/2) cos(2 ea v); the constant + ib/2 is added once per output (sum-1 down filter)
+    const float2 nlo = make_float2(-ib_lo.x, -ib_lo.y), nhi = make_float2(-ib_hi.x, -ib_hi.y);
+    float2 t, c;
+    t = __fmul2_rn(olo, ea_lo); c = make_float2(__cosf(t.x), __cosf(t.y)); olo = ffma2(nlo, c, olo);
+    t = __fmul2_rn(ohi, ea_hi); c = make_float2(__cosf(t.x), __cosf(t.y)); ohi = ffma2(nhi, c, ohi);
+    t = __fmul2_rn(elo, ea_lo); c = make_float2(__cosf(t.x), __cosf(t.y)); elo = ffma2(nlo, c, elo);
+    t = __fmul2_rn(ehi, ea_hi); c = make_float2(__cosf(t.x), __cosf(t.y)); ehi = ffma2(nhi, c, ehi);
+  } else {
+    olo.x = snake_acc(olo.x, ea_lo.x, ib_lo.x); olo.y = snake_acc(olo.y, ea_lo.y, ib_lo.y);
+    ohi.x = snake_acc(ohi.x, ea_hi.x, ib_hi.x); ohi.y = snake_acc(ohi.y, ea_hi.y, ib_hi.y);
+    elo.x = snake_acc(elo.x, ea_lo.x, ib_lo.x); elo.y = snake_acc(elo.y, ea_lo.y, ib_lo.y);
+    ehi.x = snake_acc(ehi.x, ea_hi.x, ib_hi.x); ehi.y = snake_acc(ehi.y, ea_hi.y, ib_hi.y);
+  }
+  yo = make_float4(olo.x, olo.y, ohi.x, ohi.y);
+  ye = make_float4(elo.x, elo.y, ehi.x, ehi.y);
+}
+
+template <int NPL, bool FAST, int UR, int THREADS, int MINB>  // NPL input planes per output unit: 1 -> fp32 out, 2 -> bf16 out
+__global__ void __launch_bounds__(THREADS, MINB) act1d_v2_kernel(const __grid_constant__ ActArgs a) {
+  using G = ActV2Geom<UR, THREADS>;
+  extern __shared__ __align__(128) uint8_t act_smem[];
+  float4* sx = reinterpret_cast<float4*>(act_smem);                                  // [NPL][kRows]
+  float4* yo = reinterpret_cast<float4*>(act_smem + (size_t)NPL * G::kXBytes);       // [kPairs]
+  float4* ye = yo + G::kPairs;                                                        // [kPairs]
+  const uint32_t bar = smem_u32(act_smem + (size_t)NPL * G::kXBytes + 2 * (size_t)G::kYBytes);
+  const int tid = threadIdx.x;
+  const int t0 = blockIdx.x * G::kTile;
+  const int oc = blockIdx.y, b = blockIdx.z;
+  const int T = a.T;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
+  // ---- stage: one bulk copy per plane (rows t0-5 .. ; the plane's zero halo supplies rows outside [0,T) for now) ----
+  const int row0 = a.xg.pad + t0 - 5;                                   // >= pad - 5 > 0
+  const int nrows = min(G::kRows, a.xg.Tp - row0);
+  if (tid == 0) {
+    mbar_expect_tx(bar, (uint32_t)(NPL * nrows * 16));
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) {
+      const float4* src = reinterpret_cast<const float4*>(a.x) + ((size_t)b * a.xg.nchunk + (oc * NPL + p)) * a.xg.Tp + row0;
+      bulk_g2s(smem_u32(sx + p * G::kRows), src, (uint32_t)(nrows * 16), bar);
+    }
+  }
+  float2 f2[6], g2[6];  // broadcast taps: f[k] (down) and 2 f[k] (up), k = 0..5 (symmetric filter)
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    f2[k] = make_float2(c_fir[k], c_fir[k]);
+    g2[k] = make_float2(2.f * c_fir[k], 2.f * c_fir[k]);
+  }
+  mbar_wait(bar, 0);
+  // replicate padding of the up-sampling FIR (resample.py:28): rows before t = 0 / after t = T-1 take the edge sample
+  const bool first = (t0 == 0), last = t0 + G::kTile + 4 > T - 1;       // block-uniform (t0 is a multiple of the tile)
+  if (first || last) {
+    for (int i = tid; i < NPL * G::kRows; i += THREADS) {
+      const int p = i / G::kRows, lr = i - p * G::kRows;
+      const int t = t0 - 5 + lr;
+      const int tc = min(max(t, 0), T - 1);
+      const int src = tc - (t0 - 5);
+      if (tc != t && src >= 0 && src < G::kRows) sx[p * G::kRows + lr] = sx[p * G::kRows + src];
+    }
+    __syncthreads();
+  }
+
+  const int m0 = t0 + UR * tid;
+  uint2 held[UR];
+#pragma unroll 1
+  for (int p = 0; p < NPL; ++p) {
+    const int chunk = oc * NPL + p;
+    const float4 ea = *reinterpret_cast<const float4*>(a.ea + chunk * 4);
+    const float4 ib = *reinterpret_cast<const float4*>(a.ib + chunk * 4);
+    const float2 ea_lo = FAST ? make_float2(2.f * ea.x, 2.f * ea.y) : make_float2(ea.x, ea.y);
+    const float2 ea_hi = FAST ? make_float2(2.f * ea.z, 2.f * ea.w) : make_float2(ea.z, ea.w);
+    const float2 ib_lo = FAST ? make_float2(0.5f * ib.x, 0.5f * ib.y) : make_float2(ib.x, ib.y);
+    const float2 ib_hi = FAST ? make_float2(0.5f * ib.z, 0.5f * ib.w) : make_float2(ib.z, ib.w);
+    const float4* xp = sx + p * G::kRows;
+    // ---- phase 1: UR shifted pairs per thread (+ the 5 pairs beyond the tile, one each by threads 0..4) ----
+    {
+      float2 xlo[UR + 5], xhi[UR + 5];
+#pragma unroll
+      for (int k = 0; k < UR + 5; ++k) {
+        const float4 v = xp[UR * tid + k];
+        xlo[k] = make_float2(v.x, v.y);
+        xhi[k] = make_float2(v.z, v.w);
+      }
+#pragma unroll
+      for (int j = 0; j < UR; ++j) {
+        float2 wl[6], wh[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { wl[q] = xlo[j + q]; wh[q] = xhi[j + q]; }
+        float4 o, e;
+        act_pair<FAST>(wl, wh, g2, ea_lo, ea_hi, ib_lo, ib_hi, o, e);
+        yo[UR * tid + j] = o;
+        ye[UR * tid + j] = e;
+      }
+    }
+    if (tid < 5) {
+      const int s = G::kTile + tid;
+      float2 wl[6], wh[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const float4 v = xp[s + q];
+        wl[q] = make_float2(v.x, v.y);
+        wh[q] = make_float2(v.z, v.w);
+      }
+      float4 o, e;
+      act_pair<FAST>(wl, wh, g2, ea_lo, ea_hi, ib_lo, ib_hi, o, e);
+      yo[s] = o;
+      ye[s] = e;
+    }
+    __syncthreads();
+    // replicate padding of the down filter acts on y (filter.py:89-91): y[j<0] = y[0], y[j>=2T] = y[2T-1].
+    // yo[s] = y[2t0-5+2s], ye[s] = y[2t0-4+2s];  y[0] = ye[2-t0],  y[2T-1] = yo[T-t0+2].
+    if (first || last) {
+      if (first) {
+        const float4 y0 = ye[2 - t0];
+        for (int s = tid; s < 3 - t0; s += THREADS) {   // s <= 2-t0: jo = 2t0-5+2s < 0 ; je < 0 for s < 2-t0
+          yo[s] = y0;
+          if (s < 2 - t0) ye[s] = y0;
+        }
+      }
+      if (last) {
+        const int sl = T - t0 + 2;                      // yo[sl] = y[2T-1]
+        if (sl >= 0 && sl < G::kPairs) {
+          const float4 yl = yo[sl];
+          for (int s = sl + tid; s < G::kPairs; s += THREADS) {  // je = 2t0-4+2s >= 2T for s >= sl ; jo >= 2T for s > sl
+            ye[s] = yl;
+            if (s > sl) yo[s] = yl;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- phase 2: UR consecutive outputs per thread ----
+    float2 alo[UR], ahi[UR];
+#pragma unroll
+    for (int r = 0; r < UR; ++r) alo[r] = ahi[r] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < UR + 5; ++s) {
+      const float4 o = yo[UR * tid + s], e = ye[UR * tid + s];
+      const float2 olo = make_float2(o.x, o.y), ohi = make_float2(o.z, o.w), elo = make_float2(e.x, e.y), ehi = make_float2(e.z, e.w);
+#pragma unroll
+      for (int r = 0; r < UR; ++r) {
+        const int d = s - r;
+        if (d >= 0 && d <= 5) {
+          const int k0 = 2 * d, k1 = 2 * d + 1;
+          const float2 w0 = f2[k0 < 6 ? k0 : 11 - k0], w1 = f2[k1 < 6 ? k1 : 11 - k1];
+          alo[r] = ffma2(olo, w0, alo[r]); ahi[r] = ffma2(ohi, w0, ahi[r]);
+          alo[r] = ffma2(elo, w1, alo[r]); ahi[r] = ffma2(ehi, w1, ahi[r]);
+        }
+      }
+    }
+    float4 res[UR];
+    if (FAST) {
+      const float fs = fir_sum();
+      const float2 add_lo = make_float2(ib_lo.x * fs, ib_lo.y * fs), add_hi = make_float2(ib_hi.x * fs, ib_hi.y * fs);
+#pragma unroll
+      for (int r = 0; r < UR; ++r) res[r] = make_float4(alo[r].x + add_lo.x, alo[r].y + add_lo.y, ahi[r].x + add_hi.x, ahi[r].y + add_hi.y);
+    } else {
+#pragma unroll
+      for (int r = 0; r < UR; ++r) res[r] = make_float4(alo[r].x, alo[r].y, ahi[r].x, ahi[r].y);
+    }
+    if (NPL == 1) {
+      float4* op = reinterpret_cast<float4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
+#pragma unroll
+      for (int r = 0; r < UR; ++r) {
+        if (m0 + r >= T) break;
+        float4 o = res[r];
+        if (a.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+        op[m0 + r] = o;
+      }
+    } else {
+      uint2 pk[UR];
+#pragma unroll
+      for (int r = 0; r < UR; ++r) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(res[r].x, res[r].y), h1 = __floats2bfloat162_rn(res[r].z, res[r].w);
+        pk[r] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
+      if (p == 0) {
+#pragma unroll
+        for (int r = 0; r < UR; ++r) held[r] = pk[r];
+        __syncthreads();  // phase 2 of this plane is done with yo / ye before phase 1 of the next plane overwrites them
+      } else {
+        uint4* op = reinterpret_cast<uint4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
+#pragma unroll
+        for (int r = 0; r < UR; ++r) {
+          if (m0 + r >= T) break;
+          op[m0 + r] = make_uint4(held[r].x, held[r].y, pk[r].x, pk[r].y);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace alcm

@@ -271,6 +271,17 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
     tmem_alloc(smem_u32(tmem_slot), a.tmem_cols);
     tmem_relinquish();
   }
+  if (a.xg.nchunk < a.kchunks) {
+    // Narrow operands (24 / 20 channels): the planes hold fewer 16-byte K chunks than the MMA's K (a multiple of two
+    // chunks).  The missing chunk is never read from HBM - its slab is zeroed here, once, in every ring slot (such
+    // launches have a single k-block, so no copy ever lands there), and made visible to the tensor core's async proxy.
+    const uint32_t lo = (uint32_t)a.xg.nchunk * (uint32_t)rowsA, hi = (uint32_t)a.kblk * (uint32_t)rowsA;  // 16-byte units
+    for (int s = 0; s < AS; ++s) {
+      uint4* base = reinterpret_cast<uint4*>(smem + L.a_off + (size_t)s * L.a_stage);
+      for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) base[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -325,10 +336,12 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
           if (leader) mbar_arrive(a_full + 8 * as);
           xsrc += plane_bytes * a.kblk;
         } else {
-          if (leader) mbar_expect_tx(a_full + 8 * as, (uint32_t)a.kblk * a_bytes);
+          const int cv = min(a.kblk, a.xg.nchunk - kb * a.kblk);  // K chunks of this k-block that exist in memory
+          if (leader) mbar_expect_tx(a_full + 8 * as, (uint32_t)cv * a_bytes);
           uint32_t dst = sA + as * L.a_stage;
-          for (int c = 0; c < a.kblk; ++c, dst += a_pitch, xsrc += plane_bytes)
+          for (int c = 0; c < cv; ++c, dst += a_pitch, xsrc += plane_bytes)
             if (leader) bulk_g2s(dst, xsrc, a_bytes, a_full + 8 * as);
+          xsrc += plane_bytes * (a.kblk - cv);
         }
         for (int j0 = 0; j0 < ntaps; j0 += tpg, ++gi)
           if (gi >= 1) load_w(j0);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +11,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -55,15 +57,92 @@ static int guarded(F&& f) {
 }
 
 // ------------------------------------------------------------------------------------------ ctx
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+// Run-time knobs.  Read ONCE - when a model handle is created, or at the top of a
+// single-op entry point - and carried by value from there: plan-time decisions (N tile, split-K, workspace sizes)
+// and launch-time geometry come from the same snapshot, and no launch ever calls getenv.
+struct Knobs {
+  int pdl, graph, lanes, lane_waves, persist, cluster_splitk, splitk, retile, retile_mode;
+  int smem_budget, smem_budget_1w, smem_budget_mw, tpg, astages, kblk_max, nt, tmem2;
+  int act_variant, act_v2, act_v2_min_waves, fuse_act, fuse_stages, gn_fused, max_plans, trace, bench_fused, attn_tc;
+  static Knobs from_env() {
+    Knobs k;
+    k.pdl = env_int("ALCM_PDL", -1);  // -1 unset (per-plan default), 0 never, 1 always
+    k.graph = env_int("ALCM_GRAPH", 1);
+    k.lanes = env_int("ALCM_LANES", 1);
+    k.lane_waves = env_int("ALCM_LANE_WAVES", 20);
+    k.persist = env_int("ALCM_PERSIST", 1);
+    k.cluster_splitk = env_int("ALCM_CLUSTER_SPLITK", 1);
+    k.splitk = env_int("ALCM_SPLITK", 1);
+    k.retile = env_int("ALCM_RETILE", 1);
+    k.retile_mode = env_int("ALCM_RETILE_MODE", 1);
+    k.smem_budget = env_int("ALCM_SMEM_BUDGET", 0);
+    k.smem_budget_1w = env_int("ALCM_SMEM_BUDGET_1W", 120 * 1000);
+    k.smem_budget_mw = env_int("ALCM_SMEM_BUDGET_MW", 100 * 1024);
+    k.tpg = env_int("ALCM_TPG", 0);
+    k.astages = env_int("ALCM_ASTAGES", 0);
+    k.kblk_max = env_int("ALCM_KBLK_MAX", 8);
+    k.nt = env_int("ALCM_NT", 128);
+    k.tmem2 = env_int("ALCM_TMEM2", 0);
+    k.act_variant = env_int("ALCM_ACT_VARIANT", -1);
+    k.act_v2 = env_int("ALCM_ACT_V2", 7);                 // 0: off, 7 / 8: two-phase Activation1d with 5 / 7 outputs per thread
+    k.act_v2_min_waves = env_int("ALCM_ACT_V2_MIN_WAVES", 4);
+    k.fuse_act = env_int("ALCM_FUSE_ACT", 0);
+    k.fuse_stages = env_int("ALCM_FUSE_STAGES", 0);
+    k.gn_fused = env_int("ALCM_GN_FUSED", 1);
+    k.max_plans = std::max(1, env_int("ALCM_MAX_PLANS", 16));
+    k.trace = env_int("ALCM_TRACE", 0);
+    k.bench_fused = env_int("ALCM_BENCH_FUSED", 0);
+    k.attn_tc = env_int("ALCM_ATTN_TC", 1);
+    return k;
+  }
+};
+
+// Per-device context.  Everything the host side caches about the device lives here (no process-global mutable
+// state): two ctxs - two devices, or two host threads on one device - never share anything.
 struct alcm_ctx {
   int device = 0;
   int sm_count = 148;
+  std::mutex mu;                             // guards cluster_cap (a ctx may be shared by host threads)
+  long cluster_cap[2][9] = {{0}};            // co-resident CTAs when launched as clusters of n (per operand type)
+  std::atomic<unsigned long long> plan_clock{0};  // LRU stamps of the per-shape plans
+  // micro-benchmark instrumentation (alcm_bench_conv only)
+  int conv_dbg = 0;
+  long long* conv_trace = nullptr;
+  int conv_last_grid = 0;
 };
 
-struct Arena {  // owns device allocations
+// Device memory owner.  Three modes:
+//   * plain: one cudaMalloc per allocation (weights, single-op entry points);
+//   * measuring: hands out fake addresses and only adds up sizes (the sizing pass of a plan);
+//   * slab: sub-allocates from ONE stream-ordered allocation (cudaMallocAsync) that was zero-filled once - the
+//     buffers of a (B,T) plan.  Retiring a plan is a cudaFreeAsync: no device-wide synchronisation anywhere.
+struct Arena {
   std::vector<void*> ptrs;
   size_t total = 0;
+  bool measuring = false;
+  uint8_t* slab = nullptr;
+  size_t slab_bytes = 0, off = 0;
+  cudaStream_t slab_stream = nullptr;
+  static size_t align_up(size_t b) { return (std::max<size_t>(b, 16) + 255) & ~(size_t)255; }
   void* alloc(size_t bytes, bool zero = true) {
+    if (measuring) {
+      void* p = reinterpret_cast<void*>((uintptr_t)0x10000 + off);
+      off += align_up(bytes);
+      total = off;
+      return p;
+    }
+    if (slab) {
+      const size_t b = align_up(bytes);
+      if (off + b > slab_bytes) throw AlcmError(ALCM_ERR_INTERNAL, "plan slab overflow: the sizing pass and the build pass disagree");
+      void* p = slab + off;
+      off += b;
+      return p;
+    }
     void* p = nullptr;
     bytes = std::max<size_t>(bytes, 16);
     CUDA_CHECK(cudaMalloc(&p, bytes));
@@ -72,9 +151,23 @@ struct Arena {  // owns device allocations
     total += bytes;
     return p;
   }
+  void reserve(size_t bytes, cudaStream_t st) {  // slab mode: one stream-ordered allocation, zeroed once
+    bytes = align_up(bytes);
+    void* p = nullptr;
+    CUDA_CHECK(cudaMallocAsync(&p, bytes, st));
+    slab = static_cast<uint8_t*>(p);
+    slab_bytes = bytes; slab_stream = st; total = bytes; off = 0;
+    CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st));
+  }
+  void release_async(cudaStream_t st) {  // after the plan's last use has been ordered before `st`
+    if (slab) cudaFreeAsync(slab, st);
+    slab = nullptr;
+  }
   void release() {
     for (void* p : ptrs) cudaFree(p);
     ptrs.clear();
+    if (slab) cudaFreeAsync(slab, nullptr);  // owners synchronise the device before destroying a plan this way
+    slab = nullptr;
     total = 0;
   }
   ~Arena() { release(); }
@@ -88,11 +181,19 @@ struct PlaneT {
   float* f() const { return reinterpret_cast<float*>(p); }
 };
 
+// Channels held in memory per time step.  The MMA consumes K in 16-channel steps (bf16) and the bf16 planes pack 8
+// channels per unit, so planes are padded to a multiple of 8 - NOT 16: for the narrow tensors (C <= 48, i.e. the
+// 24-channel last vocoder stage and the 20-channel latent) the missing K chunk of a conv operand is never stored
+// in, written to or read from HBM; the conv kernel keeps an all-zero shared-memory slab for it instead (every such
+// launch has a single k-block).  Wider tensors are padded to 16 (at most 8 of > 48 channels).
+static const bool g_unpadded = env_int("ALCM_UNPADDED", 1) != 0;  // 0: 16-channel padding everywhere (A/B measurements); constant for the process
+static inline int plane_cpad(int C) { return (g_unpadded && round_up(C, 16) <= 48) ? round_up(C, 8) : round_up(C, 16); }
+
 static PlaneT make_planes(Arena& ar, int B, int C, int T, int esz) {
   PlaneT t;
   t.B = B; t.C = C; t.T = T; t.esz = esz;
   const int E = 16 / esz;
-  t.g.nchunk = round_up(C, 16) / E;
+  t.g.nchunk = plane_cpad(C) / E;
   t.g.pad = kPad;
   t.g.Tp = T + 2 * kPad;
   t.bytes = (size_t)B * t.g.nchunk * t.g.Tp * 16;
@@ -110,19 +211,16 @@ static inline int opnd_esz(int prec) { return prec == ALCM_PREC_BF16 ? 2 : 4; }
 // the VAE chain only, 3.89 ms without - graph kernel->kernel edges are already cheap, and early-resident
 // dependents (up to 200 KB of shared memory each, idle in griddepcontrol.wait) keep other lanes' CTAs off
 // the SMs.  So it is off by default and a per-plan choice (OpList::pdl, or ALCM_PDL=1 to force it).
-static int g_pdl = -1;          // ALCM_PDL: -1 unset (per-plan default), 0 never, 1 always
-static thread_local int t_pdl = 0;  // set by OpList::run / run_lanes around the launches of a plan
+static thread_local int t_pdl = 0;        // set by OpList::run / run_lanes around the launches of a plan
 static thread_local int t_cluster_x = 1;  // >1: the next launch_k() launches thread-block clusters of this many CTAs (x)
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  static const int env_pdl = [] { const char* e = getenv("ALCM_PDL"); return e ? atoi(e) : -1; }();
-  g_pdl = env_pdl < 0 ? t_pdl : env_pdl;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[2];
   int n = 0;
-  if (g_pdl) {
+  if (t_pdl) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
@@ -155,13 +253,8 @@ struct ConvLayer {
   int prec = 0;
 };
 
-static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return s ? atoi(s) : dflt;
-}
-
 // w: folded weight on device (Conv1d [Cout,Cin,K] or ConvTranspose1d [Cin,Cout,K]); bias may be null
-static ConvLayer prepare_conv(Arena& ar, int prec, ConvKind kind, const float* w, const float* bias, int Cout, int Cin, int K,
+static ConvLayer prepare_conv(Arena& ar, const Knobs& K_, int prec, ConvKind kind, const float* w, const float* bias, int Cout, int Cin, int K,
                               int dil_or_stride) {
   ConvLayer L;
   L.Cin = Cin; L.Cout = Cout; L.prec = prec;
@@ -218,17 +311,17 @@ static ConvLayer prepare_conv(Arena& ar, int prec, ConvKind kind, const float* w
   }
   const int E = (prec == ALCM_PREC_BF16) ? 8 : 4;
   const int cout_pad = round_up(Cout, 16);
-  int nt_pref = env_int("ALCM_NT", 128);
+  int nt_pref = K_.nt;
   if (cout_pad <= 256 && (cout_pad <= nt_pref || cout_pad % nt_pref != 0)) L.NT = cout_pad;
   else L.NT = nt_pref;
   REQUIRE(L.NT % 16 == 0 && L.NT >= 16 && L.NT <= 256, "bad N tile");
   L.n_tiles = (cout_pad + L.NT - 1) / L.NT;
   L.tmem_cols = 32;
-  while (L.tmem_cols < L.NT * (env_int("ALCM_TMEM2", 0) ? 2 : 1)) L.tmem_cols *= 2;
+  while (L.tmem_cols < L.NT * (K_.tmem2 ? 2 : 1)) L.tmem_cols *= 2;
   L.kchunks = round_up(Cin, 16) / E;
   L.kblk = 0;
   if (L.kchunks <= 12) L.kblk = L.kchunks;
-  else for (int d = std::min(12, env_int("ALCM_KBLK_MAX", 8)); d >= 2; d -= 2) if (L.kchunks % d == 0) { L.kblk = d; break; }
+  else for (int d = std::min(12, K_.kblk_max); d >= 2; d -= 2) if (L.kchunks % d == 0) { L.kblk = d; break; }
   REQUIRE(L.kblk >= 2 && L.kblk % 2 == 0 && L.kblk <= 12, "bad k-block");
   L.nkb = L.kchunks / L.kblk;
   L.idesc = umma_idesc(prec == ALCM_PREC_BF16 ? 1 : 2, L.NT);
@@ -248,22 +341,26 @@ static ConvLayer prepare_conv(Arena& ar, int prec, ConvKind kind, const float* w
   return L;
 }
 
-static int g_sm_count = 148;
+// Everything a planning decision depends on: the device context and the knob snapshot of the model (or entry point).
+struct Env {
+  alcm_ctx* cx = nullptr;
+  Knobs k;
+  int sms() const { return cx->sm_count; }
+};
 
 // ---- per-launch N tile -----------------------------------------------------------------------------------
 // Weights are packed for N = 128 (or the whole padded Cout when smaller).  A launch with few time tiles
 // (the VAE at T = 312/624, conv_pre) fills the GPU better with narrower N tiles: more CTAs per launch and a
 // split-K factor of at most 2, so the last-arriver fix-up reads 2 small partial tiles instead of 4-8 big ones.
-static int pick_nt(const ConvLayer& L, int M, int B) {
-  if (L.prec == ALCM_PREC_FP32 || !env_int("ALCM_RETILE", 1)) return L.NT;
+static int pick_nt(const Env& env, const ConvLayer& L, int M, int B) {
+  if (L.prec == ALCM_PREC_FP32 || !env.k.retile) return L.NT;
   const int cout_pad = round_up(L.Cout, 16);
   const long m = (long)((M + kTileM - 1) / kTileM) * B * L.nphase;
-  const long want = (long)(0.6 * g_sm_count);
+  const long want = (long)(0.6 * env.sms());
   // Measured (ALCM_TRACE, dbg flags): these launches are bound by fixed per-CTA costs and the split-K fix-up, not by
   // operand traffic - so first look for the widest tile that fills the GPU WITHOUT a K split, then with a split of 2.
   int best = L.NT;
-  const int mode = env_int("ALCM_RETILE_MODE", 1);
-  for (int pass = (mode ? 0 : 1); pass < 2; ++pass) {
+  for (int pass = (env.k.retile_mode ? 0 : 1); pass < 2; ++pass) {
     for (int nt : {L.NT, 64, 32}) {
       if (nt > L.NT || cout_pad % nt != 0) continue;
       best = nt;
@@ -279,17 +376,19 @@ static int pick_nt(const ConvLayer& L, int M, int B) {
 // mbarrier round trip) plus the cluster reduce-scatter (two cluster barriers, N/16 TMEM->DSMEM pushes) - among the
 // shapes that fit one wave.  Measured: at these sizes the launch is bound by per-CTA fixed costs, not by operand
 // traffic, so wide tiles (efficient MMAs) with a split of 4-8 reduced through DSMEM beat narrow un-split ones.
-static void conv_kernel_for(int prec, int NT, bool fused, void (**kern)(ConvArgs), int* threads);
+static void conv_kernel_for(int prec, bool fused, void (**kern)(ConvArgs), int* threads);
 
-// CTAs that can be co-resident when launched as clusters of `ks` (GPC boundaries cost a few SMs): one big-smem CTA per SM
-static long cluster_capacity(int prec, int ks) {
-  static long cap[2][9] = {{0}};
+// CTAs that can be co-resident when launched as clusters of `ks` (GPC boundaries cost a few SMs): one big-smem CTA per SM.
+// Cached in the ctx (per device).
+static long cluster_capacity(const Env& env, int prec, int ks) {
+  long (&cap)[2][9] = env.cx->cluster_cap;
   const int pi = prec == ALCM_PREC_BF16 ? 0 : 1;
-  if (ks <= 1) return g_sm_count;
+  if (ks <= 1) return env.sms();
+  std::lock_guard<std::mutex> lock(env.cx->mu);
   if (cap[pi][ks] == 0) {
     void (*kern)(ConvArgs) = nullptr;
     int threads = 192;
-    conv_kernel_for(prec, 128, false, &kern, &threads);
+    conv_kernel_for(prec, false, &kern, &threads);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(ks * 64); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 200 * 1024;
@@ -298,17 +397,17 @@ static long cluster_capacity(int prec, int ks) {
     at[0].val.clusterDim.x = (unsigned)ks; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_sm_count / ks * 3 / 4; }
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = env.sms() / ks * 3 / 4; }
     cap[pi][ks] = (long)n * ks;
   }
   return cap[pi][ks];
 }
 
-static bool choose_cluster_tile(const ConvLayer& L, int M, int B, int* nt_out, int* ks_out) {
-  if (L.prec == ALCM_PREC_FP32 || !env_int("ALCM_CLUSTER_SPLITK", 1)) return false;
+static bool choose_cluster_tile(const Env& env, const ConvLayer& L, int M, int B, int* nt_out, int* ks_out) {
+  if (L.prec == ALCM_PREC_FP32 || !env.k.cluster_splitk) return false;
   const int cout_pad = round_up(L.Cout, 16);
   const long m = (long)((M + kTileM - 1) / kTileM) * B * L.nphase;
-  if (m * ((cout_pad + L.NT - 1) / L.NT) * 2 > (long)g_sm_count) return false;  // the default tiling already fills the GPU
+  if (m * ((cout_pad + L.NT - 1) / L.NT) * 2 > (long)env.sms()) return false;  // the default tiling already fills the GPU
   double best = 1e30;
   bool found = false;
   for (int nt : {256, 128, 64, 32}) {
@@ -316,13 +415,13 @@ static bool choose_cluster_tile(const ConvLayer& L, int M, int B, int* nt_out, i
     for (int ks : {1, 2, 4, 8}) {
       if (ks > L.nkb || (nt / 4) % ks != 0) continue;
       const long ctas = m * (cout_pad / nt) * ks;
-      if (ctas > cluster_capacity(L.prec, ks)) continue;
+      if (ctas > cluster_capacity(env, L.prec, ks)) continue;
       const double cyc_mma = std::max(nt / 2.0, 32.0 + nt / 4.0);
       const int kbs = (L.nkb + ks - 1) / ks;
       double cost = kbs * (L.ntaps * (L.kblk / 2) * cyc_mma + 300.0);
       if (ks > 1) cost += 900.0 + (nt / 16) * 70.0 + (nt / 4 / ks) * ks * 8.0;
       cost += (nt / 16) * 40.0 / (ks > 1 ? ks : 1);                                  // epilogue stores
-      cost *= std::max(1.0, 0.6 * g_sm_count / (double)ctas);                        // idle SMs
+      cost *= std::max(1.0, 0.6 * env.sms() / (double)ctas);                         // idle SMs
       if (cost < best) { best = cost; *nt_out = nt; *ks_out = ks; found = true; }
     }
   }
@@ -374,6 +473,7 @@ struct Op {
   double flops, bytes;
   std::function<void(cudaStream_t)> fn;
   int lane = 0;
+  int stage = -1;  // vocoder stage (0-based) / -1: VAE or glue; for the per-stage roofline of alcm_profile_stages
 };
 
 
@@ -381,20 +481,22 @@ struct Op {
 // ~1024 tensor cycles (see conv.cuh).  Ring depth: ~100 KB (2 CTAs/SM) for multi-wave grids; single-wave grids
 // get 120 KB - measured on the batch-1 decode (tools/sweep_env.sh): 200 KB 3.450 ms, 150 KB 3.496, 120 KB 3.424
 // (operand traffic is not the limiter at that size, and a smaller footprint leaves room for the other lanes' blocks).
-static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused, bool cluster, int* stages, int* tpg, int* a_stages, uint32_t* smem) {
-  const uint32_t budget = (uint32_t)env_int("ALCM_SMEM_BUDGET", ctas <= (long)g_sm_count ? env_int("ALCM_SMEM_BUDGET_1W", 120 * 1000)
-                                                                                          : env_int("ALCM_SMEM_BUDGET_MW", 100 * 1024));
+static void pick_pipeline(const Env& env, const ConvLayer& L, long ctas, int ksplit, bool fused, bool cluster, int* stages, int* tpg,
+                          int* a_stages, uint32_t* smem) {
+  const uint32_t budget = (uint32_t)(env.k.smem_budget > 0 ? env.k.smem_budget
+                                                           : (ctas <= (long)env.sms() ? env.k.smem_budget_1w : env.k.smem_budget_mw));
   const double cyc_mma = std::max(L.NT / 2.0, 32.0 + L.NT / 4.0);
   const double cyc_tap = (L.kblk / 2) * cyc_mma;
   // ~1024 tensor cycles per weight stage (measured: stage-1 conv at batch 1, taps per stage 1/2/3/4 -> 802/978/1039/1046 TFLOP/s)
   int tmin = std::max(1, std::min(L.ntaps, (int)std::ceil(1024.0 / cyc_tap)));
   const int ngrp = (L.ntaps + tmin - 1) / tmin;
   int t = (L.ntaps + ngrp - 1) / ngrp;
-  if (env_int("ALCM_TPG", 0) > 0) t = std::min(L.ntaps, env_int("ALCM_TPG", 0));
+  if (env.k.tpg > 0) t = std::min(L.ntaps, env.k.tpg);
   // A-slab ring: a k-block whose MMAs take less than the slab's load latency (~1300 cycles) needs more than 2 slabs in flight
   const uint32_t a1 = (uint32_t)L.kblk * (kTileM + L.span) * 16, blob = (uint32_t)L.kblk * L.NT * 16;
   int AS = (L.ntaps * cyc_tap < 1500.0) ? 4 : 2;
-  AS = std::max(2, std::min(4, env_int("ALCM_ASTAGES", AS)));
+  if (env.k.astages > 0) AS = env.k.astages;
+  AS = std::max(2, std::min(4, AS));
   while (AS > 2 && AS * a1 > budget / 2) --AS;
   const int nkb_local = (L.nkb + ksplit - 1) / ksplit;
   AS = std::max(2, std::min(AS, nkb_local));
@@ -420,10 +522,6 @@ static void pick_pipeline(const ConvLayer& L, long ctas, int ksplit, bool fused,
   REQUIRE(*smem <= 227 * 1024, "conv tile does not fit shared memory");
 }
 
-static int g_conv_dbg = 0;
-static long long* g_conv_trace = nullptr;  // micro-benchmark only
-static int g_conv_last_grid = 0;            // micro-benchmark only: CTAs of the last tcgen05 conv launch
-
 struct SplitK {  // per-launch split-K resources (see ConvArgs::ksplit)
   int ksplit = 1;
   int cluster = 0;  // reduce through a thread-block cluster's distributed shared memory instead of the global workspace
@@ -442,26 +540,46 @@ struct FusedAct {
 static inline int conv_m_tiles(int M, bool fused) { return fused ? (M + kFuseOwn - 1) / kFuseOwn : (M + kTileM - 1) / kTileM; }
 
 // How many K splits a conv launch gets: only launches whose output tiles cannot fill the GPU are split.
-static int pick_ksplit(const ConvLayer& L, int M, int B, bool fused = false) {
-  if (L.prec == ALCM_PREC_FP32 || !env_int("ALCM_SPLITK", 1) || L.nkb < 2) return 1;
+static int pick_ksplit(const Env& env, const ConvLayer& L, int M, int B, bool fused = false) {
+  if (L.prec == ALCM_PREC_FP32 || !env.k.splitk || L.nkb < 2) return 1;
   const long ctas = (long)conv_m_tiles(M, fused) * L.n_tiles * B * L.nphase;
-  if (ctas * 2 > (long)g_sm_count) return 1;
-  return (int)std::max<long>(1, std::min<long>(std::min<long>(L.nkb, g_sm_count / ctas), 8));
+  if (ctas * 2 > (long)env.sms()) return 1;
+  return (int)std::max<long>(1, std::min<long>(std::min<long>(L.nkb, env.sms() / ctas), 8));
 }
 
-static void conv_kernel_for(int prec, int NT, bool fused, void (**kern)(ConvArgs), int* threads) {
+static void conv_kernel_for(int prec, bool fused, void (**kern)(ConvArgs), int* threads) {
   *threads = 192;
   if (fused) { *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, true> : conv_umma_kernel<1, 2, true>; *threads = 256; }
   // one register budget for every tile width (128/thread, 2 CTAs of 192 threads per SM): a narrower, spilling
   // 80-register build for N < 128 (4 CTAs/SM) measured slower at every batch size (batch 1: 3.31 -> 3.24 ms)
   else *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, false> : conv_umma_kernel<1, 2, false>;
-  (void)NT;
 }
 
-// `out` may be empty (p == nullptr) for a fused launch that only produces the activated operand planes.
-static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const float* res, int M, float scale, int accum,
-                        const SplitK& sk, const FusedAct& fa, cudaStream_t st) {
+// One conv launch, fully decided at PLAN time (kernel, grid, shared memory, pipeline shape, cluster size): replaying
+// the plan - eagerly or as a CUDA graph - can never disagree with the split-K / workspace decisions taken when it was built.
+struct ConvLaunch {
   ConvArgs a;
+  void (*kern)(ConvArgs) = nullptr;
+  dim3 grid, block;
+  uint32_t smem = 0;
+  int cluster_x = 1;
+  alcm_ctx* cx = nullptr;
+  void run(cudaStream_t st) const {
+    ConvArgs args = a;
+    args.dbg = cx->conv_dbg;        // micro-benchmark instrumentation only (0 / null otherwise)
+    args.trace = cx->conv_trace;
+    cx->conv_last_grid = (int)grid.x;
+    if (cluster_x > 1) t_cluster_x = cluster_x;
+    launch_k(kern, grid, block, smem, st, args);
+  }
+};
+
+// `out` may be empty (p == nullptr) for a fused launch that only produces the activated operand planes.
+static ConvLaunch plan_conv(const Env& env, const ConvLayer& L, const PlaneT& x, const PlaneT& out, const float* res, int M, float scale,
+                            int accum, const SplitK& sk, const FusedAct& fa) {
+  ConvLaunch cl;
+  cl.cx = env.cx;
+  ConvArgs& a = cl.a;
   memset(&a, 0, sizeof(a));
   a.x = x.p; a.xg = x.g;
   a.bias = L.bias;
@@ -474,64 +592,67 @@ static void launch_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, 
   a.span = L.span;
   a.Cin = L.Cin; a.Cout = L.Cout;
   a.scale = scale; a.accum = accum;
-  a.dbg = g_conv_dbg;
   a.ksplit = 1;
   const int B = x.B;
   const bool fused = fa.out.p != nullptr;
   if (L.prec == ALCM_PREC_FP32) {
     REQUIRE(!fused, "conv: the fp32 (CUDA-core) path has no fused activation");
     a.w = reinterpret_cast<const uint8_t*>(L.weff);
-    dim3 grid((M + kSimtTM - 1) / kSimtTM, (L.Cout + kSimtTN - 1) / kSimtTN, B * L.nphase);
-    launch_k(conv_simt_kernel, dim3(grid), dim3(256), 0, st, a);
-  } else {
-    a.w = L.wpack;
-    a.kchunks = L.kchunks; a.kblk = L.kblk; a.nkb = L.nkb;
-    a.NT = L.NT; a.n_tiles = L.n_tiles; a.tmem_cols = L.tmem_cols;
-    a.idesc = L.idesc; a.w_phase_stride = L.phase_stride;
-    a.ksplit = sk.ksplit; a.ws = sk.ws; a.tile_ctr = sk.ctr; a.cluster_splitk = sk.cluster;
-    a.trace = g_conv_trace;
-    if (fused) {
-      a.act_out = fa.out.p; a.ag = fa.out.g; a.ea = fa.ea; a.ib = fa.ib;
-      a.act_bf16 = fa.out.esz == 2; a.act_round_tf32 = fa.round_tf32;
-    }
-    a.tiles_m = conv_m_tiles(M, fused);
-    a.tiles_total = a.tiles_m * L.n_tiles * B * L.nphase * sk.ksplit;
-    a.acc_stages = 1;
-    uint32_t smem = 0;
-    pick_pipeline(L, (long)a.tiles_total, sk.ksplit, fused, sk.cluster != 0, &a.w_stages, &a.tpg, &a.a_stages, &smem);
-    // wide tiles are limited to 2 CTAs/SM by shared memory anyway and get the registers; narrow ones want
-    // occupancy; the fused epilogue runs the (register-hungry) activation on 8 warps
-    void (*kern)(ConvArgs) = nullptr;
-    int threads = 192;
-    conv_kernel_for(L.prec, L.NT, fused, &kern, &threads);
-    // Persistent launch for multi-wave grids: one CTA per resident slot loops over tiles with two TMEM accumulators,
-    // so barrier/TMEM setup is paid once per CTA and the epilogue of tile i overlaps the main loop of tile i+1.
-    int grid = a.tiles_total;
-    if (!fused && sk.ksplit == 1 && 2 * L.NT <= 512 && env_int("ALCM_PERSIST", 1)) {
-      int tcols2 = 32;
-      while (tcols2 < 2 * L.NT) tcols2 *= 2;
-      // resident CTAs per SM: shared memory (1 KB reserved per CTA), registers (128/thread -> 2 CTAs of 192 threads),
-      // TMEM columns.  Persistent only if doubling the TMEM columns does
-      // not cost a resident CTA (N = 192 would drop from 2 to 1 CTA/SM) and there is more than one wave of tiles.
-      int occ = (int)((227u * 1024u) / (smem + 1024u));
-      occ = std::min(occ, 2);
-      const int occ_np = std::min(occ, 512 / L.tmem_cols), occ_p = std::min(occ, 512 / tcols2);
-      if (occ_p >= 1 && occ_p == occ_np && a.tiles_total > occ_p * g_sm_count) {
-        grid = occ_p * g_sm_count;
-        a.acc_stages = 2;
-        a.tmem_cols = tcols2;
-      }
-    }
-    g_conv_last_grid = grid;
-    if (sk.cluster) t_cluster_x = sk.ksplit;
-    launch_k(kern, dim3(grid), dim3(threads), smem, st, a);
+    cl.kern = conv_simt_kernel;
+    cl.grid = dim3((M + kSimtTM - 1) / kSimtTM, (L.Cout + kSimtTN - 1) / kSimtTN, B * L.nphase);
+    cl.block = dim3(256);
+    cl.smem = 0;
+    return cl;
   }
+  a.w = L.wpack;
+  a.kchunks = L.kchunks; a.kblk = L.kblk; a.nkb = L.nkb;
+  a.NT = L.NT; a.n_tiles = L.n_tiles; a.tmem_cols = L.tmem_cols;
+  a.idesc = L.idesc; a.w_phase_stride = L.phase_stride;
+  a.ksplit = sk.ksplit; a.ws = sk.ws; a.tile_ctr = sk.ctr; a.cluster_splitk = sk.cluster;
+  // K chunks that exist in memory (plane_cpad): the others are an all-zero shared-memory slab
+  REQUIRE(x.g.nchunk >= L.kchunks || L.nkb == 1, "conv: operand planes narrower than K need a single k-block");
+  if (fused) {
+    a.act_out = fa.out.p; a.ag = fa.out.g; a.ea = fa.ea; a.ib = fa.ib;
+    a.act_bf16 = fa.out.esz == 2; a.act_round_tf32 = fa.round_tf32;
+  }
+  a.tiles_m = conv_m_tiles(M, fused);
+  a.tiles_total = a.tiles_m * L.n_tiles * B * L.nphase * sk.ksplit;
+  a.acc_stages = 1;
+  uint32_t smem = 0;
+  pick_pipeline(env, L, (long)a.tiles_total, sk.ksplit, fused, sk.cluster != 0, &a.w_stages, &a.tpg, &a.a_stages, &smem);
+  int threads = 192;
+  conv_kernel_for(L.prec, fused, &cl.kern, &threads);
+  // Persistent launch for multi-wave grids: one CTA per resident slot loops over tiles with two TMEM accumulators,
+  // so barrier/TMEM setup is paid once per CTA and the epilogue of tile i overlaps the main loop of tile i+1.
+  int grid = a.tiles_total;
+  if (!fused && sk.ksplit == 1 && 2 * L.NT <= 512 && env.k.persist) {
+    int tcols2 = 32;
+    while (tcols2 < 2 * L.NT) tcols2 *= 2;
+    // resident CTAs per SM: shared memory (1 KB reserved per CTA), registers (128/thread -> 2 CTAs of 192 threads),
+    // TMEM columns.  Persistent only if doubling the TMEM columns does
+    // not cost a resident CTA (N = 192 would drop from 2 to 1 CTA/SM) and there is more than one wave of tiles.
+    int occ = (int)((227u * 1024u) / (smem + 1024u));
+    occ = std::min(occ, 2);
+    const int occ_np = std::min(occ, 512 / L.tmem_cols), occ_p = std::min(occ, 512 / tcols2);
+    if (occ_p >= 1 && occ_p == occ_np && a.tiles_total > occ_p * env.sms()) {
+      grid = occ_p * env.sms();
+      a.acc_stages = 2;
+      a.tmem_cols = tcols2;
+    }
+  }
+  cl.grid = dim3(grid);
+  cl.block = dim3(threads);
+  cl.smem = smem;
+  cl.cluster_x = sk.cluster ? sk.ksplit : 1;
+  return cl;
 }
 
 struct OpList {
   std::vector<Op> ops;
+  Env env;              // device context + knob snapshot every planning decision below depends on
   Arena* ar = nullptr;  // where split-K workspaces come from (null: never split)
   int pdl = 0;          // launch this plan's kernels with programmatic dependent launch
+  int cur_stage = -1;   // tag for the per-stage profile
   Arena* war = nullptr;          // model-owned arena + cache for re-tiled weights (null: keep the packed N tile)
   RetileCache* cache = nullptr;
   double fused_act_bytes = 0;  // Activation1d work absorbed by conv epilogues
@@ -547,8 +668,8 @@ struct OpList {
                 const PlaneT* aout, const float* ea, const float* ib, int round_tf32) {
     const int M = x.T;  // rows per batch item are input time steps (== output steps / nphase)
     int nt_c = 0, ks_c = 1;
-    const bool clustered = war && cache && ar && aout == nullptr && choose_cluster_tile(L0, M, x.B, &nt_c, &ks_c);
-    const ConvLayer& L = (war && cache) ? retile(*war, *cache, L0, clustered ? nt_c : pick_nt(L0, M, x.B)) : L0;
+    const bool clustered = war && cache && ar && aout == nullptr && choose_cluster_tile(env, L0, M, x.B, &nt_c, &ks_c);
+    const ConvLayer& L = (war && cache) ? retile(*war, *cache, L0, clustered ? nt_c : pick_nt(env, L0, M, x.B)) : L0;
     const bool fused = aout != nullptr;
     REQUIRE(out || fused, "conv: no output");
     REQUIRE(x.esz == opnd_esz(L.prec), "conv: operand dtype mismatch");
@@ -577,7 +698,7 @@ struct OpList {
     if (fused) { fa.out = *aout; fa.ea = ea; fa.ib = ib; fa.round_tf32 = round_tf32; }
     SplitK sk;
     if (clustered) { sk.ksplit = ks_c; sk.cluster = ks_c > 1; }
-    else if (ar) sk.ksplit = pick_ksplit(L, M, x.B, fused);
+    else if (ar) sk.ksplit = pick_ksplit(env, L, M, x.B, fused);
     if (sk.ksplit > 1 && !sk.cluster) {
       const size_t tiles = (size_t)conv_m_tiles(M, fused) * L.n_tiles * x.B * L.nphase;
       const size_t need = tiles * sk.ksplit * (size_t)L.NT * kTileM * 4;
@@ -588,10 +709,11 @@ struct OpList {
       sk.ws = ws[cur_lane];
       sk.ctr = static_cast<unsigned int*>(ar->alloc(tiles * sizeof(unsigned int), true));
     }
-    op.fn = [=](cudaStream_t st) { launch_conv(Lc, xc, oc, rp, M, scale, accum, sk, fa, st); };
+    const ConvLaunch cl = plan_conv(env, Lc, xc, oc, rp, M, scale, accum, sk, fa);
+    op.fn = [cl](cudaStream_t st) { cl.run(st); };
     push(op);
     if (fused) {  // count the activation the launch absorbs in the act class' algorithmic bytes (bench roofline_act)
-      fused_act_bytes += (double)x.B * x.T * round_up(L.Cout, 16) * (4.0 + aout->esz);
+      fused_act_bytes += (double)x.B * x.T * L.Cout * (4.0 + aout->esz);
       ++fused_acts;
     }
   }
@@ -604,7 +726,7 @@ struct OpList {
     Op op;
     op.cls = ALCM_CLS_ACT;
     op.flops = 0;
-    op.bytes = (double)B * T * round_up(x.C, 16) * (4.0 + oesz);
+    op.bytes = (double)B * T * x.C * (4.0 + oesz);  // algorithmic: unpadded channels, one read + one write
     const int nch32 = x.g.nchunk;
     // two kernels, same arithmetic: the "pair" form (2 planes side by side, 256-output tiles) has half the serial
     // work per block and twice the blocks - better while a launch cannot fill the GPU several times over
@@ -615,11 +737,36 @@ struct OpList {
     // 3: 6 outputs/thread (96 registers, 5 blocks/SM) - measured best or equal on every launch that fills the GPU
     // (batch 64, last stage: 3.48 TB/s bf16 out, 4.63 TB/s = 72 % of the HBM peak fp32 out)
     const long blocks_r6 = (long)((T + 6 * kActThreads - 1) / (6 * kActThreads)) * nch * B;
+    // 7 / 8: two-phase form (act1d_v2_kernel; every up-sampled value computed once per block), 5 / 7 outputs per thread
+    const long blocks_v2 = (long)((T + 5 * kActThreads - 1) / (5 * kActThreads)) * nch * B;
     int variant = 0;
-    if (oesz == 2 && blocks_wide < 24L * g_sm_count) variant = 5;  // pair form, 6 outputs/thread: batch-1 decode 3.53 -> 3.45 ms vs 4 outputs/thread
-    else if (blocks_r6 >= 8L * g_sm_count) variant = 3;
-    variant = env_int("ALCM_ACT_VARIANT", variant);
+    if (oesz == 2 && blocks_wide < 24L * env.sms()) variant = 5;  // pair form, 6 outputs/thread: batch-1 decode 3.53 -> 3.45 ms vs 4 outputs/thread
+    else if (blocks_r6 >= 8L * env.sms()) variant = 3;
+    if (env.k.act_v2 && blocks_v2 >= (long)env.k.act_v2_min_waves * env.sms()) variant = env.k.act_v2;
+    if (env.k.act_variant >= 0) variant = env.k.act_variant;
     op.fn = [=](cudaStream_t st) {
+      if (variant == 7 || variant == 8) {  // two-phase form
+        const int ur = variant == 7 ? 5 : 7;
+        const dim3 grid((T + ur * kActThreads - 1) / (ur * kActThreads), nch, B);
+        const int npl = oesz == 4 ? 1 : 2;
+        const size_t sm = ur == 5 ? ActV2Geom<5, kActThreads>::smem(npl) : ActV2Geom<7, kActThreads>::smem(npl);
+        if (ur == 5) {
+          if (oesz == 4) {
+            if (fast) launch_k(act1d_v2_kernel<1, true, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a);
+            else launch_k(act1d_v2_kernel<1, false, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a);
+          } else {
+            launch_k(act1d_v2_kernel<2, true, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a);
+          }
+        } else {
+          if (oesz == 4) {
+            if (fast) launch_k(act1d_v2_kernel<1, true, 7, kActThreads, 3>, grid, dim3(kActThreads), sm, st, a);
+            else launch_k(act1d_v2_kernel<1, false, 7, kActThreads, 3>, grid, dim3(kActThreads), sm, st, a);
+          } else {
+            launch_k(act1d_v2_kernel<2, true, 7, kActThreads, 3>, grid, dim3(kActThreads), sm, st, a);
+          }
+        }
+        return;
+      }
       if (variant == 1 || variant == 5 || variant == 6) {  // pair form, 4 / 6 / 8 outputs per thread
         const int tile = kPairHalf * (variant == 1 ? 4 : (variant == 5 ? 6 : 8));
         const dim3 grid((T + tile - 1) / tile, nch32 / 2, B);
@@ -671,7 +818,7 @@ struct OpList {
     const int B = x.B, T = x.T, nch = out.g.nchunk, oesz = out.esz;
     PlaneT xc = x, oc = out;
     Op op;
-    op.cls = ALCM_CLS_MISC; op.flops = 0; op.bytes = (double)B * T * round_up(x.C, 16) * (4.0 + oesz);
+    op.cls = ALCM_CLS_MISC; op.flops = 0; op.bytes = (double)B * T * x.C * (4.0 + oesz);
     op.fn = [=](cudaStream_t st) {
       dim3 grid((T + 255) / 256, nch, B);
       if (oesz == 2) launch_k(cast_planes_kernel<8>, dim3(grid), dim3(256), 0, st, xc.f(), xc.g, oc.p, oc.g, T);
@@ -704,7 +851,7 @@ struct OpList {
   void fork() { Op m; m.cls = OP_FORK; m.flops = m.bytes = 0; ops.push_back(m); }
   void join() { Op m; m.cls = OP_JOIN; m.flops = m.bytes = 0; cur_lane = 0; ops.push_back(m); }
   void lane(int l) { cur_lane = l; }
-  void push(Op& op) { op.lane = cur_lane; ops.push_back(op); }
+  void push(Op& op) { op.lane = cur_lane; op.stage = cur_stage; ops.push_back(op); }
   int cur_lane = 0;
   int launches() const {
     int n = 0;
@@ -712,8 +859,9 @@ struct OpList {
     return n;
   }
   // serial execution on one stream (eager mode / profiling): lanes simply run one after another
+  int pdl_eff() const { return env.k.pdl < 0 ? pdl : env.k.pdl; }
   void run(cudaStream_t st) const {
-    t_pdl = pdl;
+    t_pdl = pdl_eff();
     for (const Op& o : ops) if (o.cls >= 0) o.fn(st);
     t_pdl = 0;
   }
@@ -728,13 +876,12 @@ struct OpList {
       }
       return evs[ei++];
     };
-    bool used[kMaxLanes] = {false, false, false, false};
-    t_pdl = pdl;
+    t_pdl = pdl_eff();
     for (const Op& o : ops) {
       if (o.cls == OP_FORK) {
         cudaEvent_t e = next_ev();
         CUDA_CHECK(cudaEventRecord(e, st));
-        for (int l = 1; l < kMaxLanes; ++l) { CUDA_CHECK(cudaStreamWaitEvent(side[l - 1], e, 0)); used[l] = false; }
+        for (int l = 1; l < kMaxLanes; ++l) CUDA_CHECK(cudaStreamWaitEvent(side[l - 1], e, 0));
       } else if (o.cls == OP_JOIN) {
         for (int l = 1; l < kMaxLanes; ++l) {
           cudaEvent_t e = next_ev();
@@ -745,7 +892,6 @@ struct OpList {
         o.fn(o.lane == 0 ? st : side[o.lane - 1]);
       }
     }
-    (void)used;
     t_pdl = 0;
   }
 };
@@ -764,8 +910,6 @@ struct GraphExec {
   cudaGraphExec_t exec = nullptr;
   ~GraphExec() { if (exec) cudaGraphExecDestroy(exec); }
 };
-
-static bool use_graph() { return env_int("ALCM_GRAPH", 1) != 0; }
 
 static void capture_graph(const OpList& ol, GraphExec& ge) {
   cudaStream_t cs, side[kMaxLanes - 1];
@@ -794,21 +938,110 @@ static void capture_graph(const OpList& ol, GraphExec& ge) {
   }
 }
 
-// ------------------------------------------------------------------------------------------ vocoder
-// Plans (buffers + CUDA graph per (B,T) shape) are cached per model; a caller that keeps changing the shape
-// (variable-length clips) must not grow the cache without bound: beyond ALCM_MAX_PLANS (default 16) the least
-// recently used plan is destroyed (cudaFree synchronises, so no kernel of it can still be in flight).
-static unsigned long long g_plan_clock = 0;
-template <class Map>
-static void evict_plans(Map& plans) {
-  const size_t cap = (size_t)std::max(1, env_int("ALCM_MAX_PLANS", 16));
-  while (plans.size() >= cap) {
-    auto victim = plans.begin();
-    for (auto it = plans.begin(); it != plans.end(); ++it)
-      if (it->second->stamp < victim->second->stamp) victim = it;
-    CUDA_CHECK(cudaDeviceSynchronize());
-    plans.erase(victim);
+// ------------------------------------------------------------------------------------------ plans
+// A plan = everything one (B,T) shape needs: ONE device slab (activation planes, split-K workspaces and counters,
+// zero-filled once - the plane halos are never written again), the kernel list with every launch geometry decided,
+// and its CUDA graph.  Plans are built by alcm_*_plan() (or on the first call for a shape) and cached per model;
+// alcm_*_workspace_bytes() runs only the sizing pass.  Once a shape is planned, alcm_vocode / alcm_vae_decode /
+// alcm_decode_to_wav do no allocation and no synchronisation: they enqueue on the caller's stream and return.
+//   * The slab is stream-ordered memory (cudaMallocAsync / cudaFreeAsync): building or retiring a plan never
+//     synchronises the device.
+//   * A model keeps at most ALCM_MAX_PLANS (default 16) plans.  The least recently used one is RETIRED: it leaves the
+//     cache at once and is destroyed later, when the event recorded after its last launch has completed (checked with
+//     cudaEventQuery on later calls) - never by waiting.
+//   * The buffers of a plan are shared by all calls for that shape: a call on another stream than the previous one
+//     first waits (on the device) for that event, so two streams cannot race on one plan.
+//   * A plan that was launched while the caller's stream was being captured is pinned (the caller's graph holds its
+//     addresses) and is never retired.
+struct PlanBase {
+  Arena ar;
+  unsigned long long stamp = 0;  // last use (LRU)
+  int B = 0, T = 0, Tout = 0;
+  OpList ol;
+  GraphExec ge;
+  cudaEvent_t done = nullptr;    // recorded after the last launch of this plan
+  cudaStream_t last_stream = nullptr;
+  bool used = false, pinned = false;
+  virtual ~PlanBase() { if (done) cudaEventDestroy(done); }
+  bool idle() const { return !used || cudaEventQuery(done) == cudaSuccess; }
+};
+
+struct PlanCache {
+  std::vector<std::unique_ptr<PlanBase>> retired;
+  void reap(cudaStream_t st) {  // destroy retired plans whose last launch has finished (non-blocking)
+    for (size_t i = 0; i < retired.size();) {
+      if (retired[i]->idle()) {
+        retired[i]->ar.release_async(st);
+        retired.erase(retired.begin() + i);
+      } else {
+        ++i;
+      }
+    }
   }
+  template <class Map>
+  void make_room(Map& plans, size_t cap, cudaStream_t st) {
+    reap(st);
+    while (plans.size() >= cap) {
+      auto victim = plans.end();
+      for (auto it = plans.begin(); it != plans.end(); ++it)
+        if (!it->second->pinned && (victim == plans.end() || it->second->stamp < victim->second->stamp)) victim = it;
+      if (victim == plans.end()) break;  // everything is pinned by caller graphs
+      retired.emplace_back(std::move(victim->second));
+      plans.erase(victim);
+    }
+    reap(st);
+  }
+  void drain() {  // model destruction: the owner has synchronised the device
+    retired.clear();
+  }
+};
+
+// Order a plan's launches after its previous use (other stream) and keep the retire event current.
+struct PlanUse {
+  PlanBase* P;
+  cudaStream_t st;
+  bool capturing = false;
+  PlanUse(PlanBase* p, cudaStream_t s) : P(p), st(s) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) capturing = true;
+    if (capturing) { P->pinned = true; return; }
+    if (P->used && P->last_stream != st) CUDA_CHECK(cudaStreamWaitEvent(st, P->done, 0));
+  }
+  void finish() {
+    if (capturing) return;
+    CUDA_CHECK(cudaEventRecord(P->done, st));
+    P->used = true;
+    P->last_stream = st;
+  }
+};
+
+// Sizing pass + build pass.  `build(plan)` must be deterministic in its allocation sequence.
+template <class Plan, class Build>
+static std::unique_ptr<Plan> build_plan(const Env& env, Arena* war, RetileCache* cache, int B, int T, cudaStream_t st, bool size_only,
+                                        size_t* bytes_out, Build&& build) {
+  auto setup = [&](Plan& P) {
+    P.B = B; P.T = T;
+    P.ol.env = env;
+    P.ol.ar = &P.ar;
+    P.ol.war = war; P.ol.cache = cache;
+  };
+  size_t need = 0;
+  {
+    Plan probe;
+    probe.ar.measuring = true;
+    setup(probe);
+    build(probe);
+    need = probe.ar.off;
+  }
+  if (bytes_out) *bytes_out = need;
+  if (size_only) return nullptr;
+  std::unique_ptr<Plan> pl(new Plan());
+  setup(*pl);
+  pl->ar.reserve(need, st);
+  build(*pl);
+  CUDA_CHECK(cudaEventCreateWithFlags(&pl->done, cudaEventDisableTiming));
+  if (env.k.graph) capture_graph(pl->ol, pl->ge);
+  return pl;
 }
 
 struct SnakeP { float* ea; float* ib; };
@@ -823,29 +1056,26 @@ struct VocStage {
   int C, u;
 };
 
-struct VocPlan {
-  Arena ar;
-  unsigned long long stamp = 0;  // last use (plan cache eviction)
-  int B, T, Tout;
+struct VocPlan : PlanBase {
   PlaneT mel_in;   // operand planes
   PlaneT post_in;  // fp32 planes feeding conv_post
-  OpList ol;
-  GraphExec ge;
 };
 
 struct alcm_vocoder {
   alcm_ctx* ctx;
+  Env env;
   alcm_bigvgan_cfg cfg;
   int prec;
   Arena war;  // weights
   ConvLayer conv_pre;
   std::vector<VocStage> stages;
   SnakeP act_post;
-  float* post_w = nullptr;  // [7][Cpad] tap-major fp32
+  float* post_w = nullptr;  // [7][plane_cpad(C)] tap-major fp32
   float post_bias = 0.f;
   int post_C = 0, hop = 1;
   RetileCache retiled;
   std::map<std::pair<int, int>, std::unique_ptr<VocPlan>> plans;
+  PlanCache pcache;
 };
 
 static SnakeP make_snake(Arena& ar, const float* alpha, const float* beta, int C) {
@@ -858,17 +1088,10 @@ static SnakeP make_snake(Arena& ar, const float* alpha, const float* beta, int C
   return s;
 }
 
-static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
-  auto key = std::make_pair(B, T);
-  auto it = v->plans.find(key);
-  if (it != v->plans.end()) { it->second->stamp = ++g_plan_clock; return it->second.get(); }
-  evict_plans(v->plans);
-  std::unique_ptr<VocPlan> pl(new VocPlan());
-  pl->stamp = ++g_plan_clock;
-  VocPlan& P = *pl;
-  P.B = B; P.T = T;
-  P.ol.ar = &P.ar;
-  P.ol.war = &v->war; P.ol.cache = &v->retiled;
+// Kernel list of one vocode of shape (B,T): models.py:181-203.
+static void voc_build(const alcm_vocoder* v, VocPlan& P) {
+  const int B = P.B, T = P.T;
+  const Knobs& K = v->env.k;
   const int prec = v->prec, oe = opnd_esz(prec);
   const int rtf = (prec == ALCM_PREC_TF32);
   const bool fast = (prec != ALCM_PREC_FP32);  // MUFU.COS snake; the exact-fp32 mode keeps the range-reduced sin
@@ -876,11 +1099,13 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
   P.mel_in = make_planes(P.ar, B, v->cfg.num_mels, T, oe);
   int C = v->cfg.upsample_initial_channel, Tc = T;
   PlaneT xprev = make_planes(P.ar, B, C, Tc, 4);
+  P.ol.cur_stage = 1;  // stage tags of the per-stage profile: 0 VAE, 1 conv_pre, 2..7 vocoder stages 1..6, 8 post
   P.ol.conv(v->conv_pre, P.mel_in, xprev, nullptr);
   PlaneT next_up_in;
   bool have_next_up_in = false;
   for (size_t i = 0; i < v->stages.size(); ++i) {
     const VocStage& S = v->stages[i];
+    P.ol.cur_stage = 2 + (int)i;
     PlaneT up_in = xprev;
     if (have_next_up_in) {
       up_in = next_up_in;
@@ -897,14 +1122,14 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
     // with a 3-wave threshold, 3.30 ms with every stage in lanes; batch 4: 10.84 -> 10.05 ms); beyond that (batch 64)
     // they run back to back, share buffers and accumulate straight into XS.
     const long conv_ctas = (long)((Tc + kTileM - 1) / kTileM) * std::max(1, round_up(C, 16) / 128) * B;
-    const bool parallel = nk > 1 && nk <= kMaxLanes && env_int("ALCM_LANES", 1) && conv_ctas < (long)env_int("ALCM_LANE_WAVES", 20) * g_sm_count;
+    const bool parallel = nk > 1 && nk <= kMaxLanes && K.lanes && conv_ctas < (long)K.lane_waves * v->env.sms();
     PlaneT XS = make_planes(P.ar, B, C, Tc, 4);
     std::vector<PlaneT> Z;
     PlaneT R, R2, Y, A, A2;
     // Measured on B200 (round 1): with the current register-blocked activation code the fused epilogue leaves the
     // tensor pipe idle for longer than a separate launch costs (batch-1 decode 4.53 ms fused vs 4.05 ms unfused), so
     // the fused chain is opt-in until the activation phase overlaps the next tile's main loop.
-    const bool fuse = (prec != ALCM_PREC_FP32) && (env_int("ALCM_FUSE_ACT", 0) || ((env_int("ALCM_FUSE_STAGES", 0) >> i) & 1));
+    const bool fuse = (prec != ALCM_PREC_FP32) && (K.fuse_act || ((K.fuse_stages >> i) & 1));
     if (parallel) P.ol.fork();
     for (int j = 0; j < nk; ++j) {
       const AmpBlock& bk = S.blocks[j];
@@ -964,26 +1189,36 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T) {
     }
     xprev = XS;
   }
+  P.ol.cur_stage = 2 + (int)v->stages.size();
   P.post_in = make_planes(P.ar, B, C, Tc, 4);
   P.ol.act(xprev, P.post_in, v->act_post.ea, v->act_post.ib, 0, fast);
   P.Tout = Tc;
-  CUDA_CHECK(cudaDeviceSynchronize());
-  if (use_graph()) capture_graph(P.ol, P.ge);
+}
+
+static VocPlan* voc_plan(alcm_vocoder* v, int B, int T, cudaStream_t st) {
+  auto key = std::make_pair(B, T);
+  auto it = v->plans.find(key);
+  if (it != v->plans.end()) { it->second->stamp = ++v->ctx->plan_clock; return it->second.get(); }
+  v->pcache.make_room(v->plans, (size_t)v->env.k.max_plans, st);
+  std::unique_ptr<VocPlan> pl = build_plan<VocPlan>(v->env, &v->war, &v->retiled, B, T, st, false, nullptr,
+                                                    [&](VocPlan& P) { voc_build(v, P); });
+  pl->stamp = ++v->ctx->plan_clock;
   VocPlan* raw = pl.get();
   v->plans[key] = std::move(pl);
   return raw;
 }
 
-static void voc_run(alcm_vocoder* v, VocPlan* P, const float* mel, const PlaneT* mel_planes, float* wav, cudaStream_t st) {
+// out: fp32 waveform [B, Tout] (pcm16 = 0) or 16-bit PCM [B, Tout] (pcm16 = 1, the WAV payload soundfile.write produces)
+static void voc_run(alcm_vocoder* v, VocPlan* P, const float* mel, void* out, int pcm16, cudaStream_t st) {
   // mel either as [B,C,T] device tensor (packed here) or already resident in P->mel_in (decode_to_wav)
   if (mel) launch_pack(mel, P->mel_in, v->cfg.num_mels, P->T, 1.f, v->prec, st);
-  (void)mel_planes;
   if (P->ge.exec) CUDA_CHECK(cudaGraphLaunch(P->ge.exec, st));
   else P->ol.run(st);
   const int threads = 256;
   dim3 grid((P->Tout + threads - 1) / threads, P->B);
   const size_t sm = (size_t)7 * P->post_in.g.nchunk * 4 * sizeof(float);
-  launch_k(conv_post_tanh_kernel, dim3(grid), dim3(threads), sm, st, P->post_in.f(), P->post_in.g, v->post_w, v->post_bias, wav, P->Tout, 7);
+  if (pcm16) launch_k(conv_post_tanh_kernel<true>, dim3(grid), dim3(threads), sm, st, P->post_in.f(), P->post_in.g, v->post_w, v->post_bias, out, P->Tout, 7);
+  else launch_k(conv_post_tanh_kernel<false>, dim3(grid), dim3(threads), sm, st, P->post_in.f(), P->post_in.g, v->post_w, v->post_bias, out, P->Tout, 7);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -998,17 +1233,13 @@ struct ResBlock {
 struct AttnBlk { GnP norm; ConvLayer qkv, proj; int C; };  // q, k, v 1x1 convs run as one launch (Cout = 3C)
 struct VaeLevel { std::vector<ResBlock> blocks; bool has_up = false; ConvLayer up; int C; };
 
-struct VaePlan {
-  Arena ar;
-  unsigned long long stamp = 0;
-  int B, T, Tout;
+struct VaePlan : PlanBase {
   PlaneT z_in, mel_out;
-  OpList ol;
-  GraphExec ge;
 };
 
 struct alcm_vae {
   alcm_ctx* ctx;
+  Env env;
   alcm_vae_cfg cfg;
   int prec;
   Arena war;
@@ -1020,6 +1251,7 @@ struct alcm_vae {
   int up_factor = 1;
   RetileCache retiled;
   std::map<std::pair<int, int>, std::unique_ptr<VaePlan>> plans;
+  PlanCache pcache;
 };
 
 static void op_gn(OpList& ol, Arena& ar, const PlaneT& x, const PlaneT& out, const GnP& n, int swish, int prec) {
@@ -1032,7 +1264,7 @@ static void op_gn(OpList& ol, Arena& ar, const PlaneT& x, const PlaneT& out, con
     int gpb = 1;
     while (gpb <= 4 && (gpb * cpg) % E != 0) ++gpb;
     const size_t smem = (size_t)gpb * (cpg / 4) * T * 16;
-    if ((cpg % 4) == 0 && gpb <= 4 && groups % gpb == 0 && smem <= 200 * 1024 && env_int("ALCM_GN_FUSED", 1)) {
+    if ((cpg % 4) == 0 && gpb <= 4 && groups % gpb == 0 && smem <= 200 * 1024 && ol.env.k.gn_fused) {
       Op f;
       f.cls = ALCM_CLS_NORM; f.flops = 0; f.bytes = (double)B * C * T * (4.0 + out.esz);
       const int oesz = out.esz, rtf = (prec == ALCM_PREC_TF32);
@@ -1135,17 +1367,10 @@ static PlaneT op_attn(OpList& ol, Arena& ar, const AttnBlk& at, const PlaneT& x,
   return out;
 }
 
-static VaePlan* vae_plan(alcm_vae* v, int B, int T) {
-  auto key = std::make_pair(B, T);
-  auto it = v->plans.find(key);
-  if (it != v->plans.end()) { it->second->stamp = ++g_plan_clock; return it->second.get(); }
-  evict_plans(v->plans);
-  std::unique_ptr<VaePlan> pl(new VaePlan());
-  pl->stamp = ++g_plan_clock;
-  VaePlan& P = *pl;
-  P.B = B; P.T = T;
-  P.ol.ar = &P.ar;
-  P.ol.war = &v->war; P.ol.cache = &v->retiled;
+// Kernel list of one decode of shape (B,T): autoencoder1d.py:59-62,484-517.
+static void vae_build(const alcm_vae* v, VaePlan& P) {
+  const int B = P.B, T = P.T;
+  P.ol.cur_stage = 0;
   const int prec = v->prec, oe = opnd_esz(prec);
   P.z_in = make_planes(P.ar, B, v->cfg.embed_dim, T, oe);
   PlaneT h0 = make_planes(P.ar, B, v->cfg.z_channels, T, 4);
@@ -1168,8 +1393,16 @@ static VaePlan* vae_plan(alcm_vae* v, int B, int T) {
   P.mel_out = make_planes(P.ar, B, v->cfg.out_ch, h.T, 4);
   P.ol.conv(v->conv_out, a, P.mel_out, nullptr);
   P.Tout = h.T;
-  CUDA_CHECK(cudaDeviceSynchronize());
-  if (use_graph()) capture_graph(P.ol, P.ge);
+}
+
+static VaePlan* vae_plan(alcm_vae* v, int B, int T, cudaStream_t st) {
+  auto key = std::make_pair(B, T);
+  auto it = v->plans.find(key);
+  if (it != v->plans.end()) { it->second->stamp = ++v->ctx->plan_clock; return it->second.get(); }
+  v->pcache.make_room(v->plans, (size_t)v->env.k.max_plans, st);
+  std::unique_ptr<VaePlan> pl = build_plan<VaePlan>(v->env, &v->war, &v->retiled, B, T, st, false, nullptr,
+                                                    [&](VaePlan& P) { vae_build(v, P); });
+  pl->stamp = ++v->ctx->plan_clock;
   VaePlan* raw = pl.get();
   v->plans[key] = std::move(pl);
   return raw;
@@ -1188,6 +1421,9 @@ static void set_kernel_attrs() {
   CUDA_CHECK(cudaFuncSetAttribute(softmax_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<1, true, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<1, false, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<2, true, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -1212,7 +1448,6 @@ int alcm_ctx_create(alcm_ctx** out, int device) {
     alcm_ctx* c = new alcm_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    g_sm_count = c->sm_count;
     *out = c;
   });
 }
@@ -1235,12 +1470,14 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
     CUDA_CHECK(cudaSetDevice(ctx->device));
     std::unique_ptr<alcm_vocoder> v(new alcm_vocoder());
     v->ctx = ctx; v->cfg = *cfg; v->prec = precision;
+    v->env.cx = ctx; v->env.k = Knobs::from_env();  // the knob snapshot of this model
+    const Knobs& K = v->env.k;
     Arena tmp;
     int ti = 0;
     const int c0 = cfg->upsample_initial_channel;
     {
       const float* w = fold_wn(tmp, t[ti], t[ti + 1], c0, cfg->num_mels * 7);
-      v->conv_pre = prepare_conv(v->war, precision, KIND_CONV, w, t[ti + 2], c0, cfg->num_mels, 7, 1);
+      v->conv_pre = prepare_conv(v->war, K, precision, KIND_CONV, w, t[ti + 2], c0, cfg->num_mels, 7, 1);
       ti += 3;
     }
     int C = c0;
@@ -1253,7 +1490,7 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
       v->hop *= u;
       {  // ConvTranspose1d weight (Cin,Cout,k): weight_norm dim 0 = input channel
         const float* w = fold_wn(tmp, t[ti], t[ti + 1], C, S.C * k);
-        S.up = prepare_conv(v->war, precision, KIND_CONVT, w, t[ti + 2], S.C, C, k, u);
+        S.up = prepare_conv(v->war, K, precision, KIND_CONVT, w, t[ti + 2], S.C, C, k, u);
         ti += 3;
       }
       C = S.C;
@@ -1262,12 +1499,12 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
         const int kk = cfg->resblock_kernel_sizes[j];
         for (int l = 0; l < 3; ++l) {
           const float* w = fold_wn(tmp, t[ti], t[ti + 1], C, C * kk);
-          bk.c1[l] = prepare_conv(v->war, precision, KIND_CONV, w, t[ti + 2], C, C, kk, cfg->resblock_dilation_sizes[j][l]);
+          bk.c1[l] = prepare_conv(v->war, K, precision, KIND_CONV, w, t[ti + 2], C, C, kk, cfg->resblock_dilation_sizes[j][l]);
           ti += 3;
         }
         for (int l = 0; l < 3; ++l) {
           const float* w = fold_wn(tmp, t[ti], t[ti + 1], C, C * kk);
-          bk.c2[l] = prepare_conv(v->war, precision, KIND_CONV, w, t[ti + 2], C, C, kk, 1);
+          bk.c2[l] = prepare_conv(v->war, K, precision, KIND_CONV, w, t[ti + 2], C, C, kk, 1);
           ti += 3;
         }
         for (int m = 0; m < 6; ++m) {
@@ -1283,10 +1520,11 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
     ti += 2;
     {  // conv_post (1,C,7) -> tap-major [7][Cpad] fp32 on device
       const float* w = fold_wn(tmp, t[ti], t[ti + 1], 1, C * 7);
-      std::vector<float> hw((size_t)C * 7), hp((size_t)7 * round_up(C, 16), 0.f);
+      const int cp = plane_cpad(C);  // row pitch = channels held by the fp32 planes feeding conv_post
+      std::vector<float> hw((size_t)C * 7), hp((size_t)7 * cp, 0.f);
       CUDA_CHECK(cudaMemcpy(hw.data(), w, hw.size() * 4, cudaMemcpyDeviceToHost));
       for (int c = 0; c < C; ++c)
-        for (int j = 0; j < 7; ++j) hp[(size_t)j * round_up(C, 16) + c] = hw[(size_t)c * 7 + j];
+        for (int j = 0; j < 7; ++j) hp[(size_t)j * cp + c] = hw[(size_t)c * 7 + j];
       v->post_w = static_cast<float*>(v->war.alloc(hp.size() * 4, false));
       CUDA_CHECK(cudaMemcpy(v->post_w, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice));
       CUDA_CHECK(cudaMemcpy(&v->post_bias, t[ti + 2], 4, cudaMemcpyDeviceToHost));
@@ -1297,17 +1535,55 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
     *out = v.release();
   });
 }
-void alcm_vocoder_destroy(alcm_vocoder* v) { delete v; }
+void alcm_vocoder_destroy(alcm_vocoder* v) {
+  if (!v) return;
+  cudaSetDevice(v->ctx->device);
+  cudaDeviceSynchronize();  // plans may still be in flight on caller streams
+  v->pcache.drain();
+  delete v;
+}
+
+static void check_voc_shape(alcm_vocoder* v, int B, int T) {
+  REQUIRE(B >= 1 && T >= 1, "vocode: B and T must be positive");
+  REQUIRE((long long)T * v->hop < (1ll << 30), "vocode: clip too long for one call; shard it along time");
+}
+
+int alcm_vocoder_plan(alcm_vocoder* v, int B, int T, void* stream) {
+  return guarded([&] {
+    REQUIRE(v, "vocoder_plan: NULL argument");
+    check_voc_shape(v, B, T);
+    CUDA_CHECK(cudaSetDevice(v->ctx->device));
+    voc_plan(v, B, T, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int alcm_vocoder_workspace_bytes(alcm_vocoder* v, int B, int T, size_t* bytes) {
+  return guarded([&] {
+    REQUIRE(v && bytes, "vocoder_workspace_bytes: NULL argument");
+    check_voc_shape(v, B, T);
+    CUDA_CHECK(cudaSetDevice(v->ctx->device));
+    auto it = v->plans.find(std::make_pair(B, T));
+    if (it != v->plans.end()) { *bytes = it->second->ar.total; return; }
+    build_plan<VocPlan>(v->env, &v->war, &v->retiled, B, T, nullptr, true, bytes, [&](VocPlan& P) { voc_build(v, P); });
+  });
+}
+
+static void vocode_any(alcm_vocoder* v, const float* mel, int B, int T, void* out, int pcm16, void* stream) {
+  REQUIRE(v && mel && out, "vocode: NULL argument");
+  check_voc_shape(v, B, T);
+  CUDA_CHECK(cudaSetDevice(v->ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VocPlan* P = voc_plan(v, B, T, st);
+  PlanUse use(P, st);
+  voc_run(v, P, mel, out, pcm16, st);
+  use.finish();
+}
 
 int alcm_vocode(alcm_vocoder* v, const float* mel, int B, int T, float* wav, void* stream) {
-  return guarded([&] {
-    REQUIRE(v && mel && wav, "vocode: NULL argument");
-    REQUIRE(B >= 1 && T >= 1, "vocode: B and T must be positive");
-    REQUIRE((long long)T * v->hop < (1ll << 30), "vocode: clip too long for one call; shard it along time");
-    CUDA_CHECK(cudaSetDevice(v->ctx->device));
-    VocPlan* P = voc_plan(v, B, T);
-    voc_run(v, P, mel, nullptr, wav, static_cast<cudaStream_t>(stream));
-  });
+  return guarded([&] { vocode_any(v, mel, B, T, wav, 0, stream); });
+}
+int alcm_vocode_pcm16(alcm_vocoder* v, const float* mel, int B, int T, short* pcm, void* stream) {
+  return guarded([&] { vocode_any(v, mel, B, T, pcm, 1, stream); });
 }
 
 // ---- VAE
@@ -1349,9 +1625,11 @@ int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* 
     CUDA_CHECK(cudaSetDevice(ctx->device));
     std::unique_ptr<alcm_vae> v(new alcm_vae());
     v->ctx = ctx; v->cfg = *cfg; v->prec = precision;
+    v->env.cx = ctx; v->env.k = Knobs::from_env();
+    const Knobs& K = v->env.k;
     int ti = 0;
     auto conv = [&](int cout, int cin, int k, ConvKind kind = KIND_CONV) {
-      ConvLayer L = prepare_conv(v->war, precision, kind, t[ti], t[ti + 1], cout, cin, k, 1);
+      ConvLayer L = prepare_conv(v->war, K, precision, kind, t[ti], t[ti + 1], cout, cin, k, 1);
       ti += 2;
       return L;
     };
@@ -1386,7 +1664,7 @@ int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* 
         CUDA_CHECK(cudaMemcpy(wcat + i * wn, t[ti + 2 * i], wn * 4, cudaMemcpyDeviceToDevice));
         CUDA_CHECK(cudaMemcpy(bcat + i * bn, t[ti + 2 * i + 1], bn * 4, cudaMemcpyDeviceToDevice));
       }
-      v->attn.qkv = prepare_conv(v->war, precision, KIND_CONV, wcat, bcat, 3 * block_in, block_in, 1, 1);
+      v->attn.qkv = prepare_conv(v->war, K, precision, KIND_CONV, wcat, bcat, 3 * block_in, block_in, 1, 1);
       ti += 6;
     }
     v->attn.proj = conv(block_in, block_in, 1);
@@ -1414,7 +1692,33 @@ int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* 
     *out = v.release();
   });
 }
-void alcm_vae_destroy(alcm_vae* v) { delete v; }
+void alcm_vae_destroy(alcm_vae* v) {
+  if (!v) return;
+  cudaSetDevice(v->ctx->device);
+  cudaDeviceSynchronize();
+  v->pcache.drain();
+  delete v;
+}
+
+int alcm_vae_plan(alcm_vae* v, int B, int T, void* stream) {
+  return guarded([&] {
+    REQUIRE(v, "vae_plan: NULL argument");
+    REQUIRE(B >= 1 && T >= 1, "vae_plan: B and T must be positive");
+    CUDA_CHECK(cudaSetDevice(v->ctx->device));
+    vae_plan(v, B, T, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int alcm_vae_workspace_bytes(alcm_vae* v, int B, int T, size_t* bytes) {
+  return guarded([&] {
+    REQUIRE(v && bytes, "vae_workspace_bytes: NULL argument");
+    REQUIRE(B >= 1 && T >= 1, "vae_workspace_bytes: B and T must be positive");
+    CUDA_CHECK(cudaSetDevice(v->ctx->device));
+    auto it = v->plans.find(std::make_pair(B, T));
+    if (it != v->plans.end()) { *bytes = it->second->ar.total; return; }
+    build_plan<VaePlan>(v->env, &v->war, &v->retiled, B, T, nullptr, true, bytes, [&](VaePlan& P) { vae_build(v, P); });
+  });
+}
 
 int alcm_vae_decode(alcm_vae* v, const float* z, int B, int T, float inv_scale, float* mel, void* stream) {
   return guarded([&] {
@@ -1422,37 +1726,50 @@ int alcm_vae_decode(alcm_vae* v, const float* z, int B, int T, float inv_scale, 
     REQUIRE(B >= 1 && T >= 1, "vae_decode: B and T must be positive");
     CUDA_CHECK(cudaSetDevice(v->ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    VaePlan* P = vae_plan(v, B, T);
+    VaePlan* P = vae_plan(v, B, T, st);
+    PlanUse use(P, st);
     vae_run(v, P, z, inv_scale, st);
     launch_unpack(P->mel_out, mel, v->cfg.out_ch, P->Tout, st);
     CUDA_CHECK(cudaGetLastError());
+    use.finish();
   });
+}
+
+static void decode_any(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, int T, float inv_scale, float* mel_out, void* out,
+                       int pcm16, void* stream) {
+  REQUIRE(vae && voc && z && out, "decode_to_wav: NULL argument");
+  REQUIRE(B >= 1 && T >= 1, "decode_to_wav: B and T must be positive");
+  REQUIRE(vae->cfg.out_ch == voc->cfg.num_mels, "decode_to_wav: VAE out_ch != vocoder num_mels");
+  REQUIRE(vae->ctx->device == voc->ctx->device, "decode_to_wav: handles live on different devices");
+  CUDA_CHECK(cudaSetDevice(vae->ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  VaePlan* PV = vae_plan(vae, B, T, st);
+  check_voc_shape(voc, B, PV->Tout);
+  VocPlan* PW = voc_plan(voc, B, PV->Tout, st);
+  PlanUse uv(PV, st), uw(PW, st);
+  vae_run(vae, PV, z, inv_scale, st);
+  if (mel_out) launch_unpack(PV->mel_out, mel_out, vae->cfg.out_ch, PV->Tout, st);
+  // mel stays on the device in plane form: fp32 planes -> the vocoder's operand planes
+  {
+    const PlaneT& src = PV->mel_out;
+    const PlaneT& dst = PW->mel_in;
+    dim3 grid((src.T + 255) / 256, dst.g.nchunk, B);
+    if (dst.esz == 2) launch_k(cast_planes_kernel<8>, dim3(grid), dim3(256), 0, st, src.f(), src.g, dst.p, dst.g, src.T);
+    else if (voc->prec == ALCM_PREC_TF32) launch_k(cast_planes_kernel<4>, dim3(grid), dim3(256), 0, st, src.f(), src.g, dst.p, dst.g, src.T);
+    else CUDA_CHECK(cudaMemcpyAsync(dst.p, src.p, src.bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  voc_run(voc, PW, nullptr, out, pcm16, st);
+  uv.finish();
+  uw.finish();
 }
 
 int alcm_decode_to_wav(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, int T, float inv_scale, float* mel_out,
                        float* wav, void* stream) {
-  return guarded([&] {
-    REQUIRE(vae && voc && z && wav, "decode_to_wav: NULL argument");
-    REQUIRE(B >= 1 && T >= 1, "decode_to_wav: B and T must be positive");
-    REQUIRE(vae->cfg.out_ch == voc->cfg.num_mels, "decode_to_wav: VAE out_ch != vocoder num_mels");
-    REQUIRE(vae->ctx->device == voc->ctx->device, "decode_to_wav: handles live on different devices");
-    CUDA_CHECK(cudaSetDevice(vae->ctx->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    VaePlan* PV = vae_plan(vae, B, T);
-    VocPlan* PW = voc_plan(voc, B, PV->Tout);
-    vae_run(vae, PV, z, inv_scale, st);
-    if (mel_out) launch_unpack(PV->mel_out, mel_out, vae->cfg.out_ch, PV->Tout, st);
-    // mel stays on the device in plane form: fp32 planes -> the vocoder's operand planes
-    {
-      const PlaneT& src = PV->mel_out;
-      const PlaneT& dst = PW->mel_in;
-      dim3 grid((src.T + 255) / 256, dst.g.nchunk, B);
-      if (dst.esz == 2) launch_k(cast_planes_kernel<8>, dim3(grid), dim3(256), 0, st, src.f(), src.g, dst.p, dst.g, src.T);
-      else if (voc->prec == ALCM_PREC_TF32) launch_k(cast_planes_kernel<4>, dim3(grid), dim3(256), 0, st, src.f(), src.g, dst.p, dst.g, src.T);
-      else CUDA_CHECK(cudaMemcpyAsync(dst.p, src.p, src.bytes, cudaMemcpyDeviceToDevice, st));
-    }
-    voc_run(voc, PW, nullptr, nullptr, wav, st);
-  });
+  return guarded([&] { decode_any(vae, voc, z, B, T, inv_scale, mel_out, wav, 0, stream); });
+}
+int alcm_decode_to_pcm16(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, int T, float inv_scale, float* mel_out,
+                         short* pcm, void* stream) {
+  return guarded([&] { decode_any(vae, voc, z, B, T, inv_scale, mel_out, pcm, 1, stream); });
 }
 
 // ---- single-op entry points ---------------------------------------------------------------
@@ -1472,6 +1789,7 @@ int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, con
     CUDA_CHECK(cudaDeviceSynchronize());
     launch_pack(x, xin, C, T, 1.f, ALCM_PREC_FP32, st);
     OpList ol;
+    ol.env = Env{ctx, Knobs::from_env()};
     ol.act(xin, out, sp.ea, sp.ib, precision == ALCM_PREC_TF32, precision != ALCM_PREC_FP32);
     ol.run(st);
     if (precision == ALCM_PREC_BF16) {
@@ -1492,7 +1810,8 @@ static void run_conv_test(alcm_ctx* ctx, ConvKind kind, const float* x, const fl
   REQUIRE(precision >= 0 && precision <= 2, "conv: bad precision");
   CUDA_CHECK(cudaSetDevice(ctx->device));
   Arena ar;
-  ConvLayer L = prepare_conv(ar, precision, kind, w, bias, Cout, Cin, K, p);
+  const Env env{ctx, Knobs::from_env()};
+  ConvLayer L = prepare_conv(ar, env.k, precision, kind, w, bias, Cout, Cin, K, p);
   PlaneT xin = make_planes(ar, B, Cin, T, opnd_esz(precision));
   PlaneT out = make_planes(ar, B, Cout, T * L.nphase, 4);
   PlaneT rp;
@@ -1502,6 +1821,7 @@ static void run_conv_test(alcm_ctx* ctx, ConvKind kind, const float* x, const fl
   if (res) launch_pack(res, rp, Cout, T * L.nphase, 1.f, ALCM_PREC_FP32, st);
   OpList ol;
   RetileCache rcache;
+  ol.env = env;
   ol.ar = &ar;
   ol.war = &ar; ol.cache = &rcache;  // same per-launch tile choice (N tile, K split, cluster reduction) as the plans
   ol.conv(L, xin, out, res ? &rp : nullptr);
@@ -1529,7 +1849,8 @@ int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const flo
     CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar;
-    ConvLayer L = prepare_conv(ar, precision, KIND_CONV, w, bias, Cout, Cin, K, dilation);
+    const Env env{ctx, Knobs::from_env()};
+    ConvLayer L = prepare_conv(ar, env.k, precision, KIND_CONV, w, bias, Cout, Cin, K, dilation);
     PlaneT xin = make_planes(ar, B, Cin, T, opnd_esz(precision));
     PlaneT out = make_planes(ar, B, Cout, T, 4), aout = make_planes(ar, B, Cout, T, opnd_esz(precision));
     PlaneT rp;
@@ -1539,6 +1860,7 @@ int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const flo
     launch_pack(x, xin, Cin, T, 1.f, precision, st);
     if (res) launch_pack(res, rp, Cout, T, 1.f, ALCM_PREC_FP32, st);
     OpList ol;
+    ol.env = env;
     ol.ar = &ar;
     ol.conv_act(L, xin, y_conv ? &out : nullptr, res ? &rp : nullptr, 1.f, 0, &aout, sp.ea, sp.ib, precision == ALCM_PREC_TF32);
     CUDA_CHECK(cudaDeviceSynchronize());  // workspace memsets
@@ -1580,6 +1902,7 @@ int alcm_groupnorm_swish_fwd(alcm_ctx* ctx, const float* x, const float* gamma, 
     PlaneT xin = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, 4);
     GnP g = make_gn(ar, gamma, beta, C);
     OpList ol;
+    ol.env = Env{ctx, Knobs::from_env()};
     op_gn(ol, ar, xin, out, g, swish, ALCM_PREC_FP32);
     CUDA_CHECK(cudaDeviceSynchronize());
     launch_pack(x, xin, C, T, 1.f, ALCM_PREC_FP32, st);
@@ -1604,6 +1927,7 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
     launch_pack(k, pk, C, T, 1.f, ALCM_PREC_FP32, st);
     launch_pack(v, pv, C, T, 1.f, ALCM_PREC_FP32, st);
     OpList ol;
+    ol.env = Env{ctx, Knobs::from_env()};
     float* Pm = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
     float* Sp = static_cast<float*>(ar.alloc((size_t)kAttnSplit * B * T * T * 4, false));
     push_attention(ol, pq, pk, pv, ph, Sp, Pm, B, C, T);
@@ -1616,9 +1940,14 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
 }
 
 // ---- measurement ----------------------------------------------------------------------------
-static void profile_ops(const OpList& ol, int iters, alcm_profile* out, cudaStream_t st) {
+// per-kernel CUDA-event timing of an op list (eager, serialised); accumulates into per-class and per-(stage, class) bins
+static void profile_ops(const OpList& ol, int iters, alcm_profile* out, alcm_stage_profile* stages, int max_stages, cudaStream_t st) {
   std::vector<cudaEvent_t> ev(ol.ops.size() + 1);
   for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+  auto bin = [&](const Op& o) -> alcm_stage_profile* {
+    if (!stages || o.stage < 0 || o.stage >= max_stages) return nullptr;
+    return &stages[o.stage];
+  };
   for (int it = 0; it < iters; ++it) {
     t_pdl = 0;  // per-kernel timing: no overlap between neighbours
     CUDA_CHECK(cudaEventRecord(ev[0], st));
@@ -1630,33 +1959,62 @@ static void profile_ops(const OpList& ol, int iters, alcm_profile* out, cudaStre
     for (size_t i = 0; i < ol.ops.size(); ++i) {
       float ms = 0.f;
       CUDA_CHECK(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
-      if (ol.ops[i].cls >= 0) out->ms[ol.ops[i].cls] += ms;
+      const Op& o = ol.ops[i];
+      if (o.cls < 0) continue;
+      if (out) out->ms[o.cls] += ms;
+      if (alcm_stage_profile* b = bin(o)) b->ms[o.cls] += ms;
     }
   }
   for (const Op& o : ol.ops) {
     if (o.cls < 0) continue;
-    out->flops[o.cls] += o.flops;
-    out->bytes[o.cls] += o.bytes;
-    out->launches[o.cls] += 1;
+    if (out) { out->flops[o.cls] += o.flops; out->bytes[o.cls] += o.bytes; out->launches[o.cls] += 1; }
+    if (alcm_stage_profile* b = bin(o)) { b->flops[o.cls] += o.flops; b->bytes[o.cls] += o.bytes; b->launches[o.cls] += 1; }
   }
   for (auto& e : ev) cudaEventDestroy(e);
 }
 
+static void profile_any(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iters, alcm_profile* out, alcm_stage_profile* stages,
+                        int max_stages, void* stream) {
+  REQUIRE(voc && iters >= 1, "profile: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_CHECK(cudaSetDevice(voc->ctx->device));
+  int Tmel = T;
+  if (vae) {
+    VaePlan* PV = vae_plan(vae, B, T, st);
+    PlanUse u(PV, st);
+    profile_ops(PV->ol, iters, out, stages, max_stages, st);
+    u.finish();
+    Tmel = PV->Tout;
+  }
+  VocPlan* PW = voc_plan(voc, B, Tmel, st);
+  PlanUse u(PW, st);
+  profile_ops(PW->ol, iters, out, stages, max_stages, st);
+  u.finish();
+}
+
 int alcm_profile_decode(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iters, alcm_profile* out, void* stream) {
   return guarded([&] {
-    REQUIRE(voc && out && iters >= 1, "profile: bad argument");
+    REQUIRE(out, "profile: bad argument");
     memset(out, 0, sizeof(*out));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUDA_CHECK(cudaSetDevice(voc->ctx->device));
-    int Tmel = T;
-    if (vae) {
-      VaePlan* PV = vae_plan(vae, B, T);
-      profile_ops(PV->ol, iters, out, st);
-      Tmel = PV->Tout;
-    }
-    VocPlan* PW = voc_plan(voc, B, Tmel);
-    profile_ops(PW->ol, iters, out, st);
+    profile_any(vae, voc, B, T, iters, out, nullptr, 0, stream);
   });
+}
+
+int alcm_profile_stages(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iters, alcm_stage_profile* stages, int max_stages,
+                        void* stream) {
+  return guarded([&] {
+    REQUIRE(stages && max_stages >= 1, "profile_stages: bad argument");
+    memset(stages, 0, sizeof(*stages) * (size_t)max_stages);
+    profile_any(vae, voc, B, T, iters, nullptr, stages, max_stages, stream);
+  });
+}
+
+// Micro-benchmarks run on RANDOM operands (seeded, generated on the device): zero-filled operands draw far less
+// power, so the SM clock - and with it the measured rate - would not be the one real data sees.
+static void fill_uniform(void* p, size_t n, int bf16, float lo, float hi, unsigned seed) {
+  const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 16384);
+  fill_uniform_kernel<<<blocks, 256>>>(p, n, bf16, lo, hi, seed);
+  CUDA_CHECK(cudaGetLastError());
 }
 
 int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int dilation, int precision, int iters, int dbg,
@@ -1666,48 +2024,59 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     REQUIRE(precision == ALCM_PREC_TF32 || precision == ALCM_PREC_BF16 || dbg == 0, "bench_conv: dbg flags need a tcgen05 mode");
     CUDA_CHECK(cudaSetDevice(ctx->device));
     Arena ar;
-    float* w = static_cast<float*>(ar.alloc((size_t)Cout * Cin * K * 4, true));
-    ConvLayer L = prepare_conv(ar, precision, KIND_CONV, w, nullptr, Cout, Cin, K, dilation);
+    const Env env{ctx, Knobs::from_env()};
+    // Kaiming-uniform-like weights, N(0,1)-like activations: the magnitudes of the real model
+    const float wb = 1.0f / sqrtf((float)Cin * K);
+    float* w = static_cast<float*>(ar.alloc((size_t)Cout * Cin * K * 4, false));
+    float* bias = static_cast<float*>(ar.alloc((size_t)Cout * 4, false));
+    fill_uniform(w, (size_t)Cout * Cin * K, 0, -wb, wb, 1u);
+    fill_uniform(bias, (size_t)Cout, 0, -wb, wb, 2u);
+    ConvLayer L = prepare_conv(ar, env.k, precision, KIND_CONV, w, bias, Cout, Cin, K, dilation);
     PlaneT x = make_planes(ar, B, Cin, T, opnd_esz(precision)), out = make_planes(ar, B, Cout, T, 4);
+    // fill whole planes (pads included - they only feed the first/last rows of each clip; irrelevant for timing)
+    fill_uniform(x.p, x.bytes / (size_t)x.esz, x.esz == 2, -1.7f, 1.7f, 3u);
     OpList ol;
     RetileCache rcache;
+    ol.env = env;
     ol.ar = &ar;
     ol.war = &ar; ol.cache = &rcache;  // same per-launch N tile choice as the plans
-    const bool bench_fused = env_int("ALCM_BENCH_FUSED", 0) && precision != ALCM_PREC_FP32;
+    const bool bench_fused = env.k.bench_fused && precision != ALCM_PREC_FP32;
     if (bench_fused) {  // conv + fused Activation1d, operand planes only (the c1 launches of the AMP blocks)
       PlaneT aout = make_planes(ar, B, Cout, T, opnd_esz(precision));
-      float* ab = static_cast<float*>(ar.alloc((size_t)(round_up(Cout, 16) + 256) * 4, true));
+      float* ab = static_cast<float*>(ar.alloc((size_t)(round_up(Cout, 16) + 256) * 4, false));
+      fill_uniform(ab, (size_t)round_up(Cout, 16) + 256, 0, -0.5f, 0.5f, 4u);
       SnakeP sp = make_snake(ar, ab, ab, Cout);
       ol.conv_act(L, x, nullptr, nullptr, 1.f, 0, &aout, sp.ea, sp.ib, precision == ALCM_PREC_TF32);
     } else {
       ol.conv(L, x, out, nullptr);
     }
+    CUDA_CHECK(cudaDeviceSynchronize());
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0));
     CUDA_CHECK(cudaEventCreate(&e1));
-    g_conv_dbg = dbg;
+    ctx->conv_dbg = dbg;
     for (int i = 0; i < 3; ++i) ol.run(0);
     CUDA_CHECK(cudaEventRecord(e0, 0));
     for (int i = 0; i < iters; ++i) ol.run(0);
     CUDA_CHECK(cudaEventRecord(e1, 0));
     cudaError_t err = cudaEventSynchronize(e1);
-    g_conv_dbg = 0;
+    ctx->conv_dbg = 0;
     CUDA_CHECK(err);
-    if (env_int("ALCM_TRACE", 0) && precision != ALCM_PREC_FP32) {  // one more launch with per-CTA timestamps
+    if (env.k.trace && precision != ALCM_PREC_FP32) {  // one more launch with per-CTA timestamps
       int nt_c = 0, ks_c = 1;
-      const bool clustered = !bench_fused && choose_cluster_tile(L, T, B, &nt_c, &ks_c);
-      const ConvLayer& Lt = retile(ar, rcache, L, clustered ? nt_c : pick_nt(L, T, B));
-      const int ks = clustered ? ks_c : pick_ksplit(Lt, T, B, bench_fused);
+      const bool clustered = !bench_fused && choose_cluster_tile(env, L, T, B, &nt_c, &ks_c);
+      const ConvLayer& Lt = retile(ar, rcache, L, clustered ? nt_c : pick_nt(env, L, T, B));
+      const int ks = clustered ? ks_c : pick_ksplit(env, Lt, T, B, bench_fused);
       const size_t nctas = (size_t)conv_m_tiles(T, bench_fused) * Lt.n_tiles * B * Lt.nphase * ks;
       long long* tr = static_cast<long long*>(ar.alloc(nctas * 8 * sizeof(long long), true));
       CUDA_CHECK(cudaDeviceSynchronize());
-      g_conv_trace = tr;
+      ctx->conv_trace = tr;
       ol.run(0);
-      g_conv_trace = nullptr;
+      ctx->conv_trace = nullptr;
       CUDA_CHECK(cudaDeviceSynchronize());
       std::vector<long long> h(nctas * 8);
       CUDA_CHECK(cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost));
-      const size_t launched = (size_t)g_conv_last_grid;
+      const size_t launched = (size_t)ctx->conv_last_grid;
       long long t_min = h[0], t_max = h[7], s_max = h[0];
       double d[5] = {0, 0, 0, 0, 0}, life = 0;
       for (size_t c = 0; c < launched; ++c) {
@@ -1735,10 +2104,16 @@ int alcm_bench_act(alcm_ctx* ctx, int B, int C, int T, int precision, int iters,
     CUDA_CHECK(cudaSetDevice(ctx->device));
     Arena ar;
     PlaneT x = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, opnd_esz(precision));
-    float* ab = static_cast<float*>(ar.alloc((size_t)round_up(C, 16) * 4, true));
-    SnakeP sp = make_snake(ar, ab, ab, C);
+    fill_uniform(x.p, x.bytes / 4, 0, -1.7f, 1.7f, 5u);
+    float* al = static_cast<float*>(ar.alloc((size_t)round_up(C, 16) * 4, false));
+    float* be = static_cast<float*>(ar.alloc((size_t)round_up(C, 16) * 4, false));
+    fill_uniform(al, (size_t)round_up(C, 16), 0, -0.9f, 0.9f, 6u);   // alpha, beta ~ spread of N(0, 0.5)
+    fill_uniform(be, (size_t)round_up(C, 16), 0, -0.9f, 0.9f, 7u);
+    SnakeP sp = make_snake(ar, al, be, C);
     OpList ol;
+    ol.env = Env{ctx, Knobs::from_env()};
     ol.act(x, out, sp.ea, sp.ib, precision == ALCM_PREC_TF32, precision != ALCM_PREC_FP32);
+    CUDA_CHECK(cudaDeviceSynchronize());
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0));
     CUDA_CHECK(cudaEventCreate(&e1));
@@ -1760,7 +2135,7 @@ int alcm_vocoder_launches(alcm_vocoder* v, int B, int T) {
   int n = -1;
   guarded([&] {
     REQUIRE(v, "NULL vocoder");
-    n = voc_plan(v, B, T)->ol.launches() + 2;  // + mel pack + conv_post
+    n = voc_plan(v, B, T, nullptr)->ol.launches() + 2;  // + mel pack + conv_post
   });
   return n;
 }
@@ -1768,7 +2143,7 @@ int alcm_vae_launches(alcm_vae* v, int B, int T) {
   int n = -1;
   guarded([&] {
     REQUIRE(v, "NULL vae");
-    n = vae_plan(v, B, T)->ol.launches() + 2;  // + latent pack + mel unpack
+    n = vae_plan(v, B, T, nullptr)->ol.launches() + 2;  // + latent pack + mel unpack
   });
   return n;
 }

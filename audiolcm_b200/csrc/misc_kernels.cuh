@@ -253,9 +253,13 @@ __global__ void snake_params_kernel(const float* __restrict__ alpha, const float
 }
 
 // ------------------------------------------------------------------------------- conv_post + tanh
-// models.py:199-201: Conv1d(C -> 1, k=7, p=3) + tanh on fp32 planes; w is [7][Cpad] (tap-major).
+// models.py:199-201: Conv1d(C -> 1, k=7, p=3) + tanh on fp32 planes; w is [7][nchunk*4] (tap-major).
+// PCM16: the sample is written as 16-bit PCM, rint(x * 32767) - what soundfile.write(path, wav, sr) stores for a
+// float waveform (libsndfile's default float -> PCM_16 conversion; pythonscripts/InferAPI.py:98) - so the WAV payload
+// leaves the GPU ready to be written and the device->host copy is half the size.
+template <bool PCM16>
 __global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg, const float* __restrict__ w, float bias,
-                                      float* __restrict__ wav, int T, int ktaps) {
+                                      void* __restrict__ wav, int T, int ktaps) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float sw[];
@@ -275,7 +279,21 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg,
       acc = fmaf(v.x, wj[0], acc); acc = fmaf(v.y, wj[1], acc); acc = fmaf(v.z, wj[2], acc); acc = fmaf(v.w, wj[3], acc);
     }
   }
-  wav[(size_t)b * T + t] = tanhf(acc);
+  const float y = tanhf(acc);
+  if (PCM16) reinterpret_cast<short*>(wav)[(size_t)b * T + t] = (short)__float2int_rn(y * 32767.0f);
+  else reinterpret_cast<float*>(wav)[(size_t)b * T + t] = y;
+}
+
+// Seeded uniform fill in [lo, hi) (micro-benchmark operands): counter-based hash, fp32 or bf16 elements.
+__global__ void fill_uniform_kernel(void* __restrict__ p, size_t n, int bf16, float lo, float hi, unsigned seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned h = (unsigned)i * 2654435761u ^ (unsigned)(i >> 32) * 40503u ^ seed * 0x9E3779B9u;
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+    const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+    const float v = lo + (hi - lo) * u;
+    if (bf16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+    else reinterpret_cast<float*>(p)[i] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------- GroupNorm

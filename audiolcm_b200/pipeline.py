@@ -96,6 +96,23 @@ class LatentToWaveform(object):
                                                       None if mel is None else mel.data_ptr(), wav.data_ptr(), stream))
         return (wav, mel) if return_mel else wav
 
+    def decode_pcm16_tensor(self, z, scale_factor: float = 1.0):
+        """latents (B,20,T) -> (B, 512*T) int16 CUDA tensor (16-bit PCM packed by the conv_post kernel)."""
+        z = z.to(dtype=torch.float32, device=self.device).contiguous()
+        if z.dim() != 3 or z.shape[1] != self.vae.embed_dim:
+            raise ValueError(f"expected a (B,{self.vae.embed_dim},T) latent, got {tuple(z.shape)}")
+        B, _, T = z.shape
+        with torch.cuda.device(self.device):
+            pcm = torch.empty((B, T * self.vae.up_factor * self.voc.hop), dtype=torch.int16, device=self.device)
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.load().alcm_decode_to_pcm16(self.vae._h, self.voc._h, z.data_ptr(), B, T, 1.0 / float(scale_factor),
+                                                        None, pcm.data_ptr(), stream))
+        return pcm
+
+    def plan(self, B, T):
+        """Pre-plan both models for latents of shape (B,20,T); returns the total workspace bytes."""
+        return self.vae.plan(B, T) + self.voc.plan(B, T * self.vae.up_factor)
+
     def decode(self, z, scale_factor: float = 1.0) -> np.ndarray:
         """latents (B,20,T) (tensor or ndarray) -> host float32 waveforms (B, 512*T)."""
         if isinstance(z, np.ndarray):
@@ -125,4 +142,20 @@ class LatentToWaveform(object):
         out = {}
         for i, name in enumerate(_lib.CLASSES):
             out[name] = dict(ms=prof.ms[i] / iters, flops=prof.flops[i], bytes=prof.bytes[i], launches=prof.launches[i])
+        return out
+
+    STAGES = ("vae", "conv_pre", "stage1", "stage2", "stage3", "stage4", "stage5", "stage6", "post")
+
+    def profile_stages(self, B, T, iters=3):
+        """The same measurement binned by pipeline stage: {stage: {class: {ms, flops, bytes, launches}}}."""
+        import ctypes as C
+        n = len(self.STAGES)
+        arr = (_lib.Profile * n)()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.load().alcm_profile_stages(self.vae._h, self.voc._h, B, T, iters, arr, n, stream))
+        out = {}
+        for s, sname in enumerate(self.STAGES):
+            out[sname] = {name: dict(ms=arr[s].ms[i] / iters, flops=arr[s].flops[i], bytes=arr[s].bytes[i], launches=arr[s].launches[i])
+                          for i, name in enumerate(_lib.CLASSES) if arr[s].launches[i]}
         return out

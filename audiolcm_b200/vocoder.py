@@ -192,6 +192,32 @@ class VocoderBigVGAN(object):
             _lib.check(_lib.load().alcm_vocode(self._h, spec.data_ptr(), B, T, wav.data_ptr(), stream))
         return wav
 
+    def vocode_pcm16_tensor(self, spec):
+        """(B,num_mels,T) tensor -> (B, T*hop) int16 CUDA tensor: 16-bit PCM packed on the device,
+        ``rint(wav * 32767)`` - the samples ``soundfile.write(path, wav, 16000)`` stores
+        (pythonscripts/InferAPI.py:98)."""
+        spec = spec.to(dtype=torch.float32, device=self.device).contiguous()
+        if spec.dim() != 3 or spec.shape[1] != self.num_mels or spec.shape[0] == 0 or spec.shape[2] == 0:
+            raise ValueError(f"expected a non-empty (B,{self.num_mels},T) spectrogram, got {tuple(spec.shape)}")
+        B, _, T = spec.shape
+        with torch.cuda.device(self.device):
+            pcm = torch.empty((B, T * self.hop), dtype=torch.int16, device=self.device)
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.load().alcm_vocode_pcm16(self._h, spec.data_ptr(), B, T, pcm.data_ptr(), stream))
+        return pcm
+
+    def plan(self, B, T):
+        """Build the (B,T) plan now (workspace slab, kernel list, CUDA graph) on the current stream, so that
+        later ``vocode`` calls of this shape neither allocate nor synchronise.  Returns its size in bytes."""
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().alcm_vocoder_plan(self._h, int(B), int(T), torch.cuda.current_stream().cuda_stream))
+        return self.workspace_bytes(B, T)
+
+    def workspace_bytes(self, B, T):
+        n = C.c_size_t()
+        _lib.check(_lib.load().alcm_vocoder_workspace_bytes(self._h, int(B), int(T), C.byref(n)))
+        return int(n.value)
+
     def vocode(self, spec):
         """models.py:406-411."""
         with torch.no_grad():

@@ -15,11 +15,20 @@
  *
  * Conventions: plain pointers and sizes only.  All tensor pointers are DEVICE pointers to
  * contiguous fp32 arrays in the reference's own layouts ([B,C,T], weights as in the state_dict).
- * The caller owns inputs and outputs; the library owns packed weights and per-(B,T) workspaces
- * (allocated on the first call for a shape, reused afterwards - no allocation on later calls).
+ * The caller owns inputs and outputs; the library owns packed weights and one workspace slab per
+ * (B,T) shape ("plan").  alcm_*_plan() builds the plan of a shape ahead of time and
+ * alcm_*_workspace_bytes() reports its size; a shape that was not planned is planned by the first
+ * call that uses it.  Once a shape is planned, the decode calls perform NO allocation and NO
+ * synchronisation: they enqueue kernels on `stream` and return.  Plan memory is stream-ordered
+ * (cudaMallocAsync); the least recently used plans beyond ALCM_MAX_PLANS are retired without waiting.
  * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Functions return
- * 0 on success or a negative code; alcm_last_error() gives the message.  Nothing aborts or
- * throws across this boundary.  Handles are not thread-safe; use one ctx per host thread.
+ * 0 on success or a negative code; alcm_last_error() gives the message (per calling thread).  Nothing
+ * aborts or throws across this boundary.
+ * Threading: the library keeps no process-global mutable state.  An alcm_ctx may be shared by
+ * threads; a model handle (alcm_vocoder / alcm_vae) may be used by one thread at a time.  Calls on
+ * one handle from different streams are ordered on the device (they share the plan's buffers).
+ * Run-time knobs (ALCM_* environment variables) are read once, when a model handle is
+ * created.
  */
 #ifndef AUDIOLCM_B200_H
 #define AUDIOLCM_B200_H
@@ -84,6 +93,13 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
 void alcm_vocoder_destroy(alcm_vocoder* v);
 /* mel [B,num_mels,T] -> wav [B, T*prod(upsample_rates)] (conv_post + tanh applied) */
 int alcm_vocode(alcm_vocoder* v, const float* mel, int B, int T, float* wav, void* stream);
+/* same, output as 16-bit PCM: pcm[b][t] = rint(wav * 32767) - the payload soundfile.write(path, wav, 16000) stores
+ * (pythonscripts/InferAPI.py:98) */
+int alcm_vocode_pcm16(alcm_vocoder* v, const float* mel, int B, int T, short* pcm, void* stream);
+/* build the plan (workspace slab + kernel list + CUDA graph) of shape (B,T) now, on `stream` */
+int alcm_vocoder_plan(alcm_vocoder* v, int B, int T, void* stream);
+/* device bytes the plan of shape (B,T) occupies (sizing pass only when the shape is not planned yet) */
+int alcm_vocoder_workspace_bytes(alcm_vocoder* v, int B, int T, size_t* bytes);
 
 /* ---- 1-D KL-VAE decoder -----------------------------------------------------------------------
  * cfg mirrors ddconfig of configs/audiolcm.yaml:54-70.  upsample_levels[l] = 1 when level l ends
@@ -112,10 +128,15 @@ int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* 
 void alcm_vae_destroy(alcm_vae* v);
 /* z [B,embed_dim,T] -> mel [B,out_ch,T*2^n_up];  inv_scale = 1/scale_factor (lcm_audio.py:400) */
 int alcm_vae_decode(alcm_vae* v, const float* z, int B, int T, float inv_scale, float* mel, void* stream);
+int alcm_vae_plan(alcm_vae* v, int B, int T, void* stream);
+int alcm_vae_workspace_bytes(alcm_vae* v, int B, int T, size_t* bytes);
 
 /* latent -> waveform with the mel kept on the device (mel_out may be NULL) */
 int alcm_decode_to_wav(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, int T, float inv_scale, float* mel_out,
                        float* wav, void* stream);
+/* same with the waveform packed as 16-bit PCM on the device (the batched driver that replaces InferAPI.py:87-98) */
+int alcm_decode_to_pcm16(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, int T, float inv_scale, float* mel_out,
+                         short* pcm, void* stream);
 
 /* ---- single-op entry points (tests / micro-benchmarks); tensors are [B,C,T] fp32 on device -----*/
 /* Activation1d(SnakeBeta logscale): act.py:23-28.  precision BF16 returns bf16-rounded values. */
@@ -155,11 +176,17 @@ typedef struct {
 /* runs the vocoder (vae may be NULL) / vae+vocoder op lists eagerly with an event pair around every
  * kernel; the normal path replays a CUDA graph and has no events inside. */
 int alcm_profile_decode(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iters, alcm_profile* out, void* stream);
-/* times `iters` back-to-back launches of one Conv1d(Cin,Cout,K,dilation) on synthetic (zero) data of
- * shape [B,Cin,T]; dbg is for kernel bring-up (bit0/bit1 skip the weight/activation copies) */
+/* the same measurement binned by pipeline stage: stages[0] = VAE decoder, [1] = conv_pre, [2..7] = vocoder stages
+ * 1..6 (upsampler + 3 AMP blocks each), [8] = activation_post (conv_post+tanh is outside the op list) */
+typedef alcm_profile alcm_stage_profile;
+int alcm_profile_stages(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iters, alcm_stage_profile* stages, int max_stages,
+                        void* stream);
+/* times `iters` back-to-back launches of one Conv1d(Cin,Cout,K,dilation) on seeded RANDOM weights and
+ * activations of shape [B,Cin,T] (generated on the device; zero operands would run at a different power / clock
+ * point); dbg is for kernel bring-up (bit0/bit1 skip the weight/activation copies) */
 int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int dilation, int precision, int iters, int dbg,
                     float* ms_per_launch);
-/* same for one Activation1d launch on [B,C,T] */
+/* same for one Activation1d launch on [B,C,T] (random x, alpha, beta) */
 int alcm_bench_act(alcm_ctx* ctx, int B, int C, int T, int precision, int iters, float* ms_per_launch);
 /* kernels launched by one alcm_vocode / alcm_vae_decode call for this shape (after planning) */
 int alcm_vocoder_launches(alcm_vocoder* v, int B, int T);

@@ -10,6 +10,6 @@ Parity pinning: the reference ships no tests / golden vectors for this path
 (SURVEY.md section 4), so the oracle is pinned against the *live reference
 modules* instead: ``oracle/make_golden.py`` imports the unmodified reference
 from ``/root/reference``, loads deterministic synthetic weights
-(``oracle/synth.py``) into it, and commits its outputs under ``tests/golden/``.
+(``audiolcm_b200/synth.py``) into it, and commits its outputs under ``tests/golden/``.
 ``tests/test_oracle_golden.py`` checks this restatement against those vectors.
 """

@@ -10,7 +10,7 @@ are absent here and unused on the forward path:
 ``omegaconf`` (only VocoderBigVGAN.__init__, models.py:397) and
 ``pytorch_lightning`` (base class only, autoencoder1d.py:18).
 
-Weights come from oracle/synth.py (seeded numpy), loaded with load_state_dict,
+Weights come from audiolcm_b200/synth.py (seeded numpy), loaded with load_state_dict,
 so fixtures hold only inputs' seeds and the reference's outputs.
 """
 from __future__ import annotations

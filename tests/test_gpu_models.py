@@ -117,14 +117,15 @@ def test_full_path_vs_reference(golden_dir, precision):
     assert pipe.decode(z).shape == (1, 24 * 512)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_batch_and_time_shard_properties(precision):
     """Size-independent properties at a mid-size config: batching does not mix samples and the
     34-frame-halo time sharding (config 4) reproduces the un-sharded result in the interior.
-    fp32 (CUDA-core convs, fixed summation order): equal to 2e-6.  tf32: the split-K factor of small
-    launches depends on the launch geometry, and a 1-ulp fp32 difference can flip the tf32 rounding of
-    an operand, so the bound is the path's parity gate (1e-3) - mixing samples would be O(0.1)."""
-    tol = {"fp32": 2e-6, "tf32": 1e-3}[precision]
+    fp32 (CUDA-core convs, fixed summation order): equal to 2e-6 (the halo covers the receptive field up to the
+    numerically vanishing Kaiser-sinc tails: exact to rounding, not bit-exact).  tf32 / bf16: the split-K factor and
+    the Activation1d kernel form of small launches depend on the launch geometry, and a 1-ulp fp32 difference can
+    flip the rounding of an operand, so the bound is the mode's parity gate - mixing samples would be O(0.1)."""
+    tol = {"fp32": 2e-6, "tf32": 1e-3, "bf16": 5e-3}[precision]
     h = synth.bigvgan_config(256)
     sd = synth.bigvgan_state_dict(h, seed=2)
     voc = _voc(h, sd, precision)
@@ -139,6 +140,181 @@ def test_batch_and_time_shard_properties(precision):
     stitched = torch.cat([left, right], dim=-1)
     assert stitched.shape == full.shape
     assert float((stitched - full).abs().max()) < tol
+    if precision == "bf16":
+        assert snr_db(full.cpu().numpy(), stitched.cpu().numpy()) >= SNR_MIN["bf16"]
+
+
+# ----------------------------------------------------------------------------------- the plans the benchmark runs
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_batch64_full_size_decode_vs_oracle(precision):
+    """BASELINE.json configs[2] at full size: 64 x 10 s clips in ONE call.  This shape takes a different plan than
+    the batch-1 headline - AMP blocks back to back accumulating in place (accum = 1), persistent two-accumulator conv
+    launches, the two-phase Activation1d - so it gets its own parity check: three clips against the CPU oracle
+    (fp32 reference arithmetic on the same weights and latents) and every clip against its own batch-1 decode."""
+    from audiolcm_b200 import LatentToWaveform
+    dd, h = synth.vae_config(), synth.bigvgan_config()
+    vsd, gsd = synth.vae_decoder_state_dict(dd, seed=3), synth.bigvgan_state_dict(h, seed=0)
+    pipe = LatentToWaveform(_vae(dd, vsd, precision), _voc(h, gsd, precision))
+    B, T = 64, 312
+    z = np.concatenate([synth.synth_latent(1, T, seed=200 + i) for i in range(B)], axis=0)
+    wav = pipe.decode_tensor(torch.from_numpy(z)).cpu().numpy()
+    assert wav.shape == (B, T * 512) and np.isfinite(wav).all()
+    vt = {k: torch.from_numpy(v) for k, v in vsd.items()}
+    gt = {k: torch.from_numpy(v) for k, v in gsd.items()}
+    for i in (0, 29, 63):
+        with torch.no_grad():
+            ref = O.bigvgan_forward(gt, h, O.decode_first_stage(vt, dd, torch.from_numpy(z[i:i + 1]))).reshape(-1).numpy()
+        err = np.abs(wav[i] - ref).max()
+        print(f"\n[batch64 {precision}] clip {i}: max-abs {err:.3e} (ref abs-max {np.abs(ref).max():.3f}) SNR {snr_db(ref, wav[i]):.1f} dB")
+        assert err <= WAV_TOL[precision], (i, err)
+        assert snr_db(ref, wav[i]) >= SNR_MIN[precision]
+    for i in (1, 40):  # a batch item must not depend on its neighbours: compare with its own batch-1 decode
+        one = pipe.decode_tensor(torch.from_numpy(z[i:i + 1])).cpu().numpy()[0]
+        assert np.abs(one - wav[i]).max() <= WAV_TOL[precision]
+
+
+@pytest.mark.parametrize("knobs", [{"ALCM_LANES": "0"}, {"ALCM_ACT_VARIANT": "3"}, {"ALCM_ACT_VARIANT": "2"}, {"ALCM_ACT_VARIANT": "7"},
+                                   {"ALCM_ACT_VARIANT": "8"}, {"ALCM_PERSIST": "0"}, {"ALCM_CLUSTER_SPLITK": "0"},
+                                   {"ALCM_GRAPH": "0"}, {"ALCM_PDL": "1"}])
+def test_forced_plan_variants_match_reference(golden_dir, monkeypatch, knobs):
+    """Every plan-shaping knob the batch-64 / long-form plans flip (serial AMP blocks with in-place accumulation, the
+    big-launch Activation1d forms, non-persistent convs, workspace split-K, eager launches, PDL), forced on a small
+    batch-4 model and checked against the reference golden - in bf16 (the benchmarked mode) and tf32."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    g = np.load(os.path.join(golden_dir, "bigvgan_c256.npz"))
+    h = synth.bigvgan_config(int(g["c0"]))
+    mel = synth.synth_mel(int(g["B"]), int(g["T"]), seed=int(g["xseed"]))
+    for precision in ("tf32", "bf16"):
+        voc = _voc(h, synth.bigvgan_state_dict(h, seed=int(g["wseed"])), precision)
+        wav = voc.vocode(torch.from_numpy(mel))
+        ref = g["wav"].reshape(wav.shape)
+        err = np.abs(wav - ref).max()
+        assert err <= WAV_TOL[precision], (knobs, precision, err)
+        assert snr_db(ref, wav) >= SNR_MIN[precision]
+
+
+def _nccl_worker(rank, world, port, T, precision, out_q):
+    import torch.distributed as dist
+    from audiolcm_b200 import VocoderBigVGAN
+    from audiolcm_b200.pipeline import shard_range, vocode_time_sharded
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=torch.device(dev))
+    h = synth.bigvgan_config(256)
+    voc = VocoderBigVGAN.from_state_dict(synth.bigvgan_state_dict(h, seed=5), h, device=dev, precision=precision)
+    mel = torch.from_numpy(synth.synth_mel(1, T, seed=9))
+    s, e = shard_range(T, rank, world)
+    part = vocode_time_sharded(voc.vocode_tensor, mel[..., s:e].contiguous().to(dev), rank, world, hop=voc.hop)
+    full = voc.vocode_tensor(mel.to(dev)) if rank == 0 else None
+    out_q.put((rank, part.cpu().numpy(), None if full is None else full.cpu().numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_time_sharded_vocode_over_nccl_vs_oracle(precision):
+    """BASELINE.json configs[3] on real hardware: two ranks, two GPUs, the 34-frame halo exchanged with NCCL P2P
+    (batch_isend_irecv), each rank vocoding its extended chunk; the stitched waveform is compared with the CPU oracle
+    (float64) and with the un-sharded vocode of the same clip on one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    T, world = 300, 2
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, T, precision, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(world):
+        r, part, full = q.get(timeout=600)
+        got[r] = (part, full)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    stitched = np.concatenate([got[r][0] for r in range(world)], axis=-1)
+    full = got[0][1]
+    h = synth.bigvgan_config(256)
+    sd = synth.bigvgan_state_dict(h, seed=5)
+    with torch.no_grad():
+        ref = O.bigvgan_forward(sd, h, torch.from_numpy(synth.synth_mel(1, T, seed=9)), torch.float64).squeeze(1).numpy()
+    assert stitched.shape == ref.shape == full.shape
+    err_ref, err_full = np.abs(stitched - ref).max(), np.abs(stitched - full).max()
+    print(f"\n[time-sharded NCCL {precision}] vs oracle {err_ref:.3e}, vs un-sharded GPU {err_full:.3e}")
+    assert err_ref <= WAV_TOL[precision] and err_full <= WAV_TOL[precision]
+    assert snr_db(ref, stitched) >= SNR_MIN[precision]
+
+
+def test_preplanned_calls_do_not_allocate_and_pcm16_matches():
+    """SURVEY 8b 'no hidden cudaMalloc on the hot path': after plan(B,T) the decode calls leave the device's free
+    memory untouched; workspace_bytes() of an unplanned shape (sizing pass) equals the planned size.  The PCM16
+    output is rint(wav * 32767), the samples soundfile.write would store (InferAPI.py:98)."""
+    from audiolcm_b200 import LatentToWaveform
+    dd, h = synth.vae_config(32), synth.bigvgan_config(64)
+    pipe = LatentToWaveform(_vae(dd, synth.vae_decoder_state_dict(dd, seed=1), "bf16"),
+                            _voc(h, synth.bigvgan_state_dict(h, seed=1), "bf16"))
+    B, T = 3, 40
+    want = pipe.vae.workspace_bytes(B, T) + pipe.voc.workspace_bytes(B, 2 * T)
+    assert want > 0
+    got = pipe.plan(B, T)
+    assert got == want
+    z = torch.from_numpy(synth.synth_latent(B, T, seed=4)).to(DEV)
+    wav = torch.empty((B, T * 512), dtype=torch.float32, device=DEV)
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for _ in range(5):
+        w = pipe.decode_tensor(z)           # torch's caching allocator serves `w` from its pool after the first call
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    for _ in range(5):
+        w = pipe.decode_tensor(z)
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] == free1 and free0 - free1 <= (4 << 20)
+    pcm = pipe.decode_pcm16_tensor(z)
+    assert pcm.dtype == torch.int16 and pcm.shape == w.shape
+    want_pcm = torch.round(w * 32767.0).to(torch.int16)
+    assert torch.equal(pcm, want_pcm)      # same kernel, same arithmetic, round-half-even both sides
+    del wav
+
+
+def test_two_threads_two_contexts():
+    """No process-global state: two host threads, each with its own alcm_ctx, models and CUDA stream, decode
+    concurrently and reproduce the single-threaded results bit for bit."""
+    import threading
+    h = synth.bigvgan_config(64)
+    sd = synth.bigvgan_state_dict(h, seed=8)
+    mels = [torch.from_numpy(synth.synth_mel(2, 30 + 7 * i, seed=50 + i)).to(DEV) for i in range(4)]
+    base = _voc(h, sd, "bf16")
+    want = [base.vocode_tensor(m).clone() for m in mels]
+    errs, outs = [], {}
+
+    def worker(tid):
+        try:
+            stream = torch.cuda.Stream(device=DEV)
+            with torch.cuda.stream(stream):
+                voc = _voc(h, sd, "bf16")          # own ctx (audiolcm_b200._lib.ctx is per thread) and own handle
+                for it in range(6):
+                    for i, m in enumerate(mels):
+                        out = voc.vocode_tensor(m)
+                        stream.synchronize()
+                        if not torch.equal(out, want[i]):
+                            errs.append((tid, it, i))
+            outs[tid] = True
+        except Exception as e:  # noqa: BLE001
+            errs.append((tid, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs and len(outs) == 2, errs
 
 
 def test_fused_activation_chain_matches_reference(golden_dir, monkeypatch):

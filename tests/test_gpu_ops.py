@@ -212,3 +212,45 @@ def test_bad_arguments_raise(ops):
         ops.groupnorm_swish(torch.zeros(1, 20, 8, device=DEV), torch.ones(20, device=DEV), torch.zeros(20, device=DEV))
     with pytest.raises(AlcmError):
         ops.activation1d(torch.zeros(1, 4, 8), torch.zeros(4), torch.zeros(4))  # CPU tensor: no fallback
+
+
+# ----------------------------------------------------------------------------------- every Activation1d kernel form
+ACT_VARIANTS = {0: "R=4", 1: "pair R=4", 2: "R=8", 3: "R=6", 5: "pair R=6", 6: "pair R=8", 7: "two-phase UR=5", 8: "two-phase UR=7"}
+ACT_EDGE_SHAPES = [(1, 8, 1), (1, 8, 3), (2, 24, 4099), (1, 16, 640), (1, 16, 641), (1, 8, 637), (1, 8, 1283), (1, 8, 896),
+                   (1, 8, 899), (1, 24, 6), (1, 40, 1925)]
+
+
+@pytest.mark.parametrize("variant", sorted(ACT_VARIANTS))
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_activation1d_every_kernel_form(ops, monkeypatch, variant, precision):
+    """The plans pick one of several Activation1d kernels by launch size; here each form is forced
+    (ALCM_ACT_VARIANT) and run over tile-boundary and tiny shapes (T = 1: every tap is replicate padding;
+    T = tile, tile+1, tile-3: the halo'd edges of the two-phase form) against the float64 oracle."""
+    from oracle import decode_oracle as O
+    monkeypatch.setenv("ALCM_ACT_VARIANT", str(variant))
+    tol = {"fp32": 1e-5, "tf32": 2.0 ** -11, "bf16": 2.0 ** -8}[precision]
+    for i, (B, C, T) in enumerate(ACT_EDGE_SHAPES):
+        x = _rand(B, C, T, seed=30 + i, scale=1.5)
+        al, be = _rand(C, seed=2, scale=0.5), _rand(C, seed=3, scale=0.5)
+        ref = O.activation1d(x.double(), al.double(), be.double(), O.kaiser_sinc_filter().double())
+        y = ops.activation1d(x.to(DEV), al.to(DEV), be.to(DEV), precision).cpu()
+        err = (y.double() - ref).abs()
+        assert float((err / (ref.abs() + 1.0)).max()) < tol * 1.01 + 1e-5, (ACT_VARIANTS[variant], (B, C, T), float(err.max()))
+
+
+def test_narrow_operand_planes_are_not_padded_to_16(ops):
+    """C = 24 / 20 / 8 operands: the conv's missing K chunk is a zeroed shared-memory slab, not an HBM plane.
+    Checked against the same conv with the 16-channel padding forced in a separate process (ALCM_UNPADDED=0)
+    would need a re-import; instead: results must match the float64 reference for every narrow shape in all modes
+    (a stale or non-zero slab shows up as O(1) error)."""
+    for (B, Cin, Cout, T, K, d) in [(2, 24, 24, 1000, 11, 5), (1, 20, 20, 77, 1, 1), (1, 8, 8, 300, 7, 1), (3, 24, 48, 513, 3, 3),
+                                    (1, 40, 24, 260, 7, 1)]:
+        for precision in ("tf32", "bf16", "fp32"):
+            x = _rand(B, Cin, T, seed=41)
+            w = _rand(Cout, Cin, K, seed=42, scale=1.0 / np.sqrt(Cin * K))
+            b = _rand(Cout, seed=43, scale=0.1)
+            xr, wr = round_operand(x, precision), round_operand(w, precision)
+            ref = F.conv1d(xr.double(), wr.double(), b.double(), dilation=d, padding=(K * d - d) // 2)
+            for _ in range(2):  # twice: persistent ring slots are reused
+                y = ops.conv1d(x.to(DEV), w.to(DEV), b.to(DEV), None, dilation=d, precision=precision).cpu()
+                assert float((y.double() - ref).abs().max()) < 3e-5 * max(1.0, float(ref.abs().max())), (Cin, Cout, precision)

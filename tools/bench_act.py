@@ -1,4 +1,5 @@
-"""Activation1d micro-benchmark: algorithmic GB/s (fp32 in + operand out) of single launches."""
+"""Activation1d micro-benchmark: algorithmic GB/s (fp32 in + operand out, unpadded channels) of single launches on random
+operands.  ALCM_ACT_VARIANT=n forces a kernel form (3: R=6 register-blocked, 7 / 8: two-phase UR=5 / 7)."""
 import ctypes as C
 import os
 import sys
@@ -12,8 +13,7 @@ SHAPES = [(1, 768, 2500), (1, 384, 10000), (1, 192, 20000), (1, 96, 40000), (1, 
 for prec in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["bf16", "tf32"]):
     osz = 2 if prec == "bf16" else 4
     for (B, Cc, T) in SHAPES:
-        cpad = (Cc + 15) // 16 * 16
-        byt = B * cpad * T * (4 + osz)
+        byt = B * Cc * T * (4 + osz)   # algorithmic, unpadded channels
         ms = C.c_float()
         _lib.check(lib.alcm_bench_act(ctx, B, Cc, T, _lib.PREC[prec], 100, C.byref(ms)))
         print(f"{prec} B={B} C={Cc} T={T} ({byt / 1e6:.0f} MB): {ms.value * 1e3:8.1f} us {byt / ms.value / 1e6:7.0f} GB/s", flush=True)

@@ -13,5 +13,5 @@ lib = _lib.load()
 ctx = _lib.ctx(0)
 ms = C.c_float()
 _lib.check(lib.alcm_bench_act(ctx, B, Cc, T, _lib.PREC[prec], iters, C.byref(ms)))
-byt = B * ((Cc + 15) // 16 * 16) * T * (4 + (2 if prec == "bf16" else 4))
+byt = B * Cc * T * (4 + (2 if prec == "bf16" else 4))  # algorithmic, unpadded
 print(f"{prec} B={B} C={Cc} T={T}: {ms.value * 1e3:.1f} us  {byt / ms.value / 1e6:.0f} GB/s (algorithmic bytes {byt / 1e6:.0f} MB)")

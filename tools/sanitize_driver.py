@@ -1,0 +1,88 @@
+"""Small-shape workload for compute-sanitizer (tools/sanitize.sh): every form of the conv kernel (plain, persistent
+two-accumulator, workspace split-K, cluster/DSMEM split-K, fused Activation1d epilogue, narrow operands with the
+zeroed K slab), every Activation1d kernel form, GroupNorm, attention and one small end-to-end decode per mode.
+Each case is also checked numerically, so a sanitizer-clean run is a correct run."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from audiolcm_b200 import AutoencoderKLDecoder, LatentToWaveform, VocoderBigVGAN, ops, synth  # noqa: E402
+from tests.util import round_operand  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).float()
+
+
+def conv_case(name, B, Cin, Cout, T, K, d, precision="bf16", env=None):
+    for k, v in (env or {}).items():
+        os.environ[k] = v
+    x, w, b = rnd(B, Cin, T, seed=1), rnd(Cout, Cin, K, seed=2, scale=1 / np.sqrt(Cin * K)), rnd(Cout, seed=3, scale=0.1)
+    ref = F.conv1d(round_operand(x, precision).double(), round_operand(w, precision).double(), b.double(), dilation=d,
+                   padding=(K * d - d) // 2)
+    y = ops.conv1d(x.to(DEV), w.to(DEV), b.to(DEV), None, dilation=d, precision=precision).cpu()
+    err = float((y.double() - ref).abs().max())
+    for k in (env or {}):
+        os.environ.pop(k)
+    print(f"  conv {name:28s} {precision} err {err:.2e}", flush=True)
+    assert err < 3e-5 * max(1.0, float(ref.abs().max()))
+
+
+def main():
+    from oracle import decode_oracle as O
+    conv_case("plain", 1, 96, 96, 129, 5, 1)
+    conv_case("plain tf32", 1, 96, 96, 129, 5, 1, "tf32")
+    conv_case("persistent 2-acc", 8, 32, 32, 6000, 3, 1)
+    conv_case("persistent narrow C=24", 8, 24, 24, 6000, 11, 5)
+    conv_case("workspace split-K", 1, 1536, 768, 100, 1, 1, env={"ALCM_CLUSTER_SPLITK": "0"})
+    conv_case("cluster split-K", 1, 1536, 1536, 312, 3, 1)
+    conv_case("cluster split-K tf32", 1, 1536, 1536, 100, 3, 1, "tf32")
+    # fused Activation1d epilogue
+    x, w, b = rnd(1, 96, 117, seed=4), rnd(96, 96, 3, seed=5, scale=0.06), rnd(96, seed=6, scale=0.1)
+    al, be = rnd(96, seed=7, scale=0.5), rnd(96, seed=8, scale=0.5)
+    _, ya = ops.conv1d_act(x.to(DEV), w.to(DEV), b.to(DEV), None, al.to(DEV), be.to(DEV), dilation=5, precision="bf16", want_conv=False)
+    cref = F.conv1d(round_operand(x, "bf16").double(), round_operand(w, "bf16").double(), b.double(), dilation=5, padding=5)
+    aref = O.activation1d(cref, al.double(), be.double(), O.kaiser_sinc_filter().double())
+    err = float(((ya.cpu().double() - aref).abs() / (aref.abs() + 1)).max())
+    print(f"  conv fused Activation1d epilogue     bf16 err {err:.2e}", flush=True)
+    assert err < 2.0 ** -8 * 1.01 + 3e-5
+    # every Activation1d kernel form
+    for variant in (0, 1, 2, 3, 5, 6, 7, 8):
+        os.environ["ALCM_ACT_VARIANT"] = str(variant)
+        for prec in ("bf16", "tf32"):
+            for (B, C, T) in ((1, 8, 3), (2, 24, 1300)):
+                x, al, be = rnd(B, C, T, seed=9, scale=1.5), rnd(C, seed=10, scale=0.5), rnd(C, seed=11, scale=0.5)
+                ref = O.activation1d(x.double(), al.double(), be.double(), O.kaiser_sinc_filter().double())
+                y = ops.activation1d(x.to(DEV), al.to(DEV), be.to(DEV), prec).cpu()
+                err = float(((y.double() - ref).abs() / (ref.abs() + 1)).max())
+                assert err < {"bf16": 2.0 ** -8, "tf32": 2.0 ** -11}[prec] * 1.01 + 1e-5, (variant, prec, err)
+        print(f"  act1d variant {variant} ok", flush=True)
+    os.environ.pop("ALCM_ACT_VARIANT")
+    x = rnd(2, 64, 33, seed=12)
+    ops.groupnorm_swish(x.to(DEV), torch.ones(64, device=DEV), torch.zeros(64, device=DEV))
+    q = rnd(1, 64, 33, seed=13)
+    ops.attn1d(q.to(DEV), q.to(DEV), q.to(DEV))
+    print("  groupnorm, attention ok", flush=True)
+    dd, h = synth.vae_config(32), synth.bigvgan_config(64)
+    vsd, gsd = synth.vae_decoder_state_dict(dd, seed=1), synth.bigvgan_state_dict(h, seed=1)
+    z = synth.synth_latent(2, 16, seed=1)
+    with torch.no_grad():
+        ref = O.bigvgan_forward(gsd, h, O.decode_first_stage(vsd, dd, z)).squeeze(1).numpy()
+    for prec, tol in (("bf16", 5e-3), ("tf32", 1e-3)):
+        pipe = LatentToWaveform(AutoencoderKLDecoder(vsd, dd, synth.VAE_EMBED_DIM, DEV, prec), VocoderBigVGAN.from_state_dict(gsd, h, DEV, prec))
+        err = float(np.abs(pipe.decode(z) - ref).max())
+        print(f"  decode[{prec}] err {err:.2e}", flush=True)
+        assert err <= tol
+    torch.cuda.synchronize()
+    print("sanitize driver: all cases numerically correct", flush=True)
+
+
+if __name__ == "__main__":
+    main()
