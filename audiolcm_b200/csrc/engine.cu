@@ -236,6 +236,8 @@ static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
 }
 
+static cudaError_t sync_setup();
+
 // ------------------------------------------------------------------------------------------ conv layers
 enum ConvKind { KIND_CONV = 0, KIND_CONVT = 1, KIND_UPCONV3 = 2 };
 
@@ -306,7 +308,7 @@ static ConvLayer prepare_conv(Arena& ar, const Knobs& K_, int prec, ConvKind kin
       L.bias = static_cast<float*>(ar.alloc((size_t)Cout * 4, false));
       CUDA_CHECK(cudaMemcpy(L.bias, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice));
     }
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(sync_setup());
     return L;
   }
   const int E = (prec == ALCM_PREC_BF16) ? 8 : 4;
@@ -336,7 +338,7 @@ static ConvLayer prepare_conv(Arena& ar, const Knobs& K_, int prec, ConvKind kin
   CUDA_CHECK(cudaGetLastError());
   L.bias = static_cast<float*>(ar.alloc((size_t)L.n_tiles * L.NT * 4, true));
   if (bias) CUDA_CHECK(cudaMemcpy(L.bias, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice));
-  CUDA_CHECK(cudaDeviceSynchronize());
+  CUDA_CHECK(sync_setup());
   L.weff = nullptr;  // tmp arena frees it
   return L;
 }
@@ -453,7 +455,7 @@ static const ConvLayer& retile(Arena& ar, RetileCache& cache, const ConvLayer& L
   CUDA_CHECK(cudaGetLastError());
   R.bias = static_cast<float*>(ar.alloc((size_t)R.n_tiles * NT2 * 4, true));
   CUDA_CHECK(cudaMemcpy(R.bias, L.bias, (size_t)std::min(L.n_tiles * L.NT, R.n_tiles * NT2) * 4, cudaMemcpyDeviceToDevice));
-  CUDA_CHECK(cudaDeviceSynchronize());
+  CUDA_CHECK(sync_setup());
   return cache.m.emplace(key, R).first->second;
 }
 
@@ -771,8 +773,16 @@ struct OpList {
         const int tile = kPairHalf * (variant == 1 ? 4 : (variant == 5 ? 6 : 8));
         const dim3 grid((T + tile - 1) / tile, nch32 / 2, B);
         if (oesz == 4) {
-          if (fast) launch_k(act1d_pair_kernel<false, true, 4>, grid, dim3(kPairThreads), 0, st, a);
-          else launch_k(act1d_pair_kernel<false, false, 4>, grid, dim3(kPairThreads), 0, st, a);
+          if (variant == 1) {
+            if (fast) launch_k(act1d_pair_kernel<false, true, 4>, grid, dim3(kPairThreads), 0, st, a);
+            else launch_k(act1d_pair_kernel<false, false, 4>, grid, dim3(kPairThreads), 0, st, a);
+          } else if (variant == 5) {
+            if (fast) launch_k(act1d_pair_kernel<false, true, 6>, grid, dim3(kPairThreads), 0, st, a);
+            else launch_k(act1d_pair_kernel<false, false, 6>, grid, dim3(kPairThreads), 0, st, a);
+          } else {
+            if (fast) launch_k(act1d_pair_kernel<false, true, 8>, grid, dim3(kPairThreads), 0, st, a);
+            else launch_k(act1d_pair_kernel<false, false, 8>, grid, dim3(kPairThreads), 0, st, a);
+          }
         } else if (variant == 1) {
           launch_k(act1d_pair_kernel<true, true, 4>, grid, dim3(kPairThreads), 0, st, a);
         } else if (variant == 5) {
@@ -991,10 +1001,22 @@ struct PlanCache {
     }
     reap(st);
   }
-  void drain() {  // model destruction: the owner has synchronised the device
-    retired.clear();
-  }
 };
+
+// Weight preparation, plan building and the single-op entry points run their set-up kernels on the legacy default
+// stream and wait for THAT stream only - never cudaDeviceSynchronize(): a device-wide wait would also touch streams
+// that another host thread is capturing into a CUDA graph (which fails both the wait and the other thread's capture).
+static cudaError_t sync_setup() { return cudaStreamSynchronize(nullptr); }
+
+// Model destruction: wait for the last launch of every plan (cached or retired) through the plans' own events.
+template <class Map>
+static void wait_plans(Map& plans, PlanCache& pc) {
+  for (auto& kv : plans)
+    if (kv.second->used) cudaEventSynchronize(kv.second->done);
+  for (auto& r : pc.retired)
+    if (r->used) cudaEventSynchronize(r->done);
+  pc.retired.clear();
+}
 
 // Order a plan's launches after its previous use (other stream) and keep the retire event current.
 struct PlanUse {
@@ -1040,6 +1062,13 @@ static std::unique_ptr<Plan> build_plan(const Env& env, Arena* war, RetileCache*
   pl->ar.reserve(need, st);
   build(*pl);
   CUDA_CHECK(cudaEventCreateWithFlags(&pl->done, cudaEventDisableTiming));
+  // the slab's zero-fill is ordered on `st`: a first use on another stream must wait for it (PlanUse)
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+    CUDA_CHECK(cudaEventRecord(pl->done, st));
+    pl->used = true;
+    pl->last_stream = st;
+  }
   if (env.k.graph) capture_graph(pl->ol, pl->ge);
   return pl;
 }
@@ -1531,15 +1560,14 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
       v->post_C = C;
       ti += 3;
     }
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(sync_setup());
     *out = v.release();
   });
 }
 void alcm_vocoder_destroy(alcm_vocoder* v) {
   if (!v) return;
   cudaSetDevice(v->ctx->device);
-  cudaDeviceSynchronize();  // plans may still be in flight on caller streams
-  v->pcache.drain();
+  wait_plans(v->plans, v->pcache);  // plans may still be in flight on caller streams
   delete v;
 }
 
@@ -1688,15 +1716,14 @@ int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* 
     v->norm_out = gn(block_in);
     v->conv_out = conv(cfg->out_ch, block_in, cfg->kernel_size);
     REQUIRE(ti == n_tensors, "vae_create: tensor walk mismatch");
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(sync_setup());
     *out = v.release();
   });
 }
 void alcm_vae_destroy(alcm_vae* v) {
   if (!v) return;
   cudaSetDevice(v->ctx->device);
-  cudaDeviceSynchronize();
-  v->pcache.drain();
+  wait_plans(v->plans, v->pcache);
   delete v;
 }
 
@@ -1786,7 +1813,7 @@ int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, con
     Arena ar;
     PlaneT xin = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, opnd_esz(precision));
     SnakeP sp = make_snake(ar, alpha, beta, C);
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(sync_setup());
     launch_pack(x, xin, C, T, 1.f, ALCM_PREC_FP32, st);
     OpList ol;
     ol.env = Env{ctx, Knobs::from_env()};
@@ -1816,7 +1843,7 @@ static void run_conv_test(alcm_ctx* ctx, ConvKind kind, const float* x, const fl
   PlaneT out = make_planes(ar, B, Cout, T * L.nphase, 4);
   PlaneT rp;
   if (res) rp = make_planes(ar, B, Cout, T * L.nphase, 4);
-  CUDA_CHECK(cudaDeviceSynchronize());
+  CUDA_CHECK(sync_setup());
   launch_pack(x, xin, Cin, T, 1.f, precision, st);
   if (res) launch_pack(res, rp, Cout, T * L.nphase, 1.f, ALCM_PREC_FP32, st);
   OpList ol;
@@ -1825,7 +1852,7 @@ static void run_conv_test(alcm_ctx* ctx, ConvKind kind, const float* x, const fl
   ol.ar = &ar;
   ol.war = &ar; ol.cache = &rcache;  // same per-launch tile choice (N tile, K split, cluster reduction) as the plans
   ol.conv(L, xin, out, res ? &rp : nullptr);
-  CUDA_CHECK(cudaDeviceSynchronize());  // workspace memsets
+  CUDA_CHECK(sync_setup());  // workspace memsets
   ol.run(st);
   launch_unpack(out, y, Cout, T * L.nphase, st);
   CUDA_CHECK(cudaGetLastError());
@@ -1856,14 +1883,14 @@ int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const flo
     PlaneT rp;
     if (res) rp = make_planes(ar, B, Cout, T, 4);
     SnakeP sp = make_snake(ar, alpha, beta, Cout);
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(sync_setup());
     launch_pack(x, xin, Cin, T, 1.f, precision, st);
     if (res) launch_pack(res, rp, Cout, T, 1.f, ALCM_PREC_FP32, st);
     OpList ol;
     ol.env = env;
     ol.ar = &ar;
     ol.conv_act(L, xin, y_conv ? &out : nullptr, res ? &rp : nullptr, 1.f, 0, &aout, sp.ea, sp.ib, precision == ALCM_PREC_TF32);
-    CUDA_CHECK(cudaDeviceSynchronize());  // workspace memsets
+    CUDA_CHECK(sync_setup());  // workspace memsets
     ol.run(st);
     if (y_conv) launch_unpack(out, y_conv, Cout, T, st);
     if (precision == ALCM_PREC_BF16) {
@@ -1904,7 +1931,7 @@ int alcm_groupnorm_swish_fwd(alcm_ctx* ctx, const float* x, const float* gamma, 
     OpList ol;
     ol.env = Env{ctx, Knobs::from_env()};
     op_gn(ol, ar, xin, out, g, swish, ALCM_PREC_FP32);
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(sync_setup());
     launch_pack(x, xin, C, T, 1.f, ALCM_PREC_FP32, st);
     ol.run(st);
     launch_unpack(out, y, C, T, st);
@@ -1922,7 +1949,7 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
     Arena ar;
     PlaneT pq = make_planes(ar, B, C, T, 4), pk = make_planes(ar, B, C, T, 4), pv = make_planes(ar, B, C, T, 4);
     PlaneT ph = make_planes(ar, B, C, T, 4);
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(sync_setup());
     launch_pack(q, pq, C, T, 1.f, ALCM_PREC_FP32, st);
     launch_pack(k, pk, C, T, 1.f, ALCM_PREC_FP32, st);
     launch_pack(v, pv, C, T, 1.f, ALCM_PREC_FP32, st);
@@ -1931,7 +1958,7 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
     float* Pm = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
     float* Sp = static_cast<float*>(ar.alloc((size_t)kAttnSplit * B * T * T * 4, false));
     push_attention(ol, pq, pk, pv, ph, Sp, Pm, B, C, T);
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(sync_setup());
     ol.run(st);
     launch_unpack(ph, out, C, T, st);
     CUDA_CHECK(cudaGetLastError());
@@ -2050,7 +2077,7 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     } else {
       ol.conv(L, x, out, nullptr);
     }
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(sync_setup());
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0));
     CUDA_CHECK(cudaEventCreate(&e1));
@@ -2069,11 +2096,11 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
       const int ks = clustered ? ks_c : pick_ksplit(env, Lt, T, B, bench_fused);
       const size_t nctas = (size_t)conv_m_tiles(T, bench_fused) * Lt.n_tiles * B * Lt.nphase * ks;
       long long* tr = static_cast<long long*>(ar.alloc(nctas * 8 * sizeof(long long), true));
-      CUDA_CHECK(cudaDeviceSynchronize());
+      CUDA_CHECK(sync_setup());
       ctx->conv_trace = tr;
       ol.run(0);
       ctx->conv_trace = nullptr;
-      CUDA_CHECK(cudaDeviceSynchronize());
+      CUDA_CHECK(sync_setup());
       std::vector<long long> h(nctas * 8);
       CUDA_CHECK(cudaMemcpy(h.data(), tr, h.size() * 8, cudaMemcpyDeviceToHost));
       const size_t launched = (size_t)ctx->conv_last_grid;
@@ -2113,7 +2140,7 @@ int alcm_bench_act(alcm_ctx* ctx, int B, int C, int T, int precision, int iters,
     OpList ol;
     ol.env = Env{ctx, Knobs::from_env()};
     ol.act(x, out, sp.ea, sp.ib, precision == ALCM_PREC_TF32, precision != ALCM_PREC_FP32);
-    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(sync_setup());
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0));
     CUDA_CHECK(cudaEventCreate(&e1));
