@@ -86,6 +86,8 @@ SYMBOLS = {
     "alcm_profile_stages": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Profile), C.c_int, _P]),
     "alcm_bench_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "alcm_bench_act": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "alcm_vocoder_check_guards": (C.c_int, [_P, C.POINTER(C.c_longlong)]),
+    "alcm_vae_check_guards": (C.c_int, [_P, C.POINTER(C.c_longlong)]),
     "alcm_vocoder_launches": (C.c_int, [_P, C.c_int, C.c_int]),
     "alcm_vae_launches": (C.c_int, [_P, C.c_int, C.c_int]),
 }

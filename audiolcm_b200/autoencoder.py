@@ -135,6 +135,11 @@ class AutoencoderKLDecoder(object):
         _lib.check(_lib.load().alcm_vae_workspace_bytes(self._h, int(B), int(T), C.byref(n)))
         return int(n.value)
 
+    def check_guards(self):
+        n = C.c_longlong()
+        _lib.check(_lib.load().alcm_vae_check_guards(self._h, C.byref(n)))
+        return int(n.value)
+
     def launches(self, B, T):
         return _lib.load().alcm_vae_launches(self._h, B, T)
 

@@ -68,7 +68,7 @@ static int env_int(const char* name, int dflt) {
 struct Knobs {
   int pdl, graph, lanes, lane_waves, persist, cluster_splitk, splitk, retile, retile_mode;
   int smem_budget, smem_budget_1w, smem_budget_mw, tpg, astages, kblk_max, nt, tmem2;
-  int act_variant, act_v2, act_v2_min_waves, fuse_act, fuse_stages, gn_fused, max_plans, trace, bench_fused, attn_tc;
+  int act_variant, act_v2, act_v2_min_waves, fuse_act, fuse_stages, gn_fused, max_plans, trace, bench_fused, attn_tc, guard;
   static Knobs from_env() {
     Knobs k;
     k.pdl = env_int("ALCM_PDL", -1);  // -1 unset (per-plan default), 0 never, 1 always
@@ -98,6 +98,7 @@ struct Knobs {
     k.trace = env_int("ALCM_TRACE", 0);
     k.bench_fused = env_int("ALCM_BENCH_FUSED", 0);
     k.attn_tc = env_int("ALCM_ATTN_TC", 1);
+    k.guard = env_int("ALCM_GUARD", 0);                   // 1: 4 KB zero guard zones between device buffers, verified by alcm_*_check_guards
     return k;
   }
 };
@@ -128,29 +129,42 @@ struct Arena {
   uint8_t* slab = nullptr;
   size_t slab_bytes = 0, off = 0;
   cudaStream_t slab_stream = nullptr;
+  // ALCM_GUARD=1 (self-check mode; compute-sanitizer is not available on every pool): every buffer is followed - and,
+  // outside slabs, preceded - by a kGuard-byte zone of zeros that no kernel may touch; guard_violations() counts the
+  // bytes that changed.  An out-of-bounds WRITE of any kernel shows up there (or in a neighbour's zero halo rows, which
+  // the repeat-call bit-identity tests catch).
+  static constexpr size_t kGuard = 4096;
+  bool guard = false;
+  std::vector<std::pair<uint8_t*, size_t>> gaps;
   static size_t align_up(size_t b) { return (std::max<size_t>(b, 16) + 255) & ~(size_t)255; }
   void* alloc(size_t bytes, bool zero = true) {
+    const size_t g = guard ? kGuard : 0;
     if (measuring) {
       void* p = reinterpret_cast<void*>((uintptr_t)0x10000 + off);
-      off += align_up(bytes);
+      off += align_up(bytes) + g;
       total = off;
       return p;
     }
     if (slab) {
       const size_t b = align_up(bytes);
-      if (off + b > slab_bytes) throw AlcmError(ALCM_ERR_INTERNAL, "plan slab overflow: the sizing pass and the build pass disagree");
-      void* p = slab + off;
-      off += b;
+      if (off + b + g > slab_bytes) throw AlcmError(ALCM_ERR_INTERNAL, "plan slab overflow: the sizing pass and the build pass disagree");
+      uint8_t* p = slab + off;
+      off += b + g;
+      if (g) gaps.emplace_back(p + b, g);   // the slab was zero-filled as a whole
       return p;
     }
     void* p = nullptr;
     bytes = std::max<size_t>(bytes, 16);
-    CUDA_CHECK(cudaMalloc(&p, bytes));
-    if (zero) CUDA_CHECK(cudaMemset(p, 0, bytes));
+    const size_t b = guard ? align_up(bytes) : bytes;
+    CUDA_CHECK(cudaMalloc(&p, b + 2 * g));
+    if (zero) CUDA_CHECK(cudaMemset(p, 0, b + 2 * g));
+    else if (g) { CUDA_CHECK(cudaMemset(p, 0, g)); CUDA_CHECK(cudaMemset(static_cast<uint8_t*>(p) + g + b, 0, g)); }
     ptrs.push_back(p);
-    total += bytes;
-    return p;
+    total += b + 2 * g;
+    if (g) { gaps.emplace_back(static_cast<uint8_t*>(p), g); gaps.emplace_back(static_cast<uint8_t*>(p) + g + b, g); }
+    return static_cast<uint8_t*>(p) + g;
   }
+  long long guard_violations() const;  // bytes of the guard zones that are no longer zero (synchronises)
   void reserve(size_t bytes, cudaStream_t st) {  // slab mode: one stream-ordered allocation, zeroed once
     bytes = align_up(bytes);
     void* p = nullptr;
@@ -202,6 +216,22 @@ static PlaneT make_planes(Arena& ar, int B, int C, int T, int esz) {
 }
 
 static inline int opnd_esz(int prec) { return prec == ALCM_PREC_BF16 ? 2 : 4; }
+
+long long Arena::guard_violations() const {
+  if (gaps.empty()) return 0;
+  unsigned long long* d = nullptr;
+  CUDA_CHECK(cudaMalloc(&d, sizeof(*d)));
+  CUDA_CHECK(cudaMemset(d, 0, sizeof(*d)));
+  CUDA_CHECK(cudaStreamSynchronize(nullptr));
+  for (const auto& g : gaps) {
+    count_nonzero_kernel<<<4, 256>>>(reinterpret_cast<const uint4*>(g.first), g.second / 16, d);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  unsigned long long h = 0;
+  CUDA_CHECK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return (long long)h;
+}
 
 // ------------------------------------------------------------------------------------------ launches
 // Every kernel of a plan is launched with the programmatic-stream-serialization attribute (PDL): it may be
@@ -1050,6 +1080,7 @@ static std::unique_ptr<Plan> build_plan(const Env& env, Arena* war, RetileCache*
   size_t need = 0;
   {
     Plan probe;
+    probe.ar.guard = env.k.guard != 0;
     probe.ar.measuring = true;
     setup(probe);
     build(probe);
@@ -1059,6 +1090,7 @@ static std::unique_ptr<Plan> build_plan(const Env& env, Arena* war, RetileCache*
   if (size_only) return nullptr;
   std::unique_ptr<Plan> pl(new Plan());
   setup(*pl);
+  pl->ar.guard = env.k.guard != 0;
   pl->ar.reserve(need, st);
   build(*pl);
   CUDA_CHECK(cudaEventCreateWithFlags(&pl->done, cudaEventDisableTiming));
@@ -1500,6 +1532,7 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
     std::unique_ptr<alcm_vocoder> v(new alcm_vocoder());
     v->ctx = ctx; v->cfg = *cfg; v->prec = precision;
     v->env.cx = ctx; v->env.k = Knobs::from_env();  // the knob snapshot of this model
+    v->war.guard = v->env.k.guard != 0;
     const Knobs& K = v->env.k;
     Arena tmp;
     int ti = 0;
@@ -1654,6 +1687,7 @@ int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* 
     std::unique_ptr<alcm_vae> v(new alcm_vae());
     v->ctx = ctx; v->cfg = *cfg; v->prec = precision;
     v->env.cx = ctx; v->env.k = Knobs::from_env();
+    v->war.guard = v->env.k.guard != 0;
     const Knobs& K = v->env.k;
     int ti = 0;
     auto conv = [&](int cout, int cin, int k, ConvKind kind = KIND_CONV) {
@@ -1800,7 +1834,10 @@ int alcm_decode_to_pcm16(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B
 }
 
 // ---- single-op entry points ---------------------------------------------------------------
-static void sync_free(cudaStream_t st) { CUDA_CHECK(cudaStreamSynchronize(st)); }
+static void sync_free(const Arena& ar, cudaStream_t st) {
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  if (ar.guard) REQUIRE(ar.guard_violations() == 0, "ALCM_GUARD: a kernel wrote outside its buffers (guard zone modified)");
+}
 
 int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, const float* beta, float* y, int B, int C, int T,
                           int precision, void* stream) {
@@ -1811,6 +1848,7 @@ int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, con
     CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar;
+    ar.guard = env_int("ALCM_GUARD", 0) != 0;
     PlaneT xin = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, opnd_esz(precision));
     SnakeP sp = make_snake(ar, alpha, beta, C);
     CUDA_CHECK(sync_setup());
@@ -1826,7 +1864,7 @@ int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, con
       launch_unpack(out, y, C, T, st);
     }
     CUDA_CHECK(cudaGetLastError());
-    sync_free(st);
+    sync_free(ar, st);
   });
 }
 
@@ -1837,6 +1875,7 @@ static void run_conv_test(alcm_ctx* ctx, ConvKind kind, const float* x, const fl
   REQUIRE(precision >= 0 && precision <= 2, "conv: bad precision");
   CUDA_CHECK(cudaSetDevice(ctx->device));
   Arena ar;
+  ar.guard = env_int("ALCM_GUARD", 0) != 0;
   const Env env{ctx, Knobs::from_env()};
   ConvLayer L = prepare_conv(ar, env.k, precision, kind, w, bias, Cout, Cin, K, p);
   PlaneT xin = make_planes(ar, B, Cin, T, opnd_esz(precision));
@@ -1856,7 +1895,7 @@ static void run_conv_test(alcm_ctx* ctx, ConvKind kind, const float* x, const fl
   ol.run(st);
   launch_unpack(out, y, Cout, T * L.nphase, st);
   CUDA_CHECK(cudaGetLastError());
-  sync_free(st);
+  sync_free(ar, st);
 }
 
 int alcm_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, float* y, int B, int Cin,
@@ -1876,6 +1915,7 @@ int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const flo
     CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar;
+    ar.guard = env_int("ALCM_GUARD", 0) != 0;
     const Env env{ctx, Knobs::from_env()};
     ConvLayer L = prepare_conv(ar, env.k, precision, KIND_CONV, w, bias, Cout, Cin, K, dilation);
     PlaneT xin = make_planes(ar, B, Cin, T, opnd_esz(precision));
@@ -1900,7 +1940,7 @@ int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const flo
       launch_unpack(aout, y_act, Cout, T, st);
     }
     CUDA_CHECK(cudaGetLastError());
-    sync_free(st);
+    sync_free(ar, st);
   });
 }
 int alcm_conv_transpose1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
@@ -1926,6 +1966,7 @@ int alcm_groupnorm_swish_fwd(alcm_ctx* ctx, const float* x, const float* gamma, 
     CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar;
+    ar.guard = env_int("ALCM_GUARD", 0) != 0;
     PlaneT xin = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, 4);
     GnP g = make_gn(ar, gamma, beta, C);
     OpList ol;
@@ -1936,7 +1977,7 @@ int alcm_groupnorm_swish_fwd(alcm_ctx* ctx, const float* x, const float* gamma, 
     ol.run(st);
     launch_unpack(out, y, C, T, st);
     CUDA_CHECK(cudaGetLastError());
-    sync_free(st);
+    sync_free(ar, st);
   });
 }
 
@@ -1947,6 +1988,7 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
     CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar;
+    ar.guard = env_int("ALCM_GUARD", 0) != 0;
     PlaneT pq = make_planes(ar, B, C, T, 4), pk = make_planes(ar, B, C, T, 4), pv = make_planes(ar, B, C, T, 4);
     PlaneT ph = make_planes(ar, B, C, T, 4);
     CUDA_CHECK(sync_setup());
@@ -1962,7 +2004,7 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
     ol.run(st);
     launch_unpack(ph, out, C, T, st);
     CUDA_CHECK(cudaGetLastError());
-    sync_free(st);
+    sync_free(ar, st);
   });
 }
 
@@ -2051,6 +2093,7 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     REQUIRE(precision == ALCM_PREC_TF32 || precision == ALCM_PREC_BF16 || dbg == 0, "bench_conv: dbg flags need a tcgen05 mode");
     CUDA_CHECK(cudaSetDevice(ctx->device));
     Arena ar;
+    ar.guard = env_int("ALCM_GUARD", 0) != 0;
     const Env env{ctx, Knobs::from_env()};
     // Kaiming-uniform-like weights, N(0,1)-like activations: the magnitudes of the real model
     const float wb = 1.0f / sqrtf((float)Cin * K);
@@ -2130,6 +2173,7 @@ int alcm_bench_act(alcm_ctx* ctx, int B, int C, int T, int precision, int iters,
     REQUIRE(ctx && ms_per_launch && iters >= 1, "bench_act: bad argument");
     CUDA_CHECK(cudaSetDevice(ctx->device));
     Arena ar;
+    ar.guard = env_int("ALCM_GUARD", 0) != 0;
     PlaneT x = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, opnd_esz(precision));
     fill_uniform(x.p, x.bytes / 4, 0, -1.7f, 1.7f, 5u);
     float* al = static_cast<float*>(ar.alloc((size_t)round_up(C, 16) * 4, false));
@@ -2155,6 +2199,33 @@ int alcm_bench_act(alcm_ctx* ctx, int B, int C, int T, int precision, int iters,
     *ms_per_launch = ms / iters;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+  });
+}
+
+// ALCM_GUARD=1 self-check: bytes of the guard zones around the model's weights and between the buffers of its plans
+// that are no longer zero (0 = no kernel wrote out of bounds).  Waits for the plans' pending launches.
+int alcm_vocoder_check_guards(alcm_vocoder* v, long long* bad) {
+  return guarded([&] {
+    REQUIRE(v && bad, "check_guards: NULL argument");
+    CUDA_CHECK(cudaSetDevice(v->ctx->device));
+    long long n = v->war.guard_violations();
+    for (auto& kv : v->plans) {
+      if (kv.second->used) CUDA_CHECK(cudaEventSynchronize(kv.second->done));
+      n += kv.second->ar.guard_violations();
+    }
+    *bad = n;
+  });
+}
+int alcm_vae_check_guards(alcm_vae* v, long long* bad) {
+  return guarded([&] {
+    REQUIRE(v && bad, "check_guards: NULL argument");
+    CUDA_CHECK(cudaSetDevice(v->ctx->device));
+    long long n = v->war.guard_violations();
+    for (auto& kv : v->plans) {
+      if (kv.second->used) CUDA_CHECK(cudaEventSynchronize(kv.second->done));
+      n += kv.second->ar.guard_violations();
+    }
+    *bad = n;
   });
 }
 

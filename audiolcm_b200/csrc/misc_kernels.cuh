@@ -284,6 +284,20 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg,
   else reinterpret_cast<float*>(wav)[(size_t)b * T + t] = y;
 }
 
+// ALCM_GUARD self-check: number of non-zero bytes in a guard zone (n 16-byte units)
+__global__ void count_nonzero_kernel(const uint4* __restrict__ p, size_t n, unsigned long long* __restrict__ out) {
+  unsigned long long c = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = p[i];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) c += ((w[k] >> (8 * b)) & 0xffu) != 0u;
+  }
+  if (c) atomicAdd(out, c);
+}
+
 // Seeded uniform fill in [lo, hi) (micro-benchmark operands): counter-based hash, fp32 or bf16 elements.
 __global__ void fill_uniform_kernel(void* __restrict__ p, size_t n, int bf16, float lo, float hi, unsigned seed) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

@@ -228,5 +228,11 @@ class VocoderBigVGAN(object):
     def __call__(self, wav):
         return self.vocode(wav)
 
+    def check_guards(self):
+        """ALCM_GUARD=1 self-check: bytes of the guard zones around this handle's buffers that a kernel overwrote."""
+        n = C.c_longlong()
+        _lib.check(_lib.load().alcm_vocoder_check_guards(self._h, C.byref(n)))
+        return int(n.value)
+
     def launches(self, B, T):
         return _lib.load().alcm_vocoder_launches(self._h, B, T)

@@ -188,6 +188,11 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
                     float* ms_per_launch);
 /* same for one Activation1d launch on [B,C,T] (random x, alpha, beta) */
 int alcm_bench_act(alcm_ctx* ctx, int B, int C, int T, int precision, int iters, float* ms_per_launch);
+/* ALCM_GUARD=1 self-check (set before the handle is created): every device buffer the handle owns is separated from
+ * its neighbours by 4 KB zones of zeros that no kernel may touch; *bad = bytes of those zones that changed (0 = no
+ * out-of-bounds write since the handle was created).  Waits for the handle's pending launches. */
+int alcm_vocoder_check_guards(alcm_vocoder* v, long long* bad);
+int alcm_vae_check_guards(alcm_vae* v, long long* bad);
 /* kernels launched by one alcm_vocode / alcm_vae_decode call for this shape (after planning) */
 int alcm_vocoder_launches(alcm_vocoder* v, int B, int T);
 int alcm_vae_launches(alcm_vae* v, int B, int T);

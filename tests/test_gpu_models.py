@@ -460,3 +460,18 @@ def test_faster_than_aten_eager_on_the_same_gpu():
     print(f"\n[vs ATen eager on this GPU] eager {t_eager:.2f} ms, ours (tf32 mode) {t_ours:.2f} ms -> {t_eager / t_ours:.1f}x; max-abs diff {err:.2e}")
     assert err <= 2e-3          # both sides use tensor-core tf32 convs here; the fp32 gates are the golden tests above
     assert t_ours * 2.0 < t_eager
+
+
+def test_guard_zones_stay_clean_over_every_kernel_form():
+    """compute-sanitizer is closed on the GPU pool, so the library carries its own out-of-bounds-write check
+    (ALCM_GUARD=1: 4 KB zero guard zones around every device buffer, verified by alcm_*_check_guards and at the end of
+    every single-op call).  tools/sanitize_driver.py runs every conv form (plain, persistent, both split-K reductions,
+    fused epilogue, narrow operands), every Activation1d form, GroupNorm, attention and small decodes under it."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sanitize_driver.py")], capture_output=True, text=True,
+                         timeout=900, env=dict(os.environ, ALCM_GUARD="1"), cwd=root)
+    print(out.stdout[-1500:])
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "no guard zone touched (ALCM_GUARD=1)" in out.stdout

@@ -1,9 +1,13 @@
-"""Small-shape workload for compute-sanitizer (tools/sanitize.sh): every form of the conv kernel (plain, persistent
+"""Small-shape self-check workload - run plain (ALCM_GUARD=1 is set below: every device buffer is fenced by 4 KB zero
+guard zones that are verified after each op and after the decodes) or under compute-sanitizer where the pool allows
+it (tools/sanitize.sh).  Covers every form of the conv kernel (plain, persistent
 two-accumulator, workspace split-K, cluster/DSMEM split-K, fused Activation1d epilogue, narrow operands with the
 zeroed K slab), every Activation1d kernel form, GroupNorm, attention and one small end-to-end decode per mode.
 Each case is also checked numerically, so a sanitizer-clean run is a correct run."""
 import os
 import sys
+
+os.environ.setdefault("ALCM_GUARD", "1")
 
 import numpy as np
 import torch
@@ -78,10 +82,13 @@ def main():
     for prec, tol in (("bf16", 5e-3), ("tf32", 1e-3)):
         pipe = LatentToWaveform(AutoencoderKLDecoder(vsd, dd, synth.VAE_EMBED_DIM, DEV, prec), VocoderBigVGAN.from_state_dict(gsd, h, DEV, prec))
         err = float(np.abs(pipe.decode(z) - ref).max())
-        print(f"  decode[{prec}] err {err:.2e}", flush=True)
-        assert err <= tol
+        for shape in ((1, 7), (3, 33), (2, 16)):      # more plans, replays of a cached plan
+            pipe.decode(synth.synth_latent(*shape, seed=2))
+        bad = pipe.vae.check_guards() + pipe.voc.check_guards()
+        print(f"  decode[{prec}] err {err:.2e}; guard-zone bytes modified: {bad}", flush=True)
+        assert err <= tol and bad == 0
     torch.cuda.synchronize()
-    print("sanitize driver: all cases numerically correct", flush=True)
+    print(f"sanitize driver: all cases numerically correct, no guard zone touched (ALCM_GUARD={os.environ.get('ALCM_GUARD')})", flush=True)
 
 
 if __name__ == "__main__":
