@@ -22,6 +22,7 @@ Prints ONE JSON line (rank 0):
   configs1_batch1    BASELINE.json configs[1]: one 10 s clip, batch 1 (latency), both modes            (N = 1 only)
   longform           BASELINE.json configs[3]: one 300 s clip, vocoder time-sharded over the N ranks with the NCCL P2P
                      halo exchange inside the timed region; max-abs vs the un-sharded vocode and vs the CPU oracle
+  configs4_end_to_end_batch256   BASELINE.json configs[4]: 256 prompts, reference sampler + DiT in eager PyTorch, new decode (N = 1 only)
   parity_check       a batch item against its own batch-1 decode and clip 0 against the CPU oracle, from this very run
   cpu_baseline       the oracle port of the reference's CPU path on this box's host cores (bounded sample)
 """
@@ -443,6 +444,66 @@ def longform(pipe, device, world, rank, steps, barrier, precision):
                 abs_max=float(ref.abs().max()))
 
 
+def config5(pipe, device, precision, prompts=256, chunk=64):
+    """BASELINE.json configs[4]: AudioLCMBatchInfer-shaped run - `prompts` text contexts (stubbed: random
+    [B,154,1024], the text encoders need absent checkpoints), 2-step LCM sampling with the reference's sampler and
+    ConcatDiT2MLP denoiser in eager PyTorch (baseline/lcm_denoiser_port.py - the reference Python cannot travel to
+    this box; the port is pinned to it by tests/golden/lcm_denoiser.npz), then the new batched decode
+    (GenSamplesBatched: 16-bit PCM packed on the GPU, pinned double-buffered copies, WAV files written)."""
+    import shutil
+    import tempfile
+    import torch
+    from audiolcm_b200 import GenSamplesBatched
+    from baseline.lcm_denoiser_port import PortedDenoiser
+    den = PortedDenoiser(device=device, seed=7)
+    g = torch.Generator(device=device).manual_seed(5)
+    cond = torch.randn(prompts, 154, 1024, generator=g, device=device)
+    out = tempfile.mkdtemp(prefix="alcm_cfg5_")
+    t_den = [0.0]
+
+    def sample_fn(c):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        zs = []
+        for s in range(0, c.shape[0], 128):        # bound the eager DiT's activation memory
+            zs.append(den.sample(c[s:s + 128], T=T_LAT, steps=2, guidance_scale=5.0))
+        z = torch.cat(zs, dim=0)
+        z = torch.nan_to_num(z).clamp_(-4.0, 4.0)  # random-init denoiser: keep the latents in the trained range
+        e1.record()
+        e1.synchronize()
+        t_den[0] = e0.elapsed_time(e1)
+        return z
+
+    gen = GenSamplesBatched(sample_fn, pipe, out, save_wav=True, chunk=chunk)
+    names = [f"prompt{i:03d}" for i in range(prompts)]
+    try:
+        pipe.plan(chunk, T_LAT)
+        gen.gen_test_samples(cond[:chunk], names[:chunk])            # warm-up (plans, pinned buffers, cuDNN autotune)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        recs = gen.gen_test_samples(cond, names)
+        total = time.perf_counter() - t0
+        den_ms = t_den[0]                                             # CUDA-event time of the sampler inside the timed run
+        z = sample_fn(cond[:chunk])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pipe.decode_pcm16_tensor(z)
+        e1.record()
+        e1.synchronize()
+        dec_ms = e0.elapsed_time(e1) * (prompts / chunk)
+        nbytes = sum(os.path.getsize(r["audio_path"]) for r in recs)
+    finally:
+        shutil.rmtree(out, ignore_errors=True)
+    asec = audio_seconds(prompts, T_LAT)
+    return dict(workload=f"configs[4]: {prompts} prompts, 2-step LCM sampling (reference sampler + ConcatDiT2MLP in eager PyTorch, stubbed "
+                         f"text context [B,154,1024]) -> new batched decode ({precision}) -> {prompts} WAV files",
+                value=round(asec / total, 1), unit="audio-s/s", wall_s=round(total, 3), denoiser_ms=round(den_ms, 1),
+                decode_device_ms=round(dec_ms, 1), rest_ms=round(1e3 * total - den_ms - dec_ms, 1),
+                wav_bytes_written=nbytes, decode_share=round(dec_ms / (1e3 * total), 3),
+                note="denoiser_ms: CUDA-event time of the 2-step sampler for all prompts inside the timed run; decode_device_ms: CUDA-event "
+                     "time of one 64-clip decode x 4 measured right after; rest = device->host copies, WAV writing, Python")
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -489,6 +550,8 @@ def run_gpu(args):
                 extra["longform"] = lf
         if rank == 0 and world == 1 and not args.no_micro:
             extra[mode]["kernel_rooflines"] = kernel_rooflines(mode, peaks, local)
+        if rank == 0 and world == 1 and not args.no_config5 and mode == modes[-1]:
+            extra["config5"] = config5(pipe, device, mode)
         del pipe
         torch.cuda.empty_cache()
     if rank == 0:
@@ -512,6 +575,8 @@ def run_gpu(args):
             line["configs1_batch1"] = {mode: extra[mode]["batch1"] for mode in modes if "batch1" in extra[mode]}
         if "longform" in extra:
             line["longform"] = extra["longform"]
+        if "config5" in extra:
+            line["configs4_end_to_end_batch256"] = extra["config5"]
         parity = {mode: dict(max_abs_item_vs_batch1=extra[mode]["max_abs_item_vs_batch1"]) for mode in modes}
         if not args.no_cpu:
             cb, ref = cpu_baseline()
@@ -560,6 +625,7 @@ def main():
     ap.add_argument("--no-batch1", action="store_true", help="skip the configs[1] (batch 1) latency measurement")
     ap.add_argument("--no-longform", action="store_true", help="skip the configs[3] (300 s clip) measurement")
     ap.add_argument("--no-micro", action="store_true", help="skip the isolated-kernel rooflines")
+    ap.add_argument("--no-config5", action="store_true", help="skip the configs[4] (256-prompt end-to-end) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     protect_stdout()

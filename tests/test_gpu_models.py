@@ -475,3 +475,44 @@ def test_guard_zones_stay_clean_over_every_kernel_form():
     print(out.stdout[-1500:])
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "no guard zone touched (ALCM_GUARD=1)" in out.stdout
+
+
+# ----------------------------------------------------------------------------------- config 5 / SURVEY 8(f) row 1
+def test_decode_first_stage_vs_real_lcm_audio_golden(golden_dir):
+    """tests/golden/lcm_decode_first_stage.npz is the output of the REAL LCM_audio.decode_first_stage (lcm_audio.py:392-406,
+    scale_factor 0.7, oracle/make_golden_lcm.py); the CUDA decoder behind install() must reproduce it with
+    inv_scale = 1/scale_factor (install() itself is exercised on the real class in tests/test_denoiser_port.py)."""
+    g = np.load(os.path.join(golden_dir, "lcm_decode_first_stage.npz"))
+    dd = synth.vae_config()
+    sd = synth.vae_decoder_state_dict(dd, seed=int(g["wseed"]))
+    z = torch.from_numpy(synth.synth_latent(int(g["B"]), int(g["T"]), seed=int(g["xseed"]))).to(DEV)
+    for precision in ("fp32", "tf32", "bf16"):
+        mel = _vae(dd, sd, precision).decode(z, inv_scale=1.0 / float(g["scale_factor"])).cpu().numpy()
+        err = np.abs(mel - g["mel"]).max()
+        print(f"\n[decode_first_stage vs real LCM_audio, {precision}] max-abs {err:.3e} (abs-max {np.abs(g['mel']).max():.2f})")
+        assert err <= MEL_TOL[precision]
+
+
+def test_batched_driver_writes_the_wavs_the_reference_loop_would(tmp_path):
+    """GenSamplesBatched (InferAPI.py:63-101 batched): 5 'prompts' through a stand-in sampler, decoded in chunks of 2
+    with the double-buffered pinned copies; every WAV file holds rint(wav * 32767) of the float decode of its own latent
+    (what soundfile.write(path, vocode(spec), 16000) stores), mono, 16 kHz, 16 bit."""
+    import wave
+    from audiolcm_b200 import GenSamplesBatched, LatentToWaveform
+    dd, h = synth.vae_config(32), synth.bigvgan_config(64)
+    pipe = LatentToWaveform(_vae(dd, synth.vae_decoder_state_dict(dd, seed=1), "tf32"), _voc(h, synth.bigvgan_state_dict(h, seed=1), "tf32"))
+    zs = torch.from_numpy(synth.synth_latent(5, 20, seed=9)).to(DEV)
+    gen = GenSamplesBatched(lambda cond: zs[: cond.shape[0]], pipe, str(tmp_path), save_wav=True, save_mel=True, chunk=2)
+    recs = gen.gen_test_samples(torch.zeros(5, 154, 1024), [f"clip{i}" for i in range(5)])
+    assert len(recs) == 5
+    ref = pipe.decode_tensor(zs, return_mel=True)
+    want = torch.round(ref[0] * 32767.0).to(torch.int16).cpu().numpy()
+    for i, r in enumerate(recs):
+        with wave.open(r["audio_path"], "rb") as f:
+            assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 2, 16000, 20 * 512)
+            pcm = np.frombuffer(f.readframes(f.getnframes()), "<i2")
+        assert np.abs(pcm.astype(np.int32) - want[i].astype(np.int32)).max() <= 1      # chunk plans may differ in split-K order
+        np.testing.assert_allclose(np.load(r["mel_path"]), ref[1][i].cpu().numpy(), atol=1e-2)
+    gen2 = GenSamplesBatched(lambda cond: zs[: cond.shape[0]], pipe, str(tmp_path / "b"), save_wav=True, chunk=64)
+    pcm2, _ = gen2.decode_latents(zs)                       # one chunk, PCM packed by the conv_post kernel
+    assert np.array_equal(pcm2, want)
