@@ -78,6 +78,7 @@ SYMBOLS = {
     "alcm_activation1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_conv1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_conv1d_act_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "alcm_act_conv1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_conv_transpose1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_upsample_conv3_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_groupnorm_swish_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),

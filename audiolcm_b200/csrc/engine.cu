@@ -20,6 +20,7 @@
 #include "act1d.cuh"
 #include "common.cuh"
 #include "conv.cuh"
+#include "convpro.cuh"
 #include "misc_kernels.cuh"
 
 using namespace alcm;
@@ -68,7 +69,7 @@ static int env_int(const char* name, int dflt) {
 struct Knobs {
   int pdl, graph, lanes, lane_waves, persist, cluster_splitk, splitk, retile, retile_mode;
   int smem_budget, smem_budget_1w, smem_budget_mw, tpg, astages, kblk_max, nt, tmem2;
-  int act_variant, act_v2, act_v2_min_waves, fuse_act, fuse_stages, gn_fused, max_plans, trace, bench_fused, attn_tc, guard;
+  int act_variant, act_v2, act_v2_min_waves, fuse_act, fuse_stages, gn_fused, max_plans, trace, bench_fused, attn_tc, guard, actpro;
   static Knobs from_env() {
     Knobs k;
     k.pdl = env_int("ALCM_PDL", -1);  // -1 unset (per-plan default), 0 never, 1 always
@@ -98,6 +99,7 @@ struct Knobs {
     k.trace = env_int("ALCM_TRACE", 0);
     k.bench_fused = env_int("ALCM_BENCH_FUSED", 0);
     k.attn_tc = env_int("ALCM_ATTN_TC", 1);
+    k.actpro = env_int("ALCM_ACTPRO", 1);                 // Activation1d fused into the conv operand producer for the narrow stages
     k.guard = env_int("ALCM_GUARD", 0);                   // 1: 4 KB zero guard zones between device buffers, verified by alcm_*_check_guards
     return k;
   }
@@ -679,6 +681,66 @@ static ConvLaunch plan_conv(const Env& env, const ConvLayer& L, const PlaneT& x,
   return cl;
 }
 
+// "act -> conv" launch (conv_actpro_kernel, convpro.cuh): x are the fp32 planes the Activation1d reads.
+static bool actpro_eligible(const Env& env, const ConvLayer& L, const PlaneT& x) {
+  if (!env.k.actpro || L.prec == ALCM_PREC_FP32 || L.nphase != 1 || L.nkb != 1 || L.n_tiles != 1 || x.esz != 4) return false;
+  const int npl = L.prec == ALCM_PREC_BF16 ? 2 : 1;
+  if (-L.min_off[0] + 5 > kPad) return false;
+  // shared memory: two A slabs + activation warps' areas + at least two weight stages of one tap
+  const ProSmem P = pro_smem_layout(L.kblk, L.span, L.NT, 2, 1, 2, npl);
+  return P.total <= 227u * 1024u;
+}
+
+static ConvLaunch plan_conv_pro(const Env& env, const ConvLayer& L, const PlaneT& x, const PlaneT& out, const float* res, int M, float scale,
+                                int accum, const float* ea, const float* ib) {
+  ConvLaunch cl;
+  cl.cx = env.cx;
+  ConvArgs& a = cl.a;
+  memset(&a, 0, sizeof(a));
+  a.x = x.p; a.xg = x.g;
+  a.w = L.wpack;
+  a.bias = L.bias;
+  a.out = out.f(); a.og = out.g;
+  a.res = res;
+  a.M = M;
+  a.ostride = 1; a.nphase = 1; a.ntaps = L.ntaps;
+  memcpy(a.tap_off, L.tap_off, sizeof(a.tap_off));
+  memcpy(a.min_off, L.min_off, sizeof(a.min_off));
+  a.span = L.span;
+  a.Cin = L.Cin; a.Cout = L.Cout;
+  a.scale = scale; a.accum = accum;
+  a.ksplit = 1;
+  a.kchunks = L.kchunks; a.kblk = L.kblk; a.nkb = 1;
+  a.NT = L.NT; a.n_tiles = 1;
+  a.idesc = L.idesc; a.w_phase_stride = L.phase_stride;
+  a.ea = ea; a.ib = ib;
+  a.tiles_m = (M + kTileM - 1) / kTileM;
+  a.tiles_total = a.tiles_m * x.B;
+  a.acc_stages = 2;
+  a.tmem_cols = 32;
+  while (a.tmem_cols < 2 * L.NT) a.tmem_cols *= 2;
+  a.a_stages = 2;
+  const int npl = L.prec == ALCM_PREC_BF16 ? 2 : 1;
+  // weight ring: as many taps per stage as the ~1024-tensor-cycle rule wants, shrunk until two stages fit
+  const double cyc_tap = (L.kblk / 2) * std::max(L.NT / 2.0, 32.0 + L.NT / 4.0);
+  const int tmin = std::max(1, std::min(L.ntaps, (int)std::ceil(1024.0 / cyc_tap)));
+  const int ngrp = (L.ntaps + tmin - 1) / tmin;
+  int t = (L.ntaps + ngrp - 1) / ngrp;
+  const uint32_t cap = 227u * 1024u;
+  while (t > 1 && pro_smem_layout(L.kblk, L.span, L.NT, 2, t, 2, npl).total > cap) --t;
+  int S = 2;
+  while (S < 8 && S < (L.ntaps + t - 1) / t * 2 && pro_smem_layout(L.kblk, L.span, L.NT, S + 1, t, 2, npl).total <= cap) ++S;
+  a.tpg = t; a.w_stages = S;
+  const ProSmem P = pro_smem_layout(L.kblk, L.span, L.NT, S, t, 2, npl);
+  REQUIRE(P.total <= cap, "act->conv: tile does not fit shared memory");
+  cl.kern = L.prec == ALCM_PREC_BF16 ? conv_actpro_kernel<0> : conv_actpro_kernel<1>;
+  cl.grid = dim3((unsigned)std::min<long>(a.tiles_total, env.sms()));
+  cl.block = dim3(kProThreads);
+  cl.smem = P.total;
+  cl.cluster_x = 1;
+  return cl;
+}
+
 struct OpList {
   std::vector<Op> ops;
   Env env;              // device context + knob snapshot every planning decision below depends on
@@ -748,6 +810,24 @@ struct OpList {
       fused_act_bytes += (double)x.B * x.T * L.Cout * (4.0 + aout->esz);
       ++fused_acts;
     }
+  }
+  // Activation1d(x) -> conv (+bias, +residual, scale, accumulate) as ONE launch (convpro.cuh); x: fp32 planes.
+  // Caller checks actpro_eligible().  Counts as a conv launch plus the activation's algorithmic bytes.
+  void act_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const PlaneT* res, const float* ea, const float* ib, float scale = 1.f,
+                int accum = 0) {
+    REQUIRE(actpro_eligible(env, L, x), "act->conv: layer not eligible");
+    REQUIRE(out.esz == 4 && out.T == x.T && out.B == x.B && out.g.nchunk * 4 >= L.Cout, "act->conv: bad output planes");
+    REQUIRE(x.g.nchunk * 4 >= L.Cin, "act->conv: channel mismatch");
+    const int M = x.T;
+    Op op;
+    op.cls = ALCM_CLS_CONV;
+    op.flops = 2.0 * L.Cin * L.Cout * L.ntaps * (double)M * x.B;
+    op.bytes = (double)x.B * x.T * ((double)L.Cin * 4 + (double)L.Cout * 4 + (res ? (double)L.Cout * 4 : 0.0));
+    const ConvLaunch cl = plan_conv_pro(env, L, x, out, res ? res->f() : nullptr, M, scale, accum, ea, ib);
+    op.fn = [cl](cudaStream_t st) { cl.run(st); };
+    push(op);
+    fused_act_bytes += (double)x.B * x.T * L.Cin * (4.0 + opnd_esz(L.prec));
+    ++fused_acts;
   }
   void act(const PlaneT& x, const PlaneT& out, const float* ea, const float* ib, int round_tf32, bool fast) {
     REQUIRE(x.esz == 4 && x.T == out.T && x.B == out.B, "act: bad planes");
@@ -1222,7 +1302,23 @@ static void voc_build(const alcm_vocoder* v, VocPlan& P) {
         }
         continue;
       }
+      // narrow stages: each (Activation1d, conv) pair is ONE launch - the activation runs in the conv's operand producer
+      const bool pro = actpro_eligible(v->env, bk.c1[0], X) && actpro_eligible(v->env, bk.c2[0], X) &&
+                       actpro_eligible(v->env, bk.c1[2], X);
       for (int l = 0; l < 3; ++l) {  // models.py:72-81
+        if (pro) {
+          P.ol.act_conv(bk.c1[l], *cur, Y, nullptr, bk.a[2 * l].ea, bk.a[2 * l].ib);
+          if (l < 2) {
+            P.ol.act_conv(bk.c2[l], Y, R, cur, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib);
+            cur = &R;
+          } else if (parallel) {
+            P.ol.act_conv(bk.c2[l], Y, R, cur, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, 1.0f / nk, 0);
+            Z.push_back(R);
+          } else {
+            P.ol.act_conv(bk.c2[l], Y, XS, cur, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, 1.0f / nk, j > 0);
+          }
+          continue;
+        }
         P.ol.act(*cur, A, bk.a[2 * l].ea, bk.a[2 * l].ib, rtf, fast);
         P.ol.conv(bk.c1[l], A, Y, nullptr);
         P.ol.act(Y, A, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, rtf, fast);
@@ -1485,6 +1581,8 @@ static void set_kernel_attrs() {
   CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<1, true, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<1, false, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<2, true, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_actpro_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_actpro_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
@@ -1939,6 +2037,36 @@ int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const flo
     } else {
       launch_unpack(aout, y_act, Cout, T, st);
     }
+    CUDA_CHECK(cudaGetLastError());
+    sync_free(ar, st);
+  });
+}
+int alcm_act_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, const float* beta, const float* w, const float* bias,
+                        const float* res, float* y, int B, int Cin, int Cout, int T, int K, int dilation, int precision, void* stream) {
+  return guarded([&] {
+    REQUIRE(ctx && x && alpha && beta && w && y, "act_conv1d: NULL argument");
+    REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T >= 1 && dilation >= 1, "act_conv1d: bad shape");
+    REQUIRE(precision == ALCM_PREC_TF32 || precision == ALCM_PREC_BF16, "act_conv1d: tf32 / bf16 only");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Arena ar;
+    ar.guard = env_int("ALCM_GUARD", 0) != 0;
+    const Env env{ctx, Knobs::from_env()};
+    ConvLayer L = prepare_conv(ar, env.k, precision, KIND_CONV, w, bias, Cout, Cin, K, dilation);
+    PlaneT xin = make_planes(ar, B, Cin, T, 4), out = make_planes(ar, B, Cout, T, 4);
+    PlaneT rp;
+    if (res) rp = make_planes(ar, B, Cout, T, 4);
+    SnakeP sp = make_snake(ar, alpha, beta, Cin);
+    REQUIRE(actpro_eligible(env, L, xin), "act_conv1d: shape not eligible for the fused producer (needs a single k-block: bf16 C <= 96, tf32 C <= 48)");
+    CUDA_CHECK(sync_setup());
+    launch_pack(x, xin, Cin, T, 1.f, ALCM_PREC_FP32, st);
+    if (res) launch_pack(res, rp, Cout, T, 1.f, ALCM_PREC_FP32, st);
+    OpList ol;
+    ol.env = env;
+    ol.ar = &ar;
+    ol.act_conv(L, xin, out, res ? &rp : nullptr, sp.ea, sp.ib);
+    ol.run(st);
+    launch_unpack(out, y, Cout, T, st);
     CUDA_CHECK(cudaGetLastError());
     sync_free(ar, st);
   });

@@ -66,6 +66,19 @@ def conv1d_act(x, w, bias, res, alpha, beta, dilation=1, precision="bf16", want_
     return yc, ya
 
 
+def act_conv1d(x, alpha, beta, w, bias=None, res=None, dilation=1, precision="bf16"):
+    """conv(Activation1d(x)) + bias (+ res) in one launch (activation in the conv's operand producer) - models.py:72-81."""
+    (x, alpha, beta, w, bias, res), dev = _prep(x, alpha, beta, w, bias, res)
+    B, Cin, T = x.shape
+    Cout, Cin2, K = w.shape
+    assert Cin2 == Cin
+    y = torch.empty((B, Cout, T), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().alcm_act_conv1d_fwd(_lib.ctx(dev.index), _p(x), _p(alpha), _p(beta), _p(w), _p(bias), _p(res), _p(y),
+                                                   B, Cin, Cout, T, K, int(dilation), _lib.PREC[precision], _stream()))
+    return y
+
+
 def conv_transpose1d(x, w, bias=None, stride=2, precision="fp32"):
     """ConvTranspose1d(k=2*stride, stride, padding=stride/2) - vocoder/bigvgan/models.py:150-155."""
     (x, w, bias), dev = _prep(x, w, bias)

@@ -148,6 +148,11 @@ int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, con
 int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, const float* alpha,
                         const float* beta, float* y_conv, float* y_act, int B, int Cin, int Cout, int T, int K, int dilation,
                         int precision, void* stream);
+/* Activation1d(SnakeBeta) followed by Conv1d (+bias, +res) in ONE launch, the activation computed by the conv's operand
+ * producer - the a1 -> c1 and a2 -> c2 (+x) steps of AMPBlock1.forward (models.py:72-81) for the narrow stages.
+ * y = conv(act(x)) + bias (+ res).  TF32 (Cin <= 48) / BF16 (Cin <= 96) only. */
+int alcm_act_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, const float* beta, const float* w, const float* bias,
+                        const float* res, float* y, int B, int Cin, int Cout, int T, int K, int dilation, int precision, void* stream);
 /* Conv1d(Cin,Cout,K,dilation, padding=(K*d-d)/2) (+bias, +res if non-NULL); w [Cout,Cin,K] */
 int alcm_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, float* y, int B,
                     int Cin, int Cout, int T, int K, int dilation, int precision, void* stream);

@@ -175,7 +175,7 @@ def test_batch64_full_size_decode_vs_oracle(precision):
 
 @pytest.mark.parametrize("knobs", [{"ALCM_LANES": "0"}, {"ALCM_ACT_VARIANT": "3"}, {"ALCM_ACT_VARIANT": "2"}, {"ALCM_ACT_VARIANT": "7"},
                                    {"ALCM_ACT_VARIANT": "8"}, {"ALCM_PERSIST": "0"}, {"ALCM_CLUSTER_SPLITK": "0"},
-                                   {"ALCM_GRAPH": "0"}, {"ALCM_PDL": "1"}])
+                                   {"ALCM_GRAPH": "0"}, {"ALCM_PDL": "1"}, {"ALCM_ACTPRO": "0"}])
 def test_forced_plan_variants_match_reference(golden_dir, monkeypatch, knobs):
     """Every plan-shaping knob the batch-64 / long-form plans flip (serial AMP blocks with in-place accumulation, the
     big-launch Activation1d forms, non-persistent convs, workspace split-K, eager launches, PDL), forced on a small

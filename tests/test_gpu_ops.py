@@ -254,3 +254,48 @@ def test_narrow_operand_planes_are_not_padded_to_16(ops):
             for _ in range(2):  # twice: persistent ring slots are reused
                 y = ops.conv1d(x.to(DEV), w.to(DEV), b.to(DEV), None, dilation=d, precision=precision).cpu()
                 assert float((y.double() - ref).abs().max()) < 3e-5 * max(1.0, float(ref.abs().max())), (Cin, Cout, precision)
+
+
+# ----------------------------------------------------------------------------------- Activation1d in the conv's operand producer
+ACTPRO_CASES = [
+    # B, Cin, Cout, T, K, d
+    (2, 24, 24, 4099, 11, 5),    # narrow operand (zeroed K slab), widest halo: 25 (conv) + 5 (FIR)
+    (1, 96, 96, 1000, 7, 3),     # 12 K chunks, 8 tiles
+    (1, 48, 48, 300, 3, 1),
+    (3, 96, 96, 129, 11, 5),     # one row spills into a second tile
+    (1, 24, 24, 1, 3, 1),        # T = 1: every FIR tap is replicate padding, every other conv tap zero padding
+    (1, 48, 48, 7, 11, 1),
+    (8, 32, 32, 6000, 3, 1),     # several tiles per persistent CTA
+    (1, 96, 48, 257, 1, 1),      # k = 1, Cout != Cin
+    (2, 40, 24, 515, 7, 1),
+]
+
+
+@pytest.mark.parametrize("case", ACTPRO_CASES)
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("with_res", [True, False])
+def test_act_conv1d_fused_producer(ops, case, precision, with_res):
+    """conv(Activation1d(x)) + bias (+ res) as ONE launch (convpro.cuh) against the float64 oracle: activation in
+    float64, rounded to the operand type as the device rounds it, conv in float64.  The device computes the activation in
+    fp32, so an operand may round the other way (1 ulp of the operand type); the bound allows a few such flips, a wrong
+    halo / tap shift / zero- vs replicate-padding mix-up is O(0.1 - 1)."""
+    from oracle import decode_oracle as O
+    B, Cin, Cout, T, K, d = case
+    if precision == "tf32" and Cin > 48:
+        pytest.skip("tf32 operands: single k-block only up to 48 channels")
+    x = _rand(B, Cin, T, seed=50, scale=1.5)
+    al, be = _rand(Cin, seed=51, scale=0.5), _rand(Cin, seed=52, scale=0.5)
+    w = _rand(Cout, Cin, K, seed=53, scale=1.0 / np.sqrt(Cin * K))
+    b = _rand(Cout, seed=54, scale=0.1)
+    res = _rand(B, Cout, T, seed=55) if with_res else None
+    act = O.activation1d(x.double(), al.double(), be.double(), O.kaiser_sinc_filter().double())
+    ar, wr = round_operand(act.float(), precision).double(), round_operand(w, precision).double()
+    ref = F.conv1d(ar, wr, b.double(), dilation=d, padding=(K * d - d) // 2)
+    if with_res:
+        ref = ref + res.double()
+    for _ in range(2):
+        y = ops.act_conv1d(x.to(DEV), al.to(DEV), be.to(DEV), w.to(DEV), b.to(DEV), None if res is None else res.to(DEV), dilation=d,
+                           precision=precision).cpu()
+        err = float((y.double() - ref).abs().max())
+        tol = {"tf32": 4e-4, "bf16": 3e-3}[precision]
+        assert err < tol * max(1.0, float(ref.abs().max())), err

@@ -57,6 +57,16 @@ def main():
     err = float(((ya.cpu().double() - aref).abs() / (aref.abs() + 1)).max())
     print(f"  conv fused Activation1d epilogue     bf16 err {err:.2e}", flush=True)
     assert err < 2.0 ** -8 * 1.01 + 3e-5
+    # Activation1d in the conv's operand producer (convpro.cuh)
+    for (B, C, T, K, d) in ((2, 24, 700, 11, 5), (1, 96, 300, 7, 3), (1, 48, 5, 3, 1)):
+        x, w, b = rnd(B, C, T, seed=14, scale=1.5), rnd(C, C, K, seed=15, scale=1 / np.sqrt(C * K)), rnd(C, seed=16, scale=0.1)
+        al, be = rnd(C, seed=17, scale=0.5), rnd(C, seed=18, scale=0.5)
+        act = O.activation1d(x.double(), al.double(), be.double(), O.kaiser_sinc_filter().double())
+        ref = F.conv1d(round_operand(act.float(), "bf16").double(), round_operand(w, "bf16").double(), b.double(), dilation=d, padding=(K * d - d) // 2)
+        y = ops.act_conv1d(x.to(DEV), al.to(DEV), be.to(DEV), w.to(DEV), b.to(DEV), None, dilation=d, precision="bf16").cpu()
+        err = float((y.double() - ref).abs().max())
+        print(f"  act->conv fused producer C={C} T={T} k={K} d={d}: err {err:.2e}", flush=True)
+        assert err < 3e-3 * max(1.0, float(ref.abs().max()))
     # every Activation1d kernel form
     for variant in (0, 1, 2, 3, 5, 6, 7, 8):
         os.environ["ALCM_ACT_VARIANT"] = str(variant)
