@@ -849,14 +849,30 @@ struct OpList {
     // 3: 6 outputs/thread (96 registers, 5 blocks/SM) - measured best or equal on every launch that fills the GPU
     // (batch 64, last stage: 3.48 TB/s bf16 out, 4.63 TB/s = 72 % of the HBM peak fp32 out)
     const long blocks_r6 = (long)((T + 6 * kActThreads - 1) / (6 * kActThreads)) * nch * B;
-    // 7 / 8: two-phase form (act1d_v2_kernel; every up-sampled value computed once per block), 5 / 7 outputs per thread
+    // 7 / 8: two-phase form (act1d_v2_kernel; every up-sampled value computed once per block), 5 / 7 outputs per thread;
+    // 9: the same, persistent with prefetch (act1d_v3_kernel)
     const long blocks_v2 = (long)((T + 5 * kActThreads - 1) / (5 * kActThreads)) * nch * B;
     int variant = 0;
     if (oesz == 2 && blocks_wide < 24L * env.sms()) variant = 5;  // pair form, 6 outputs/thread: batch-1 decode 3.53 -> 3.45 ms vs 4 outputs/thread
     else if (blocks_r6 >= 8L * env.sms()) variant = 3;
     if (env.k.act_v2 && blocks_v2 >= (long)env.k.act_v2_min_waves * env.sms()) variant = env.k.act_v2;
     if (env.k.act_variant >= 0) variant = env.k.act_variant;
+    const int sms = env.sms();
     op.fn = [=](cudaStream_t st) {
+      if (variant == 9) {  // persistent two-phase form (prefetching), 5 outputs per thread
+        using G = ActV2Geom<5, kActThreads>;
+        const int ntt = (T + G::kTile - 1) / G::kTile;
+        const long ntiles = (long)ntt * nch * B;
+        const dim3 grid((unsigned)std::min<long>(ntiles, 5L * sms));
+        const size_t sm = 2 * (size_t)G::kXBytes + 2 * (size_t)G::kYBytes + 16;
+        if (oesz == 4) {
+          if (fast) launch_k(act1d_v3_kernel<1, true, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a, ntt, (int)ntiles);
+          else launch_k(act1d_v3_kernel<1, false, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a, ntt, (int)ntiles);
+        } else {
+          launch_k(act1d_v3_kernel<2, true, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a, ntt, (int)ntiles);
+        }
+        return;
+      }
       if (variant == 7 || variant == 8) {  // two-phase form
         const int ur = variant == 7 ? 5 : 7;
         const dim3 grid((T + ur * kActThreads - 1) / (ur * kActThreads), nch, B);

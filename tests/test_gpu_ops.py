@@ -215,8 +215,8 @@ def test_bad_arguments_raise(ops):
 
 
 # ----------------------------------------------------------------------------------- every Activation1d kernel form
-ACT_VARIANTS = {0: "R=4", 1: "pair R=4", 2: "R=8", 3: "R=6", 5: "pair R=6", 6: "pair R=8", 7: "two-phase UR=5", 8: "two-phase UR=7"}
-ACT_EDGE_SHAPES = [(1, 8, 1), (1, 8, 3), (2, 24, 4099), (1, 16, 640), (1, 16, 641), (1, 8, 637), (1, 8, 1283), (1, 8, 896),
+ACT_VARIANTS = {0: "R=4", 1: "pair R=4", 2: "R=8", 3: "R=6", 5: "pair R=6", 6: "pair R=8", 7: "two-phase UR=5", 8: "two-phase UR=7", 9: "persistent two-phase UR=5"}
+ACT_EDGE_SHAPES = [(1, 8, 1), (1, 8, 3), (2, 24, 4099), (3, 16, 160000), (1, 16, 640), (1, 16, 641), (1, 8, 637), (1, 8, 1283), (1, 8, 896),
                    (1, 8, 899), (1, 24, 6), (1, 40, 1925)]
 
 

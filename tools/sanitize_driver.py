@@ -68,7 +68,7 @@ def main():
         print(f"  act->conv fused producer C={C} T={T} k={K} d={d}: err {err:.2e}", flush=True)
         assert err < 3e-3 * max(1.0, float(ref.abs().max()))
     # every Activation1d kernel form
-    for variant in (0, 1, 2, 3, 5, 6, 7, 8):
+    for variant in (0, 1, 2, 3, 5, 6, 7, 8, 9):
         os.environ["ALCM_ACT_VARIANT"] = str(variant)
         for prec in ("bf16", "tf32"):
             for (B, C, T) in ((1, 8, 3), (2, 24, 1300)):
