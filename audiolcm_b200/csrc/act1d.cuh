@@ -575,201 +575,4 @@ __global__ void __launch_bounds__(THREADS, MINB) act1d_v2_kernel(const __grid_co
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Persistent two-phase form (the default for launches of many tiles).  ncu of act1d_v2_kernel (profiles/
-// r2_act_v2_b64_*.txt) showed 17 % (bf16 out) / 29 % (fp32 out) of all warp samples waiting for the tile's bulk copy, plus
-// block launch / drain time: a block did nothing while its x tile was in flight.  Here a block loops over tiles
-// (tile = blockIdx.x, += gridDim.x; time fastest) with TWO x buffers and prefetches:
-//   NPL = 2 (bf16 out): buffer p holds plane p; the next tile's plane p is requested as soon as phase 1 of plane p has
-//                       consumed the buffer - its copy overlaps phase 2 and the other plane's two phases;
-//   NPL = 1 (fp32 out): the buffers alternate between tiles; tile i+1 is requested when tile i starts.
-// Same arithmetic as act1d_v2_kernel, same shared-memory footprint (5 blocks of 128 threads per SM).
-// ---------------------------------------------------------------------------------------------------------------
-template <int NPL, bool FAST, int UR, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) act1d_v3_kernel(const __grid_constant__ ActArgs a, int ntt, int ntiles) {
-  using G = ActV2Geom<UR, THREADS>;
-  extern __shared__ __align__(128) uint8_t act_smem[];
-  float4* sx = reinterpret_cast<float4*>(act_smem);                                  // [2][kRows]
-  float4* yo = reinterpret_cast<float4*>(act_smem + 2 * (size_t)G::kXBytes);         // [kPairs]
-  float4* ye = yo + G::kPairs;                                                        // [kPairs]
-  const uint32_t bar = smem_u32(act_smem + 2 * (size_t)G::kXBytes + 2 * (size_t)G::kYBytes);   // two mbarriers
-  const int tid = threadIdx.x;
-  const int T = a.T, nch = a.og.nchunk;
-
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    mbar_init(bar + 8, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  pdl_launch_dependents();
-  pdl_wait();
-  // request plane `p` (NPL = 2) / the whole tile (NPL = 1) of `tile` into x buffer `buf` (thread 0 only)
-  auto request = [&](int tile, int p, int buf) {
-    const int tt = tile % ntt, oc = (tile / ntt) % nch, b = tile / (ntt * nch);
-    const int row0 = a.xg.pad + tt * G::kTile - 5;
-    const int nrows = min(G::kRows, a.xg.Tp - row0);
-    const float4* src = reinterpret_cast<const float4*>(a.x) + ((size_t)b * a.xg.nchunk + (oc * NPL + p)) * a.xg.Tp + row0;
-    fence_proxy_async_smem();   // the block's earlier generic reads of this buffer (ordered by the preceding barrier) -> async write
-    mbar_expect_tx(bar + 8 * buf, (uint32_t)(nrows * 16));
-    bulk_g2s(smem_u32(sx + buf * G::kRows), src, (uint32_t)(nrows * 16), bar + 8 * buf);
-  };
-  float2 f2[6], g2[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    f2[k] = make_float2(c_fir[k], c_fir[k]);
-    g2[k] = make_float2(2.f * c_fir[k], 2.f * c_fir[k]);
-  }
-  uint32_t par0 = 0, par1 = 0;
-  if (tid == 0 && (int)blockIdx.x < ntiles) {
-    request(blockIdx.x, 0, 0);
-    if (NPL == 2) request(blockIdx.x, 1, 1);
-  }
-  int it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int tt = tile % ntt, oc = (tile / ntt) % nch, b = tile / (ntt * nch);
-    const int t0 = tt * G::kTile;
-    const int next = tile + gridDim.x;
-    const bool first = (t0 == 0), last = t0 + G::kTile + 4 > T - 1;       // block-uniform
-    const int m0 = t0 + UR * tid;
-    uint2 held[UR];
-#pragma unroll 1
-    for (int p = 0; p < NPL; ++p) {
-      const int buf = (NPL == 2) ? p : (it & 1);
-      if (NPL == 1 && tid == 0 && next < ntiles) request(next, 0, buf ^ 1);   // the other buffer was consumed a tile ago
-      if (buf == 0) { mbar_wait(bar, par0); par0 ^= 1u; } else { mbar_wait(bar + 8, par1); par1 ^= 1u; }
-      float4* xp = sx + buf * G::kRows;
-      if (first || last) {   // replicate padding of the up-sampling FIR (resample.py:28)
-        for (int lr = tid; lr < G::kRows; lr += THREADS) {
-          const int t = t0 - 5 + lr;
-          const int tc = min(max(t, 0), T - 1);
-          const int src = tc - (t0 - 5);
-          if (tc != t && src >= 0 && src < G::kRows) xp[lr] = xp[src];
-        }
-        __syncthreads();
-      }
-      const int chunk = oc * NPL + p;
-      const float4 ea = *reinterpret_cast<const float4*>(a.ea + chunk * 4);
-      const float4 ib = *reinterpret_cast<const float4*>(a.ib + chunk * 4);
-      const float2 ea_lo = FAST ? make_float2(2.f * ea.x, 2.f * ea.y) : make_float2(ea.x, ea.y);
-      const float2 ea_hi = FAST ? make_float2(2.f * ea.z, 2.f * ea.w) : make_float2(ea.z, ea.w);
-      const float2 ib_lo = FAST ? make_float2(0.5f * ib.x, 0.5f * ib.y) : make_float2(ib.x, ib.y);
-      const float2 ib_hi = FAST ? make_float2(0.5f * ib.z, 0.5f * ib.w) : make_float2(ib.z, ib.w);
-      {  // phase 1
-        float2 xlo[UR + 5], xhi[UR + 5];
-#pragma unroll
-        for (int k = 0; k < UR + 5; ++k) {
-          const float4 v = xp[UR * tid + k];
-          xlo[k] = make_float2(v.x, v.y);
-          xhi[k] = make_float2(v.z, v.w);
-        }
-#pragma unroll
-        for (int j = 0; j < UR; ++j) {
-          float2 wl[6], wh[6];
-#pragma unroll
-          for (int q = 0; q < 6; ++q) { wl[q] = xlo[j + q]; wh[q] = xhi[j + q]; }
-          float4 o, e;
-          act_pair<FAST>(wl, wh, g2, ea_lo, ea_hi, ib_lo, ib_hi, o, e);
-          yo[UR * tid + j] = o;
-          ye[UR * tid + j] = e;
-        }
-      }
-      if (tid < 5) {
-        const int s = G::kTile + tid;
-        float2 wl[6], wh[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const float4 v = xp[s + q];
-          wl[q] = make_float2(v.x, v.y);
-          wh[q] = make_float2(v.z, v.w);
-        }
-        float4 o, e;
-        act_pair<FAST>(wl, wh, g2, ea_lo, ea_hi, ib_lo, ib_hi, o, e);
-        yo[s] = o;
-        ye[s] = e;
-      }
-      __syncthreads();   // y strip complete; x buffer `buf` consumed
-      if (NPL == 2 && tid == 0 && next < ntiles) request(next, p, buf);
-      if (first || last) {   // replicate padding of the down filter on y (filter.py:89-91)
-        if (first) {
-          const float4 y0 = ye[2 - t0];
-          for (int s = tid; s < 3 - t0; s += THREADS) {
-            yo[s] = y0;
-            if (s < 2 - t0) ye[s] = y0;
-          }
-        }
-        if (last) {
-          const int sl = T - t0 + 2;
-          if (sl >= 0 && sl < G::kPairs) {
-            const float4 yl = yo[sl];
-            for (int s = sl + tid; s < G::kPairs; s += THREADS) {
-              ye[s] = yl;
-              if (s > sl) yo[s] = yl;
-            }
-          }
-        }
-        __syncthreads();
-      }
-      // phase 2
-      float2 alo[UR], ahi[UR];
-#pragma unroll
-      for (int r = 0; r < UR; ++r) alo[r] = ahi[r] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int s = 0; s < UR + 5; ++s) {
-        const float4 o = yo[UR * tid + s], e = ye[UR * tid + s];
-        const float2 olo = make_float2(o.x, o.y), ohi = make_float2(o.z, o.w), elo = make_float2(e.x, e.y), ehi = make_float2(e.z, e.w);
-#pragma unroll
-        for (int r = 0; r < UR; ++r) {
-          const int d = s - r;
-          if (d >= 0 && d <= 5) {
-            const int k0 = 2 * d, k1 = 2 * d + 1;
-            const float2 w0 = f2[k0 < 6 ? k0 : 11 - k0], w1 = f2[k1 < 6 ? k1 : 11 - k1];
-            alo[r] = ffma2(olo, w0, alo[r]); ahi[r] = ffma2(ohi, w0, ahi[r]);
-            alo[r] = ffma2(elo, w1, alo[r]); ahi[r] = ffma2(ehi, w1, ahi[r]);
-          }
-        }
-      }
-      __syncthreads();   // phase 2 is done with yo / ye before the next phase 1 (next plane or next tile) overwrites them
-      float4 res[UR];
-      if (FAST) {
-        const float fs = fir_sum();
-        const float2 add_lo = make_float2(ib_lo.x * fs, ib_lo.y * fs), add_hi = make_float2(ib_hi.x * fs, ib_hi.y * fs);
-#pragma unroll
-        for (int r = 0; r < UR; ++r) res[r] = make_float4(alo[r].x + add_lo.x, alo[r].y + add_lo.y, ahi[r].x + add_hi.x, ahi[r].y + add_hi.y);
-      } else {
-#pragma unroll
-        for (int r = 0; r < UR; ++r) res[r] = make_float4(alo[r].x, alo[r].y, ahi[r].x, ahi[r].y);
-      }
-      if (NPL == 1) {
-        float4* op = reinterpret_cast<float4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
-#pragma unroll
-        for (int r = 0; r < UR; ++r) {
-          if (m0 + r >= T) break;
-          float4 o = res[r];
-          if (a.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-          op[m0 + r] = o;
-        }
-      } else {
-        uint2 pk[UR];
-#pragma unroll
-        for (int r = 0; r < UR; ++r) {
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(res[r].x, res[r].y), h1 = __floats2bfloat162_rn(res[r].z, res[r].w);
-          pk[r] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-        }
-        if (p == 0) {
-#pragma unroll
-          for (int r = 0; r < UR; ++r) held[r] = pk[r];
-        } else {
-          uint4* op = reinterpret_cast<uint4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
-#pragma unroll
-          for (int r = 0; r < UR; ++r) {
-            if (m0 + r >= T) break;
-            op[m0 + r] = make_uint4(held[r].x, held[r].y, pk[r].x, pk[r].y);
-          }
-        }
-      }
-    }
-  }
-}
-
 }  // namespace alcm

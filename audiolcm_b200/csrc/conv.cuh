@@ -13,17 +13,11 @@
 // ldm/models/autoencoder1d.py:186-213,291-295 (Conv1d, Upsample1D); bias / residual add
 // (models.py:79) / block mean (models.py:193-196) are fused in the epilogue.
 #pragma once
-#include "act1d.cuh"
 #include "common.cuh"
 
 namespace alcm {
 
 constexpr int kTileM = 128;
-// Fused Activation1d epilogue: a tile of 128 conv rows yields the 116 activation outputs whose +-5-row
-// FIR support lies inside the tile (rows 5..120 of the tile = 29 threads x 4 outputs); tiles overlap by 12 rows.
-constexpr int kFuseOwn = 116, kFuseHalo = 5;
-constexpr int kFuseVT = kFuseOwn / kActR;                       // 29 four-output work items per plane
-constexpr int kFuseSlots = kTileM + (kTileM >> 3) + 1;           // staged rows incl. the anti-conflict pad slots
 
 struct ConvArgs {
   const uint8_t* x;   // input planes (operand dtype)
@@ -64,21 +58,10 @@ struct ConvArgs {
   // 1-D; a CTA processes tiles blockIdx.x, blockIdx.x + gridDim.x, ... (persistent launch when gridDim.x < tiles_total,
   // with two TMEM accumulators so that the epilogue of one tile overlaps the main loop of the next).
   int tiles_m, tiles_total, acc_stages;
-  // Fused Activation1d epilogue (models.py:72-81: the SnakeBeta between c1/c2 and between AMP layers):
-  // act_out != null -> the tile is staged in shared memory, run through UpSample1d -> SnakeBeta ->
-  // DownSample1d and written as operand planes for the next conv.  `out` (fp32, the residual stream) is
-  // then optional.  Tiles advance by kFuseOwn rows; nphase = 1, scale = 1, accum = 0, res must not alias out.
-  void* act_out;
-  PlaneGeom ag;
-  const float* ea;         // exp(alpha)          [n_tiles*NT]
-  const float* ib;         // 1/(exp(beta)+1e-9)  [n_tiles*NT]
-  int act_bf16;            // operand planes are bf16 (E=8) / fp32 (E=4)
-  int act_round_tf32;
 };
 
 // ---------------------------------------------------------------------------------------------
-// tcgen05 kernel.  1-D grid over output tiles (or over resident CTA slots for a persistent launch), block = 192
-// threads (256 with the fused Activation1d epilogue).
+// tcgen05 kernel.  1-D grid over output tiles (or over resident CTA slots for a persistent launch), block = 192 threads.
 //   warp 0   : producer - per k-block one A slab per K chunk ([128+span rows] x 16 B, contiguous in
 //              the plane) and per group of `tpg` taps one bulk copy of their (contiguous) pre-packed
 //              weight blobs, all cp.async.bulk + mbarrier tx.
@@ -110,7 +93,6 @@ __host__ __device__ inline ConvSmemLayout conv_smem_layout(int kblk, int span, i
 struct ConvTile {
   int mt, nt, zb, zs, b, ph, kb0, kb1, q0;
 };
-template <bool FUSED>
 __device__ __forceinline__ ConvTile conv_tile(const ConvArgs& a, int tile) {
   ConvTile t;
   // the K splits of one output tile are consecutive CTAs (= one cluster when the reduction goes through DSMEM)
@@ -124,15 +106,14 @@ __device__ __forceinline__ ConvTile conv_tile(const ConvArgs& a, int tile) {
   t.ph = t.zb % a.nphase;
   t.kb0 = (int)((long)t.zs * a.nkb / a.ksplit);
   t.kb1 = (int)((long)(t.zs + 1) * a.nkb / a.ksplit);
-  // fused tiles overlap: tile mt owns activation outputs [mt*116, mt*116+116) and computes conv rows from 5 earlier
-  t.q0 = FUSED ? t.mt * kFuseOwn - kFuseHalo : t.mt * kTileM;
+  t.q0 = t.mt * kTileM;
   return t;
 }
 
 // MMA-issuing warp.  NK2 = MMAs per (k-block, tap) (two 16-byte K chunks per MMA); static so that
 // the burst is straight-line code (a rolled loop re-writes the uniform descriptor registers of
 // in-flight UTCHMMAs and stalls ~300 cycles per trip).
-template <int KIND, int NK2, bool FUSED>
+template <int KIND, int NK2>
 __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, uint32_t sA, uint32_t sW, const ConvSmemLayout& L, int rowsA,
                                               uint32_t tmem_base, uint32_t a_full, uint32_t a_empty, uint32_t w_full,
                                               uint32_t w_empty, uint32_t acc_full, uint32_t acc_empty, long long* trace) {
@@ -153,7 +134,7 @@ __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, uint32_t sA, ui
   uint32_t wpar = 0, apar = 0;
   int it = 0;  // tiles done by this CTA
   for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++it) {
-    const ConvTile T = conv_tile<FUSED>(a, tile);
+    const ConvTile T = conv_tile(a, tile);
     const uint32_t shift0 = (uint32_t)(a.tap_off[T.ph][0] - a.min_off[T.ph]);
     const uint64_t dshift = (uint64_t)(int64_t)(ntaps > 1 ? a.tap_off[T.ph][1] - a.tap_off[T.ph][0] : 0);
     const int st = (a.acc_stages > 1) ? (it & 1) : 0;
@@ -193,53 +174,8 @@ __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, uint32_t sA, ui
   __syncwarp();
 }
 
-// Activation1d on the staged tile (all warps of the CTA): work item = (output unit, 4 consecutive rows).
-template <int NPL>  // fp32 planes per output unit: 1 -> fp32/tf32 operand planes, 2 -> bf16
-__device__ __forceinline__ void conv_fused_act(const ConvArgs& a, const float4* ys, int b, int nt, int q0) {
-  const int T = a.M;
-  const int units = (a.NT >> 2) / NPL;
-  const int units_valid = min(units, a.ag.nchunk - nt * units);
-  const int t0 = q0 + kFuseHalo;  // first activation output of this tile; staged row lr <-> time t0 - 5 + lr
-  for (int item = threadIdx.x; item < units * kFuseVT; item += blockDim.x) {
-    const int u = item / kFuseVT, vt = item - u * kFuseVT;
-    const int m0 = t0 + kActR * vt;
-    const bool live = (u < units_valid) && (m0 < T);
-    const bool edge = live && ((m0 < 3) || (m0 + 6 > T - 1));
-    const bool any_edge = __any_sync(__activemask(), edge);
-    if (!live) continue;
-    float4 res[NPL][kActR];
-#pragma unroll
-    for (int p = 0; p < NPL; ++p) {
-      const int pl = u * NPL + p;  // plane within the tile
-      const float4 ea = *reinterpret_cast<const float4*>(a.ea + nt * a.NT + pl * 4);
-      const float4 ib = *reinterpret_cast<const float4*>(a.ib + nt * a.NT + pl * 4);
-      if (any_edge) act_plane<true, true>(ys + pl * kFuseSlots, vt, m0, t0, T, ea, ib, res[p]);
-      else act_plane<true, false>(ys + pl * kFuseSlots, vt, m0, t0, T, ea, ib, res[p]);
-    }
-    const size_t base = ((size_t)b * a.ag.nchunk + (size_t)nt * units + u) * a.ag.Tp + a.ag.pad;
-#pragma unroll
-    for (int r = 0; r < kActR; ++r) {
-      const int m = m0 + r;
-      if (m >= T) break;
-      if (NPL == 1) {
-        float4 o = res[0][r];
-        if (a.act_round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        reinterpret_cast<float4*>(a.act_out)[base + m] = o;
-      } else {
-        const float4 lo = res[0][r], hi = res[NPL - 1][r];
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(lo.x, lo.y), h1 = __floats2bfloat162_rn(lo.z, lo.w);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(hi.x, hi.y), h3 = __floats2bfloat162_rn(hi.z, hi.w);
-        uint4 o;
-        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
-        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
-        reinterpret_cast<uint4*>(a.act_out)[base + m] = o;
-      }
-    }
-  }
-}
-
-template <int KIND, int MINB, bool FUSED>
-__global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
+template <int KIND, int MINB>
+__global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_constant__ ConvArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ksplit = a.ksplit;
@@ -288,8 +224,6 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   if (trace && threadIdx.x == 0) trace[2] = clock64();
   pdl_launch_dependents();  // the next kernel may start its own setup / weight prefetch now
-  // the (single) tile of a fused launch, for the activation phase after the role branches
-  const ConvTile T0 = conv_tile<FUSED>(a, blockIdx.x);
 
   // Both asynchronous roles keep their warp CONVERGENT and predicate the async instructions with
   // elect.sync: UBLKCP / UTCHMMA / UTCBAR take warp-uniform operands, and issuing them from a
@@ -304,8 +238,8 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
     uint32_t wpar = 1, apar = 1;  // producer waits on the "previous" phase of the empty barriers first
     bool waited = false;
     for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
-      const ConvTile T = conv_tile<FUSED>(a, tile);
-      const int row0 = T.q0 + a.min_off[T.ph] + a.xg.pad;  // >= 0: |min_off| + kFuseHalo <= pad
+      const ConvTile T = conv_tile(a, tile);
+      const int row0 = T.q0 + a.min_off[T.ph] + a.xg.pad;  // >= 0: |min_off| <= pad
       const int nrows = min(rowsA, a.xg.Tp - row0);
       const uint8_t* wsrc = a.w + (size_t)T.ph * a.w_phase_stride + ((size_t)T.nt * a.nkb + T.kb0) * ntaps * L.w_blob;
       const uint8_t* xsrc = a.x + (((size_t)T.b * a.xg.nchunk + (size_t)T.kb0 * a.kblk) * a.xg.Tp + row0) * 16;
@@ -351,12 +285,12 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
     __syncwarp();
   } else if (warp == 1) {
     switch (a.kblk >> 1) {
-      case 1: conv_mma_loop<KIND, 1, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
-      case 2: conv_mma_loop<KIND, 2, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
-      case 3: conv_mma_loop<KIND, 3, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
-      case 4: conv_mma_loop<KIND, 4, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
-      case 5: conv_mma_loop<KIND, 5, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
-      default: conv_mma_loop<KIND, 6, FUSED>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      case 1: conv_mma_loop<KIND, 1>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      case 2: conv_mma_loop<KIND, 2>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      case 3: conv_mma_loop<KIND, 3>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      case 4: conv_mma_loop<KIND, 4>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      case 5: conv_mma_loop<KIND, 5>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
+      default: conv_mma_loop<KIND, 6>(a, sA, sW, L, rowsA, tmem_base, a_full, a_empty, w_full, w_empty, acc_full, acc_empty, trace); break;
     }
   } else if (warp < 6) {
     const int et = threadIdx.x - 64;
@@ -367,11 +301,9 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
     const size_t plane4 = (size_t)a.og.Tp;                 // float4 units between consecutive chunks
     const float4* res4 = reinterpret_cast<const float4*>(a.res);
     float4* out4 = reinterpret_cast<float4*>(a.out);
-    float4* ys = reinterpret_cast<float4*>(smem);  // fused: staged tile [plane][kFuseSlots] float4, over the drained pipeline buffers
-    const int yrow = row + (row >> 3);
     int it = 0, nt_staged = -1;
     for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x, ++it) {
-      const ConvTile T = conv_tile<FUSED>(a, tile);
+      const ConvTile T = conv_tile(a, tile);
       const int st = (a.acc_stages > 1) ? (it & 1) : 0;
       const uint32_t tmem_d = tmem_base + (uint32_t)(st * a.NT);
       // while the main loop runs: stage this N tile's bias in shared memory (the epilogue reads it as broadcasts)
@@ -384,8 +316,7 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
       if (it == 0) pdl_wait();  // residual / accumulate reads, output and split-K workspace writes come after the previous kernel
       const int q = T.q0 + row;
       const bool in_seq = q >= 0 && q < a.M;
-      // rows whose fp32 result this tile stores: all of them, or only the ones it owns when tiles overlap
-      const bool valid = in_seq && (!FUSED || (row >= kFuseHalo && row < kFuseHalo + kFuseOwn));
+      const bool valid = in_seq;
       const size_t orow = (size_t)q * a.ostride + T.ph;
       const int nq_valid = min(nq, a.og.nchunk - T.nt * nq);   // column groups that exist in the output planes
       const size_t off0 = ((size_t)T.b * a.og.nchunk + (size_t)T.nt * nq) * a.og.Tp + a.og.pad + orow;  // float4 units
@@ -393,7 +324,7 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
       mbar_wait(acc_full + 8 * st, (it >> 1) & 1);
       tc_fence_after();
       if (trace && it == 0 && threadIdx.x == 64) trace[5] = clock64();
-      // bias / residual / scale / accumulate of 16 consecutive output channels of this thread's row; fp32 store and/or staging
+      // bias / residual / scale / accumulate of 16 consecutive output channels of this thread's row; fp32 store
       auto emit = [&](int c0, const float (&v)[16], const float4 (&rr)[4], const float4 (&oo)[4]) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -403,7 +334,6 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
           r.x = (r.x + rr[g].x) * scale + oo[g].x; r.y = (r.y + rr[g].y) * scale + oo[g].y;
           r.z = (r.z + rr[g].z) * scale + oo[g].z; r.w = (r.w + rr[g].w) * scale + oo[g].w;
           if (store && cq < nq_valid) out4[off0 + (size_t)cq * plane4] = r;
-          if (FUSED) ys[cq * kFuseSlots + yrow] = r;
         }
       };
       // residual / accumulate operands of 16 channels (issued before the TMEM load they are combined with)
@@ -525,32 +455,11 @@ __global__ void __launch_bounds__(256, MINB) conv_umma_kernel(const __grid_const
       if (trace && it == 0 && threadIdx.x == 64) trace[6] = clock64();
     }
   }
-  if (!FUSED && ksplit > 1 && a.cluster_splitk && !(warp >= 2 && warp < 6)) {
+  if (ksplit > 1 && a.cluster_splitk && !(warp >= 2 && warp < 6)) {
     cluster_arrive();  // barrier A and B of the DSMEM split-K reduction (the epilogue warps arrive inside their branch)
     cluster_wait();
     cluster_arrive();
     cluster_wait();
-  }
-  if constexpr (FUSED) {
-    pdl_wait();
-    // ---- Activation1d on the staged tile, by every warp of the CTA (the async warps are done by now) ----
-    __syncthreads();  // tile staged (and, for split-K, s_last decided)
-    if (*s_last) {
-      float4* ys = reinterpret_cast<float4*>(smem);
-      const int T = a.M, npl = a.NT >> 2, q0 = T0.q0;
-      // replicate padding of the up-sampling FIR (resample.py:28): rows before t=0 / after t=T-1 take the edge sample
-      const int lo = -q0, hi = T - q0;  // staged rows [lo, hi) are inside the sequence
-      if (lo > 0 || hi < kTileM) {
-        for (int i = threadIdx.x; i < npl * kTileM; i += blockDim.x) {
-          const int pl = i / kTileM, r = i - pl * kTileM;
-          const int src = r < lo ? lo : (r >= hi ? hi - 1 : r);
-          if (src != r && src >= 0 && src < kTileM) ys[pl * kFuseSlots + r + (r >> 3)] = ys[pl * kFuseSlots + src + (src >> 3)];
-        }
-        __syncthreads();
-      }
-      if (a.act_bf16) conv_fused_act<2>(a, ys, T0.b, T0.nt, q0);
-      else conv_fused_act<1>(a, ys, T0.b, T0.nt, q0);
-    }
   }
   if (trace && threadIdx.x == 64) trace[7] = (long long)global_timer_ns();
   tc_fence_before();

@@ -20,7 +20,6 @@
 #include "act1d.cuh"
 #include "common.cuh"
 #include "conv.cuh"
-#include "convpro.cuh"
 #include "misc_kernels.cuh"
 
 using namespace alcm;
@@ -69,7 +68,7 @@ static int env_int(const char* name, int dflt) {
 struct Knobs {
   int pdl, graph, lanes, lane_waves, persist, cluster_splitk, splitk, retile, retile_mode;
   int smem_budget, smem_budget_1w, smem_budget_mw, tpg, astages, kblk_max, nt, tmem2;
-  int act_variant, act_v2, act_v2_min_waves, fuse_act, fuse_stages, gn_fused, max_plans, trace, bench_fused, attn_tc, guard, actpro;
+  int act_variant, act_v2, act_v2_min_waves, gn_fused, max_plans, trace, guard, nt192;
   static Knobs from_env() {
     Knobs k;
     k.pdl = env_int("ALCM_PDL", -1);  // -1 unset (per-plan default), 0 never, 1 always
@@ -92,14 +91,10 @@ struct Knobs {
     k.act_variant = env_int("ALCM_ACT_VARIANT", -1);
     k.act_v2 = env_int("ALCM_ACT_V2", 7);                 // 0: off, 7 / 8: two-phase Activation1d with 5 / 7 outputs per thread
     k.act_v2_min_waves = env_int("ALCM_ACT_V2_MIN_WAVES", 4);
-    k.fuse_act = env_int("ALCM_FUSE_ACT", 0);
-    k.fuse_stages = env_int("ALCM_FUSE_STAGES", 0);
     k.gn_fused = env_int("ALCM_GN_FUSED", 1);
     k.max_plans = std::max(1, env_int("ALCM_MAX_PLANS", 16));
     k.trace = env_int("ALCM_TRACE", 0);
-    k.bench_fused = env_int("ALCM_BENCH_FUSED", 0);
-    k.attn_tc = env_int("ALCM_ATTN_TC", 1);
-    k.actpro = env_int("ALCM_ACTPRO", 1);                 // Activation1d fused into the conv operand producer for the narrow stages
+    k.nt192 = env_int("ALCM_NT192", 192);                 // N tile of the 192-channel layers (192: one tile, 96: two persistent tiles)
     k.guard = env_int("ALCM_GUARD", 0);                   // 1: 4 KB zero guard zones between device buffers, verified by alcm_*_check_guards
     return k;
   }
@@ -346,6 +341,7 @@ static ConvLayer prepare_conv(Arena& ar, const Knobs& K_, int prec, ConvKind kin
   const int E = (prec == ALCM_PREC_BF16) ? 8 : 4;
   const int cout_pad = round_up(Cout, 16);
   int nt_pref = K_.nt;
+  if (cout_pad == 192 && K_.nt192 > 0 && 192 % K_.nt192 == 0) nt_pref = K_.nt192 < 192 ? K_.nt192 : nt_pref;
   if (cout_pad <= 256 && (cout_pad <= nt_pref || cout_pad % nt_pref != 0)) L.NT = cout_pad;
   else L.NT = nt_pref;
   REQUIRE(L.NT % 16 == 0 && L.NT >= 16 && L.NT <= 256, "bad N tile");
@@ -410,7 +406,7 @@ static int pick_nt(const Env& env, const ConvLayer& L, int M, int B) {
 // mbarrier round trip) plus the cluster reduce-scatter (two cluster barriers, N/16 TMEM->DSMEM pushes) - among the
 // shapes that fit one wave.  Measured: at these sizes the launch is bound by per-CTA fixed costs, not by operand
 // traffic, so wide tiles (efficient MMAs) with a split of 4-8 reduced through DSMEM beat narrow un-split ones.
-static void conv_kernel_for(int prec, bool fused, void (**kern)(ConvArgs), int* threads);
+static void conv_kernel_for(int prec, void (**kern)(ConvArgs), int* threads);
 
 // CTAs that can be co-resident when launched as clusters of `ks` (GPC boundaries cost a few SMs): one big-smem CTA per SM.
 // Cached in the ctx (per device).
@@ -422,7 +418,7 @@ static long cluster_capacity(const Env& env, int prec, int ks) {
   if (cap[pi][ks] == 0) {
     void (*kern)(ConvArgs) = nullptr;
     int threads = 192;
-    conv_kernel_for(prec, false, &kern, &threads);
+    conv_kernel_for(prec, &kern, &threads);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(ks * 64); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 200 * 1024;
@@ -515,7 +511,7 @@ struct Op {
 // ~1024 tensor cycles (see conv.cuh).  Ring depth: ~100 KB (2 CTAs/SM) for multi-wave grids; single-wave grids
 // get 120 KB - measured on the batch-1 decode (tools/sweep_env.sh): 200 KB 3.450 ms, 150 KB 3.496, 120 KB 3.424
 // (operand traffic is not the limiter at that size, and a smaller footprint leaves room for the other lanes' blocks).
-static void pick_pipeline(const Env& env, const ConvLayer& L, long ctas, int ksplit, bool fused, bool cluster, int* stages, int* tpg,
+static void pick_pipeline(const Env& env, const ConvLayer& L, long ctas, int ksplit, bool cluster, int* stages, int* tpg,
                           int* a_stages, uint32_t* smem) {
   const uint32_t budget = (uint32_t)(env.k.smem_budget > 0 ? env.k.smem_budget
                                                            : (ctas <= (long)env.sms() ? env.k.smem_budget_1w : env.k.smem_budget_mw));
@@ -539,11 +535,6 @@ static void pick_pipeline(const Env& env, const ConvLayer& L, long ctas, int ksp
   int S = (budget > fixed) ? (int)((budget - fixed) / (t * blob)) : 0;
   S = std::max(2, std::min(12, S));
   S = std::min(S, std::max(2, nkb_local * ((L.ntaps + t - 1) / t)));
-  if (fused) {  // the staged output tile overlays the (drained) A and W buffers
-    const uint32_t staging = (uint32_t)(L.NT / 4) * kFuseSlots * 16;
-    while (a2 + (uint32_t)S * t * blob < staging && S < 12) ++S;
-    REQUIRE(a2 + (uint32_t)S * t * blob >= staging, "fused activation: staging tile does not fit under the pipeline buffers");
-  }
   if (cluster) {  // DSMEM split-K: the partial tiles pushed by the other CTAs overlay the (drained) A and W buffers
     const uint32_t staging = (uint32_t)L.NT * 512u;
     while (a2 + (uint32_t)S * t * blob < staging && S < 12 && fixed + (uint32_t)(S + 1) * t * blob <= 220u * 1024u) ++S;
@@ -563,30 +554,21 @@ struct SplitK {  // per-launch split-K resources (see ConvArgs::ksplit)
   unsigned int* ctr = nullptr;
 };
 
-// Fused Activation1d epilogue of a conv launch (ConvArgs::act_out)
-struct FusedAct {
-  PlaneT out;          // operand planes written by the epilogue (p == nullptr: not fused)
-  const float* ea = nullptr;
-  const float* ib = nullptr;
-  int round_tf32 = 0;
-};
-
-static inline int conv_m_tiles(int M, bool fused) { return fused ? (M + kFuseOwn - 1) / kFuseOwn : (M + kTileM - 1) / kTileM; }
+static inline int conv_m_tiles(int M) { return (M + kTileM - 1) / kTileM; }
 
 // How many K splits a conv launch gets: only launches whose output tiles cannot fill the GPU are split.
-static int pick_ksplit(const Env& env, const ConvLayer& L, int M, int B, bool fused = false) {
+static int pick_ksplit(const Env& env, const ConvLayer& L, int M, int B) {
   if (L.prec == ALCM_PREC_FP32 || !env.k.splitk || L.nkb < 2) return 1;
-  const long ctas = (long)conv_m_tiles(M, fused) * L.n_tiles * B * L.nphase;
+  const long ctas = (long)conv_m_tiles(M) * L.n_tiles * B * L.nphase;
   if (ctas * 2 > (long)env.sms()) return 1;
   return (int)std::max<long>(1, std::min<long>(std::min<long>(L.nkb, env.sms() / ctas), 8));
 }
 
-static void conv_kernel_for(int prec, bool fused, void (**kern)(ConvArgs), int* threads) {
-  *threads = 192;
-  if (fused) { *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, true> : conv_umma_kernel<1, 2, true>; *threads = 256; }
+static void conv_kernel_for(int prec, void (**kern)(ConvArgs), int* threads) {
   // one register budget for every tile width (128/thread, 2 CTAs of 192 threads per SM): a narrower, spilling
   // 80-register build for N < 128 (4 CTAs/SM) measured slower at every batch size (batch 1: 3.31 -> 3.24 ms)
-  else *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2, false> : conv_umma_kernel<1, 2, false>;
+  *threads = 192;
+  *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2> : conv_umma_kernel<1, 2>;
 }
 
 // One conv launch, fully decided at PLAN time (kernel, grid, shared memory, pipeline shape, cluster size): replaying
@@ -608,9 +590,8 @@ struct ConvLaunch {
   }
 };
 
-// `out` may be empty (p == nullptr) for a fused launch that only produces the activated operand planes.
 static ConvLaunch plan_conv(const Env& env, const ConvLayer& L, const PlaneT& x, const PlaneT& out, const float* res, int M, float scale,
-                            int accum, const SplitK& sk, const FusedAct& fa) {
+                            int accum, const SplitK& sk) {
   ConvLaunch cl;
   cl.cx = env.cx;
   ConvArgs& a = cl.a;
@@ -628,9 +609,7 @@ static ConvLaunch plan_conv(const Env& env, const ConvLayer& L, const PlaneT& x,
   a.scale = scale; a.accum = accum;
   a.ksplit = 1;
   const int B = x.B;
-  const bool fused = fa.out.p != nullptr;
   if (L.prec == ALCM_PREC_FP32) {
-    REQUIRE(!fused, "conv: the fp32 (CUDA-core) path has no fused activation");
     a.w = reinterpret_cast<const uint8_t*>(L.weff);
     cl.kern = conv_simt_kernel;
     cl.grid = dim3((M + kSimtTM - 1) / kSimtTM, (L.Cout + kSimtTN - 1) / kSimtTN, B * L.nphase);
@@ -645,21 +624,17 @@ static ConvLaunch plan_conv(const Env& env, const ConvLayer& L, const PlaneT& x,
   a.ksplit = sk.ksplit; a.ws = sk.ws; a.tile_ctr = sk.ctr; a.cluster_splitk = sk.cluster;
   // K chunks that exist in memory (plane_cpad): the others are an all-zero shared-memory slab
   REQUIRE(x.g.nchunk >= L.kchunks || L.nkb == 1, "conv: operand planes narrower than K need a single k-block");
-  if (fused) {
-    a.act_out = fa.out.p; a.ag = fa.out.g; a.ea = fa.ea; a.ib = fa.ib;
-    a.act_bf16 = fa.out.esz == 2; a.act_round_tf32 = fa.round_tf32;
-  }
-  a.tiles_m = conv_m_tiles(M, fused);
+  a.tiles_m = conv_m_tiles(M);
   a.tiles_total = a.tiles_m * L.n_tiles * B * L.nphase * sk.ksplit;
   a.acc_stages = 1;
   uint32_t smem = 0;
-  pick_pipeline(env, L, (long)a.tiles_total, sk.ksplit, fused, sk.cluster != 0, &a.w_stages, &a.tpg, &a.a_stages, &smem);
+  pick_pipeline(env, L, (long)a.tiles_total, sk.ksplit, sk.cluster != 0, &a.w_stages, &a.tpg, &a.a_stages, &smem);
   int threads = 192;
-  conv_kernel_for(L.prec, fused, &cl.kern, &threads);
+  conv_kernel_for(L.prec, &cl.kern, &threads);
   // Persistent launch for multi-wave grids: one CTA per resident slot loops over tiles with two TMEM accumulators,
   // so barrier/TMEM setup is paid once per CTA and the epilogue of tile i overlaps the main loop of tile i+1.
   int grid = a.tiles_total;
-  if (!fused && sk.ksplit == 1 && 2 * L.NT <= 512 && env.k.persist) {
+  if (sk.ksplit == 1 && 2 * L.NT <= 512 && env.k.persist) {
     int tcols2 = 32;
     while (tcols2 < 2 * L.NT) tcols2 *= 2;
     // resident CTAs per SM: shared memory (1 KB reserved per CTA), registers (128/thread -> 2 CTAs of 192 threads),
@@ -681,66 +656,6 @@ static ConvLaunch plan_conv(const Env& env, const ConvLayer& L, const PlaneT& x,
   return cl;
 }
 
-// "act -> conv" launch (conv_actpro_kernel, convpro.cuh): x are the fp32 planes the Activation1d reads.
-static bool actpro_eligible(const Env& env, const ConvLayer& L, const PlaneT& x) {
-  if (!env.k.actpro || L.prec == ALCM_PREC_FP32 || L.nphase != 1 || L.nkb != 1 || L.n_tiles != 1 || x.esz != 4) return false;
-  const int npl = L.prec == ALCM_PREC_BF16 ? 2 : 1;
-  if (-L.min_off[0] + 5 > kPad) return false;
-  // shared memory: two A slabs + activation warps' areas + at least two weight stages of one tap
-  const ProSmem P = pro_smem_layout(L.kblk, L.span, L.NT, 2, 1, 2, npl);
-  return P.total <= 227u * 1024u;
-}
-
-static ConvLaunch plan_conv_pro(const Env& env, const ConvLayer& L, const PlaneT& x, const PlaneT& out, const float* res, int M, float scale,
-                                int accum, const float* ea, const float* ib) {
-  ConvLaunch cl;
-  cl.cx = env.cx;
-  ConvArgs& a = cl.a;
-  memset(&a, 0, sizeof(a));
-  a.x = x.p; a.xg = x.g;
-  a.w = L.wpack;
-  a.bias = L.bias;
-  a.out = out.f(); a.og = out.g;
-  a.res = res;
-  a.M = M;
-  a.ostride = 1; a.nphase = 1; a.ntaps = L.ntaps;
-  memcpy(a.tap_off, L.tap_off, sizeof(a.tap_off));
-  memcpy(a.min_off, L.min_off, sizeof(a.min_off));
-  a.span = L.span;
-  a.Cin = L.Cin; a.Cout = L.Cout;
-  a.scale = scale; a.accum = accum;
-  a.ksplit = 1;
-  a.kchunks = L.kchunks; a.kblk = L.kblk; a.nkb = 1;
-  a.NT = L.NT; a.n_tiles = 1;
-  a.idesc = L.idesc; a.w_phase_stride = L.phase_stride;
-  a.ea = ea; a.ib = ib;
-  a.tiles_m = (M + kTileM - 1) / kTileM;
-  a.tiles_total = a.tiles_m * x.B;
-  a.acc_stages = 2;
-  a.tmem_cols = 32;
-  while (a.tmem_cols < 2 * L.NT) a.tmem_cols *= 2;
-  a.a_stages = 2;
-  const int npl = L.prec == ALCM_PREC_BF16 ? 2 : 1;
-  // weight ring: as many taps per stage as the ~1024-tensor-cycle rule wants, shrunk until two stages fit
-  const double cyc_tap = (L.kblk / 2) * std::max(L.NT / 2.0, 32.0 + L.NT / 4.0);
-  const int tmin = std::max(1, std::min(L.ntaps, (int)std::ceil(1024.0 / cyc_tap)));
-  const int ngrp = (L.ntaps + tmin - 1) / tmin;
-  int t = (L.ntaps + ngrp - 1) / ngrp;
-  const uint32_t cap = 227u * 1024u;
-  while (t > 1 && pro_smem_layout(L.kblk, L.span, L.NT, 2, t, 2, npl).total > cap) --t;
-  int S = 2;
-  while (S < 8 && S < (L.ntaps + t - 1) / t * 2 && pro_smem_layout(L.kblk, L.span, L.NT, S + 1, t, 2, npl).total <= cap) ++S;
-  a.tpg = t; a.w_stages = S;
-  const ProSmem P = pro_smem_layout(L.kblk, L.span, L.NT, S, t, 2, npl);
-  REQUIRE(P.total <= cap, "act->conv: tile does not fit shared memory");
-  cl.kern = L.prec == ALCM_PREC_BF16 ? conv_actpro_kernel<0> : conv_actpro_kernel<1>;
-  cl.grid = dim3((unsigned)std::min<long>(a.tiles_total, env.sms()));
-  cl.block = dim3(kProThreads);
-  cl.smem = P.total;
-  cl.cluster_x = 1;
-  return cl;
-}
-
 struct OpList {
   std::vector<Op> ops;
   Env env;              // device context + knob snapshot every planning decision below depends on
@@ -749,52 +664,28 @@ struct OpList {
   int cur_stage = -1;   // tag for the per-stage profile
   Arena* war = nullptr;          // model-owned arena + cache for re-tiled weights (null: keep the packed N tile)
   RetileCache* cache = nullptr;
-  double fused_act_bytes = 0;  // Activation1d work absorbed by conv epilogues
-  int fused_acts = 0;
   float* ws[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
   size_t ws_bytes[kMaxLanes] = {0, 0, 0, 0};
-  void conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const PlaneT* res, float scale = 1.f, int accum = 0) {
-    conv_act(L, x, &out, res, scale, accum, nullptr, nullptr, nullptr, 0);
-  }
-  // conv (+bias, +residual) with the following Activation1d fused into the epilogue: `out` (fp32, optional)
-  // receives the conv result, `aout` (operand planes) the activated one.  aout == nullptr: plain conv.
-  void conv_act(const ConvLayer& L0, const PlaneT& x, const PlaneT* out, const PlaneT* res, float scale, int accum,
-                const PlaneT* aout, const float* ea, const float* ib, int round_tf32) {
+  // conv (+bias, +residual, scale, accumulate): `out` fp32 planes, `x` operand planes
+  void conv(const ConvLayer& L0, const PlaneT& x, const PlaneT& out, const PlaneT* res, float scale = 1.f, int accum = 0) {
     const int M = x.T;  // rows per batch item are input time steps (== output steps / nphase)
     int nt_c = 0, ks_c = 1;
-    const bool clustered = war && cache && ar && aout == nullptr && choose_cluster_tile(env, L0, M, x.B, &nt_c, &ks_c);
+    const bool clustered = war && cache && ar && choose_cluster_tile(env, L0, M, x.B, &nt_c, &ks_c);
     const ConvLayer& L = (war && cache) ? retile(*war, *cache, L0, clustered ? nt_c : pick_nt(env, L0, M, x.B)) : L0;
-    const bool fused = aout != nullptr;
-    REQUIRE(out || fused, "conv: no output");
     REQUIRE(x.esz == opnd_esz(L.prec), "conv: operand dtype mismatch");
-    if (out) {
-      REQUIRE(out->esz == 4 && out->T == x.T * L.nphase, "conv: bad output planes");
-      REQUIRE(out->g.nchunk * 4 >= L.Cout, "conv: channel mismatch");
-    }
+    REQUIRE(out.esz == 4 && out.T == x.T * L.nphase, "conv: bad output planes");
+    REQUIRE(out.g.nchunk * 4 >= L.Cout, "conv: channel mismatch");
     REQUIRE(x.g.nchunk * (16 / x.esz) >= L.Cin, "conv: channel mismatch");
-    if (fused) {
-      REQUIRE(L.prec != ALCM_PREC_FP32 && L.nphase == 1 && scale == 1.f && accum == 0, "fused activation: plain Conv1d launches only");
-      REQUIRE(aout->esz == opnd_esz(L.prec) && aout->T == x.T && aout->B == x.B && aout->g.nchunk * (16 / aout->esz) >= L.Cout,
-              "fused activation: bad operand planes");
-      REQUIRE(!(res && out && res->p == out->p), "fused activation: the residual is read with a halo and must not alias the output");
-      REQUIRE(L.n_tiles * L.NT == round_up(L.Cout, 16), "fused activation: N tiles must cover the padded channels exactly");
-      REQUIRE(-L.min_off[0] + kFuseHalo <= kPad, "fused activation: conv halo + FIR halo exceed the plane padding");
-    }
     Op op;
     op.cls = ALCM_CLS_CONV;
     op.flops = 2.0 * L.Cin * L.Cout * L.ntaps * L.nphase * (double)M * x.B;
-    op.bytes = (double)x.B * x.T * ((double)L.Cin * x.esz + (out ? (double)L.Cout * L.nphase * 4 : 0.0) +
-                                    (res ? (double)L.Cout * 4 : 0.0) + (fused ? (double)L.Cout * aout->esz : 0.0));
+    op.bytes = (double)x.B * x.T * ((double)L.Cin * x.esz + (double)L.Cout * L.nphase * 4 + (res ? (double)L.Cout * 4 : 0.0));
     const float* rp = res ? res->f() : nullptr;
-    ConvLayer Lc = L;
-    PlaneT xc = x, oc = out ? *out : PlaneT();
-    FusedAct fa;
-    if (fused) { fa.out = *aout; fa.ea = ea; fa.ib = ib; fa.round_tf32 = round_tf32; }
     SplitK sk;
     if (clustered) { sk.ksplit = ks_c; sk.cluster = ks_c > 1; }
-    else if (ar) sk.ksplit = pick_ksplit(env, L, M, x.B, fused);
+    else if (ar) sk.ksplit = pick_ksplit(env, L, M, x.B);
     if (sk.ksplit > 1 && !sk.cluster) {
-      const size_t tiles = (size_t)conv_m_tiles(M, fused) * L.n_tiles * x.B * L.nphase;
+      const size_t tiles = (size_t)conv_m_tiles(M) * L.n_tiles * x.B * L.nphase;
       const size_t need = tiles * sk.ksplit * (size_t)L.NT * kTileM * 4;
       if (need > ws_bytes[cur_lane]) {  // ops of one lane run in stream order and can share the partial-tile workspace
         ws_bytes[cur_lane] = std::max<size_t>(need, (size_t)16 << 20);
@@ -803,31 +694,9 @@ struct OpList {
       sk.ws = ws[cur_lane];
       sk.ctr = static_cast<unsigned int*>(ar->alloc(tiles * sizeof(unsigned int), true));
     }
-    const ConvLaunch cl = plan_conv(env, Lc, xc, oc, rp, M, scale, accum, sk, fa);
+    const ConvLaunch cl = plan_conv(env, L, x, out, rp, M, scale, accum, sk);
     op.fn = [cl](cudaStream_t st) { cl.run(st); };
     push(op);
-    if (fused) {  // count the activation the launch absorbs in the act class' algorithmic bytes (bench roofline_act)
-      fused_act_bytes += (double)x.B * x.T * L.Cout * (4.0 + aout->esz);
-      ++fused_acts;
-    }
-  }
-  // Activation1d(x) -> conv (+bias, +residual, scale, accumulate) as ONE launch (convpro.cuh); x: fp32 planes.
-  // Caller checks actpro_eligible().  Counts as a conv launch plus the activation's algorithmic bytes.
-  void act_conv(const ConvLayer& L, const PlaneT& x, const PlaneT& out, const PlaneT* res, const float* ea, const float* ib, float scale = 1.f,
-                int accum = 0) {
-    REQUIRE(actpro_eligible(env, L, x), "act->conv: layer not eligible");
-    REQUIRE(out.esz == 4 && out.T == x.T && out.B == x.B && out.g.nchunk * 4 >= L.Cout, "act->conv: bad output planes");
-    REQUIRE(x.g.nchunk * 4 >= L.Cin, "act->conv: channel mismatch");
-    const int M = x.T;
-    Op op;
-    op.cls = ALCM_CLS_CONV;
-    op.flops = 2.0 * L.Cin * L.Cout * L.ntaps * (double)M * x.B;
-    op.bytes = (double)x.B * x.T * ((double)L.Cin * 4 + (double)L.Cout * 4 + (res ? (double)L.Cout * 4 : 0.0));
-    const ConvLaunch cl = plan_conv_pro(env, L, x, out, res ? res->f() : nullptr, M, scale, accum, ea, ib);
-    op.fn = [cl](cudaStream_t st) { cl.run(st); };
-    push(op);
-    fused_act_bytes += (double)x.B * x.T * L.Cin * (4.0 + opnd_esz(L.prec));
-    ++fused_acts;
   }
   void act(const PlaneT& x, const PlaneT& out, const float* ea, const float* ib, int round_tf32, bool fast) {
     REQUIRE(x.esz == 4 && x.T == out.T && x.B == out.B, "act: bad planes");
@@ -849,30 +718,14 @@ struct OpList {
     // 3: 6 outputs/thread (96 registers, 5 blocks/SM) - measured best or equal on every launch that fills the GPU
     // (batch 64, last stage: 3.48 TB/s bf16 out, 4.63 TB/s = 72 % of the HBM peak fp32 out)
     const long blocks_r6 = (long)((T + 6 * kActThreads - 1) / (6 * kActThreads)) * nch * B;
-    // 7 / 8: two-phase form (act1d_v2_kernel; every up-sampled value computed once per block), 5 / 7 outputs per thread;
-    // 9: the same, persistent with prefetch (act1d_v3_kernel)
+    // 7 / 8: two-phase form (act1d_v2_kernel; every up-sampled value computed once per block), 5 / 7 outputs per thread
     const long blocks_v2 = (long)((T + 5 * kActThreads - 1) / (5 * kActThreads)) * nch * B;
     int variant = 0;
     if (oesz == 2 && blocks_wide < 24L * env.sms()) variant = 5;  // pair form, 6 outputs/thread: batch-1 decode 3.53 -> 3.45 ms vs 4 outputs/thread
     else if (blocks_r6 >= 8L * env.sms()) variant = 3;
     if (env.k.act_v2 && blocks_v2 >= (long)env.k.act_v2_min_waves * env.sms()) variant = env.k.act_v2;
     if (env.k.act_variant >= 0) variant = env.k.act_variant;
-    const int sms = env.sms();
     op.fn = [=](cudaStream_t st) {
-      if (variant == 9) {  // persistent two-phase form (prefetching), 5 outputs per thread
-        using G = ActV2Geom<5, kActThreads>;
-        const int ntt = (T + G::kTile - 1) / G::kTile;
-        const long ntiles = (long)ntt * nch * B;
-        const dim3 grid((unsigned)std::min<long>(ntiles, 5L * sms));
-        const size_t sm = 2 * (size_t)G::kXBytes + 2 * (size_t)G::kYBytes + 16;
-        if (oesz == 4) {
-          if (fast) launch_k(act1d_v3_kernel<1, true, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a, ntt, (int)ntiles);
-          else launch_k(act1d_v3_kernel<1, false, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a, ntt, (int)ntiles);
-        } else {
-          launch_k(act1d_v3_kernel<2, true, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a, ntt, (int)ntiles);
-        }
-        return;
-      }
       if (variant == 7 || variant == 8) {  // two-phase form
         const int ur = variant == 7 ? 5 : 7;
         const dim3 grid((T + ur * kActThreads - 1) / (ur * kActThreads), nch, B);
@@ -1236,7 +1089,7 @@ struct alcm_vocoder {
 };
 
 static SnakeP make_snake(Arena& ar, const float* alpha, const float* beta, int C) {
-  const int Cpad = round_up(C, 16) + 256;  // the fused conv epilogue indexes by (N tile, column)
+  const int Cpad = round_up(C, 16);
   SnakeP s;
   s.ea = static_cast<float*>(ar.alloc((size_t)Cpad * 4, false));
   s.ib = static_cast<float*>(ar.alloc((size_t)Cpad * 4, false));
@@ -1282,59 +1135,17 @@ static void voc_build(const alcm_vocoder* v, VocPlan& P) {
     const bool parallel = nk > 1 && nk <= kMaxLanes && K.lanes && conv_ctas < (long)K.lane_waves * v->env.sms();
     PlaneT XS = make_planes(P.ar, B, C, Tc, 4);
     std::vector<PlaneT> Z;
-    PlaneT R, R2, Y, A, A2;
-    // Measured on B200 (round 1): with the current register-blocked activation code the fused epilogue leaves the
-    // tensor pipe idle for longer than a separate launch costs (batch-1 decode 4.53 ms fused vs 4.05 ms unfused), so
-    // the fused chain is opt-in until the activation phase overlaps the next tile's main loop.
-    const bool fuse = (prec != ALCM_PREC_FP32) && (K.fuse_act || ((K.fuse_stages >> i) & 1));
+    PlaneT R, Y, A;
     if (parallel) P.ol.fork();
     for (int j = 0; j < nk; ++j) {
       const AmpBlock& bk = S.blocks[j];
       if (parallel || j == 0) {
         R = make_planes(P.ar, B, C, Tc, 4); A = make_planes(P.ar, B, C, Tc, oe);
-        if (fuse) { R2 = make_planes(P.ar, B, C, Tc, 4); A2 = make_planes(P.ar, B, C, Tc, oe); }
-        else Y = make_planes(P.ar, B, C, Tc, 4);
+        Y = make_planes(P.ar, B, C, Tc, 4);
       }
       if (parallel) P.ol.lane(j);
       const PlaneT* cur = &X;
-      if (fuse) {
-        // models.py:72-81 with every Activation1d but the first of the block running in the epilogue of the
-        // conv that produces its input: c1 emits only the activated operand (its fp32 output is never
-        // needed), c2 emits the new residual stream (fp32, ping-pong R/R2) and its activation.
-        P.ol.act(X, A, bk.a[0].ea, bk.a[0].ib, rtf, fast);
-        PlaneT* rnext = &R;
-        for (int l = 0; l < 3; ++l) {
-          P.ol.conv_act(bk.c1[l], A, nullptr, nullptr, 1.f, 0, &A2, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, rtf);
-          if (l < 2) {
-            P.ol.conv_act(bk.c2[l], A2, rnext, cur, 1.f, 0, &A, bk.a[2 * l + 2].ea, bk.a[2 * l + 2].ib, rtf);
-            cur = rnext;
-            rnext = (rnext == &R) ? &R2 : &R;
-          } else if (parallel) {
-            P.ol.conv(bk.c2[l], A2, *rnext, cur, 1.0f / nk, 0);
-            Z.push_back(*rnext);
-          } else {
-            P.ol.conv(bk.c2[l], A2, XS, cur, 1.0f / nk, j > 0);
-          }
-        }
-        continue;
-      }
-      // narrow stages: each (Activation1d, conv) pair is ONE launch - the activation runs in the conv's operand producer
-      const bool pro = actpro_eligible(v->env, bk.c1[0], X) && actpro_eligible(v->env, bk.c2[0], X) &&
-                       actpro_eligible(v->env, bk.c1[2], X);
       for (int l = 0; l < 3; ++l) {  // models.py:72-81
-        if (pro) {
-          P.ol.act_conv(bk.c1[l], *cur, Y, nullptr, bk.a[2 * l].ea, bk.a[2 * l].ib);
-          if (l < 2) {
-            P.ol.act_conv(bk.c2[l], Y, R, cur, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib);
-            cur = &R;
-          } else if (parallel) {
-            P.ol.act_conv(bk.c2[l], Y, R, cur, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, 1.0f / nk, 0);
-            Z.push_back(R);
-          } else {
-            P.ol.act_conv(bk.c2[l], Y, XS, cur, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, 1.0f / nk, j > 0);
-          }
-          continue;
-        }
         P.ol.act(*cur, A, bk.a[2 * l].ea, bk.a[2 * l].ib, rtf, fast);
         P.ol.conv(bk.c1[l], A, Y, nullptr);
         P.ol.act(Y, A, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, rtf, fast);
@@ -1597,12 +1408,8 @@ static void set_kernel_attrs() {
   CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<1, true, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<1, false, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<2, true, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_actpro_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_actpro_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
 }
 
 extern "C" {
@@ -1947,6 +1754,28 @@ int alcm_decode_to_pcm16(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B
   return guarded([&] { decode_any(vae, voc, z, B, T, inv_scale, mel_out, pcm, 1, stream); });
 }
 
+// ---- LCM sampler step (the scalar half of SURVEY 8f row 2; the DiT denoiser stays reference PyTorch) ----------
+int alcm_lcm_step(alcm_ctx* ctx, const float* sample, const float* eps, const float* noise, float* prev, float* denoised, long long n,
+                  float sqrt_alpha_prod_t, float sqrt_beta_prod_t, float c_out, float c_skip, float sqrt_alpha_prod_prev,
+                  float sqrt_beta_prod_prev, int last_step, void* stream) {
+  return guarded([&] {
+    REQUIRE(ctx && sample && eps && prev && denoised, "lcm_step: NULL argument");
+    REQUIRE(last_step || noise, "lcm_step: noise is required on every step but the last");
+    REQUIRE(n > 0 && (n % 4) == 0, "lcm_step: element count must be a positive multiple of 4");
+    REQUIRE(sqrt_alpha_prod_t > 0.f, "lcm_step: sqrt(alpha_prod_t) must be positive");
+    REQUIRE(((uintptr_t)sample | (uintptr_t)eps | (uintptr_t)(noise ? noise : sample) | (uintptr_t)prev | (uintptr_t)denoised) % 16 == 0,
+            "lcm_step: tensors must be 16-byte aligned");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    LcmStepCoef k{sqrt_beta_prod_t, 1.0f / sqrt_alpha_prod_t, c_out, c_skip, sqrt_alpha_prod_prev, sqrt_beta_prod_prev, last_step};
+    const size_t n4 = (size_t)n / 4;
+    const unsigned blocks = (unsigned)std::min<size_t>((n4 + 255) / 256, (size_t)ctx->sm_count * 8);
+    launch_k(lcm_step_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4*>(sample),
+             reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(noise), reinterpret_cast<float4*>(prev),
+             reinterpret_cast<float4*>(denoised), n4, k);
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
 // ---- single-op entry points ---------------------------------------------------------------
 static void sync_free(const Arena& ar, cudaStream_t st) {
   CUDA_CHECK(cudaStreamSynchronize(st));
@@ -2017,74 +1846,6 @@ int alcm_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* 
   return guarded([&] {
     REQUIRE(dilation >= 1, "conv1d: dilation must be >= 1");
     run_conv_test(ctx, KIND_CONV, x, w, bias, res, y, B, Cin, Cout, T, K, dilation, precision, static_cast<cudaStream_t>(stream));
-  });
-}
-int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, const float* alpha,
-                        const float* beta, float* y_conv, float* y_act, int B, int Cin, int Cout, int T, int K, int dilation,
-                        int precision, void* stream) {
-  return guarded([&] {
-    REQUIRE(ctx && x && w && alpha && beta && y_act, "conv1d_act: NULL argument");
-    REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T >= 1 && dilation >= 1, "conv1d_act: bad shape");
-    REQUIRE(precision == ALCM_PREC_TF32 || precision == ALCM_PREC_BF16, "conv1d_act: tf32 / bf16 only");
-    CUDA_CHECK(cudaSetDevice(ctx->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    Arena ar;
-    ar.guard = env_int("ALCM_GUARD", 0) != 0;
-    const Env env{ctx, Knobs::from_env()};
-    ConvLayer L = prepare_conv(ar, env.k, precision, KIND_CONV, w, bias, Cout, Cin, K, dilation);
-    PlaneT xin = make_planes(ar, B, Cin, T, opnd_esz(precision));
-    PlaneT out = make_planes(ar, B, Cout, T, 4), aout = make_planes(ar, B, Cout, T, opnd_esz(precision));
-    PlaneT rp;
-    if (res) rp = make_planes(ar, B, Cout, T, 4);
-    SnakeP sp = make_snake(ar, alpha, beta, Cout);
-    CUDA_CHECK(sync_setup());
-    launch_pack(x, xin, Cin, T, 1.f, precision, st);
-    if (res) launch_pack(res, rp, Cout, T, 1.f, ALCM_PREC_FP32, st);
-    OpList ol;
-    ol.env = env;
-    ol.ar = &ar;
-    ol.conv_act(L, xin, y_conv ? &out : nullptr, res ? &rp : nullptr, 1.f, 0, &aout, sp.ea, sp.ib, precision == ALCM_PREC_TF32);
-    CUDA_CHECK(sync_setup());  // workspace memsets
-    ol.run(st);
-    if (y_conv) launch_unpack(out, y_conv, Cout, T, st);
-    if (precision == ALCM_PREC_BF16) {
-      dim3 grid((T + 255) / 256, aout.g.nchunk, B);
-      launch_k(unpack_cf_bf16_kernel, dim3(grid), dim3(256), 0, st, aout.p, aout.g, y_act, Cout, T);
-    } else {
-      launch_unpack(aout, y_act, Cout, T, st);
-    }
-    CUDA_CHECK(cudaGetLastError());
-    sync_free(ar, st);
-  });
-}
-int alcm_act_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, const float* beta, const float* w, const float* bias,
-                        const float* res, float* y, int B, int Cin, int Cout, int T, int K, int dilation, int precision, void* stream) {
-  return guarded([&] {
-    REQUIRE(ctx && x && alpha && beta && w && y, "act_conv1d: NULL argument");
-    REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T >= 1 && dilation >= 1, "act_conv1d: bad shape");
-    REQUIRE(precision == ALCM_PREC_TF32 || precision == ALCM_PREC_BF16, "act_conv1d: tf32 / bf16 only");
-    CUDA_CHECK(cudaSetDevice(ctx->device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    Arena ar;
-    ar.guard = env_int("ALCM_GUARD", 0) != 0;
-    const Env env{ctx, Knobs::from_env()};
-    ConvLayer L = prepare_conv(ar, env.k, precision, KIND_CONV, w, bias, Cout, Cin, K, dilation);
-    PlaneT xin = make_planes(ar, B, Cin, T, 4), out = make_planes(ar, B, Cout, T, 4);
-    PlaneT rp;
-    if (res) rp = make_planes(ar, B, Cout, T, 4);
-    SnakeP sp = make_snake(ar, alpha, beta, Cin);
-    REQUIRE(actpro_eligible(env, L, xin), "act_conv1d: shape not eligible for the fused producer (needs a single k-block: bf16 C <= 96, tf32 C <= 48)");
-    CUDA_CHECK(sync_setup());
-    launch_pack(x, xin, Cin, T, 1.f, ALCM_PREC_FP32, st);
-    if (res) launch_pack(res, rp, Cout, T, 1.f, ALCM_PREC_FP32, st);
-    OpList ol;
-    ol.env = env;
-    ol.ar = &ar;
-    ol.act_conv(L, xin, out, res ? &rp : nullptr, sp.ea, sp.ib);
-    ol.run(st);
-    launch_unpack(out, y, Cout, T, st);
-    CUDA_CHECK(cudaGetLastError());
-    sync_free(ar, st);
   });
 }
 int alcm_conv_transpose1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Cout,
@@ -2254,16 +2015,7 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     ol.env = env;
     ol.ar = &ar;
     ol.war = &ar; ol.cache = &rcache;  // same per-launch N tile choice as the plans
-    const bool bench_fused = env.k.bench_fused && precision != ALCM_PREC_FP32;
-    if (bench_fused) {  // conv + fused Activation1d, operand planes only (the c1 launches of the AMP blocks)
-      PlaneT aout = make_planes(ar, B, Cout, T, opnd_esz(precision));
-      float* ab = static_cast<float*>(ar.alloc((size_t)(round_up(Cout, 16) + 256) * 4, false));
-      fill_uniform(ab, (size_t)round_up(Cout, 16) + 256, 0, -0.5f, 0.5f, 4u);
-      SnakeP sp = make_snake(ar, ab, ab, Cout);
-      ol.conv_act(L, x, nullptr, nullptr, 1.f, 0, &aout, sp.ea, sp.ib, precision == ALCM_PREC_TF32);
-    } else {
-      ol.conv(L, x, out, nullptr);
-    }
+    ol.conv(L, x, out, nullptr);
     CUDA_CHECK(sync_setup());
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0));
@@ -2278,10 +2030,10 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     CUDA_CHECK(err);
     if (env.k.trace && precision != ALCM_PREC_FP32) {  // one more launch with per-CTA timestamps
       int nt_c = 0, ks_c = 1;
-      const bool clustered = !bench_fused && choose_cluster_tile(env, L, T, B, &nt_c, &ks_c);
+      const bool clustered = choose_cluster_tile(env, L, T, B, &nt_c, &ks_c);
       const ConvLayer& Lt = retile(ar, rcache, L, clustered ? nt_c : pick_nt(env, L, T, B));
-      const int ks = clustered ? ks_c : pick_ksplit(env, Lt, T, B, bench_fused);
-      const size_t nctas = (size_t)conv_m_tiles(T, bench_fused) * Lt.n_tiles * B * Lt.nphase * ks;
+      const int ks = clustered ? ks_c : pick_ksplit(env, Lt, T, B);
+      const size_t nctas = (size_t)conv_m_tiles(T) * Lt.n_tiles * B * Lt.nphase * ks;
       long long* tr = static_cast<long long*>(ar.alloc(nctas * 8 * sizeof(long long), true));
       CUDA_CHECK(sync_setup());
       ctx->conv_trace = tr;

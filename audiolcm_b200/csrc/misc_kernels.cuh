@@ -284,6 +284,33 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg,
   else reinterpret_cast<float*>(wav)[(size_t)b * T + t] = y;
 }
 
+// ------------------------------------------------------------------------------- LCM sampler step
+// LCMSampler.step (ldm/models/diffusion/scheduling_lcm.py:411-494), epsilon prediction, as ONE elementwise pass:
+//   x0       = (sample - sqrt(1-abar_t) * eps) / sqrt(abar_t)                      (:455-456)
+//   denoised = c_out * x0 + c_skip * sample                                        (:469)
+//   prev     = sqrt(abar_prev) * denoised + sqrt(1-abar_prev) * noise   (not on the last step: prev = denoised)  (:474-478)
+// The reference runs this as ~8 separate ATen kernels per step; the coefficients are host scalars of the schedule.
+struct LcmStepCoef { float b_t_sqrt, inv_a_t_sqrt, c_out, c_skip, a_prev_sqrt, b_prev_sqrt; int last; };
+__global__ void lcm_step_kernel(const float4* __restrict__ sample, const float4* __restrict__ eps, const float4* __restrict__ noise,
+                                float4* __restrict__ prev, float4* __restrict__ denoised, size_t n4, LcmStepCoef k) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 s = sample[i], e = eps[i];
+    float4 d;
+    d.x = k.c_out * ((s.x - k.b_t_sqrt * e.x) * k.inv_a_t_sqrt) + k.c_skip * s.x;
+    d.y = k.c_out * ((s.y - k.b_t_sqrt * e.y) * k.inv_a_t_sqrt) + k.c_skip * s.y;
+    d.z = k.c_out * ((s.z - k.b_t_sqrt * e.z) * k.inv_a_t_sqrt) + k.c_skip * s.z;
+    d.w = k.c_out * ((s.w - k.b_t_sqrt * e.w) * k.inv_a_t_sqrt) + k.c_skip * s.w;
+    denoised[i] = d;
+    if (k.last) {
+      prev[i] = d;
+    } else {
+      const float4 z = noise[i];
+      prev[i] = make_float4(k.a_prev_sqrt * d.x + k.b_prev_sqrt * z.x, k.a_prev_sqrt * d.y + k.b_prev_sqrt * z.y,
+                            k.a_prev_sqrt * d.z + k.b_prev_sqrt * z.z, k.a_prev_sqrt * d.w + k.b_prev_sqrt * z.w);
+    }
+  }
+}
+
 // ALCM_GUARD self-check: number of non-zero bytes in a guard zone (n 16-byte units)
 __global__ void count_nonzero_kernel(const uint4* __restrict__ p, size_t n, unsigned long long* __restrict__ out) {
   unsigned long long c = 0;

@@ -49,36 +49,6 @@ def conv1d(x, w, bias=None, res=None, dilation=1, precision="fp32"):
     return y
 
 
-def conv1d_act(x, w, bias, res, alpha, beta, dilation=1, precision="bf16", want_conv=True):
-    """Conv1d (+bias, +residual) and the Activation1d that follows it, one launch - models.py:72-81.
-
-    Returns (conv result or None, activated result)."""
-    (x, w, bias, res, alpha, beta), dev = _prep(x, w, bias, res, alpha, beta)
-    B, Cin, T = x.shape
-    Cout, Cin2, K = w.shape
-    assert Cin2 == Cin
-    yc = torch.empty((B, Cout, T), dtype=torch.float32, device=dev) if want_conv else None
-    ya = torch.empty((B, Cout, T), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.load().alcm_conv1d_act_fwd(_lib.ctx(dev.index), _p(x), _p(w), _p(bias), _p(res), _p(alpha), _p(beta),
-                                                   _p(yc), _p(ya), B, Cin, Cout, T, K, int(dilation), _lib.PREC[precision],
-                                                   _stream()))
-    return yc, ya
-
-
-def act_conv1d(x, alpha, beta, w, bias=None, res=None, dilation=1, precision="bf16"):
-    """conv(Activation1d(x)) + bias (+ res) in one launch (activation in the conv's operand producer) - models.py:72-81."""
-    (x, alpha, beta, w, bias, res), dev = _prep(x, alpha, beta, w, bias, res)
-    B, Cin, T = x.shape
-    Cout, Cin2, K = w.shape
-    assert Cin2 == Cin
-    y = torch.empty((B, Cout, T), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.load().alcm_act_conv1d_fwd(_lib.ctx(dev.index), _p(x), _p(alpha), _p(beta), _p(w), _p(bias), _p(res), _p(y),
-                                                   B, Cin, Cout, T, K, int(dilation), _lib.PREC[precision], _stream()))
-    return y
-
-
 def conv_transpose1d(x, w, bias=None, stride=2, precision="fp32"):
     """ConvTranspose1d(k=2*stride, stride, padding=stride/2) - vocoder/bigvgan/models.py:150-155."""
     (x, w, bias), dev = _prep(x, w, bias)
@@ -123,3 +93,21 @@ def attn1d(q, k, v):
     with torch.cuda.device(dev):
         _lib.check(_lib.load().alcm_attn1d_fwd(_lib.ctx(dev.index), _p(q), _p(k), _p(v), _p(out), B, C, T, _stream()))
     return out
+
+
+def lcm_step(sample, eps, noise, sqrt_alpha_prod_t, sqrt_beta_prod_t, c_out, c_skip, sqrt_alpha_prod_prev, sqrt_beta_prod_prev, last_step):
+    """LCMSampler.step (scheduling_lcm.py:411-494, epsilon prediction) as one kernel -> (prev_sample, denoised)."""
+    (sample, eps, noise), dev = _prep(sample, eps, noise)
+    n = sample.numel()
+    pad = (-n) % 4
+    if pad:      # keep the float4 kernel: work on padded flat copies
+        f = lambda t: None if t is None else torch.nn.functional.pad(t.reshape(-1), (0, pad))
+        p, d = lcm_step(f(sample), f(eps), f(noise), sqrt_alpha_prod_t, sqrt_beta_prod_t, c_out, c_skip, sqrt_alpha_prod_prev,
+                        sqrt_beta_prod_prev, last_step)
+        return p[:n].reshape(sample.shape), d[:n].reshape(sample.shape)
+    prev, den = torch.empty_like(sample), torch.empty_like(sample)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().alcm_lcm_step(_lib.ctx(dev.index), _p(sample), _p(eps), _p(noise), _p(prev), _p(den), n,
+                                             float(sqrt_alpha_prod_t), float(sqrt_beta_prod_t), float(c_out), float(c_skip),
+                                             float(sqrt_alpha_prod_prev), float(sqrt_beta_prod_prev), int(bool(last_step)), _stream()))
+    return prev, den

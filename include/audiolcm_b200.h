@@ -138,21 +138,19 @@ int alcm_decode_to_wav(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, 
 int alcm_decode_to_pcm16(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, int T, float inv_scale, float* mel_out,
                          short* pcm, void* stream);
 
+/* ---- LCM sampler step: LCMSampler.step (ldm/models/diffusion/scheduling_lcm.py:411-494, epsilon prediction) as one
+ * elementwise kernel over n fp32 elements (device pointers, 16-byte aligned, n % 4 == 0):
+ *   x0 = (sample - sqrt_beta_prod_t*eps)/sqrt_alpha_prod_t;  denoised = c_out*x0 + c_skip*sample;
+ *   prev = last_step ? denoised : sqrt_alpha_prod_prev*denoised + sqrt_beta_prod_prev*noise.
+ * The coefficients are the host scalars the reference computes per step (:441-452,401-409). */
+int alcm_lcm_step(alcm_ctx* ctx, const float* sample, const float* eps, const float* noise, float* prev, float* denoised, long long n,
+                  float sqrt_alpha_prod_t, float sqrt_beta_prod_t, float c_out, float c_skip, float sqrt_alpha_prod_prev,
+                  float sqrt_beta_prod_prev, int last_step, void* stream);
+
 /* ---- single-op entry points (tests / micro-benchmarks); tensors are [B,C,T] fp32 on device -----*/
 /* Activation1d(SnakeBeta logscale): act.py:23-28.  precision BF16 returns bf16-rounded values. */
 int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, const float* beta, float* y, int B, int C,
                           int T, int precision, void* stream);
-/* Conv1d (+bias, +res) followed by Activation1d(SnakeBeta) in ONE launch - the c1->act and c2(+x)->act steps of
- * AMPBlock1.forward (models.py:72-81).  y_conv (may be NULL) receives the conv result, y_act its activation
- * (rounded to the operand type of `precision`).  TF32 / BF16 only (the fp32 CUDA-core path is not fused). */
-int alcm_conv1d_act_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, const float* alpha,
-                        const float* beta, float* y_conv, float* y_act, int B, int Cin, int Cout, int T, int K, int dilation,
-                        int precision, void* stream);
-/* Activation1d(SnakeBeta) followed by Conv1d (+bias, +res) in ONE launch, the activation computed by the conv's operand
- * producer - the a1 -> c1 and a2 -> c2 (+x) steps of AMPBlock1.forward (models.py:72-81) for the narrow stages.
- * y = conv(act(x)) + bias (+ res).  TF32 (Cin <= 48) / BF16 (Cin <= 96) only. */
-int alcm_act_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, const float* beta, const float* w, const float* bias,
-                        const float* res, float* y, int B, int Cin, int Cout, int T, int K, int dilation, int precision, void* stream);
 /* Conv1d(Cin,Cout,K,dilation, padding=(K*d-d)/2) (+bias, +res if non-NULL); w [Cout,Cin,K] */
 int alcm_conv1d_fwd(alcm_ctx* ctx, const float* x, const float* w, const float* bias, const float* res, float* y, int B,
                     int Cin, int Cout, int T, int K, int dilation, int precision, void* stream);

@@ -175,7 +175,7 @@ def test_batch64_full_size_decode_vs_oracle(precision):
 
 @pytest.mark.parametrize("knobs", [{"ALCM_LANES": "0"}, {"ALCM_ACT_VARIANT": "3"}, {"ALCM_ACT_VARIANT": "2"}, {"ALCM_ACT_VARIANT": "7"},
                                    {"ALCM_ACT_VARIANT": "8"}, {"ALCM_PERSIST": "0"}, {"ALCM_CLUSTER_SPLITK": "0"},
-                                   {"ALCM_GRAPH": "0"}, {"ALCM_PDL": "1"}, {"ALCM_ACTPRO": "0"}])
+                                   {"ALCM_GRAPH": "0"}, {"ALCM_PDL": "1"}])
 def test_forced_plan_variants_match_reference(golden_dir, monkeypatch, knobs):
     """Every plan-shaping knob the batch-64 / long-form plans flip (serial AMP blocks with in-place accumulation, the
     big-launch Activation1d forms, non-persistent convs, workspace split-K, eager launches, PDL), forced on a small
@@ -315,21 +315,6 @@ def test_two_threads_two_contexts():
     for t in ts:
         t.join()
     assert not errs and len(outs) == 2, errs
-
-
-def test_fused_activation_chain_matches_reference(golden_dir, monkeypatch):
-    """The opt-in plan that runs Activation1d inside the conv epilogues (ALCM_FUSE_ACT=1) meets the same gates."""
-    monkeypatch.setenv("ALCM_FUSE_ACT", "1")
-    g = np.load(os.path.join(golden_dir, "bigvgan_c256.npz"))
-    h = synth.bigvgan_config(int(g["c0"]))
-    mel = synth.synth_mel(int(g["B"]), int(g["T"]), seed=int(g["xseed"]))
-    for precision in ("tf32", "bf16"):
-        voc = _voc(h, synth.bigvgan_state_dict(h, seed=int(g["wseed"])), precision)
-        wav = voc.vocode(torch.from_numpy(mel))
-        ref = g["wav"].reshape(wav.shape)
-        err = np.abs(wav - ref).max()
-        print(f"\n[fused {precision}] max-abs {err:.3e} SNR {snr_db(ref, wav):.1f} dB")
-        assert err <= WAV_TOL[precision]
 
 
 def test_shape_errors():

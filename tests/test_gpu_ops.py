@@ -95,50 +95,6 @@ def test_conv1d(ops, case, precision):
     assert float((y2.double() - ref2).abs().max()) < 3e-5 * max(1.0, float(ref2.abs().max()))
 
 
-# ----------------------------------------------------------------------------------- Conv1d + fused Activation1d
-FUSED_CASES = [
-    # B, Cin, Cout, T, K, d
-    (1, 768, 768, 250, 3, 1),     # several N tiles, split-K
-    (2, 192, 192, 1000, 7, 3),    # NT = 192, 9 overlapping M tiles
-    (1, 24, 24, 4099, 11, 5),     # padded channels, widest conv halo (25) + FIR halo (5)
-    (1, 96, 96, 116, 3, 1),       # exactly one tile
-    (1, 96, 96, 117, 3, 5),       # one row spills into a second tile
-    (2, 48, 48, 232, 7, 1),       # exactly two tiles
-    (1, 48, 48, 1, 3, 1),         # T = 1: every row is replicate padding
-    (1, 32, 32, 7, 11, 1),
-    (1, 384, 384, 123, 7, 5),
-]
-
-
-@pytest.mark.parametrize("case", FUSED_CASES)
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
-@pytest.mark.parametrize("with_res", [True, False])
-def test_conv1d_fused_activation(ops, case, precision, with_res):
-    """conv (+bias, +residual) -> Activation1d in one launch (models.py:72-81) against the float64 oracle
-    evaluated on the operands exactly as the device rounds them."""
-    from oracle import decode_oracle as O
-    B, Cin, Cout, T, K, d = case
-    x = _rand(B, Cin, T, seed=20)
-    w = _rand(Cout, Cin, K, seed=21, scale=1.0 / np.sqrt(Cin * K))
-    b = _rand(Cout, seed=22, scale=0.1)
-    res = _rand(B, Cout, T, seed=23) if with_res else None
-    al, be = _rand(Cout, seed=24, scale=0.5), _rand(Cout, seed=25, scale=0.5)
-    xr, wr = round_operand(x, precision), round_operand(w, precision)
-    conv_ref = F.conv1d(xr.double(), wr.double(), b.double(), dilation=d, padding=(K * d - d) // 2)
-    if with_res:
-        conv_ref = conv_ref + res.double()
-    act_ref = O.activation1d(conv_ref, al.double(), be.double(), O.kaiser_sinc_filter().double())
-    yc, ya = ops.conv1d_act(x.to(DEV), w.to(DEV), b.to(DEV), None if res is None else res.to(DEV), al.to(DEV), be.to(DEV),
-                            dilation=d, precision=precision, want_conv=with_res)
-    if with_res:  # the fp32 conv result (residual stream) is also produced, only for the rows each tile owns
-        assert float((yc.cpu().double() - conv_ref).abs().max()) < 3e-5 * max(1.0, float(conv_ref.abs().max()))
-    ya = ya.cpu()
-    tol = {"tf32": 2.0 ** -11, "bf16": 2.0 ** -8}[precision]
-    err = (ya.double() - act_ref).abs()
-    assert float((err / (act_ref.abs() + 1.0)).max()) < tol * 1.01 + 3e-5, float(err.max())
-    assert torch.equal(round_operand(ya, precision), ya)
-
-
 @pytest.mark.parametrize("case", [(1, 1536, 768, 625, 4), (2, 96, 48, 333, 2), (1, 48, 24, 1000, 2), (1, 8, 4, 5, 4), (1, 4, 2, 1, 2)])
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_conv_transpose1d(ops, case, precision):
@@ -215,7 +171,7 @@ def test_bad_arguments_raise(ops):
 
 
 # ----------------------------------------------------------------------------------- every Activation1d kernel form
-ACT_VARIANTS = {0: "R=4", 1: "pair R=4", 2: "R=8", 3: "R=6", 5: "pair R=6", 6: "pair R=8", 7: "two-phase UR=5", 8: "two-phase UR=7", 9: "persistent two-phase UR=5"}
+ACT_VARIANTS = {0: "R=4", 1: "pair R=4", 2: "R=8", 3: "R=6", 5: "pair R=6", 6: "pair R=8", 7: "two-phase UR=5", 8: "two-phase UR=7"}
 ACT_EDGE_SHAPES = [(1, 8, 1), (1, 8, 3), (2, 24, 4099), (3, 16, 160000), (1, 16, 640), (1, 16, 641), (1, 8, 637), (1, 8, 1283), (1, 8, 896),
                    (1, 8, 899), (1, 24, 6), (1, 40, 1925)]
 
@@ -256,46 +212,32 @@ def test_narrow_operand_planes_are_not_padded_to_16(ops):
                 assert float((y.double() - ref).abs().max()) < 3e-5 * max(1.0, float(ref.abs().max())), (Cin, Cout, precision)
 
 
-# ----------------------------------------------------------------------------------- Activation1d in the conv's operand producer
-ACTPRO_CASES = [
-    # B, Cin, Cout, T, K, d
-    (2, 24, 24, 4099, 11, 5),    # narrow operand (zeroed K slab), widest halo: 25 (conv) + 5 (FIR)
-    (1, 96, 96, 1000, 7, 3),     # 12 K chunks, 8 tiles
-    (1, 48, 48, 300, 3, 1),
-    (3, 96, 96, 129, 11, 5),     # one row spills into a second tile
-    (1, 24, 24, 1, 3, 1),        # T = 1: every FIR tap is replicate padding, every other conv tap zero padding
-    (1, 48, 48, 7, 11, 1),
-    (8, 32, 32, 6000, 3, 1),     # several tiles per persistent CTA
-    (1, 96, 48, 257, 1, 1),      # k = 1, Cout != Cin
-    (2, 40, 24, 515, 7, 1),
-]
-
-
-@pytest.mark.parametrize("case", ACTPRO_CASES)
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
-@pytest.mark.parametrize("with_res", [True, False])
-def test_act_conv1d_fused_producer(ops, case, precision, with_res):
-    """conv(Activation1d(x)) + bias (+ res) as ONE launch (convpro.cuh) against the float64 oracle: activation in
-    float64, rounded to the operand type as the device rounds it, conv in float64.  The device computes the activation in
-    fp32, so an operand may round the other way (1 ulp of the operand type); the bound allows a few such flips, a wrong
-    halo / tap shift / zero- vs replicate-padding mix-up is O(0.1 - 1)."""
-    from oracle import decode_oracle as O
-    B, Cin, Cout, T, K, d = case
-    if precision == "tf32" and Cin > 48:
-        pytest.skip("tf32 operands: single k-block only up to 48 channels")
-    x = _rand(B, Cin, T, seed=50, scale=1.5)
-    al, be = _rand(Cin, seed=51, scale=0.5), _rand(Cin, seed=52, scale=0.5)
-    w = _rand(Cout, Cin, K, seed=53, scale=1.0 / np.sqrt(Cin * K))
-    b = _rand(Cout, seed=54, scale=0.1)
-    res = _rand(B, Cout, T, seed=55) if with_res else None
-    act = O.activation1d(x.double(), al.double(), be.double(), O.kaiser_sinc_filter().double())
-    ar, wr = round_operand(act.float(), precision).double(), round_operand(w, precision).double()
-    ref = F.conv1d(ar, wr, b.double(), dilation=d, padding=(K * d - d) // 2)
-    if with_res:
-        ref = ref + res.double()
-    for _ in range(2):
-        y = ops.act_conv1d(x.to(DEV), al.to(DEV), be.to(DEV), w.to(DEV), b.to(DEV), None if res is None else res.to(DEV), dilation=d,
-                           precision=precision).cpu()
-        err = float((y.double() - ref).abs().max())
-        tol = {"tf32": 4e-4, "bf16": 3e-3}[precision]
-        assert err < tol * max(1.0, float(ref.abs().max())), err
+def test_lcm_step_matches_reference_golden(ops, golden_dir):
+    """The fused LCM step kernel driven by the ported schedule reproduces the REAL LCMSampler.lcm_sampling output
+    (tests/golden/lcm_denoiser.npz): DiT in PyTorch on the GPU, step() as alcm_lcm_step, same noise draw."""
+    from baseline import lcm_denoiser_port as P
+    g = np.load(os.path.join(golden_dir, "lcm_denoiser.npz"))
+    den = P.PortedDenoiser(P.dit_state_dict(seed=int(g["wseed"])), DEV)
+    x, ctx = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["ctx"]).to(DEV)
+    ts = den.schedule.timesteps(2)
+    w_emb = P.guidance_scale_embedding(torch.tensor(4.0).repeat(x.shape[0]), 256).to(DEV)
+    torch.manual_seed(int(g["noise_seed"]))
+    noise = torch.randn(x.shape)                 # the reference drew it on the CPU generator (golden made on CPU)
+    img = x
+    for i, t in enumerate(ts):
+        with torch.no_grad():
+            eps = den(img, torch.full((x.shape[0],), t, device=DEV, dtype=torch.long), ctx, w_emb)
+        k = den.schedule.coefficients(ts, i)
+        img, denoised = ops.lcm_step(img, eps, None if k["last"] else noise.to(DEV), k["a_t_sqrt"], k["b_t_sqrt"], k["c_out"], k["c_skip"],
+                                     k["a_prev_sqrt"], k["b_prev_sqrt"], k["last"])
+    scale = max(1.0, float(np.abs(g["denoised"]).max()))
+    assert np.abs(denoised.cpu().numpy() - g["denoised"]).max() <= 2e-3 * scale     # GPU DiT (TF32 convs by torch default) vs CPU golden
+    # and exactly the reference arithmetic on identical inputs
+    s, e, z = _rand(3, 20, 50, seed=60).to(DEV), _rand(3, 20, 50, seed=61).to(DEV), _rand(3, 20, 50, seed=62).to(DEV)
+    k = den.schedule.coefficients(ts, 0)
+    prev, d = ops.lcm_step(s, e, z, k["a_t_sqrt"], k["b_t_sqrt"], k["c_out"], k["c_skip"], k["a_prev_sqrt"], k["b_prev_sqrt"], False)
+    x0 = (s.double() - float(k["b_t_sqrt"]) * e.double()) / float(k["a_t_sqrt"])
+    dref = float(k["c_out"]) * x0 + float(k["c_skip"]) * s.double()
+    pref = float(k["a_prev_sqrt"]) * dref + float(k["b_prev_sqrt"]) * z.double()
+    assert float((d.double() - dref).abs().max()) <= 1e-5 * float(dref.abs().max())
+    assert float((prev.double() - pref).abs().max()) <= 1e-5 * float(pref.abs().max())

@@ -1,8 +1,7 @@
 """Small-shape self-check workload - run plain (ALCM_GUARD=1 is set below: every device buffer is fenced by 4 KB zero
 guard zones that are verified after each op and after the decodes) or under compute-sanitizer where the pool allows
 it (tools/sanitize.sh).  Covers every form of the conv kernel (plain, persistent
-two-accumulator, workspace split-K, cluster/DSMEM split-K, fused Activation1d epilogue, narrow operands with the
-zeroed K slab), every Activation1d kernel form, GroupNorm, attention and one small end-to-end decode per mode.
+two-accumulator, workspace split-K, cluster/DSMEM split-K, narrow operands with the zeroed K slab), every Activation1d kernel form, GroupNorm, attention and one small end-to-end decode per mode.
 Each case is also checked numerically, so a sanitizer-clean run is a correct run."""
 import os
 import sys
@@ -48,27 +47,8 @@ def main():
     conv_case("workspace split-K", 1, 1536, 768, 100, 1, 1, env={"ALCM_CLUSTER_SPLITK": "0"})
     conv_case("cluster split-K", 1, 1536, 1536, 312, 3, 1)
     conv_case("cluster split-K tf32", 1, 1536, 1536, 100, 3, 1, "tf32")
-    # fused Activation1d epilogue
-    x, w, b = rnd(1, 96, 117, seed=4), rnd(96, 96, 3, seed=5, scale=0.06), rnd(96, seed=6, scale=0.1)
-    al, be = rnd(96, seed=7, scale=0.5), rnd(96, seed=8, scale=0.5)
-    _, ya = ops.conv1d_act(x.to(DEV), w.to(DEV), b.to(DEV), None, al.to(DEV), be.to(DEV), dilation=5, precision="bf16", want_conv=False)
-    cref = F.conv1d(round_operand(x, "bf16").double(), round_operand(w, "bf16").double(), b.double(), dilation=5, padding=5)
-    aref = O.activation1d(cref, al.double(), be.double(), O.kaiser_sinc_filter().double())
-    err = float(((ya.cpu().double() - aref).abs() / (aref.abs() + 1)).max())
-    print(f"  conv fused Activation1d epilogue     bf16 err {err:.2e}", flush=True)
-    assert err < 2.0 ** -8 * 1.01 + 3e-5
-    # Activation1d in the conv's operand producer (convpro.cuh)
-    for (B, C, T, K, d) in ((2, 24, 700, 11, 5), (1, 96, 300, 7, 3), (1, 48, 5, 3, 1)):
-        x, w, b = rnd(B, C, T, seed=14, scale=1.5), rnd(C, C, K, seed=15, scale=1 / np.sqrt(C * K)), rnd(C, seed=16, scale=0.1)
-        al, be = rnd(C, seed=17, scale=0.5), rnd(C, seed=18, scale=0.5)
-        act = O.activation1d(x.double(), al.double(), be.double(), O.kaiser_sinc_filter().double())
-        ref = F.conv1d(round_operand(act.float(), "bf16").double(), round_operand(w, "bf16").double(), b.double(), dilation=d, padding=(K * d - d) // 2)
-        y = ops.act_conv1d(x.to(DEV), al.to(DEV), be.to(DEV), w.to(DEV), b.to(DEV), None, dilation=d, precision="bf16").cpu()
-        err = float((y.double() - ref).abs().max())
-        print(f"  act->conv fused producer C={C} T={T} k={K} d={d}: err {err:.2e}", flush=True)
-        assert err < 3e-3 * max(1.0, float(ref.abs().max()))
     # every Activation1d kernel form
-    for variant in (0, 1, 2, 3, 5, 6, 7, 8, 9):
+    for variant in (0, 1, 2, 3, 5, 6, 7, 8):
         os.environ["ALCM_ACT_VARIANT"] = str(variant)
         for prec in ("bf16", "tf32"):
             for (B, C, T) in ((1, 8, 3), (2, 24, 1300)):
