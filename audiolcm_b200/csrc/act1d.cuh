@@ -6,13 +6,7 @@
 //   down : out[m]  = sum_{k<12} y[clamp(2m+k-5, 0, 2T-1)] f[k]
 // c() clamps to [0,T-1] (replicate padding on both FIRs).  Input: fp32 planes (E=4).  Output:
 // fp32 planes (optionally RNE-rounded to tf32 for the tf32 MMA) or bf16 planes (E=8, two input
-// planes per output plane).
-//
-// Structure: a block stages a halo'd time tile of x in shared memory (coalesced 128-bit loads, a
-// one-slot pad every 8 rows makes the strided register-blocking reads conflict-free); every thread
-// then produces 4 consecutive outputs entirely in registers: 18 up-sampled values (9 even, 9 odd, both
-// from the same 6-row window), snake, scatter into the 4 accumulators.  FIR arithmetic is packed
-// FFMA2 (two channels per instruction).  No intermediate (2T-long) signal ever reaches memory.
+// planes per output plane).  No intermediate (2T-long) signal ever reaches HBM.
 #pragma once
 #include "common.cuh"
 
@@ -23,11 +17,7 @@ namespace alcm {
 __constant__ float c_fir[12] = {0.0020289647f, 0.0093894657f,  -0.0255434588f, -0.0576573834f, 0.1285725832f, 0.4432097971f,
                                 0.4432097971f, 0.1285725832f, -0.0576573834f, -0.0255434588f, 0.0093894657f, 0.0020289647f};
 
-constexpr int kActThreads = 128;
-constexpr int kActR = 4;                              // outputs per thread
-constexpr int kActTile = kActThreads * kActR;         // 512 outputs per block
-constexpr int kActRows = kActTile + 10;               // x[t0-5 .. t0+tile+4]
-constexpr int kActSlots = kActRows + (kActRows >> 3) + 1;
+constexpr int kActThreads = 128;   // large launches: 640-output tiles; small launches use 64 threads (320-output tiles)
 
 struct ActArgs {
   const float* x;   // fp32 planes
@@ -54,21 +44,6 @@ __device__ __forceinline__ float snake_fast(float v, float ea2, float hb) { retu
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 
-// One up-sampled value at (clamped) up-sampled index j, read from the staged tile (edge path only).
-__device__ __forceinline__ float4 act_y_at(const float4* sx, int j, int t0, int T, float4 ea, float4 ib) {
-  const int n = j >> 1, odd = j & 1;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    const int t = min(max(n - 3 + odd + q, 0), T - 1);
-    const int lr = t - (t0 - 5);
-    const float4 xv = sx[lr + (lr >> 3)];
-    const float w = 2.f * c_fir[11 - odd - 2 * q];
-    s.x = fmaf(xv.x, w, s.x); s.y = fmaf(xv.y, w, s.y); s.z = fmaf(xv.z, w, s.z); s.w = fmaf(xv.w, w, s.w);
-  }
-  return make_float4(snake_acc(s.x, ea.x, ib.x), snake_acc(s.y, ea.y, ib.y), snake_acc(s.z, ea.z, ib.z), snake_acc(s.w, ea.w, ib.w));
-}
-
 // sum of the 12 taps (the filter is normalised to 1 up to rounding): the constant part of the fast snake,
 // v + ib/2, is added once per OUTPUT (scaled by this sum) instead of once per up-sampled value.
 __device__ __forceinline__ float fir_sum() {
@@ -78,271 +53,10 @@ __device__ __forceinline__ float fir_sum() {
   return s;
 }
 
-// R consecutive outputs of one 4-channel plane, entirely in registers (see header comment): window of R+10
-// staged rows, R+5 (odd, even) up-sampled pairs, snake, scatter into R accumulators.
-// EDGE is warp-uniform: only warps holding the first / last outputs of a plane pay for the y fix-ups.
-// FAST: y = v + (ib/2) - (ib/2) cos(2 ea v); the "+ ib/2" term commutes with the (linear, sum-1) down filter
-// and is added to the outputs, and the multiply / fma run packed over channel pairs (FMUL2 / FFMA2).
-template <bool FAST, bool EDGE, int R = kActR>
-__device__ __forceinline__ void act_plane(const float4* sx, int tid, int m0, int t0, int T, float4 ea, float4 ib,
-                                          float4 (&out)[R]) {
-    // window xl[k] = x[m0-5+k], k = 0..R+9 ; local row of x[m0-5] is R*tid
-    float2 xlo[R + 10], xhi[R + 10];
-#pragma unroll
-    for (int k = 0; k < R + 10; ++k) {
-      const int lr = R * tid + k;
-      const float4 v = sx[lr + (lr >> 3)];
-      xlo[k] = make_float2(v.x, v.y);
-      xhi[k] = make_float2(v.z, v.w);
-    }
-    float2 f2[6], g2[6];  // broadcast taps: f[k] (down) and 2 f[k] (up), k = 0..5 (symmetric filter)
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      f2[k] = make_float2(c_fir[k], c_fir[k]);
-      g2[k] = make_float2(2.f * c_fir[k], 2.f * c_fir[k]);
-    }
-    const float2 ea_lo = FAST ? make_float2(2.f * ea.x, 2.f * ea.y) : make_float2(ea.x, ea.y);
-    const float2 ea_hi = FAST ? make_float2(2.f * ea.z, 2.f * ea.w) : make_float2(ea.z, ea.w);
-    const float2 ib_lo = FAST ? make_float2(0.5f * ib.x, 0.5f * ib.y) : make_float2(ib.x, ib.y);
-    const float2 ib_hi = FAST ? make_float2(0.5f * ib.z, 0.5f * ib.w) : make_float2(ib.z, ib.w);
-    const float2 nhb_lo = make_float2(-ib_lo.x, -ib_lo.y), nhb_hi = make_float2(-ib_hi.x, -ib_hi.y);
-    float4 y_first = make_float4(0.f, 0.f, 0.f, 0.f), y_last = y_first;
-    if (EDGE && m0 < 3) y_first = act_y_at(sx, 0, t0, T, ea, ib);                        // x[0..] is in this (first) tile
-    if (EDGE && m0 + R + 2 > T - 1) y_last = act_y_at(sx, 2 * T - 1, t0, T, ea, ib);     // x[..T-1] is in this (last) tile
-    if (FAST && EDGE) {  // same representation as the in-register values: without the "+ ib/2" term
-      y_first.x -= ib_lo.x; y_first.y -= ib_lo.y; y_first.z -= ib_hi.x; y_first.w -= ib_hi.y;
-      y_last.x -= ib_lo.x; y_last.y -= ib_lo.y; y_last.z -= ib_hi.x; y_last.w -= ib_hi.y;
-    }
-    float2 alo[R], ahi[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) alo[r] = ahi[r] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int s = 0; s < R + 5; ++s) {
-      // odd value  y[2(m0-3+s)+1] = sum_q xl[s+q] * 2f[10-2q] ; even value y[2(m0-2+s)] = sum_q xl[s+q] * 2f[11-2q]
-      float2 olo = make_float2(0.f, 0.f), ohi = olo, elo = olo, ehi = olo;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const int ko = 10 - 2 * q, ke = 11 - 2 * q;
-        const float2 wo = g2[ko < 6 ? ko : 11 - ko], we = g2[ke < 6 ? ke : 11 - ke];
-        olo = ffma2(xlo[s + q], wo, olo); ohi = ffma2(xhi[s + q], wo, ohi);
-        elo = ffma2(xlo[s + q], we, elo); ehi = ffma2(xhi[s + q], we, ehi);
-      }
-      if (FAST) {
-        float2 t, c;
-        t = __fmul2_rn(olo, ea_lo); c = make_float2(__cosf(t.x), __cosf(t.y)); olo = ffma2(nhb_lo, c, olo);
-        t = __fmul2_rn(ohi, ea_hi); c = make_float2(__cosf(t.x), __cosf(t.y)); ohi = ffma2(nhb_hi, c, ohi);
-        t = __fmul2_rn(elo, ea_lo); c = make_float2(__cosf(t.x), __cosf(t.y)); elo = ffma2(nhb_lo, c, elo);
-        t = __fmul2_rn(ehi, ea_hi); c = make_float2(__cosf(t.x), __cosf(t.y)); ehi = ffma2(nhb_hi, c, ehi);
-      } else {
-        olo.x = snake_acc(olo.x, ea_lo.x, ib_lo.x); olo.y = snake_acc(olo.y, ea_lo.y, ib_lo.y);
-        ohi.x = snake_acc(ohi.x, ea_hi.x, ib_hi.x); ohi.y = snake_acc(ohi.y, ea_hi.y, ib_hi.y);
-        elo.x = snake_acc(elo.x, ea_lo.x, ib_lo.x); elo.y = snake_acc(elo.y, ea_lo.y, ib_lo.y);
-        ehi.x = snake_acc(ehi.x, ea_hi.x, ib_hi.x); ehi.y = snake_acc(ehi.y, ea_hi.y, ib_hi.y);
-      }
-      if (EDGE) {  // replicate padding of the down filter acts on y: y[j<0] = y[0], y[j>=2T] = y[2T-1]
-        const int no = m0 - 3 + s, ne = m0 - 2 + s;
-        if (no < 0) { olo = make_float2(y_first.x, y_first.y); ohi = make_float2(y_first.z, y_first.w); }
-        if (ne < 0) { elo = make_float2(y_first.x, y_first.y); ehi = make_float2(y_first.z, y_first.w); }
-        if (no >= T) { olo = make_float2(y_last.x, y_last.y); ohi = make_float2(y_last.z, y_last.w); }
-        if (ne >= T) { elo = make_float2(y_last.x, y_last.y); ehi = make_float2(y_last.z, y_last.w); }
-      }
-      // scatter: out[m0+r] += yo*f[2d] + ye*f[2d+1], d = s-r in [0,5]
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int d = s - r;
-        if (d >= 0 && d <= 5) {
-          const int k0 = 2 * d, k1 = 2 * d + 1;
-          const float2 w0 = f2[k0 < 6 ? k0 : 11 - k0], w1 = f2[k1 < 6 ? k1 : 11 - k1];
-          alo[r] = ffma2(olo, w0, alo[r]); ahi[r] = ffma2(ohi, w0, ahi[r]);
-          alo[r] = ffma2(elo, w1, alo[r]); ahi[r] = ffma2(ehi, w1, ahi[r]);
-        }
-      }
-    }
-    if (FAST) {
-      const float fs = fir_sum();
-      const float2 add_lo = make_float2(ib_lo.x * fs, ib_lo.y * fs), add_hi = make_float2(ib_hi.x * fs, ib_hi.y * fs);
-#pragma unroll
-      for (int r = 0; r < R; ++r) out[r] = make_float4(alo[r].x + add_lo.x, alo[r].y + add_lo.y, ahi[r].x + add_hi.x, ahi[r].y + add_hi.y);
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; ++r) out[r] = make_float4(alo[r].x, alo[r].y, ahi[r].x, ahi[r].y);
-    }
-}
-
-// R outputs per thread: 4 (80 registers, 6 blocks/SM) or 8 (1.7x fewer instructions per element - the up-sampled
-// halo is shared by twice as many outputs - for launches big enough to fill the GPU with 4 blocks/SM).
-template <int NPL, bool FAST, int R>  // NPL input planes per output unit: 1 -> fp32 out, 2 -> bf16 out
-__global__ void __launch_bounds__(kActThreads, (R == 4 ? 6 : (R == 6 ? 5 : 4))) act1d_kernel(const __grid_constant__ ActArgs a) {
-  pdl_launch_dependents();
-  pdl_wait();
-  constexpr int kTile = kActThreads * R, kRows = kTile + 10, kSlots = kRows + (kRows >> 3) + 1;
-  __shared__ float4 sx[NPL][kSlots];
-  const int tid = threadIdx.x;
-  const int t0 = blockIdx.x * kTile;
-  const int oc = blockIdx.y, b = blockIdx.z;
-  const int T = a.T;
-
-  // ---- stage x[t0-5 .. t0+tile+4] (replicate-clamped) -----------------------------------------
-  // all global loads of the thread are issued before the first shared-memory store: a rolled
-  // load->store loop exposed one HBM round trip per row group (39 % of the warp stalls, ncu round 1)
-  constexpr int kLd = (kRows + kActThreads - 1) / kActThreads;
-  float4 stg[NPL][kLd];
-#pragma unroll
-  for (int p = 0; p < NPL; ++p) {
-    const float4* xp = reinterpret_cast<const float4*>(a.x) + ((size_t)b * a.xg.nchunk + (oc * NPL + p)) * a.xg.Tp + a.xg.pad;
-#pragma unroll
-    for (int k = 0; k < kLd; ++k) {
-      const int lr = tid + k * kActThreads;
-      const int t = min(max(t0 - 5 + lr, 0), T - 1);
-      stg[p][k] = xp[t];
-    }
-  }
-#pragma unroll
-  for (int p = 0; p < NPL; ++p) {
-#pragma unroll
-    for (int k = 0; k < kLd; ++k) {
-      const int lr = tid + k * kActThreads;
-      if (lr < kRows) sx[p][lr + (lr >> 3)] = stg[p][k];
-    }
-  }
-  __syncthreads();
-
-  const int m0 = t0 + R * tid;
-  if (m0 >= T) return;
-  // up-sampled pairs n in [m0-3, m0+6]: where n falls outside [0,T-1] the down filter's replicate
-  // padding wants y[0] / y[2T-1] instead (only the first / last one or two threads of a plane)
-  const bool edge = (m0 < 3) || (m0 + R + 2 > T - 1);
-
-  // One copy of the (fully unrolled, ~1k instruction) plane body: the kernel was instruction-fetch bound with
-  // one copy per plane.  bf16 output packs two fp32 planes into one 16-byte unit: the first plane's four results
-  // wait in registers (as packed bf16 pairs) for the second.
-  uint2 held[R];
-#pragma unroll 1
-  for (int p = 0; p < NPL; ++p) {
-    const int chunk = oc * NPL + p;
-    const float4 ea = *reinterpret_cast<const float4*>(a.ea + chunk * 4);
-    const float4 ib = *reinterpret_cast<const float4*>(a.ib + chunk * 4);
-    float4 res[R];
-    if (__any_sync(0xffffffffu, edge)) act_plane<FAST, true, R>(sx[p], tid, m0, t0, T, ea, ib, res);
-    else act_plane<FAST, false, R>(sx[p], tid, m0, t0, T, ea, ib, res);
-    if (NPL == 1) {
-      float4* op = reinterpret_cast<float4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (m0 + r >= T) break;
-        float4 o = res[r];
-        if (a.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-        op[m0 + r] = o;
-      }
-    } else {
-      uint2 pk[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(res[r].x, res[r].y), h1 = __floats2bfloat162_rn(res[r].z, res[r].w);
-        pk[r] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-      }
-      if (p == 0) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) held[r] = pk[r];
-      } else {
-        uint4* op = reinterpret_cast<uint4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          if (m0 + r >= T) break;
-          op[m0 + r] = make_uint4(held[r].x, held[r].y, pk[r].x, pk[r].y);
-        }
-      }
-    }
-  }
-}
-
-// Latency-oriented variant: a block of 128 threads works on TWO fp32 planes at once (64 threads x 4 outputs
-// each, tile = 256 outputs), so the two planes of a bf16 unit run side by side instead of back to back in one
-// thread; the halves meet through shared memory for the 16-byte store.  Twice the blocks, half the serial
-// instruction chain per block - what the small (batch-1) launches need.  fp32 / tf32 output: the two planes
-// are simply two independent output planes.
-constexpr int kPairThreads = 128, kPairHalf = 64;
-template <bool BF16OUT, bool FAST, int R>  // R outputs per thread: tile = 64 * R outputs
-__global__ void __launch_bounds__(kPairThreads, (R == 4 ? 6 : (R == 6 ? 5 : 4))) act1d_pair_kernel(const __grid_constant__ ActArgs a) {
-  pdl_launch_dependents();
-  pdl_wait();
-  constexpr int kPairTile = kPairHalf * R, kPairRows = kPairTile + 10, kPairSlots = kPairRows + (kPairRows >> 3) + 1;
-  __shared__ float4 sx[2][kPairSlots];
-  __shared__ uint2 xch[kPairHalf][R];
-  const int tid = threadIdx.x;
-  const int p = tid >> 6, ht = tid & (kPairHalf - 1);  // plane of the pair, thread within the plane
-  const int t0 = blockIdx.x * kPairTile;
-  const int pc = blockIdx.y, b = blockIdx.z;          // pair of fp32 planes 2*pc, 2*pc+1
-  const int T = a.T;
-
-  constexpr int kLd = (2 * kPairRows + kPairThreads - 1) / kPairThreads;
-  float4 stg[kLd];
-#pragma unroll
-  for (int k = 0; k < kLd; ++k) {
-    const int i = tid + k * kPairThreads;
-    const int pl = i >= kPairRows ? 1 : 0, lr = i - pl * kPairRows;
-    const float4* xp = reinterpret_cast<const float4*>(a.x) + ((size_t)b * a.xg.nchunk + (2 * pc + pl)) * a.xg.Tp + a.xg.pad;
-    const int t = min(max(t0 - 5 + min(lr, kPairRows - 1), 0), T - 1);
-    stg[k] = xp[t];
-  }
-#pragma unroll
-  for (int k = 0; k < kLd; ++k) {
-    const int i = tid + k * kPairThreads;
-    const int pl = i >= kPairRows ? 1 : 0, lr = i - pl * kPairRows;
-    if (i < 2 * kPairRows) sx[pl][lr + (lr >> 3)] = stg[k];
-  }
-  __syncthreads();
-
-  const int m0 = t0 + R * ht;
-  const bool live = m0 < T;
-  const bool edge = live && ((m0 < 3) || (m0 + R + 2 > T - 1));
-  float4 res[R];
-  if (live) {
-    const int chunk = 2 * pc + p;
-    const float4 ea = *reinterpret_cast<const float4*>(a.ea + chunk * 4);
-    const float4 ib = *reinterpret_cast<const float4*>(a.ib + chunk * 4);
-    if (__any_sync(__activemask(), edge)) act_plane<FAST, true, R>(sx[p], ht, m0, t0, T, ea, ib, res);
-    else act_plane<FAST, false, R>(sx[p], ht, m0, t0, T, ea, ib, res);
-  }
-  if (!BF16OUT) {
-    if (!live) return;
-    float4* op = reinterpret_cast<float4*>(a.out) + ((size_t)b * a.og.nchunk + (2 * pc + p)) * a.og.Tp + a.og.pad;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (m0 + r >= T) break;
-      float4 o = res[r];
-      if (a.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
-      op[m0 + r] = o;
-    }
-  } else {
-    uint2 pk[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(res[r].x, res[r].y), h1 = __floats2bfloat162_rn(res[r].z, res[r].w);
-      pk[r] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-    }
-    if (p == 0 && live) {
-#pragma unroll
-      for (int r = 0; r < R; ++r) xch[ht][r] = pk[r];
-    }
-    __syncthreads();
-    if (p == 1 && live) {
-      uint4* op = reinterpret_cast<uint4*>(a.out) + ((size_t)b * a.og.nchunk + pc) * a.og.Tp + a.og.pad;
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (m0 + r >= T) break;
-        const uint2 lo = xch[ht][r];
-        op[m0 + r] = make_uint4(lo.x, lo.y, pk[r].x, pk[r].y);
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// Two-phase form (round 2; the default for launches that fill the GPU).  The register-blocked kernels above
-// recompute the up-sampled halo in every thread ((R+5)/R = 1.8x of the up-FIR + snake work at R = 6) and were
-// issue-bound (ncu, round 1: issue slots 60-69 % busy at 41 % of the HBM peak).  Here every up-sampled value is
-// computed exactly once per block:
+// Two-phase kernel.  Round 1's register-blocked form kept R consecutive outputs per thread in registers and recomputed
+// the up-sampled halo in every thread ((R+5)/R = 1.8x of the up-FIR + snake work at R = 6); it was issue-bound (ncu:
+// issue slots 60-69 % busy at 41 % of the HBM peak).  Here every up-sampled value is computed exactly once per block:
 //   stage : ONE bulk (TMA) copy per input plane brings x[t0-5 .. t0+TILE+4] into shared memory - the rows of a plane
 //           are contiguous, so there is no per-thread load / store code at all; replicate padding is patched in by
 //           the first / last block of a plane only.
@@ -356,7 +70,7 @@ __global__ void __launch_bounds__(kPairThreads, (R == 4 ? 6 : (R == 6 ? 5 : 4)))
 // accesses - about 0.7x of the instruction count of the R = 6 register-blocked form.
 // ---------------------------------------------------------------------------------------------------------------
 template <int UR, int THREADS>
-struct ActV2Geom {
+struct ActGeom {
   static constexpr int kTile = THREADS * UR;        // outputs per block
   static constexpr int kRows = kTile + 10;          // staged x rows
   static constexpr int kPairs = kTile + 5;          // shifted pairs
@@ -395,8 +109,8 @@ __device__ __forceinline__ void act_pair(const float2 (&xlo)[6], const float2 (&
 }
 
 template <int NPL, bool FAST, int UR, int THREADS, int MINB>  // NPL input planes per output unit: 1 -> fp32 out, 2 -> bf16 out
-__global__ void __launch_bounds__(THREADS, MINB) act1d_v2_kernel(const __grid_constant__ ActArgs a) {
-  using G = ActV2Geom<UR, THREADS>;
+__global__ void __launch_bounds__(THREADS, MINB) act1d_kernel(const __grid_constant__ ActArgs a) {
+  using G = ActGeom<UR, THREADS>;
   extern __shared__ __align__(128) uint8_t act_smem[];
   float4* sx = reinterpret_cast<float4*>(act_smem);                                  // [NPL][kRows]
   float4* yo = reinterpret_cast<float4*>(act_smem + (size_t)NPL * G::kXBytes);       // [kPairs]

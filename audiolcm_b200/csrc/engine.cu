@@ -68,7 +68,7 @@ static int env_int(const char* name, int dflt) {
 struct Knobs {
   int pdl, graph, lanes, lane_waves, persist, cluster_splitk, splitk, retile, retile_mode;
   int smem_budget, smem_budget_1w, smem_budget_mw, tpg, astages, kblk_max, nt, tmem2;
-  int act_variant, act_v2, act_v2_min_waves, gn_fused, max_plans, trace, guard, nt192;
+  int act_variant, gn_fused, max_plans, trace, guard, nt192;
   static Knobs from_env() {
     Knobs k;
     k.pdl = env_int("ALCM_PDL", -1);  // -1 unset (per-plan default), 0 never, 1 always
@@ -89,12 +89,10 @@ struct Knobs {
     k.nt = env_int("ALCM_NT", 128);
     k.tmem2 = env_int("ALCM_TMEM2", 0);
     k.act_variant = env_int("ALCM_ACT_VARIANT", -1);
-    k.act_v2 = env_int("ALCM_ACT_V2", 7);                 // 0: off, 7 / 8: two-phase Activation1d with 5 / 7 outputs per thread
-    k.act_v2_min_waves = env_int("ALCM_ACT_V2_MIN_WAVES", 4);
     k.gn_fused = env_int("ALCM_GN_FUSED", 1);
     k.max_plans = std::max(1, env_int("ALCM_MAX_PLANS", 16));
     k.trace = env_int("ALCM_TRACE", 0);
-    k.nt192 = env_int("ALCM_NT192", 192);                 // N tile of the 192-channel layers (192: one tile, 96: two persistent tiles)
+    k.nt192 = env_int("ALCM_NT192", 96);                  // N tile of the 192-channel layers: two persistent 96-wide tiles (stage-3 convs at batch 64: 710 -> 893 TFLOP/s) or one 192-wide
     k.guard = env_int("ALCM_GUARD", 0);                   // 1: 4 KB zero guard zones between device buffers, verified by alcm_*_check_guards
     return k;
   }
@@ -708,95 +706,31 @@ struct OpList {
     op.cls = ALCM_CLS_ACT;
     op.flops = 0;
     op.bytes = (double)B * T * x.C * (4.0 + oesz);  // algorithmic: unpadded channels, one read + one write
-    const int nch32 = x.g.nchunk;
-    // two kernels, same arithmetic: the "pair" form (2 planes side by side, 256-output tiles) has half the serial
-    // work per block and twice the blocks - better while a launch cannot fill the GPU several times over
-    const long blocks_wide = (long)((T + kActTile - 1) / kActTile) * nch * B;
-    // variant 0: 4 outputs/thread, 512-output tiles; 1: "pair" form (small bf16 launches); 2: 8 outputs/thread
-    // (fewest instructions per element; needs enough blocks to fill 4 blocks/SM several times)
-    // 0: 4 outputs/thread (512-output tiles); 1: "pair" form for small bf16 launches; 2: 8 outputs/thread;
-    // 3: 6 outputs/thread (96 registers, 5 blocks/SM) - measured best or equal on every launch that fills the GPU
-    // (batch 64, last stage: 3.48 TB/s bf16 out, 4.63 TB/s = 72 % of the HBM peak fp32 out)
-    const long blocks_r6 = (long)((T + 6 * kActThreads - 1) / (6 * kActThreads)) * nch * B;
-    // 7 / 8: two-phase form (act1d_v2_kernel; every up-sampled value computed once per block), 5 / 7 outputs per thread
-    const long blocks_v2 = (long)((T + 5 * kActThreads - 1) / (5 * kActThreads)) * nch * B;
-    int variant = 0;
-    if (oesz == 2 && blocks_wide < 24L * env.sms()) variant = 5;  // pair form, 6 outputs/thread: batch-1 decode 3.53 -> 3.45 ms vs 4 outputs/thread
-    else if (blocks_r6 >= 8L * env.sms()) variant = 3;
-    if (env.k.act_v2 && blocks_v2 >= (long)env.k.act_v2_min_waves * env.sms()) variant = env.k.act_v2;
+    // One kernel (act1d.cuh), two tile sizes: 640-output tiles (128 threads, 5 blocks/SM) once that fills the GPU twice
+    // over, 320-output tiles (64 threads) below - twice the blocks for the launch-latency-bound small-batch launches.
+    const long blocks_big = (long)((T + 5 * kActThreads - 1) / (5 * kActThreads)) * nch * B;
+    int variant = blocks_big >= 10L * env.sms() ? 0 : 1;
     if (env.k.act_variant >= 0) variant = env.k.act_variant;
     op.fn = [=](cudaStream_t st) {
-      if (variant == 7 || variant == 8) {  // two-phase form
-        const int ur = variant == 7 ? 5 : 7;
-        const dim3 grid((T + ur * kActThreads - 1) / (ur * kActThreads), nch, B);
-        const int npl = oesz == 4 ? 1 : 2;
-        const size_t sm = ur == 5 ? ActV2Geom<5, kActThreads>::smem(npl) : ActV2Geom<7, kActThreads>::smem(npl);
-        if (ur == 5) {
-          if (oesz == 4) {
-            if (fast) launch_k(act1d_v2_kernel<1, true, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a);
-            else launch_k(act1d_v2_kernel<1, false, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a);
-          } else {
-            launch_k(act1d_v2_kernel<2, true, 5, kActThreads, 5>, grid, dim3(kActThreads), sm, st, a);
-          }
-        } else {
-          if (oesz == 4) {
-            if (fast) launch_k(act1d_v2_kernel<1, true, 7, kActThreads, 3>, grid, dim3(kActThreads), sm, st, a);
-            else launch_k(act1d_v2_kernel<1, false, 7, kActThreads, 3>, grid, dim3(kActThreads), sm, st, a);
-          } else {
-            launch_k(act1d_v2_kernel<2, true, 7, kActThreads, 3>, grid, dim3(kActThreads), sm, st, a);
-          }
-        }
-        return;
-      }
-      if (variant == 1 || variant == 5 || variant == 6) {  // pair form, 4 / 6 / 8 outputs per thread
-        const int tile = kPairHalf * (variant == 1 ? 4 : (variant == 5 ? 6 : 8));
-        const dim3 grid((T + tile - 1) / tile, nch32 / 2, B);
+      const int npl = oesz == 4 ? 1 : 2;
+      if (variant == 0) {
+        const dim3 grid((T + 5 * 128 - 1) / (5 * 128), nch, B);
+        const size_t sm = ActGeom<5, 128>::smem(npl);
         if (oesz == 4) {
-          if (variant == 1) {
-            if (fast) launch_k(act1d_pair_kernel<false, true, 4>, grid, dim3(kPairThreads), 0, st, a);
-            else launch_k(act1d_pair_kernel<false, false, 4>, grid, dim3(kPairThreads), 0, st, a);
-          } else if (variant == 5) {
-            if (fast) launch_k(act1d_pair_kernel<false, true, 6>, grid, dim3(kPairThreads), 0, st, a);
-            else launch_k(act1d_pair_kernel<false, false, 6>, grid, dim3(kPairThreads), 0, st, a);
-          } else {
-            if (fast) launch_k(act1d_pair_kernel<false, true, 8>, grid, dim3(kPairThreads), 0, st, a);
-            else launch_k(act1d_pair_kernel<false, false, 8>, grid, dim3(kPairThreads), 0, st, a);
-          }
-        } else if (variant == 1) {
-          launch_k(act1d_pair_kernel<true, true, 4>, grid, dim3(kPairThreads), 0, st, a);
-        } else if (variant == 5) {
-          launch_k(act1d_pair_kernel<true, true, 6>, grid, dim3(kPairThreads), 0, st, a);
+          if (fast) launch_k(act1d_kernel<1, true, 5, 128, 5>, grid, dim3(128), sm, st, a);
+          else launch_k(act1d_kernel<1, false, 5, 128, 5>, grid, dim3(128), sm, st, a);
         } else {
-          launch_k(act1d_pair_kernel<true, true, 8>, grid, dim3(kPairThreads), 0, st, a);
+          launch_k(act1d_kernel<2, true, 5, 128, 5>, grid, dim3(128), sm, st, a);
         }
-        return;
-      }
-      if (variant == 3) {  // 6 outputs per thread
-        const dim3 grid((T + 6 * kActThreads - 1) / (6 * kActThreads), nch, B);
-        if (oesz == 4) {
-          if (fast) launch_k(act1d_kernel<1, true, 6>, grid, dim3(kActThreads), 0, st, a);
-          else launch_k(act1d_kernel<1, false, 6>, grid, dim3(kActThreads), 0, st, a);
-        } else {
-          launch_k(act1d_kernel<2, true, 6>, grid, dim3(kActThreads), 0, st, a);
-        }
-        return;
-      }
-      if (variant == 2) {  // 8 outputs per thread
-        const dim3 grid((T + 2 * kActTile - 1) / (2 * kActTile), nch, B);
-        if (oesz == 4) {
-          if (fast) launch_k(act1d_kernel<1, true, 8>, grid, dim3(kActThreads), 0, st, a);
-          else launch_k(act1d_kernel<1, false, 8>, grid, dim3(kActThreads), 0, st, a);
-        } else {
-          launch_k(act1d_kernel<2, true, 8>, grid, dim3(kActThreads), 0, st, a);
-        }
-        return;
-      }
-      const dim3 grid((T + kActTile - 1) / kActTile, nch, B);
-      if (oesz == 4) {
-        if (fast) launch_k(act1d_kernel<1, true, 4>, grid, dim3(kActThreads), 0, st, a);
-        else launch_k(act1d_kernel<1, false, 4>, grid, dim3(kActThreads), 0, st, a);
       } else {
-        launch_k(act1d_kernel<2, true, 4>, grid, dim3(kActThreads), 0, st, a);
+        const dim3 grid((T + 5 * 64 - 1) / (5 * 64), nch, B);
+        const size_t sm = ActGeom<5, 64>::smem(npl);
+        if (oesz == 4) {
+          if (fast) launch_k(act1d_kernel<1, true, 5, 64, 10>, grid, dim3(64), sm, st, a);
+          else launch_k(act1d_kernel<1, false, 5, 64, 10>, grid, dim3(64), sm, st, a);
+        } else {
+          launch_k(act1d_kernel<2, true, 5, 64, 10>, grid, dim3(64), sm, st, a);
+        }
       }
     };
     push(op);
@@ -1405,9 +1339,6 @@ static void set_kernel_attrs() {
   CUDA_CHECK(cudaFuncSetAttribute(softmax_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<1, true, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<1, false, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  CUDA_CHECK(cudaFuncSetAttribute(act1d_v2_kernel<2, true, 7, kActThreads, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
 }

@@ -227,7 +227,7 @@ def kernel_rooflines(precision, peaks, local):
         clk = cs.stop()
         byt = B * Cc * T * (4 + osz)          # algorithmic: UNPADDED channels, one fp32 read + one write
         gbs = byt / (ms.value * 1e-3) / 1e9
-        out[key] = dict(kernel="act1d_v2_kernel", shape=f"C={Cc} T={T} batch {B}, fp32 in / {'bf16' if osz == 2 else 'fp32'} out "
+        out[key] = dict(kernel="act1d_kernel", shape=f"C={Cc} T={T} batch {B}, fp32 in / {'bf16' if osz == 2 else 'fp32'} out "
                                                          f"({byt / 1e6:.0f} MB algorithmic, unpadded)", operands="seeded random x, alpha, beta",
                         bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm"], unit="GB/s", frac=round(gbs / peaks["hbm"], 4),
                         us_per_launch=round(ms.value * 1e3, 1), launches=iters, clocks=clk)
@@ -352,7 +352,7 @@ def measure_mode(precision, device, z_host, z_dev, args, world, rank, local, flu
                  "execution order of the timed graph; whole_step_* divides ALL FLOPs by the driver-timed ms_per_step; `traffic` = ncu DRAM "
                  "bytes per conv launch of the same workload (profiles/r2_traffic.json)")
         rec["roofline_act"] = dict(bound="hbm", achieved=round(act_gbs, 1), peak=peaks["hbm"], unit="GB/s", frac=round(act_gbs / peaks["hbm"], 4),
-                                   kernel="act1d_v2_kernel (all Activation1d launches of the step)", bytes_per_step=act["bytes"],
+                                   kernel="act1d_kernel (all Activation1d launches of the step)", bytes_per_step=act["bytes"],
                                    ms_per_step=round(act["ms"], 4), share_of_step=round(act["ms"] / total_ms, 4), launches=act["launches"],
                                    note="algorithmic bytes = B*C*T*(4+out_size) with UNPADDED C (fp32 in, operand-type out)")
         rec["class_ms"] = {k: round(v["ms"], 4) for k, v in prof.items()}

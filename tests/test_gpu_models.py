@@ -173,12 +173,12 @@ def test_batch64_full_size_decode_vs_oracle(precision):
         assert np.abs(one - wav[i]).max() <= WAV_TOL[precision]
 
 
-@pytest.mark.parametrize("knobs", [{"ALCM_LANES": "0"}, {"ALCM_ACT_VARIANT": "3"}, {"ALCM_ACT_VARIANT": "2"}, {"ALCM_ACT_VARIANT": "7"},
-                                   {"ALCM_ACT_VARIANT": "8"}, {"ALCM_PERSIST": "0"}, {"ALCM_CLUSTER_SPLITK": "0"},
+@pytest.mark.parametrize("knobs", [{"ALCM_LANES": "0"}, {"ALCM_ACT_VARIANT": "0"}, {"ALCM_ACT_VARIANT": "1"}, {"ALCM_NT192": "192"},
+                                   {"ALCM_PERSIST": "0"}, {"ALCM_CLUSTER_SPLITK": "0"},
                                    {"ALCM_GRAPH": "0"}, {"ALCM_PDL": "1"}])
 def test_forced_plan_variants_match_reference(golden_dir, monkeypatch, knobs):
-    """Every plan-shaping knob the batch-64 / long-form plans flip (serial AMP blocks with in-place accumulation, the
-    big-launch Activation1d forms, non-persistent convs, workspace split-K, eager launches, PDL), forced on a small
+    """Every plan-shaping knob the batch-64 / long-form plans flip (serial AMP blocks with in-place accumulation, both
+    Activation1d tile sizes, non-persistent convs, workspace split-K, eager launches, PDL), forced on a small
     batch-4 model and checked against the reference golden - in bf16 (the benchmarked mode) and tf32."""
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
@@ -451,7 +451,7 @@ def test_guard_zones_stay_clean_over_every_kernel_form():
     """compute-sanitizer is closed on the GPU pool, so the library carries its own out-of-bounds-write check
     (ALCM_GUARD=1: 4 KB zero guard zones around every device buffer, verified by alcm_*_check_guards and at the end of
     every single-op call).  tools/sanitize_driver.py runs every conv form (plain, persistent, both split-K reductions,
-    fused epilogue, narrow operands), every Activation1d form, GroupNorm, attention and small decodes under it."""
+    narrow operands), both Activation1d tile sizes, GroupNorm, attention and small decodes under it."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

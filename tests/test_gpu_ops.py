@@ -171,17 +171,17 @@ def test_bad_arguments_raise(ops):
 
 
 # ----------------------------------------------------------------------------------- every Activation1d kernel form
-ACT_VARIANTS = {0: "R=4", 1: "pair R=4", 2: "R=8", 3: "R=6", 5: "pair R=6", 6: "pair R=8", 7: "two-phase UR=5", 8: "two-phase UR=7"}
-ACT_EDGE_SHAPES = [(1, 8, 1), (1, 8, 3), (2, 24, 4099), (3, 16, 160000), (1, 16, 640), (1, 16, 641), (1, 8, 637), (1, 8, 1283), (1, 8, 896),
-                   (1, 8, 899), (1, 24, 6), (1, 40, 1925)]
+ACT_VARIANTS = {0: "640-output tiles (128 threads)", 1: "320-output tiles (64 threads)"}
+ACT_EDGE_SHAPES = [(1, 8, 1), (1, 8, 3), (2, 24, 4099), (1, 16, 640), (1, 16, 641), (1, 8, 637), (1, 8, 1283), (1, 8, 320), (1, 8, 321),
+                   (1, 8, 317), (1, 24, 6), (1, 40, 1925), (3, 16, 160000)]
 
 
 @pytest.mark.parametrize("variant", sorted(ACT_VARIANTS))
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_activation1d_every_kernel_form(ops, monkeypatch, variant, precision):
-    """The plans pick one of several Activation1d kernels by launch size; here each form is forced
+    """The plans pick one of two tile sizes of the Activation1d kernel by launch size; here each is forced
     (ALCM_ACT_VARIANT) and run over tile-boundary and tiny shapes (T = 1: every tap is replicate padding;
-    T = tile, tile+1, tile-3: the halo'd edges of the two-phase form) against the float64 oracle."""
+    T = tile, tile+1, tile-3: the halo'd edges of the staged tile) against the float64 oracle."""
     from oracle import decode_oracle as O
     monkeypatch.setenv("ALCM_ACT_VARIANT", str(variant))
     tol = {"fp32": 1e-5, "tf32": 2.0 ** -11, "bf16": 2.0 ** -8}[precision]

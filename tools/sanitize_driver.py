@@ -1,7 +1,7 @@
 """Small-shape self-check workload - run plain (ALCM_GUARD=1 is set below: every device buffer is fenced by 4 KB zero
 guard zones that are verified after each op and after the decodes) or under compute-sanitizer where the pool allows
 it (tools/sanitize.sh).  Covers every form of the conv kernel (plain, persistent
-two-accumulator, workspace split-K, cluster/DSMEM split-K, narrow operands with the zeroed K slab), every Activation1d kernel form, GroupNorm, attention and one small end-to-end decode per mode.
+two-accumulator, workspace split-K, cluster/DSMEM split-K, narrow operands with the zeroed K slab), both Activation1d tile sizes, GroupNorm, attention and one small end-to-end decode per mode.
 Each case is also checked numerically, so a sanitizer-clean run is a correct run."""
 import os
 import sys
@@ -48,7 +48,7 @@ def main():
     conv_case("cluster split-K", 1, 1536, 1536, 312, 3, 1)
     conv_case("cluster split-K tf32", 1, 1536, 1536, 100, 3, 1, "tf32")
     # every Activation1d kernel form
-    for variant in (0, 1, 2, 3, 5, 6, 7, 8):
+    for variant in (0, 1):
         os.environ["ALCM_ACT_VARIANT"] = str(variant)
         for prec in ("bf16", "tf32"):
             for (B, C, T) in ((1, 8, 3), (2, 24, 1300)):
