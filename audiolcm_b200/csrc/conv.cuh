@@ -321,20 +321,6 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
       const int nq_valid = min(nq, a.og.nchunk - T.nt * nq);   // column groups that exist in the output planes
       const size_t off0 = ((size_t)T.b * a.og.nchunk + (size_t)T.nt * nq) * a.og.Tp + a.og.pad + orow;  // float4 units
       const bool has_res = (a.res != nullptr) && in_seq, accum = (a.accum != 0) && valid, store = (a.out != nullptr) && valid;
-      // residual / accumulate operands of 16 channels (issued before the TMEM load they are combined with)
-      auto fetch = [&](int c0, float4 (&rr)[4], float4 (&oo)[4]) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int cq = (c0 >> 2) + g;
-          rr[g] = oo[g] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (cq < nq_valid) {
-            if (has_res) rr[g] = res4[off0 + (size_t)cq * plane4];
-            if (accum) oo[g] = out4[off0 + (size_t)cq * plane4];
-          }
-        }
-      };
-      float4 rrA[4], ooA[4], rrB[4], ooB[4];
-      if (ksplit == 1) fetch(0, rrA, ooA);   // independent of this tile's MMAs: in flight while the accumulator completes
       mbar_wait(acc_full + 8 * st, (it >> 1) & 1);
       tc_fence_after();
       if (trace && it == 0 && threadIdx.x == 64) trace[5] = clock64();
@@ -350,12 +336,22 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
           if (store && cq < nq_valid) out4[off0 + (size_t)cq * plane4] = r;
         }
       };
+      // residual / accumulate operands of 16 channels (issued before the TMEM load they are combined with)
+      auto fetch = [&](int c0, float4 (&rr)[4], float4 (&oo)[4]) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cq = (c0 >> 2) + g;
+          rr[g] = oo[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (cq < nq_valid) {
+            if (has_res) rr[g] = res4[off0 + (size_t)cq * plane4];
+            if (accum) oo[g] = out4[off0 + (size_t)cq * plane4];
+          }
+        }
+      };
       if (ksplit == 1) {
-        // The residual / accumulate operands of column group g+1 are requested before group g is combined and stored
-        // (two register sets, statically alternated), and those of group 0 before the accumulator is even complete: on
-        // the narrow, HBM-bound stages the exposed load latency per group was most of the tile's epilogue time.
-        auto step = [&](int c0, const float4 (&rr)[4], const float4 (&oo)[4], float4 (&rr_n)[4], float4 (&oo_n)[4]) {
-          if (c0 + 16 < a.NT) fetch(c0 + 16, rr_n, oo_n);
+        for (int c0 = 0; c0 < a.NT; c0 += 16) {
+          float4 rr[4], oo[4];
+          fetch(c0, rr, oo);
           uint32_t u[16];
           tmem_ld_x16(tmem_d + ((uint32_t)(qd * 32) << 16) + c0, u);
           tmem_ld_wait();
@@ -363,10 +359,6 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
           emit(c0, v, rr, oo);
-        };
-        for (int c0 = 0; c0 < a.NT; c0 += 32) {
-          step(c0, rrA, ooA, rrB, ooB);
-          if (c0 + 16 < a.NT) step(c0 + 16, rrB, ooB, rrA, ooA);
         }
       } else if (a.cluster_splitk) {
         // K splits of this tile = the CTAs of this cluster.  Reduce-scatter through distributed shared memory: every CTA

@@ -68,7 +68,7 @@ static int env_int(const char* name, int dflt) {
 struct Knobs {
   int pdl, graph, lanes, lane_waves, persist, cluster_splitk, splitk, retile, retile_mode;
   int smem_budget, smem_budget_1w, smem_budget_mw, tpg, astages, kblk_max, nt, tmem2;
-  int act_variant, as_tiles, gn_fused, max_plans, trace, guard, nt192;
+  int act_variant, gn_fused, max_plans, trace, guard, nt192;
   static Knobs from_env() {
     Knobs k;
     k.pdl = env_int("ALCM_PDL", -1);  // -1 unset (per-plan default), 0 never, 1 always
@@ -89,7 +89,6 @@ struct Knobs {
     k.nt = env_int("ALCM_NT", 128);
     k.tmem2 = env_int("ALCM_TMEM2", 0);
     k.act_variant = env_int("ALCM_ACT_VARIANT", -1);
-    k.as_tiles = env_int("ALCM_AS_TILES", 1);             // persistent launches: A-slab ring sized across tiles (0: per tile only)
     k.gn_fused = env_int("ALCM_GN_FUSED", 1);
     k.max_plans = std::max(1, env_int("ALCM_MAX_PLANS", 16));
     k.trace = env_int("ALCM_TRACE", 0);
@@ -528,12 +527,7 @@ static void pick_pipeline(const Env& env, const ConvLayer& L, long ctas, int ksp
   AS = std::max(2, std::min(4, AS));
   while (AS > 2 && AS * a1 > budget / 2) --AS;
   const int nkb_local = (L.nkb + ksplit - 1) / ksplit;
-  // slabs a CTA can actually have in flight: the k-blocks of its tile, or - a persistent launch walks several tiles and
-  // its producer runs ahead across them - the k-blocks of its next tiles too.  The narrow stages (one k-block per tile,
-  // ~1 k cycles of MMAs) are bound by bytes in flight per SM: 4 slabs instead of 2.
-  const long tiles_per_cta = ksplit == 1 ? ctas / std::max(1L, 2L * env.sms()) : 1;
-  const int slabs_ahead = (int)std::min<long>(4, (long)nkb_local * std::max(1L, env.k.as_tiles ? tiles_per_cta : 1L));
-  AS = std::max(2, std::min(AS, slabs_ahead));
+  AS = std::max(2, std::min(AS, nkb_local));
   const uint32_t a2 = AS * a1, fixed = a2 + L.NT * 4 + 512;
   while (t > 1 && fixed + 2u * t * blob > budget) --t;
   int S = (budget > fixed) ? (int)((budget - fixed) / (t * blob)) : 0;
