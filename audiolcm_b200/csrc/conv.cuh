@@ -39,6 +39,8 @@ struct ConvArgs {
   int w_stages;       // weight ring depth
   int a_stages;       // A-slab ring depth (2..4): short k-blocks (few taps) are bound by the slab's load latency
   int tpg;            // taps per weight stage (one bulk copy + one mbarrier round trip per `tpg` taps)
+  int w_resident;     // persistent launch whose whole weight set (all taps, single N tile, single k-block) stays in shared
+                      // memory: w_stages == number of tap groups, loaded by the CTA's first tile only
   uint32_t idesc;
   unsigned long long w_phase_stride;  // bytes between phases in w
   float scale;
@@ -149,7 +151,7 @@ __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, uint32_t sA, ui
       uint64_t a_tap = a_desc0 + (uint64_t)(as * a_stage16 + shift0);
       for (int j0 = 0; j0 < ntaps; j0 += tpg) {
         const int g = min(tpg, ntaps - j0);
-        mbar_wait(w_full + 8 * ws, wpar);
+        if (!a.w_resident || it == 0) mbar_wait(w_full + 8 * ws, wpar);
         tc_fence_after();
         if (trace && it == 0 && acc == 0 && leader) trace[3] = clock64();
         // branch-free, warp-uniform issue: the election is the predicate of the async instructions themselves
@@ -162,7 +164,7 @@ __device__ __forceinline__ void conv_mma_loop(const ConvArgs& a, uint32_t sA, ui
             umma_ss_pred<KIND>(tmem_d, a_tap + (uint64_t)(i * a_step), bd + (uint64_t)(i * w_step), idesc, (i > 0) ? 1u : acc, lead);
           acc = 1;
         }
-        tc_commit_pred(w_empty + 8 * ws, lead);  // frees the weight slot when these MMAs retire
+        if (!a.w_resident) tc_commit_pred(w_empty + 8 * ws, lead);  // frees the weight slot when these MMAs retire
         if (j0 + g == ntaps) tc_commit_pred(a_empty + 8 * as, lead);
         if (++ws == S) { ws = 0; wpar ^= 1; }
       }
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
     int ws = 0, as = 0;
     uint32_t wpar = 1, apar = 1;  // producer waits on the "previous" phase of the empty barriers first
     bool waited = false;
+    bool w_needed = true;  // weights-resident launches copy the weights for the CTA's first tile only
     for (int tile = blockIdx.x; tile < a.tiles_total; tile += gridDim.x) {
       const ConvTile T = conv_tile(a, tile);
       const int row0 = T.q0 + a.min_off[T.ph] + a.xg.pad;  // >= 0: |min_off| <= pad
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
       };
       // Only the first weight group goes out before the first A slab: the first MMA needs exactly those two, and
       // everything queued ahead of the slab delays it (12 prefetched groups cost ~1.3 us of first-MMA latency).
-      load_w(0);
+      if (w_needed) load_w(0);
       if (!waited) { pdl_wait(); waited = true; }
       int gi = 0;
       for (int kb = T.kb0; kb < T.kb1; ++kb) {
@@ -278,9 +281,10 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
           xsrc += plane_bytes * (a.kblk - cv);
         }
         for (int j0 = 0; j0 < ntaps; j0 += tpg, ++gi)
-          if (gi >= 1) load_w(j0);
+          if (gi >= 1 && w_needed) load_w(j0);
         if (++as == AS) { as = 0; apar ^= 1; }
       }
+      if (a.w_resident) w_needed = false;
     }
     __syncwarp();
   } else if (warp == 1) {

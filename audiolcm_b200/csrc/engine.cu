@@ -68,7 +68,7 @@ static int env_int(const char* name, int dflt) {
 struct Knobs {
   int pdl, graph, lanes, lane_waves, persist, cluster_splitk, splitk, retile, retile_mode;
   int smem_budget, smem_budget_1w, smem_budget_mw, tpg, astages, kblk_max, nt, tmem2;
-  int act_variant, gn_fused, max_plans, trace, guard, nt192;
+  int act_variant, w_resident, gn_fused, max_plans, trace, guard, nt192;
   static Knobs from_env() {
     Knobs k;
     k.pdl = env_int("ALCM_PDL", -1);  // -1 unset (per-plan default), 0 never, 1 always
@@ -89,6 +89,7 @@ struct Knobs {
     k.nt = env_int("ALCM_NT", 128);
     k.tmem2 = env_int("ALCM_TMEM2", 0);
     k.act_variant = env_int("ALCM_ACT_VARIANT", -1);
+    k.w_resident = env_int("ALCM_W_RESIDENT", 1);         // persistent narrow-stage convs keep all their weights in shared memory
     k.gn_fused = env_int("ALCM_GN_FUSED", 1);
     k.max_plans = std::max(1, env_int("ALCM_MAX_PLANS", 16));
     k.trace = env_int("ALCM_TRACE", 0);
@@ -645,6 +646,20 @@ static ConvLaunch plan_conv(const Env& env, const ConvLayer& L, const PlaneT& x,
       grid = occ_p * env.sms();
       a.acc_stages = 2;
       a.tmem_cols = tcols2;
+    }
+  }
+  // Weights-stationary form for the narrow stages.  A 128-row tile of a C-channel conv streams C*C*k*2 bytes of weights
+  // from L2 but only ~128*C*(2+4[+4]) bytes of activations: at C <= 96 the weights are 2-3x the activation traffic and the
+  // launch is bound by L2 -> SM bandwidth (ncu launch list, profiles/r2_launches_bf16_b64.txt: same HBM bytes, k = 11
+  // takes 20 % longer than k = 3).  When every tap of the (single) N tile fits beside the A ring, a persistent CTA loads
+  // them once and keeps them for all its tiles.
+  if (env.k.w_resident && a.acc_stages == 2 && L.n_tiles == 1 && L.nkb == 1 && L.nphase == 1) {
+    const int groups = (L.ntaps + a.tpg - 1) / a.tpg;
+    const uint32_t smem_r = conv_smem_layout(L.kblk, L.span, L.NT, groups, a.tpg, a.a_stages).total;
+    if (groups <= 12 && smem_r + 1024u <= (227u * 1024u) / 2u) {
+      a.w_stages = groups;
+      a.w_resident = 1;
+      smem = smem_r;
     }
   }
   cl.grid = dim3(grid);
