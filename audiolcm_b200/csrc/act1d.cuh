@@ -57,7 +57,7 @@ __device__ __forceinline__ float fir_sum() {
 // Two-phase kernel.  Round 1's register-blocked form kept R consecutive outputs per thread in registers and recomputed
 // the up-sampled halo in every thread ((R+5)/R = 1.8x of the up-FIR + snake work at R = 6); it was issue-bound (ncu:
 // issue slots 60-69 % busy at 41 % of the HBM peak).  Here every up-sampled value is computed exactly once per block:
-//   stage : ONE bulk (TMA) copy per input plane brings x[t0-5 .. t0+TILE+4] into shared memory - the rows of a plane
+//   stage : ONE bulk (TMA) copy per input plane brings x[t0-5 .. t0+TILE+9] into shared memory - the rows of a plane
 //           are contiguous, so there is no per-thread load / store code at all; replicate padding is patched in by
 //           the first / last block of a plane only.
 //   phase1: thread i computes U consecutive "shifted pairs" P_s = (y[2t0-5+2s], y[2t0-4+2s]) - both values come from
@@ -71,9 +71,9 @@ __device__ __forceinline__ float fir_sum() {
 // ---------------------------------------------------------------------------------------------------------------
 template <int UR, int THREADS>
 struct ActGeom {
-  static constexpr int kTile = THREADS * UR;        // outputs per block
-  static constexpr int kRows = kTile + 10;          // staged x rows
-  static constexpr int kPairs = kTile + 5;          // shifted pairs
+  static constexpr int kPairs = THREADS * UR;       // shifted pairs per block: UR per thread, no remainder
+  static constexpr int kTile = kPairs - 5;          // outputs per block (the last thread of a UR = 5 block only feeds its neighbours)
+  static constexpr int kRows = kPairs + 5;          // staged x rows: x[t0-5 .. t0+kPairs-1]
   static constexpr int kXBytes = kRows * 16;
   static constexpr int kYBytes = kPairs * 16;       // one of yo / ye
   static constexpr size_t smem(int npl) { return (size_t)npl * kXBytes + 2 * (size_t)kYBytes + 16; }
@@ -111,32 +111,35 @@ __device__ __forceinline__ void act_pair(const float2 (&xlo)[6], const float2 (&
 template <int NPL, bool FAST, int UR, int THREADS, int MINB>  // NPL input planes per output unit: 1 -> fp32 out, 2 -> bf16 out
 __global__ void __launch_bounds__(THREADS, MINB) act1d_kernel(const __grid_constant__ ActArgs a) {
   using G = ActGeom<UR, THREADS>;
+  static_assert(UR == 5, "the last thread of a block has UR - 5 outputs: the tail handling below assumes none");
   extern __shared__ __align__(128) uint8_t act_smem[];
   float4* sx = reinterpret_cast<float4*>(act_smem);                                  // [NPL][kRows]
   float4* yo = reinterpret_cast<float4*>(act_smem + (size_t)NPL * G::kXBytes);       // [kPairs]
   float4* ye = yo + G::kPairs;                                                        // [kPairs]
-  const uint32_t bar = smem_u32(act_smem + (size_t)NPL * G::kXBytes + 2 * (size_t)G::kYBytes);
+  const uint32_t bar = smem_u32(act_smem + (size_t)NPL * G::kXBytes + 2 * (size_t)G::kYBytes);   // one mbarrier per plane
   const int tid = threadIdx.x;
   const int t0 = blockIdx.x * G::kTile;
   const int oc = blockIdx.y, b = blockIdx.z;
   const int T = a.T;
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+#pragma unroll
+    for (int p = 0; p < NPL; ++p) mbar_init(bar + 8 * p, 1);
     fence_mbar_init();
   }
   __syncthreads();
   pdl_launch_dependents();
   pdl_wait();
-  // ---- stage: one bulk copy per plane (rows t0-5 .. ; the plane's zero halo supplies rows outside [0,T) for now) ----
+  // ---- stage: one bulk copy per plane, each on its own barrier (plane 0 is worked on while plane 1 is still in flight);
+  //      rows outside [0,T) come from the plane's zero halo for now ----
   const int row0 = a.xg.pad + t0 - 5;                                   // >= pad - 5 > 0
   const int nrows = min(G::kRows, a.xg.Tp - row0);
   if (tid == 0) {
-    mbar_expect_tx(bar, (uint32_t)(NPL * nrows * 16));
 #pragma unroll
     for (int p = 0; p < NPL; ++p) {
       const float4* src = reinterpret_cast<const float4*>(a.x) + ((size_t)b * a.xg.nchunk + (oc * NPL + p)) * a.xg.Tp + row0;
-      bulk_g2s(smem_u32(sx + p * G::kRows), src, (uint32_t)(nrows * 16), bar);
+      mbar_expect_tx(bar + 8 * p, (uint32_t)(nrows * 16));
+      bulk_g2s(smem_u32(sx + p * G::kRows), src, (uint32_t)(nrows * 16), bar + 8 * p);
     }
   }
   float2 f2[6], g2[6];  // broadcast taps: f[k] (down) and 2 f[k] (up), k = 0..5 (symmetric filter)
@@ -145,24 +148,23 @@ __global__ void __launch_bounds__(THREADS, MINB) act1d_kernel(const __grid_const
     f2[k] = make_float2(c_fir[k], c_fir[k]);
     g2[k] = make_float2(2.f * c_fir[k], 2.f * c_fir[k]);
   }
-  mbar_wait(bar, 0);
-  // replicate padding of the up-sampling FIR (resample.py:28): rows before t = 0 / after t = T-1 take the edge sample
-  const bool first = (t0 == 0), last = t0 + G::kTile + 4 > T - 1;       // block-uniform (t0 is a multiple of the tile)
-  if (first || last) {
-    for (int i = tid; i < NPL * G::kRows; i += THREADS) {
-      const int p = i / G::kRows, lr = i - p * G::kRows;
-      const int t = t0 - 5 + lr;
-      const int tc = min(max(t, 0), T - 1);
-      const int src = tc - (t0 - 5);
-      if (tc != t && src >= 0 && src < G::kRows) sx[p * G::kRows + lr] = sx[p * G::kRows + src];
-    }
-    __syncthreads();
-  }
-
+  const bool first = (t0 == 0), last = t0 + G::kPairs - 1 > T - 1;      // block-uniform (t0 is a multiple of the tile)
   const int m0 = t0 + UR * tid;
+  const bool has_out = UR * tid < G::kTile;                             // false only for the last thread when UR == 5
   uint2 held[UR];
 #pragma unroll 1
   for (int p = 0; p < NPL; ++p) {
+    float4* xp = sx + p * G::kRows;
+    mbar_wait(bar + 8 * p, 0);
+    if (first || last) {  // replicate padding of the up-sampling FIR (resample.py:28): rows outside [0,T) take the edge sample
+      for (int lr = tid; lr < G::kRows; lr += THREADS) {
+        const int t = t0 - 5 + lr;
+        const int tc = min(max(t, 0), T - 1);
+        const int src = tc - (t0 - 5);
+        if (tc != t && src >= 0 && src < G::kRows) xp[lr] = xp[src];
+      }
+      __syncthreads();
+    }
     const int chunk = oc * NPL + p;
     const float4 ea = *reinterpret_cast<const float4*>(a.ea + chunk * 4);
     const float4 ib = *reinterpret_cast<const float4*>(a.ib + chunk * 4);
@@ -170,9 +172,7 @@ __global__ void __launch_bounds__(THREADS, MINB) act1d_kernel(const __grid_const
     const float2 ea_hi = FAST ? make_float2(2.f * ea.z, 2.f * ea.w) : make_float2(ea.z, ea.w);
     const float2 ib_lo = FAST ? make_float2(0.5f * ib.x, 0.5f * ib.y) : make_float2(ib.x, ib.y);
     const float2 ib_hi = FAST ? make_float2(0.5f * ib.z, 0.5f * ib.w) : make_float2(ib.z, ib.w);
-    const float4* xp = sx + p * G::kRows;
-    // ---- phase 1: UR shifted pairs per thread (+ the 5 pairs beyond the tile, one each by threads 0..4) ----
-    {
+    {  // ---- phase 1: UR shifted pairs per thread ----
       float2 xlo[UR + 5], xhi[UR + 5];
 #pragma unroll
       for (int k = 0; k < UR + 5; ++k) {
@@ -190,20 +190,6 @@ __global__ void __launch_bounds__(THREADS, MINB) act1d_kernel(const __grid_const
         yo[UR * tid + j] = o;
         ye[UR * tid + j] = e;
       }
-    }
-    if (tid < 5) {
-      const int s = G::kTile + tid;
-      float2 wl[6], wh[6];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const float4 v = xp[s + q];
-        wl[q] = make_float2(v.x, v.y);
-        wh[q] = make_float2(v.z, v.w);
-      }
-      float4 o, e;
-      act_pair<FAST>(wl, wh, g2, ea_lo, ea_hi, ib_lo, ib_hi, o, e);
-      yo[s] = o;
-      ye[s] = e;
     }
     __syncthreads();
     // replicate padding of the down filter acts on y (filter.py:89-91): y[j<0] = y[0], y[j>=2T] = y[2T-1].
@@ -232,18 +218,20 @@ __global__ void __launch_bounds__(THREADS, MINB) act1d_kernel(const __grid_const
     float2 alo[UR], ahi[UR];
 #pragma unroll
     for (int r = 0; r < UR; ++r) alo[r] = ahi[r] = make_float2(0.f, 0.f);
+    if (has_out) {
 #pragma unroll
-    for (int s = 0; s < UR + 5; ++s) {
-      const float4 o = yo[UR * tid + s], e = ye[UR * tid + s];
-      const float2 olo = make_float2(o.x, o.y), ohi = make_float2(o.z, o.w), elo = make_float2(e.x, e.y), ehi = make_float2(e.z, e.w);
+      for (int s = 0; s < UR + 5; ++s) {
+        const float4 o = yo[UR * tid + s], e = ye[UR * tid + s];
+        const float2 olo = make_float2(o.x, o.y), ohi = make_float2(o.z, o.w), elo = make_float2(e.x, e.y), ehi = make_float2(e.z, e.w);
 #pragma unroll
-      for (int r = 0; r < UR; ++r) {
-        const int d = s - r;
-        if (d >= 0 && d <= 5) {
-          const int k0 = 2 * d, k1 = 2 * d + 1;
-          const float2 w0 = f2[k0 < 6 ? k0 : 11 - k0], w1 = f2[k1 < 6 ? k1 : 11 - k1];
-          alo[r] = ffma2(olo, w0, alo[r]); ahi[r] = ffma2(ohi, w0, ahi[r]);
-          alo[r] = ffma2(elo, w1, alo[r]); ahi[r] = ffma2(ehi, w1, ahi[r]);
+        for (int r = 0; r < UR; ++r) {
+          const int d = s - r;
+          if (d >= 0 && d <= 5) {
+            const int k0 = 2 * d, k1 = 2 * d + 1;
+            const float2 w0 = f2[k0 < 6 ? k0 : 11 - k0], w1 = f2[k1 < 6 ? k1 : 11 - k1];
+            alo[r] = ffma2(olo, w0, alo[r]); ahi[r] = ffma2(ohi, w0, ahi[r]);
+            alo[r] = ffma2(elo, w1, alo[r]); ahi[r] = ffma2(ehi, w1, ahi[r]);
+          }
         }
       }
     }
@@ -261,7 +249,7 @@ __global__ void __launch_bounds__(THREADS, MINB) act1d_kernel(const __grid_const
       float4* op = reinterpret_cast<float4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
 #pragma unroll
       for (int r = 0; r < UR; ++r) {
-        if (m0 + r >= T) break;
+        if (UR * tid + r >= G::kTile || m0 + r >= T) break;
         float4 o = res[r];
         if (a.round_tf32) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
         op[m0 + r] = o;
@@ -281,7 +269,7 @@ __global__ void __launch_bounds__(THREADS, MINB) act1d_kernel(const __grid_const
         uint4* op = reinterpret_cast<uint4*>(a.out) + ((size_t)b * a.og.nchunk + oc) * a.og.Tp + a.og.pad;
 #pragma unroll
         for (int r = 0; r < UR; ++r) {
-          if (m0 + r >= T) break;
+          if (UR * tid + r >= G::kTile || m0 + r >= T) break;
           op[m0 + r] = make_uint4(held[r].x, held[r].y, pk[r].x, pk[r].y);
         }
       }

@@ -721,32 +721,27 @@ struct OpList {
     op.cls = ALCM_CLS_ACT;
     op.flops = 0;
     op.bytes = (double)B * T * x.C * (4.0 + oesz);  // algorithmic: unpadded channels, one read + one write
-    // One kernel (act1d.cuh), two tile sizes: 640-output tiles (128 threads, 5 blocks/SM) once that fills the GPU twice
-    // over, 320-output tiles (64 threads) below - twice the blocks for the launch-latency-bound small-batch launches.
-    const long blocks_big = (long)((T + 5 * kActThreads - 1) / (5 * kActThreads)) * nch * B;
-    int variant = blocks_big >= 10L * env.sms() ? 0 : 1;
+    // One kernel (act1d.cuh); three block sizes for measurements (ALCM_ACT_VARIANT): 0 = 128 threads (635 outputs per
+    // block), 1 = 64 threads (315), 2 = 32 threads (155).  Default: 64 - measured best at every launch size.
+    int variant = 1;
     if (env.k.act_variant >= 0) variant = env.k.act_variant;
     op.fn = [=](cudaStream_t st) {
       const int npl = oesz == 4 ? 1 : 2;
-      if (variant == 0) {
-        const dim3 grid((T + 5 * 128 - 1) / (5 * 128), nch, B);
-        const size_t sm = ActGeom<5, 128>::smem(npl);
+      auto go = [&](auto threads_tag, auto minb_tag) {
+        constexpr int TH = decltype(threads_tag)::value, MB = decltype(minb_tag)::value;
+        using G = ActGeom<5, TH>;
+        const dim3 grid((T + G::kTile - 1) / G::kTile, nch, B);
+        const size_t sm = G::smem(npl);
         if (oesz == 4) {
-          if (fast) launch_k(act1d_kernel<1, true, 5, 128, 5>, grid, dim3(128), sm, st, a);
-          else launch_k(act1d_kernel<1, false, 5, 128, 5>, grid, dim3(128), sm, st, a);
+          if (fast) launch_k(act1d_kernel<1, true, 5, TH, MB>, grid, dim3(TH), sm, st, a);
+          else launch_k(act1d_kernel<1, false, 5, TH, MB>, grid, dim3(TH), sm, st, a);
         } else {
-          launch_k(act1d_kernel<2, true, 5, 128, 5>, grid, dim3(128), sm, st, a);
+          launch_k(act1d_kernel<2, true, 5, TH, MB>, grid, dim3(TH), sm, st, a);
         }
-      } else {
-        const dim3 grid((T + 5 * 64 - 1) / (5 * 64), nch, B);
-        const size_t sm = ActGeom<5, 64>::smem(npl);
-        if (oesz == 4) {
-          if (fast) launch_k(act1d_kernel<1, true, 5, 64, 10>, grid, dim3(64), sm, st, a);
-          else launch_k(act1d_kernel<1, false, 5, 64, 10>, grid, dim3(64), sm, st, a);
-        } else {
-          launch_k(act1d_kernel<2, true, 5, 64, 10>, grid, dim3(64), sm, st, a);
-        }
-      }
+      };
+      if (variant == 0) go(std::integral_constant<int, 128>{}, std::integral_constant<int, 5>{});
+      else if (variant == 2) go(std::integral_constant<int, 32>{}, std::integral_constant<int, 20>{});
+      else go(std::integral_constant<int, 64>{}, std::integral_constant<int, 10>{});
     };
     push(op);
   }

@@ -60,6 +60,12 @@ def measured_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
 
 
+def tensor_peak(peaks, precision, kind="tf_sustained"):
+    """Tensor roofline of a mode: the measured bf16 figure, halved for tf32 operands (kind::tf32 runs at half the
+    kind::f16 rate on tcgen05 - 1.1 vs 2.25 PFLOP/s nominal, B200_PROFILING.md; MEASURED_PEAKS.json has bf16 only)."""
+    return peaks[kind] * (0.5 if precision == "tf32" else 1.0)
+
+
 def workload(world):
     return (f"configs[2]: {CLIPS} x 10 s clips (z [{CLIPS},20,{T_LAT}] -> wav [{CLIPS},{T_LAT * VAE_UP * HOP}]), full latent->waveform "
             f"decode (autoencoder1d VAE decoder + BigVGAN-16k), batch-sharded {CLIPS}/{world} clips per GPU")
@@ -212,10 +218,12 @@ def kernel_rooflines(precision, peaks, local):
     _lib.check(lib.alcm_bench_conv(ctx, B, Cc, Cc, T, K, 1, prec, iters, 0, C.byref(ms)))
     clk = cs.stop()
     tf = 2.0 * B * Cc * Cc * K * T / (ms.value * 1e-3) / 1e12
+    ps, pb = tensor_peak(peaks, precision), tensor_peak(peaks, precision, "tf_burst")
     out["conv_gemm"] = dict(kernel="conv_umma_kernel", shape=f"Conv1d {Cc}->{Cc} k{K}, T={T}, batch {B}", operands="seeded random (device-generated)",
-                            bound="tensor", achieved=round(tf, 1), unit="TFLOP/s", peak_sustained=peaks["tf_sustained"],
-                            frac_of_sustained=round(tf / peaks["tf_sustained"], 4), peak_burst=peaks["tf_burst"],
-                            frac_of_burst=round(tf / peaks["tf_burst"], 4), us_per_launch=round(ms.value * 1e3, 1), launches=iters, clocks=clk)
+                            bound="tensor", achieved=round(tf, 1), unit="TFLOP/s", peak_sustained=ps,
+                            frac_of_sustained=round(tf / ps, 4), peak_burst=pb,
+                            frac_of_burst=round(tf / pb, 4), us_per_launch=round(ms.value * 1e3, 1), launches=iters, clocks=clk,
+                            peak_note="measured bf16 cuBLAS figures" + (", halved for tf32 operands" if precision == "tf32" else ""))
     B, Cc, T = 64, 24, 160000               # last-stage Activation1d, batch 64: 1.5-2.0 GB, far beyond L2
     for key, p, osz in (("activation1d", precision, 2 if precision == "bf16" else 4), ("activation1d_fp32_out", "tf32", 4)):
         if key == "activation1d_fp32_out" and precision != "bf16":
@@ -269,7 +277,7 @@ def time_steps(fn, steps, warmup, flush):
     return sum(e0.elapsed_time(e1) for e0, e1 in evs) / 1e3  # seconds over `steps`
 
 
-def stage_rooflines(pipe, B, peaks):
+def stage_rooflines(pipe, B, peaks, precision):
     """Per pipeline stage, from the eager per-kernel CUDA-event profile of this batch (AMP blocks run back to back at
     batch >= 3, so the eager order IS the execution order): conv TFLOP/s vs the sustained tensor peak, and - for the
     HBM-bound small-channel stages and for Activation1d - algorithmic GB/s vs the measured HBM peak."""
@@ -281,7 +289,7 @@ def stage_rooflines(pipe, B, peaks):
         if c and c["ms"] > 0:
             tf = c["flops"] / (c["ms"] * 1e-3) / 1e12
             gbs = c["bytes"] / (c["ms"] * 1e-3) / 1e9
-            rec["conv"] = dict(ms=round(c["ms"], 3), launches=c["launches"], tflops=round(tf, 1), frac_tensor=round(tf / peaks["tf_sustained"], 3),
+            rec["conv"] = dict(ms=round(c["ms"], 3), launches=c["launches"], tflops=round(tf, 1), frac_tensor=round(tf / tensor_peak(peaks, precision), 3),
                                gbs=round(gbs, 1), frac_hbm=round(gbs / peaks["hbm"], 3))
         a = classes.get("act")
         if a and a["ms"] > 0:
@@ -339,14 +347,17 @@ def measure_mode(precision, device, z_host, z_dev, args, world, rank, local, flu
         act_gbs = act["bytes"] / (act["ms"] * 1e-3) / 1e9
         total_ms = sum(c["ms"] for c in prof.values())
         step_ms = 1e3 * dev_s / args.steps
+        tpk = tensor_peak(peaks, precision)
         rec["roofline"] = dict(
-            bound="tensor", achieved=round(tf, 2), peak=peaks["tf_sustained"], unit="TFLOP/s", frac=round(tf / peaks["tf_sustained"], 4),
+            bound="tensor", achieved=round(tf, 2), peak=tpk, unit="TFLOP/s", frac=round(tf / tpk, 4),
+            frac_of_bf16_peak=round(tf / peaks["tf_sustained"], 4),
             traffic=ncu_traffic(precision), kernel="conv_umma_kernel (all conv GEMM launches of the step)",
-            peak_source=f"{peaks['source']} bf16 sustained (in-step kernel)", flops_per_step=conv["flops"], ms_per_step=round(conv["ms"], 4),
+            peak_source=f"{peaks['source']} bf16 sustained (in-step kernel)" + (" / 2: tf32 operands run at half the bf16 tcgen05 rate" if precision == "tf32" else ""),
+            flops_per_step=conv["flops"], ms_per_step=round(conv["ms"], 4),
             share_of_step=round(conv["ms"] / total_ms, 4), launches=conv["launches"],
             flops_per_launch=round(conv["flops"] / max(conv["launches"], 1)), us_per_launch=round(1e3 * conv["ms"] / max(conv["launches"], 1), 2),
             whole_step_tflops=round(sum(c["flops"] for c in prof.values()) / (step_ms * 1e-3) / 1e12, 2),
-            whole_step_frac=round(sum(c["flops"] for c in prof.values()) / (step_ms * 1e-3) / 1e12 / peaks["tf_sustained"], 4),
+            whole_step_frac=round(sum(c["flops"] for c in prof.values()) / (step_ms * 1e-3) / 1e12 / tpk, 4),
             note="achieved = algorithmic FLOPs (2*Cin*Cout*k*T_out per conv) of all conv launches / their summed CUDA-event time, measured "
                  "eagerly in this process with one event pair per kernel - at this batch the AMP blocks run back to back, so that is the "
                  "execution order of the timed graph; whole_step_* divides ALL FLOPs by the driver-timed ms_per_step; `traffic` = ncu DRAM "
@@ -357,7 +368,7 @@ def measure_mode(precision, device, z_host, z_dev, args, world, rank, local, flu
                                    note="algorithmic bytes = B*C*T*(4+out_size) with UNPADDED C (fp32 in, operand-type out)")
         rec["class_ms"] = {k: round(v["ms"], 4) for k, v in prof.items()}
         rec["class_ms_total_eager"] = round(total_ms, 4)
-        rec["stages"] = stage_rooflines(pipe, Bl, peaks)
+        rec["stages"] = stage_rooflines(pipe, Bl, peaks, precision)
     return pipe, rec, wav
 
 

@@ -173,12 +173,12 @@ def test_batch64_full_size_decode_vs_oracle(precision):
         assert np.abs(one - wav[i]).max() <= WAV_TOL[precision]
 
 
-@pytest.mark.parametrize("knobs", [{"ALCM_LANES": "0"}, {"ALCM_ACT_VARIANT": "0"}, {"ALCM_ACT_VARIANT": "1"}, {"ALCM_NT192": "192"},
+@pytest.mark.parametrize("knobs", [{"ALCM_LANES": "0"}, {"ALCM_ACT_VARIANT": "0"}, {"ALCM_ACT_VARIANT": "2"}, {"ALCM_NT192": "192"},
                                    {"ALCM_PERSIST": "0"}, {"ALCM_CLUSTER_SPLITK": "0"},
                                    {"ALCM_GRAPH": "0"}, {"ALCM_PDL": "1"}])
 def test_forced_plan_variants_match_reference(golden_dir, monkeypatch, knobs):
-    """Every plan-shaping knob the batch-64 / long-form plans flip (serial AMP blocks with in-place accumulation, both
-    Activation1d tile sizes, non-persistent convs, workspace split-K, eager launches, PDL), forced on a small
+    """Every plan-shaping knob the batch-64 / long-form plans flip (serial AMP blocks with in-place accumulation, the other
+    Activation1d block sizes, non-persistent convs, workspace split-K, eager launches, PDL), forced on a small
     batch-4 model and checked against the reference golden - in bf16 (the benchmarked mode) and tf32."""
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)

@@ -171,15 +171,15 @@ def test_bad_arguments_raise(ops):
 
 
 # ----------------------------------------------------------------------------------- every Activation1d kernel form
-ACT_VARIANTS = {0: "640-output tiles (128 threads)", 1: "320-output tiles (64 threads)"}
-ACT_EDGE_SHAPES = [(1, 8, 1), (1, 8, 3), (2, 24, 4099), (1, 16, 640), (1, 16, 641), (1, 8, 637), (1, 8, 1283), (1, 8, 320), (1, 8, 321),
-                   (1, 8, 317), (1, 24, 6), (1, 40, 1925), (3, 16, 160000)]
+ACT_VARIANTS = {0: "128 threads, 635 outputs per block", 1: "64 threads, 315", 2: "32 threads, 155"}
+ACT_EDGE_SHAPES = [(1, 8, 1), (1, 8, 3), (2, 24, 4099), (1, 16, 635), (1, 16, 636), (1, 8, 630), (1, 8, 1283), (1, 8, 315), (1, 8, 316),
+                   (1, 8, 311), (1, 8, 155), (1, 8, 156), (1, 8, 152), (1, 24, 6), (1, 40, 1925), (3, 16, 160000)]
 
 
 @pytest.mark.parametrize("variant", sorted(ACT_VARIANTS))
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 def test_activation1d_every_kernel_form(ops, monkeypatch, variant, precision):
-    """The plans pick one of two tile sizes of the Activation1d kernel by launch size; here each is forced
+    """The plans pick one block size of the Activation1d kernel; here each of the three is forced
     (ALCM_ACT_VARIANT) and run over tile-boundary and tiny shapes (T = 1: every tap is replicate padding;
     T = tile, tile+1, tile-3: the halo'd edges of the staged tile) against the float64 oracle."""
     from oracle import decode_oracle as O

@@ -1,5 +1,5 @@
 """Activation1d micro-benchmark: algorithmic GB/s (fp32 in + operand out, unpadded channels) of single launches on random
-operands.  ALCM_ACT_VARIANT=n forces the tile size (0: 640 outputs / 128 threads, 1: 320 outputs / 64 threads)."""
+operands.  ALCM_ACT_VARIANT=n forces the block size (0: 128 threads / 635 outputs, 1: 64 / 315 (default), 2: 32 / 155)."""
 import ctypes as C
 import os
 import sys

@@ -27,7 +27,14 @@ SHAPES = [  # B, Cin, Cout, T, K, d
     (8, 192, 192, 20000, 7, 1),
     (8, 96, 96, 40000, 7, 1),
     (8, 32, 32, 160000, 7, 1),
+    (64, 24, 24, 160000, 3, 1),
+    (64, 24, 24, 160000, 11, 5),
+    (64, 48, 48, 80000, 11, 1),
+    (64, 96, 96, 40000, 11, 1),
+    (64, 192, 192, 20000, 11, 1),
 ]
+if len(sys.argv) > 3:
+    SHAPES = SHAPES[-int(sys.argv[3]):]
 precs = sys.argv[1].split(",") if len(sys.argv) > 1 else ["bf16"]
 dbgs = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 1, 2, 3]
 for prec in precs:

@@ -48,7 +48,7 @@ def main():
     conv_case("cluster split-K", 1, 1536, 1536, 312, 3, 1)
     conv_case("cluster split-K tf32", 1, 1536, 1536, 100, 3, 1, "tf32")
     # every Activation1d kernel form
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         os.environ["ALCM_ACT_VARIANT"] = str(variant)
         for prec in ("bf16", "tf32"):
             for (B, C, T) in ((1, 8, 3), (2, 24, 1300)):
