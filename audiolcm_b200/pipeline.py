@@ -3,8 +3,10 @@
 * Batch sharding (BASELINE.json configs 3/5): clips are independent (GroupNorm and attention are
   per-sample, autoencoder1d.py:169-170,267), so ``shard_range`` just splits the batch - no
   collective on the data path.
-* Long-form time sharding (config 4): BigVGAN is purely convolutional with a receptive field of
-  8631/8517 samples (< 34 mel frames) each side, so each rank receives
+* Long-form time sharding (config 4): BigVGAN is purely convolutional; a perturbed mel frame is
+  numerically visible for 8631/8517 samples (< 34 mel frames) each side (the
+  analytic support is ~36.7 frames, but the Kaiser-sinc tails beyond 34 carry < 2e-7 of the signal:
+  the stitched result equals the un-sharded one to rounding, not bit for bit), so each rank receives
   ``halo_frames()`` mel frames from each neighbour with one NCCL P2P exchange
   (``torch.distributed.batch_isend_irecv``), vocodes its extended chunk and drops the halo
   samples.  True sequence ends keep the reference's edge rules (zero pad for convs, replicate for
