@@ -75,6 +75,9 @@ SYMBOLS = {
     "alcm_vae_workspace_bytes": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "alcm_decode_to_wav": (C.c_int, [_P, _P, _FP, C.c_int, C.c_int, C.c_float, _FP, _FP, _P]),
     "alcm_decode_to_pcm16": (C.c_int, [_P, _P, _FP, C.c_int, C.c_int, C.c_float, _FP, _FP, _P]),
+    "alcm_conv1d_create": (C.c_int, [_P, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "alcm_conv1d_destroy": (None, [_P]),
+    "alcm_conv1d_run": (C.c_int, [_P, _FP, _FP, _FP, C.c_int, C.c_int, _P]),
     "alcm_lcm_step": (C.c_int, [_P, _FP, _FP, _FP, _FP, _FP, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
     "alcm_activation1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_conv1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -14,6 +14,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/audiolcm_b200.h"
@@ -1714,6 +1715,79 @@ int alcm_lcm_step(alcm_ctx* ctx, const float* sample, const float* eps, const fl
              reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(noise), reinterpret_cast<float4*>(prev),
              reinterpret_cast<float4*>(denoised), n4, k);
     CUDA_CHECK(cudaGetLastError());
+  });
+}
+
+// ---- stand-alone Conv1d layer handle (the 9-tap Conv1dFeedForward convs of the DiT denoiser,
+//      ldm/modules/new_attention.py:48-74, are 93 % of its FLOPs and have exactly the shape conv_umma_kernel handles) ----
+struct ConvRunPlan : PlanBase {
+  PlaneT x_in, res_in, out;
+};
+struct alcm_conv1d {
+  alcm_ctx* ctx;
+  Env env;
+  int prec, Cin, Cout;
+  Arena war;
+  ConvLayer L;
+  RetileCache retiled;
+  std::map<std::tuple<int, int, int>, std::unique_ptr<ConvRunPlan>> plans;   // (B, T, has_res)
+  PlanCache pcache;
+};
+
+int alcm_conv1d_create(alcm_ctx* ctx, const float* w, const float* bias, int Cout, int Cin, int K, int dilation, int precision,
+                       alcm_conv1d** out) {
+  return guarded([&] {
+    REQUIRE(ctx && w && out, "conv1d_create: NULL argument");
+    REQUIRE(Cout >= 1 && Cin >= 1 && dilation >= 1, "conv1d_create: bad shape");
+    REQUIRE(precision >= 0 && precision <= 2, "conv1d_create: bad precision");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    std::unique_ptr<alcm_conv1d> c(new alcm_conv1d());
+    c->ctx = ctx; c->prec = precision; c->Cin = Cin; c->Cout = Cout;
+    c->env.cx = ctx; c->env.k = Knobs::from_env();
+    c->war.guard = c->env.k.guard != 0;
+    c->L = prepare_conv(c->war, c->env.k, precision, KIND_CONV, w, bias, Cout, Cin, K, dilation);
+    *out = c.release();
+  });
+}
+void alcm_conv1d_destroy(alcm_conv1d* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  wait_plans(c->plans, c->pcache);
+  delete c;
+}
+int alcm_conv1d_run(alcm_conv1d* c, const float* x, const float* res, float* y, int B, int T, void* stream) {
+  return guarded([&] {
+    REQUIRE(c && x && y, "conv1d_run: NULL argument");
+    REQUIRE(B >= 1 && T >= 1, "conv1d_run: B and T must be positive");
+    CUDA_CHECK(cudaSetDevice(c->ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto key = std::make_tuple(B, T, res ? 1 : 0);
+    auto it = c->plans.find(key);
+    ConvRunPlan* P = nullptr;
+    if (it != c->plans.end()) {
+      P = it->second.get();
+    } else {
+      c->pcache.make_room(c->plans, (size_t)c->env.k.max_plans, st);
+      const bool has_res = res != nullptr;
+      std::unique_ptr<ConvRunPlan> pl = build_plan<ConvRunPlan>(c->env, &c->war, &c->retiled, B, T, st, false, nullptr, [&](ConvRunPlan& R) {
+        R.x_in = make_planes(R.ar, B, c->Cin, T, opnd_esz(c->prec));
+        R.out = make_planes(R.ar, B, c->Cout, T, 4);
+        if (has_res) R.res_in = make_planes(R.ar, B, c->Cout, T, 4);
+        R.ol.conv(c->L, R.x_in, R.out, has_res ? &R.res_in : nullptr);
+        R.Tout = T;
+      });
+      P = pl.get();
+      c->plans[key] = std::move(pl);
+    }
+    P->stamp = ++c->ctx->plan_clock;
+    PlanUse use(P, st);
+    launch_pack(x, P->x_in, c->Cin, T, 1.f, c->prec, st);
+    if (res) launch_pack(res, P->res_in, c->Cout, T, 1.f, ALCM_PREC_FP32, st);
+    if (P->ge.exec) CUDA_CHECK(cudaGraphLaunch(P->ge.exec, st));
+    else P->ol.run(st);
+    launch_unpack(P->out, y, c->Cout, T, st);
+    CUDA_CHECK(cudaGetLastError());
+    use.finish();
   });
 }
 

@@ -465,62 +465,74 @@ def longform(pipe, device, world, rank, steps, barrier, precision):
 
 def config5(pipe, device, precision, prompts=256, chunk=64):
     """BASELINE.json configs[4]: AudioLCMBatchInfer-shaped run - `prompts` text contexts (stubbed: random
-    [B,154,1024], the text encoders need absent checkpoints), 2-step LCM sampling with the reference's sampler and
-    ConcatDiT2MLP denoiser in eager PyTorch (baseline/lcm_denoiser_port.py - the reference Python cannot travel to
-    this box; the port is pinned to it by tests/golden/lcm_denoiser.npz), then the new batched decode
-    (GenSamplesBatched: 16-bit PCM packed on the GPU, pinned double-buffered copies, WAV files written)."""
+    [B,154,1024], the text encoders need absent checkpoints), 2-step LCM sampling, then the new batched decode
+    (GenSamplesBatched: 16-bit PCM packed on the GPU, pinned double-buffered copies, WAV files written).  Two denoisers:
+      reference  the reference's sampler and ConcatDiT2MLP in eager PyTorch (baseline/lcm_denoiser_port.py - the reference
+                 Python cannot travel to this box; the port is pinned to it by tests/golden/lcm_denoiser.npz): the
+                 configuration BASELINE.json names ("denoiser left as reference PyTorch");
+      hybrid     SURVEY 8f row 2: the DiT's 9-tap feed-forward convs (93 % of its FLOPs) on conv_umma_kernel and the
+                 sampler step as one kernel (audiolcm_b200/denoiser.py), the rest of the DiT still PyTorch."""
     import shutil
     import tempfile
     import torch
     from audiolcm_b200 import GenSamplesBatched
-    from baseline.lcm_denoiser_port import PortedDenoiser
-    den = PortedDenoiser(device=device, seed=7)
+    from audiolcm_b200.denoiser import ConcatDiT2MLPB200, LCMSamplerB200
+    from baseline.lcm_denoiser_port import PortedDenoiser, dit_state_dict
     g = torch.Generator(device=device).manual_seed(5)
     cond = torch.randn(prompts, 154, 1024, generator=g, device=device)
-    out = tempfile.mkdtemp(prefix="alcm_cfg5_")
-    t_den = [0.0]
-
-    def sample_fn(c):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        zs = []
-        for s in range(0, c.shape[0], 128):        # bound the eager DiT's activation memory
-            zs.append(den.sample(c[s:s + 128], T=T_LAT, steps=2, guidance_scale=5.0))
-        z = torch.cat(zs, dim=0)
-        z = torch.nan_to_num(z).clamp_(-4.0, 4.0)  # random-init denoiser: keep the latents in the trained range
-        e1.record()
-        e1.synchronize()
-        t_den[0] = e0.elapsed_time(e1)
-        return z
-
-    gen = GenSamplesBatched(sample_fn, pipe, out, save_wav=True, chunk=chunk)
     names = [f"prompt{i:03d}" for i in range(prompts)]
-    try:
-        pipe.plan(chunk, T_LAT)
-        gen.gen_test_samples(cond[:chunk], names[:chunk])            # warm-up (plans, pinned buffers, cuDNN autotune)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        recs = gen.gen_test_samples(cond, names)
-        total = time.perf_counter() - t0
-        den_ms = t_den[0]                                             # CUDA-event time of the sampler inside the timed run
-        z = sample_fn(cond[:chunk])
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        pipe.decode_pcm16_tensor(z)
-        e1.record()
-        e1.synchronize()
-        dec_ms = e0.elapsed_time(e1) * (prompts / chunk)
-        nbytes = sum(os.path.getsize(r["audio_path"]) for r in recs)
-    finally:
-        shutil.rmtree(out, ignore_errors=True)
+    dsd = dit_state_dict(seed=7)
     asec = audio_seconds(prompts, T_LAT)
-    return dict(workload=f"configs[4]: {prompts} prompts, 2-step LCM sampling (reference sampler + ConcatDiT2MLP in eager PyTorch, stubbed "
-                         f"text context [B,154,1024]) -> new batched decode ({precision}) -> {prompts} WAV files",
-                value=round(asec / total, 1), unit="audio-s/s", wall_s=round(total, 3), denoiser_ms=round(den_ms, 1),
-                decode_device_ms=round(dec_ms, 1), rest_ms=round(1e3 * total - den_ms - dec_ms, 1),
-                wav_bytes_written=nbytes, decode_share=round(dec_ms / (1e3 * total), 3),
-                note="denoiser_ms: CUDA-event time of the 2-step sampler for all prompts inside the timed run; decode_device_ms: CUDA-event "
-                     "time of one 64-clip decode x 4 measured right after; rest = device->host copies, WAV writing, Python")
+    out_rec = {}
+    for tag in ("reference", "hybrid"):
+        if tag == "reference":
+            den = PortedDenoiser(dsd, device=device)
+            sample = lambda c: den.sample(c, T=T_LAT, steps=2, guidance_scale=5.0)
+        else:
+            smp = LCMSamplerB200(ConcatDiT2MLPB200(dsd, device, precision))
+            sample = lambda c: smp.sample(c, T=T_LAT, steps=2, guidance_scale=5.0)
+        t_den = [0.0]
+
+        def sample_fn(c):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            z = torch.cat([sample(c[s:s + 128]) for s in range(0, c.shape[0], 128)], dim=0)   # bound the DiT's activation memory
+            z = torch.nan_to_num(z).clamp_(-4.0, 4.0)  # random-init denoiser: keep the latents in the trained range
+            e1.record()
+            e1.synchronize()
+            t_den[0] = e0.elapsed_time(e1)
+            return z
+
+        out = tempfile.mkdtemp(prefix="alcm_cfg5_")
+        gen = GenSamplesBatched(sample_fn, pipe, out, save_wav=True, chunk=chunk)
+        try:
+            pipe.plan(chunk, T_LAT)
+            gen.gen_test_samples(cond, names)                              # warm-up (plans, pinned buffers, cuDNN autotune)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            recs = gen.gen_test_samples(cond, names)
+            total = time.perf_counter() - t0
+            den_ms = t_den[0]                                             # CUDA-event time of the sampler inside the timed run
+            z = sample_fn(cond[:chunk])
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pipe.decode_pcm16_tensor(z)
+            e1.record()
+            e1.synchronize()
+            dec_ms = e0.elapsed_time(e1) * (prompts / chunk)
+            nbytes = sum(os.path.getsize(r["audio_path"]) for r in recs)
+        finally:
+            shutil.rmtree(out, ignore_errors=True)
+        out_rec[tag] = dict(value=round(asec / total, 1), unit="audio-s/s", wall_s=round(total, 3), denoiser_ms=round(den_ms, 1),
+                            decode_device_ms=round(dec_ms, 1), rest_ms=round(1e3 * total - den_ms - dec_ms, 1), wav_bytes_written=nbytes)
+        del gen
+        torch.cuda.empty_cache()
+    return dict(workload=f"configs[4]: {prompts} prompts, 2-step LCM sampling (stubbed text context [B,154,1024]) -> new batched decode ({precision}) "
+                         f"-> {prompts} WAV files", denoiser_reference_pytorch=out_rec["reference"], denoiser_hybrid_b200_ffn=out_rec["hybrid"],
+                value=out_rec["reference"]["value"], unit="audio-s/s",
+                note="value = the configuration BASELINE.json names (denoiser left as reference PyTorch); denoiser_ms: CUDA-event time of the 2-step "
+                     "sampler for all prompts inside the timed run; decode_device_ms: CUDA-event time of one 64-clip decode x 4 measured right after; "
+                     "rest = device->host copies, WAV writing, Python")
 
 
 def run_gpu(args):

@@ -42,6 +42,7 @@ extern "C" {
 typedef struct alcm_ctx alcm_ctx;
 typedef struct alcm_vocoder alcm_vocoder;
 typedef struct alcm_vae alcm_vae;
+typedef struct alcm_conv1d alcm_conv1d;
 
 /* arithmetic used by the conv GEMMs */
 enum {
@@ -146,6 +147,16 @@ int alcm_decode_to_pcm16(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B
 int alcm_lcm_step(alcm_ctx* ctx, const float* sample, const float* eps, const float* noise, float* prev, float* denoised, long long n,
                   float sqrt_alpha_prod_t, float sqrt_beta_prod_t, float c_out, float c_skip, float sqrt_alpha_prod_prev,
                   float sqrt_beta_prod_prev, int last_step, void* stream);
+
+/* ---- a Conv1d layer as a persistent handle: weights packed once, one plan per (B,T) shape.  Used for the 9-tap
+ * Conv1dFeedForward convs of the DiT denoiser (ldm/modules/new_attention.py:48-74; ConcatDiT2MLP blocks,
+ * concatDiT.py:108-130), 93 % of the denoiser's FLOPs.  w [Cout,Cin,K] and bias [Cout] are device fp32; padding is
+ * (K*dilation-dilation)/2, K odd <= 11.  x [B,Cin,T], res (may be NULL) and y [B,Cout,T] are device fp32:
+ * y = conv(x) + bias (+ res). */
+int alcm_conv1d_create(alcm_ctx* ctx, const float* w, const float* bias, int Cout, int Cin, int K, int dilation, int precision,
+                       alcm_conv1d** out);
+void alcm_conv1d_destroy(alcm_conv1d* c);
+int alcm_conv1d_run(alcm_conv1d* c, const float* x, const float* res, float* y, int B, int T, void* stream);
 
 /* ---- single-op entry points (tests / micro-benchmarks); tensors are [B,C,T] fp32 on device -----*/
 /* Activation1d(SnakeBeta logscale): act.py:23-28.  precision BF16 returns bf16-rounded values. */

@@ -241,3 +241,54 @@ def test_lcm_step_matches_reference_golden(ops, golden_dir):
     pref = float(k["a_prev_sqrt"]) * dref + float(k["b_prev_sqrt"]) * z.double()
     assert float((d.double() - dref).abs().max()) <= 1e-5 * float(dref.abs().max())
     assert float((prev.double() - pref).abs().max()) <= 1e-5 * float(pref.abs().max())
+
+
+# ----------------------------------------------------------------------------------- DiT feed-forward convs
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_conv1d_layer_handle(precision):
+    """alcm_conv1d_* (persistent layer: weights packed once, a plan per (B,T)) on the DiT's feed-forward shape (k = 9)."""
+    from audiolcm_b200.denoiser import Conv1dLayer
+    Cin, Cout, K = 576, 1152, 9
+    w = _rand(Cout, Cin, K, seed=70, scale=1.0 / np.sqrt(Cin * K))
+    b = _rand(Cout, seed=71, scale=0.1)
+    layer = Conv1dLayer(w, b, 1, DEV, precision)
+    wr = round_operand(w, precision).double()
+    for (B, T, with_res) in ((2, 467, False), (1, 50, True), (2, 467, True), (3, 129, False), (2, 467, False)):
+        x = _rand(B, Cin, T, seed=72 + T)
+        res = _rand(B, Cout, T, seed=73) if with_res else None
+        ref = F.conv1d(round_operand(x, precision).double(), wr, b.double(), padding=4)
+        if with_res:
+            ref = ref + res.double()
+        y = layer(x.to(DEV), None if res is None else res.to(DEV)).cpu()
+        assert float((y.double() - ref).abs().max()) < 3e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_hybrid_dit_and_sampler_match_reference_golden(golden_dir, precision):
+    """ConcatDiT2MLPB200 (feed-forward convs on conv_umma_kernel, the rest PyTorch) and LCMSamplerB200 (fused step kernel)
+    against tests/golden/lcm_denoiser.npz = outputs of the REAL ConcatDiT2MLP / LCMSampler.lcm_sampling on CPU."""
+    from baseline import lcm_denoiser_port as P
+    from audiolcm_b200.denoiser import ConcatDiT2MLPB200, LCMSamplerB200
+    g = np.load(os.path.join(golden_dir, "lcm_denoiser.npz"))
+    dit = ConcatDiT2MLPB200(P.dit_state_dict(seed=int(g["wseed"])), DEV, precision)
+    x, ctx, t = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["ctx"]).to(DEV), torch.from_numpy(g["t"]).to(DEV)
+    w_emb = LCMSamplerB200.guidance_embedding(torch.tensor(4.0).repeat(x.shape[0])).to(DEV)
+    eps = dit(x, t, ctx, w_emb).cpu().numpy()
+    tol = {"tf32": 3e-3, "bf16": 3e-2}[precision]
+    err = np.abs(eps - g["eps"]).max() / np.abs(g["eps"]).max()
+    print(f"\n[hybrid DiT {precision}] eps max-abs error relative to abs-max: {err:.2e}")
+    assert err <= tol
+    smp = LCMSamplerB200(dit)
+    assert smp.timesteps(2) == [int(v) for v in g["timesteps"]]
+    torch.manual_seed(int(g["noise_seed"]))
+    noise = torch.randn(x.shape)                      # the golden drew its step noise on the CPU generator
+    import audiolcm_b200.denoiser as D
+    real_randn = torch.randn
+    try:
+        D.torch.randn = lambda *a, **k: noise.to(DEV)   # same draw as the reference run
+        den = smp.sample(ctx, T=x.shape[-1], steps=2, guidance_scale=5.0, x_T=x)
+    finally:
+        D.torch.randn = real_randn
+    errd = np.abs(den.cpu().numpy() - g["denoised"]).max() / np.abs(g["denoised"]).max()
+    print(f"[hybrid sampler {precision}] denoised max-abs error relative to abs-max: {errd:.2e}")
+    assert errd <= 4 * tol
