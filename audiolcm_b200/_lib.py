@@ -84,7 +84,7 @@ SYMBOLS = {
     "alcm_conv_transpose1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_upsample_conv3_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_groupnorm_swish_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P]),
-    "alcm_attn1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, _P]),
+    "alcm_attn1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_profile_decode": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Profile), _P]),
     "alcm_profile_stages": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(Profile), C.c_int, _P]),
     "alcm_bench_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),

@@ -43,6 +43,7 @@ struct ConvArgs {
                       // memory: w_stages == number of tap groups, loaded by the CTA's first tile only
   uint32_t idesc;
   unsigned long long w_phase_stride;  // bytes between phases in w
+  unsigned long long w_batch_stride;  // bytes between batch items in w (0: one weight set for all; > 0: per-item operands, e.g. attention K / V)
   float scale;
   int accum;
   int dbg;  // micro-benchmark only: bit0 skip weight copies, bit1 skip activation copies (results are garbage)
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(192, MINB) conv_umma_kernel(const __grid_const
       const ConvTile T = conv_tile(a, tile);
       const int row0 = T.q0 + a.min_off[T.ph] + a.xg.pad;  // >= 0: |min_off| <= pad
       const int nrows = min(rowsA, a.xg.Tp - row0);
-      const uint8_t* wsrc = a.w + (size_t)T.ph * a.w_phase_stride + ((size_t)T.nt * a.nkb + T.kb0) * ntaps * L.w_blob;
+      const uint8_t* wsrc = a.w + (size_t)T.b * a.w_batch_stride + (size_t)T.ph * a.w_phase_stride + ((size_t)T.nt * a.nkb + T.kb0) * ntaps * L.w_blob;
       const uint8_t* xsrc = a.x + (((size_t)T.b * a.xg.nchunk + (size_t)T.kb0 * a.kblk) * a.xg.Tp + row0) * 16;
       const uint32_t a_bytes = (uint32_t)nrows * 16;
       // one weight stage (a group of taps): wait for the slot, arm the barrier, one bulk copy

@@ -69,7 +69,7 @@ static int env_int(const char* name, int dflt) {
 struct Knobs {
   int pdl, graph, lanes, lane_waves, persist, cluster_splitk, splitk, retile, retile_mode;
   int smem_budget, smem_budget_1w, smem_budget_mw, tpg, astages, kblk_max, nt, tmem2;
-  int act_variant, w_resident, gn_fused, max_plans, trace, guard, nt192;
+  int act_variant, w_resident, attn_tc, gn_fused, max_plans, trace, guard, nt192;
   static Knobs from_env() {
     Knobs k;
     k.pdl = env_int("ALCM_PDL", -1);  // -1 unset (per-plan default), 0 never, 1 always
@@ -91,6 +91,7 @@ struct Knobs {
     k.tmem2 = env_int("ALCM_TMEM2", 0);
     k.act_variant = env_int("ALCM_ACT_VARIANT", -1);
     k.w_resident = env_int("ALCM_W_RESIDENT", 1);         // persistent narrow-stage convs keep all their weights in shared memory
+    k.attn_tc = env_int("ALCM_ATTN_TC", 1);               // attention GEMMs on conv_umma_kernel (0: CUDA-core kernels)
     k.gn_fused = env_int("ALCM_GN_FUSED", 1);
     k.max_plans = std::max(1, env_int("ALCM_MAX_PLANS", 16));
     k.trace = env_int("ALCM_TRACE", 0);
@@ -280,7 +281,48 @@ struct ConvLayer {
   int NT = 0, n_tiles = 0, kchunks = 0, kblk = 0, nkb = 0, tmem_cols = 0, w_stages = 0;
   uint32_t idesc = 0, smem = 0;
   int prec = 0;
+  size_t w_batch_stride = 0;  // > 0: per-batch-item weights (dynamic_conv)
 };
+
+// Tile geometry of a tcgen05 conv layer (N tile, K chunks / blocks, TMEM columns, instruction descriptor) from its
+// channel counts, taps and arithmetic mode.
+static void conv_tiling(ConvLayer& L, const Knobs& K_) {
+  const int prec = L.prec, Cout = L.Cout, Cin = L.Cin;
+  const int E = (prec == ALCM_PREC_BF16) ? 8 : 4;
+  const int cout_pad = round_up(Cout, 16);
+  int nt_pref = K_.nt;
+  if (cout_pad == 192 && K_.nt192 > 0 && 192 % K_.nt192 == 0) nt_pref = K_.nt192 < 192 ? K_.nt192 : nt_pref;
+  if (cout_pad <= 256 && (cout_pad <= nt_pref || cout_pad % nt_pref != 0)) L.NT = cout_pad;
+  else L.NT = nt_pref;
+  REQUIRE(L.NT % 16 == 0 && L.NT >= 16 && L.NT <= 256, "bad N tile");
+  L.n_tiles = (cout_pad + L.NT - 1) / L.NT;
+  L.tmem_cols = 32;
+  while (L.tmem_cols < L.NT * (K_.tmem2 ? 2 : 1)) L.tmem_cols *= 2;
+  L.kchunks = round_up(Cin, 16) / E;
+  L.kblk = 0;
+  if (L.kchunks <= 12) L.kblk = L.kchunks;
+  else for (int d = std::min(12, K_.kblk_max); d >= 2; d -= 2) if (L.kchunks % d == 0) { L.kblk = d; break; }
+  REQUIRE(L.kblk >= 2 && L.kblk % 2 == 0 && L.kblk <= 12, "bad k-block");
+  L.nkb = L.kchunks / L.kblk;
+  L.idesc = umma_idesc(prec == ALCM_PREC_BF16 ? 1 : 2, L.NT);
+  L.w_stages = 0;  // chosen per launch (pick_pipeline)
+  L.smem = 0;
+  L.phase_stride = (size_t)L.n_tiles * L.nkb * L.ntaps * L.kblk * L.NT * 16;
+}
+
+// A 1x1 "conv" whose weights are a per-batch-item operand written by pack_dyn_w_kernel at run time (attention): only the
+// geometry is fixed here; wpack points into the plan's slab, w_batch_stride separates the items.
+static ConvLayer dynamic_conv(const Knobs& K_, int prec, int Cout, int Cin) {
+  ConvLayer L;
+  L.Cin = Cin; L.Cout = Cout; L.prec = prec;
+  L.nphase = 1; L.ntaps = 1;
+  memset(L.tap_off, 0, sizeof(L.tap_off));
+  memset(L.min_off, 0, sizeof(L.min_off));
+  L.span = 0;
+  conv_tiling(L, K_);
+  L.w_batch_stride = L.phase_stride;
+  return L;
+}
 
 // w: folded weight on device (Conv1d [Cout,Cin,K] or ConvTranspose1d [Cin,Cout,K]); bias may be null
 static ConvLayer prepare_conv(Arena& ar, const Knobs& K_, int prec, ConvKind kind, const float* w, const float* bias, int Cout, int Cin, int K,
@@ -339,25 +381,7 @@ static ConvLayer prepare_conv(Arena& ar, const Knobs& K_, int prec, ConvKind kin
     return L;
   }
   const int E = (prec == ALCM_PREC_BF16) ? 8 : 4;
-  const int cout_pad = round_up(Cout, 16);
-  int nt_pref = K_.nt;
-  if (cout_pad == 192 && K_.nt192 > 0 && 192 % K_.nt192 == 0) nt_pref = K_.nt192 < 192 ? K_.nt192 : nt_pref;
-  if (cout_pad <= 256 && (cout_pad <= nt_pref || cout_pad % nt_pref != 0)) L.NT = cout_pad;
-  else L.NT = nt_pref;
-  REQUIRE(L.NT % 16 == 0 && L.NT >= 16 && L.NT <= 256, "bad N tile");
-  L.n_tiles = (cout_pad + L.NT - 1) / L.NT;
-  L.tmem_cols = 32;
-  while (L.tmem_cols < L.NT * (K_.tmem2 ? 2 : 1)) L.tmem_cols *= 2;
-  L.kchunks = round_up(Cin, 16) / E;
-  L.kblk = 0;
-  if (L.kchunks <= 12) L.kblk = L.kchunks;
-  else for (int d = std::min(12, K_.kblk_max); d >= 2; d -= 2) if (L.kchunks % d == 0) { L.kblk = d; break; }
-  REQUIRE(L.kblk >= 2 && L.kblk % 2 == 0 && L.kblk <= 12, "bad k-block");
-  L.nkb = L.kchunks / L.kblk;
-  L.idesc = umma_idesc(prec == ALCM_PREC_BF16 ? 1 : 2, L.NT);
-  L.w_stages = 0;  // chosen per launch (pick_stages)
-  L.smem = 0;
-  L.phase_stride = (size_t)L.n_tiles * L.nkb * L.ntaps * L.kblk * L.NT * 16;
+  conv_tiling(L, K_);
   L.wpack = static_cast<uint8_t*>(ar.alloc(L.phase_stride * L.nphase, false));
   const size_t units = L.phase_stride * L.nphase / 16;
   const unsigned blocks = (unsigned)std::min<size_t>((units + 255) / 256, 8192);
@@ -620,7 +644,7 @@ static ConvLaunch plan_conv(const Env& env, const ConvLayer& L, const PlaneT& x,
   a.w = L.wpack;
   a.kchunks = L.kchunks; a.kblk = L.kblk; a.nkb = L.nkb;
   a.NT = L.NT; a.n_tiles = L.n_tiles; a.tmem_cols = L.tmem_cols;
-  a.idesc = L.idesc; a.w_phase_stride = L.phase_stride;
+  a.idesc = L.idesc; a.w_phase_stride = L.phase_stride; a.w_batch_stride = L.w_batch_stride;
   a.ksplit = sk.ksplit; a.ws = sk.ws; a.tile_ctr = sk.ctr; a.cluster_splitk = sk.cluster;
   // K chunks that exist in memory (plane_cpad): the others are an all-zero shared-memory slab
   REQUIRE(x.g.nchunk >= L.kchunks || L.nkb == 1, "conv: operand planes narrower than K need a single k-block");
@@ -654,7 +678,7 @@ static ConvLaunch plan_conv(const Env& env, const ConvLayer& L, const PlaneT& x,
   // launch is bound by L2 -> SM bandwidth (ncu launch list, profiles/r2_launches_bf16_b64.txt: same HBM bytes, k = 11
   // takes 20 % longer than k = 3).  When every tap of the (single) N tile fits beside the A ring, a persistent CTA loads
   // them once and keeps them for all its tiles.
-  if (env.k.w_resident && a.acc_stages == 2 && L.n_tiles == 1 && L.nkb == 1 && L.nphase == 1) {
+  if (env.k.w_resident && a.acc_stages == 2 && L.n_tiles == 1 && L.nkb == 1 && L.nphase == 1 && L.w_batch_stride == 0) {
     const int groups = (L.ntaps + a.tpg - 1) / a.tpg;
     const uint32_t smem_r = conv_smem_layout(L.kblk, L.span, L.NT, groups, a.tpg, a.a_stages).total;
     if (groups <= 12 && smem_r + 1024u <= (227u * 1024u) / 2u) {
@@ -684,8 +708,9 @@ struct OpList {
   void conv(const ConvLayer& L0, const PlaneT& x, const PlaneT& out, const PlaneT* res, float scale = 1.f, int accum = 0) {
     const int M = x.T;  // rows per batch item are input time steps (== output steps / nphase)
     int nt_c = 0, ks_c = 1;
-    const bool clustered = war && cache && ar && choose_cluster_tile(env, L0, M, x.B, &nt_c, &ks_c);
-    const ConvLayer& L = (war && cache) ? retile(*war, *cache, L0, clustered ? nt_c : pick_nt(env, L0, M, x.B)) : L0;
+    const bool dyn = L0.w_batch_stride != 0;   // per-item weights: packed for exactly this tiling, one K pass
+    const bool clustered = !dyn && war && cache && ar && choose_cluster_tile(env, L0, M, x.B, &nt_c, &ks_c);
+    const ConvLayer& L = (!dyn && war && cache) ? retile(*war, *cache, L0, clustered ? nt_c : pick_nt(env, L0, M, x.B)) : L0;
     REQUIRE(x.esz == opnd_esz(L.prec), "conv: operand dtype mismatch");
     REQUIRE(out.esz == 4 && out.T == x.T * L.nphase, "conv: bad output planes");
     REQUIRE(out.g.nchunk * 4 >= L.Cout, "conv: channel mismatch");
@@ -697,7 +722,7 @@ struct OpList {
     const float* rp = res ? res->f() : nullptr;
     SplitK sk;
     if (clustered) { sk.ksplit = ks_c; sk.cluster = ks_c > 1; }
-    else if (ar) sk.ksplit = pick_ksplit(env, L, M, x.B);
+    else if (ar && !dyn) sk.ksplit = pick_ksplit(env, L, M, x.B);
     if (sk.ksplit > 1 && !sk.cluster) {
       const size_t tiles = (size_t)conv_m_tiles(M) * L.n_tiles * x.B * L.nphase;
       const size_t need = tiles * sk.ksplit * (size_t)L.NT * kTileM * 4;
@@ -1279,6 +1304,53 @@ static PlaneT plane_view(const PlaneT& x, int c0, int C) {
   return v;
 }
 
+// QK^T, softmax and PV of AttnBlock1D on the tensor cores: the scores are a 1x1 conv of q whose per-item "weights" are k,
+// the output a 1x1 conv of the probabilities whose per-item weights are v (misc_kernels.cuh).  q: fp32 planes [C][T].
+static void push_attention_tc(OpList& ol, Arena& ar, const PlaneT& q, const PlaneT& k, const PlaneT& v, const PlaneT& h, int B, int C, int T,
+                              int prec) {
+  const int oe = opnd_esz(prec), rtf = prec == ALCM_PREC_TF32;
+  const float scale = 1.0f / sqrtf((float)C);  // reference unpacks (b,c,t) as (b,t,c): scale = C^-0.5
+  ConvLayer Ls = dynamic_conv(ol.env.k, prec, /*Cout=keys*/ T, /*Cin=*/C);
+  ConvLayer Lp = dynamic_conv(ol.env.k, prec, /*Cout=*/C, /*Cin=keys*/ T);
+  Ls.wpack = static_cast<uint8_t*>(ar.alloc(Ls.phase_stride * B, false));
+  Lp.wpack = static_cast<uint8_t*>(ar.alloc(Lp.phase_stride * B, false));
+  PlaneT qo = make_planes(ar, B, C, T, oe);
+  PlaneT S = make_planes(ar, B, T, T, 4);      // channels = keys, rows = queries
+  PlaneT P = make_planes(ar, B, T, T, oe);
+  auto pack = [&](const PlaneT& src, const ConvLayer& L, int mode) {
+    Op op;
+    op.cls = ALCM_CLS_ATTN; op.flops = 0; op.bytes = (double)B * C * T * (4.0 + oe);
+    const size_t units = L.phase_stride / 16;
+    const PlaneT sc = src;
+    const ConvLayer Lc = L;
+    op.fn = [=](cudaStream_t st) {
+      const dim3 grid((unsigned)std::min<size_t>((units + 255) / 256, 2048), B);
+      if (oe == 2) launch_k(pack_dyn_w_kernel<8>, grid, dim3(256), 0, st, sc.f(), sc.g, C, T, (void*)Lc.wpack, mode, Lc.NT, Lc.n_tiles, Lc.kblk, Lc.nkb, units);
+      else launch_k(pack_dyn_w_kernel<4>, grid, dim3(256), 0, st, sc.f(), sc.g, C, T, (void*)Lc.wpack, mode, Lc.NT, Lc.n_tiles, Lc.kblk, Lc.nkb, units);
+    };
+    ol.push(op);
+  };
+  ol.cast(q, qo);                     // q as operand planes (bf16 / tf32-rounded)
+  ol.ops.back().cls = ALCM_CLS_ATTN;
+  pack(k, Ls, 0);
+  pack(v, Lp, 1);
+  const size_t n0 = ol.ops.size();
+  ol.conv(Ls, qo, S, nullptr, scale);
+  {
+    Op sm;
+    sm.cls = ALCM_CLS_ATTN; sm.flops = 0; sm.bytes = (double)B * T * T * (3 * 4.0 + oe);
+    const PlaneT Sc = S, Pc = P;
+    sm.fn = [=](cudaStream_t st) {
+      const dim3 grid((T + 127) / 128, B);
+      if (oe == 2) launch_k(softmax_planes_kernel<8>, grid, dim3(128), 0, st, Sc.f(), Sc.g, (void*)Pc.p, Pc.g, T, 0);
+      else launch_k(softmax_planes_kernel<4>, grid, dim3(128), 0, st, Sc.f(), Sc.g, (void*)Pc.p, Pc.g, T, rtf);
+    };
+    ol.push(sm);
+  }
+  ol.conv(Lp, P, h, nullptr);
+  for (size_t i = n0; i < ol.ops.size(); ++i) ol.ops[i].cls = ALCM_CLS_ATTN;   // the two GEMMs count as attention, not conv
+}
+
 static PlaneT op_attn(OpList& ol, Arena& ar, const AttnBlk& at, const PlaneT& x, int prec) {  // autoencoder1d.py:257-278
   const int oe = opnd_esz(prec), B = x.B, C = at.C, T = x.T;
   PlaneT hn = make_planes(ar, B, C, T, oe);
@@ -1286,11 +1358,15 @@ static PlaneT op_attn(OpList& ol, Arena& ar, const AttnBlk& at, const PlaneT& x,
   PlaneT qkv = make_planes(ar, B, 3 * C, T, 4);
   ol.conv(at.qkv, hn, qkv, nullptr);
   const PlaneT q = plane_view(qkv, 0, C), k = plane_view(qkv, C, C), v = plane_view(qkv, 2 * C, C);
-  REQUIRE((size_t)T * 4 <= 200 * 1024, "attention: sequence too long for the row-softmax kernel");
-  float* Sp = static_cast<float*>(ar.alloc((size_t)kAttnSplit * B * T * T * 4, false));
-  float* Pm = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
   PlaneT h = make_planes(ar, B, C, T, 4);
-  push_attention(ol, q, k, v, h, Sp, Pm, B, C, T);
+  if (prec != ALCM_PREC_FP32 && ol.env.k.attn_tc) {
+    push_attention_tc(ol, ar, q, k, v, h, B, C, T, prec);
+  } else {
+    REQUIRE((size_t)T * 4 <= 200 * 1024, "attention: sequence too long for the row-softmax kernel");
+    float* Sp = static_cast<float*>(ar.alloc((size_t)kAttnSplit * B * T * T * 4, false));
+    float* Pm = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
+    push_attention(ol, q, k, v, h, Sp, Pm, B, C, T);
+  }
   PlaneT out = make_planes(ar, B, C, T, 4);
   ol.conv(at.proj, as_operand(ol, ar, h, prec), out, &x);
   return out;
@@ -1901,26 +1977,32 @@ int alcm_groupnorm_swish_fwd(alcm_ctx* ctx, const float* x, const float* gamma, 
   });
 }
 
-int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* v, float* out, int B, int C, int T, void* stream) {
+int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* v, float* out, int B, int C, int T, int precision,
+                    void* stream) {
   return guarded([&] {
     REQUIRE(ctx && q && k && v && out, "attn: NULL argument");
     REQUIRE(B >= 1 && C >= 1 && T >= 1, "attn: empty tensor");
+    REQUIRE(precision >= 0 && precision <= 2, "attn: bad precision");
     CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar;
     ar.guard = env_int("ALCM_GUARD", 0) != 0;
     PlaneT pq = make_planes(ar, B, C, T, 4), pk = make_planes(ar, B, C, T, 4), pv = make_planes(ar, B, C, T, 4);
     PlaneT ph = make_planes(ar, B, C, T, 4);
+    OpList ol;
+    ol.env = Env{ctx, Knobs::from_env()};
+    ol.ar = &ar;
+    if (precision != ALCM_PREC_FP32 && ol.env.k.attn_tc) {
+      push_attention_tc(ol, ar, pq, pk, pv, ph, B, C, T, precision);
+    } else {
+      float* Pm = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
+      float* Sp = static_cast<float*>(ar.alloc((size_t)kAttnSplit * B * T * T * 4, false));
+      push_attention(ol, pq, pk, pv, ph, Sp, Pm, B, C, T);
+    }
     CUDA_CHECK(sync_setup());
     launch_pack(q, pq, C, T, 1.f, ALCM_PREC_FP32, st);
     launch_pack(k, pk, C, T, 1.f, ALCM_PREC_FP32, st);
     launch_pack(v, pv, C, T, 1.f, ALCM_PREC_FP32, st);
-    OpList ol;
-    ol.env = Env{ctx, Knobs::from_env()};
-    float* Pm = static_cast<float*>(ar.alloc((size_t)B * T * T * 4, false));
-    float* Sp = static_cast<float*>(ar.alloc((size_t)kAttnSplit * B * T * T * 4, false));
-    push_attention(ol, pq, pk, pv, ph, Sp, Pm, B, C, T);
-    CUDA_CHECK(sync_setup());
     ol.run(st);
     launch_unpack(ph, out, C, T, st);
     CUDA_CHECK(cudaGetLastError());

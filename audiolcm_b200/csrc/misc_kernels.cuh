@@ -284,6 +284,106 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg,
   else reinterpret_cast<float*>(wav)[(size_t)b * T + t] = y;
 }
 
+// ------------------------------------------------------------------------------- attention on the tensor cores
+// AttnBlock1D (autoencoder1d.py:257-278) as two conv_umma_kernel launches with PER-ITEM "weights":
+//   S[i][j] = C^-0.5 * sum_c q[c][i] k[c][j]   = a 1x1 conv over queries i whose output channels are the keys j,  W[j][c] = k[c][j]
+//   h[c][i] = sum_j P[i][j] v[c][j]            = a 1x1 conv over queries i whose input channels are the keys j,   W[c][j] = v[c][j]
+// pack_dyn_w_kernel writes such a per-item B operand (the same blob layout as pack_w_kernel, one tap) from fp32 planes:
+//   mode 0: W[n][k] = src[b][channel k][time n]   (K of QK^T: n = key, k = channel)
+//   mode 1: W[n][k] = src[b][channel n][time k]   (V of PV:   n = channel, k = key)
+template <int E>
+__global__ void pack_dyn_w_kernel(const float* __restrict__ src, PlaneGeom sg, int C, int T, void* __restrict__ dst, int mode, int NT,
+                                  int n_tiles, int kblk, int nkb, size_t units_per_item) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int N = mode == 0 ? T : C, Kd = mode == 0 ? C : T;
+  for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < units_per_item; u += (size_t)gridDim.x * blockDim.x) {
+    size_t r = u;
+    const int n = r % NT; r /= NT;
+    const int kc = r % kblk; r /= kblk;
+    const int kb = r % nkb; r /= nkb;
+    const int nt = (int)r;
+    const int co = nt * NT + n;
+    float v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int ci = (kb * kblk + kc) * E + e;
+      float x = 0.f;
+      if (co < N && ci < Kd) {
+        const int ch = mode == 0 ? ci : co, t = mode == 0 ? co : ci;
+        x = *(reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(src) + plane_row_off(sg, b, ch >> 2, t)) + (ch & 3));
+      }
+      v[e] = x;
+    }
+    uint8_t* d = reinterpret_cast<uint8_t*>(dst) + ((size_t)b * units_per_item + u) * 16;
+    if (E == 4) {
+      *reinterpret_cast<float4*>(d) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
+    } else {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
+      *reinterpret_cast<uint4*>(d) = o;
+    }
+  }
+}
+
+// P = softmax over the keys (channels j < T) of the score planes S[b][j/4][i][4] (row = query i), written as operand planes
+// P[b][j/E][i][E] for the PV conv; channels j >= T (padding) are written as zeros.  One thread per query.
+template <int E>
+__global__ void softmax_planes_kernel(const float* __restrict__ S, PlaneGeom sg, void* __restrict__ P, PlaneGeom pg, int T, int rtf32) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= T) return;
+  const int nc = (T + 3) >> 2;
+  auto ld = [&](int c) { return *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(S) + plane_row_off(sg, b, c, i)); };
+  float m = -INFINITY;
+  for (int c = 0; c < nc; ++c) {
+    const float4 v = ld(c);
+    const int j = 4 * c;
+    m = fmaxf(m, v.x);
+    if (j + 1 < T) m = fmaxf(m, v.y);
+    if (j + 2 < T) m = fmaxf(m, v.z);
+    if (j + 3 < T) m = fmaxf(m, v.w);
+  }
+  float sum = 0.f;
+  for (int c = 0; c < nc; ++c) {
+    const float4 v = ld(c);
+    const int j = 4 * c;
+    sum += expf(v.x - m);
+    if (j + 1 < T) sum += expf(v.y - m);
+    if (j + 2 < T) sum += expf(v.z - m);
+    if (j + 3 < T) sum += expf(v.w - m);
+  }
+  const float inv = 1.f / sum;
+  for (int pc = 0; pc < pg.nchunk; ++pc) {
+    float o[E];
+#pragma unroll
+    for (int h = 0; h < E / 4; ++h) {
+      const int c = pc * (E / 4) + h;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < nc) v = ld(c);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[4 * h + e] = (4 * c + e < T) ? expf(vv[e] - m) * inv : 0.f;
+    }
+    uint8_t* d = reinterpret_cast<uint8_t*>(P) + plane_row_off(pg, b, pc, i);
+    if (E == 4) {
+      if (rtf32) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) o[e] = round_tf32(o[e]);
+      }
+      *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+      uint4 w;
+      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+      w.z = pack_bf16x2(o[4 % E], o[5 % E]); w.w = pack_bf16x2(o[6 % E], o[7 % E]);
+      *reinterpret_cast<uint4*>(d) = w;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- LCM sampler step
 // LCMSampler.step (ldm/models/diffusion/scheduling_lcm.py:411-494), epsilon prediction, as ONE elementwise pass:
 //   x0       = (sample - sqrt(1-abar_t) * eps) / sqrt(abar_t)                      (:455-456)

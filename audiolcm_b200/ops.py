@@ -85,13 +85,13 @@ def groupnorm_swish(x, gamma, beta, swish=True, groups=32, eps=1e-6):
     return y
 
 
-def attn1d(q, k, v):
+def attn1d(q, k, v, precision="fp32"):
     """softmax_j(q^T k C^-0.5) applied to v - ldm/models/autoencoder1d.py:264-275."""
     (q, k, v), dev = _prep(q, k, v)
     B, C, T = q.shape
     out = torch.empty_like(q)
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().alcm_attn1d_fwd(_lib.ctx(dev.index), _p(q), _p(k), _p(v), _p(out), B, C, T, _stream()))
+        _lib.check(_lib.load().alcm_attn1d_fwd(_lib.ctx(dev.index), _p(q), _p(k), _p(v), _p(out), B, C, T, _lib.PREC[precision], _stream()))
     return out
 
 

@@ -174,9 +174,10 @@ int alcm_upsample_conv3_fwd(alcm_ctx* ctx, const float* x, const float* w, const
 /* GroupNorm(groups, eps) [+ swish] */
 int alcm_groupnorm_swish_fwd(alcm_ctx* ctx, const float* x, const float* gamma, const float* beta, float* y, int B, int C,
                              int T, int groups, float eps, int swish, void* stream);
-/* softmax_j(q^T k * C^-0.5) applied to v: autoencoder1d.py:264-275; q,k,v,out [B,C,T] */
+/* softmax_j(q^T k * C^-0.5) applied to v: autoencoder1d.py:264-275; q,k,v,out [B,C,T].  TF32 / BF16: both GEMMs on
+ * conv_umma_kernel with per-item operands; FP32: CUDA-core kernels */
 int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* v, float* out, int B, int C, int T,
-                    void* stream);
+                    int precision, void* stream);
 
 /* ---- measurement ------------------------------------------------------------------------------
  * Kernel classes for per-class device timing. */

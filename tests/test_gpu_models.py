@@ -175,7 +175,7 @@ def test_batch64_full_size_decode_vs_oracle(precision):
 
 @pytest.mark.parametrize("knobs", [{"ALCM_LANES": "0"}, {"ALCM_ACT_VARIANT": "0"}, {"ALCM_ACT_VARIANT": "2"}, {"ALCM_NT192": "192"},
                                    {"ALCM_PERSIST": "0"}, {"ALCM_CLUSTER_SPLITK": "0"},
-                                   {"ALCM_GRAPH": "0"}, {"ALCM_PDL": "1"}])
+                                   {"ALCM_GRAPH": "0"}, {"ALCM_PDL": "1"}])   # (the VAE-side knob ALCM_ATTN_TC is covered by test_vae_attention_paths)
 def test_forced_plan_variants_match_reference(golden_dir, monkeypatch, knobs):
     """Every plan-shaping knob the batch-64 / long-form plans flip (serial AMP blocks with in-place accumulation, the other
     Activation1d block sizes, non-persistent convs, workspace split-K, eager launches, PDL), forced on a small
@@ -501,3 +501,21 @@ def test_batched_driver_writes_the_wavs_the_reference_loop_would(tmp_path):
     gen2 = GenSamplesBatched(lambda cond: zs[: cond.shape[0]], pipe, str(tmp_path / "b"), save_wav=True, chunk=64)
     pcm2, _ = gen2.decode_latents(zs)                       # one chunk, PCM packed by the conv_post kernel
     assert np.array_equal(pcm2, want)
+
+
+@pytest.mark.parametrize("attn_tc", ["0", "1"])
+def test_vae_attention_paths(golden_dir, monkeypatch, attn_tc):
+    """The VAE's mid attention on the tensor cores (default) and on the CUDA-core kernels (ALCM_ATTN_TC=0) both meet the
+    mel gates against the reference golden, full decoder, batch 1 and batch 3."""
+    monkeypatch.setenv("ALCM_ATTN_TC", attn_tc)
+    g = np.load(os.path.join(golden_dir, "vae_full_T17.npz"))
+    dd = synth.vae_config(int(g["ch"]))
+    sd = synth.vae_decoder_state_dict(dd, seed=int(g["wseed"]))
+    z = synth.synth_latent(int(g["B"]), int(g["T"]), seed=int(g["xseed"]))
+    for precision in ("tf32", "bf16"):
+        dec = _vae(dd, sd, precision)
+        got = dec.decode(torch.from_numpy(z).to(DEV)).cpu().numpy()
+        assert np.abs(got - g["mel"]).max() <= MEL_TOL[precision]
+        z3 = np.concatenate([z, z * 0.5, z * 1.5], axis=0)
+        got3 = dec.decode(torch.from_numpy(z3).to(DEV)).cpu().numpy()
+        assert np.abs(got3[: z.shape[0]] - got).max() <= MEL_TOL[precision]

@@ -147,14 +147,20 @@ def test_groupnorm_swish(ops, shape, swish):
     assert float((y.double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("shape", [(1, 1536, 312), (2, 128, 24), (1, 32, 1), (1, 64, 33)])
-def test_attn1d(ops, shape):
+@pytest.mark.parametrize("shape", [(1, 1536, 312), (2, 128, 24), (1, 32, 1), (1, 64, 33), (3, 256, 130), (1, 1536, 624)])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_attn1d(ops, shape, precision):
+    """fp32: CUDA-core kernels; tf32 / bf16: QK^T and PV on conv_umma_kernel with per-item operands.  The reference is
+    float64 on operands rounded as the device rounds them (q, k, v; the probabilities are rounded on the device too, which the
+    tolerance covers: 2^-9 relative on values <= 1 for bf16, summed with weights that add up to 1)."""
     B, C, T = shape
     q, k, v = _rand(B, C, T, seed=17), _rand(B, C, T, seed=18), _rand(B, C, T, seed=19)
-    w = torch.softmax(torch.bmm(q.double().permute(0, 2, 1), k.double()) * (C ** -0.5), dim=2)
-    ref = torch.bmm(v.double(), w.permute(0, 2, 1))
-    y = ops.attn1d(q.to(DEV), k.to(DEV), v.to(DEV)).cpu()
-    assert float((y.double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+    qr, kr, vr = (round_operand(t, precision).double() for t in (q, k, v))
+    w = torch.softmax(torch.bmm(qr.permute(0, 2, 1), kr) * (C ** -0.5), dim=2)
+    ref = torch.bmm(vr, w.permute(0, 2, 1))
+    y = ops.attn1d(q.to(DEV), k.to(DEV), v.to(DEV), precision).cpu()
+    tol = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 6e-3}[precision]
+    assert float((y.double() - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
 
 
 def test_bad_arguments_raise(ops):

@@ -63,6 +63,8 @@ def main():
     ops.groupnorm_swish(x.to(DEV), torch.ones(64, device=DEV), torch.zeros(64, device=DEV))
     q = rnd(1, 64, 33, seed=13)
     ops.attn1d(q.to(DEV), q.to(DEV), q.to(DEV))
+    ops.attn1d(q.to(DEV), q.to(DEV), q.to(DEV), "bf16")
+    ops.attn1d(rnd(2, 256, 130, seed=19).to(DEV), rnd(2, 256, 130, seed=20).to(DEV), rnd(2, 256, 130, seed=21).to(DEV), "tf32")
     print("  groupnorm, attention ok", flush=True)
     dd, h = synth.vae_config(32), synth.bigvgan_config(64)
     vsd, gsd = synth.vae_decoder_state_dict(dd, seed=1), synth.bigvgan_state_dict(h, seed=1)
