@@ -13,9 +13,9 @@ CPU, PyTorch-eager or Triton fallback: a missing library or a non-sm_100 device 
 """
 from ._lib import AlcmError, LIB_PATH  # noqa: F401
 from .vocoder import VocoderBigVGAN  # noqa: F401
-from .autoencoder import AutoencoderKLDecoder, install  # noqa: F401
+from .autoencoder import AutoencoderKLDecoder, AutoencoderKLEncoder, install  # noqa: F401
 from .pipeline import LatentToWaveform, shard_range, halo_frames  # noqa: F401
 from .infer import GenSamplesBatched, audiolcm_batch_infer, write_wav_pcm16  # noqa: F401
 
-__all__ = ["VocoderBigVGAN", "AutoencoderKLDecoder", "install", "LatentToWaveform", "shard_range", "halo_frames", "AlcmError",
+__all__ = ["VocoderBigVGAN", "AutoencoderKLDecoder", "AutoencoderKLEncoder", "install", "LatentToWaveform", "shard_range", "halo_frames", "AlcmError",
            "GenSamplesBatched", "audiolcm_batch_infer", "write_wav_pcm16"]

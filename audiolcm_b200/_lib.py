@@ -43,6 +43,21 @@ class VAECfg(C.Structure):
     ]
 
 
+class VAEEncCfg(C.Structure):
+    _fields_ = [
+        ("ch", C.c_int),
+        ("in_channels", C.c_int),
+        ("z_channels", C.c_int),
+        ("embed_dim", C.c_int),
+        ("kernel_size", C.c_int),
+        ("num_res_blocks", C.c_int),
+        ("n_levels", C.c_int),
+        ("double_z", C.c_int),
+        ("ch_mult", C.c_int * 8),
+        ("downsample_levels", C.c_int * 8),
+    ]
+
+
 class Profile(C.Structure):
     _fields_ = [
         ("ms", C.c_double * 5),
@@ -73,6 +88,10 @@ SYMBOLS = {
     "alcm_vae_decode": (C.c_int, [_P, _FP, C.c_int, C.c_int, C.c_float, _FP, _P]),
     "alcm_vae_plan": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "alcm_vae_workspace_bytes": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "alcm_vae_encoder_num_tensors": (C.c_int, [C.POINTER(VAEEncCfg)]),
+    "alcm_vae_encoder_create": (C.c_int, [_P, C.POINTER(VAEEncCfg), C.POINTER(_FP), C.c_int, C.c_int, C.POINTER(_P)]),
+    "alcm_vae_encoder_destroy": (None, [_P]),
+    "alcm_vae_encode": (C.c_int, [_P, _FP, C.c_int, C.c_int, _FP, _P]),
     "alcm_decode_to_wav": (C.c_int, [_P, _P, _FP, C.c_int, C.c_int, C.c_float, _FP, _FP, _P]),
     "alcm_decode_to_pcm16": (C.c_int, [_P, _P, _FP, C.c_int, C.c_int, C.c_float, _FP, _FP, _P]),
     "alcm_conv1d_create": (C.c_int, [_P, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),

@@ -144,6 +144,111 @@ class AutoencoderKLDecoder(object):
         return _lib.load().alcm_vae_launches(self._h, B, T)
 
 
+def vae_encoder_tensor_names(dd, prefix=""):
+    """state_dict keys in the order alcm_vae_encoder_create expects (include/audiolcm_b200.h)."""
+    ch, mult, nrb = int(dd["ch"]), [int(m) for m in dd["ch_mult"]], int(dd["num_res_blocks"])
+    wb = lambda p: [prefix + p + ".weight", prefix + p + ".bias"]
+
+    def res(p, cin, cout):
+        n = wb(p + ".norm1") + wb(p + ".conv1") + wb(p + ".norm2") + wb(p + ".conv2")
+        return n + (wb(p + ".nin_shortcut") if cin != cout else [])
+
+    names = wb("encoder.conv_in")
+    block_in = ch
+    for lv in range(len(mult)):
+        block_out = ch * mult[lv]
+        for ib in range(nrb):
+            names += res(f"encoder.down.{lv}.block.{ib}", block_in, block_out)
+            block_in = block_out
+        if lv in [int(i) for i in dd["down_layers"]]:
+            names += wb(f"encoder.down.{lv}.downsample.conv")
+    names += res("encoder.mid.block_1", block_in, block_in)
+    for n in ("norm", "q", "k", "v", "proj_out"):
+        names += wb(f"encoder.mid.attn_1.{n}")
+    names += res("encoder.mid.block_2", block_in, block_in)
+    return names + wb("encoder.norm_out") + wb("encoder.conv_out") + wb("quant_conv")
+
+
+class AutoencoderKLEncoder(object):
+    """The encode half of ``ldm.models.autoencoder1d.AutoencoderKL`` (autoencoder1d.py:52-56, Encoder1D :319-413; the call
+    site is scripts/reconstruct_audio.py:115) - SURVEY.md 8f row 4.  ``encode(x)``: (B,in_channels,T) mel ->
+    ``(mean, logvar)`` of the posterior, each (B,embed_dim,T/2^n_down) float32 CUDA tensors (logvar clamped to [-30, 20] as
+    ``DiagonalGaussianDistribution`` does); ``sample``/``mode`` follow distributions.py:24-37."""
+
+    def __init__(self, state_dict, ddconfig, embed_dim, device="cuda", precision="tf32", prefix=""):
+        if precision not in _lib.PREC:
+            raise ValueError(f"precision must be one of {sorted(_lib.PREC)}")
+        dd = {k: _get(ddconfig, k) for k in ("ch", "in_channels", "z_channels", "kernel_size", "ch_mult", "num_res_blocks", "attn_layers",
+                                              "down_layers")}
+        dd["ch_mult"] = [int(m) for m in dd["ch_mult"]]
+        dd["down_layers"] = [int(i) for i in dd["down_layers"]]
+        nl = len(dd["ch_mult"])
+        if any(int(a) in range(nl) for a in dd["attn_layers"]):
+            raise NotImplementedError("attention inside down levels is not on the shipped config's path (attn_layers: [3])")
+        try:
+            double_z = bool(_get(ddconfig, "double_z"))
+        except (AttributeError, KeyError):
+            double_z = True
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.AlcmError("audiolcm_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device, self.precision, self.dd, self.embed_dim = dev, precision, dd, int(embed_dim)
+        self.down_factor = 2 ** len([l for l in dd["down_layers"] if l < nl])
+        cfg = _lib.VAEEncCfg()
+        cfg.ch, cfg.in_channels, cfg.z_channels = int(dd["ch"]), int(dd["in_channels"]), int(dd["z_channels"])
+        cfg.embed_dim, cfg.kernel_size, cfg.num_res_blocks, cfg.n_levels = self.embed_dim, int(dd["kernel_size"]), int(dd["num_res_blocks"]), nl
+        cfg.double_z = 1 if double_z else 0
+        for i, m in enumerate(dd["ch_mult"]):
+            cfg.ch_mult[i] = m
+            cfg.downsample_levels[i] = 1 if i in dd["down_layers"] else 0
+        names = vae_encoder_tensor_names(dd, prefix)
+        missing = [n for n in names if n not in state_dict]
+        if missing:
+            raise KeyError(f"state_dict is missing {len(missing)} encoder tensors, e.g. {missing[:3]}")
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            tensors = [_as_cuda_f32(state_dict[n], dev) for n in names]
+            torch.cuda.synchronize()
+            handle = C.c_void_p()
+            _lib.check(lib.alcm_vae_encoder_create(_lib.ctx(dev.index), C.byref(cfg), _lib.ptr_array(tensors), len(tensors),
+                                                   _lib.PREC[precision], C.byref(handle)))
+        self._h = handle.value
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.load().alcm_vae_encoder_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def moments(self, x):
+        x = x.to(dtype=torch.float32, device=self.device).contiguous()
+        if x.dim() != 3 or x.shape[1] != int(self.dd["in_channels"]):
+            raise ValueError(f"expected a (B,{self.dd['in_channels']},T) spectrogram, got {tuple(x.shape)}")
+        B, _, T = x.shape
+        if B == 0 or T == 0 or T % self.down_factor:
+            raise ValueError(f"T must be a positive multiple of {self.down_factor}")
+        with torch.cuda.device(self.device):
+            mom = torch.empty((B, 2 * self.embed_dim, T // self.down_factor), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.load().alcm_vae_encode(self._h, x.data_ptr(), B, T, mom.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        return mom
+
+    def encode(self, x):
+        mean, logvar = torch.chunk(self.moments(x), 2, dim=1)
+        return mean, torch.clamp(logvar, -30.0, 20.0)
+
+    def sample(self, x):
+        mean, logvar = self.encode(x)
+        return mean + torch.exp(0.5 * logvar) * torch.randn(mean.shape, device=mean.device)
+
+    def mode(self, x):
+        return self.encode(x)[0]
+
+
 def install(model, ddconfig, device="cuda", precision="tf32"):
     """Swap ``model.first_stage_model.decode`` (the body behind ``decode_first_stage``,
     lcm_audio.py:406) for the CUDA path, in place.  Returns the decoder object."""

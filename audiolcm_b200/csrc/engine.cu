@@ -267,7 +267,7 @@ static void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
 static cudaError_t sync_setup();
 
 // ------------------------------------------------------------------------------------------ conv layers
-enum ConvKind { KIND_CONV = 0, KIND_CONVT = 1, KIND_UPCONV3 = 2 };
+enum ConvKind { KIND_CONV = 0, KIND_CONVT = 1, KIND_UPCONV3 = 2, KIND_DOWN2 = 3 };
 
 struct ConvLayer {
   int Cin = 0, Cout = 0, nphase = 1, ntaps = 1;
@@ -327,6 +327,8 @@ static ConvLayer dynamic_conv(const Knobs& K_, int prec, int Cout, int Cin) {
 // w: folded weight on device (Conv1d [Cout,Cin,K] or ConvTranspose1d [Cin,Cout,K]); bias may be null
 static ConvLayer prepare_conv(Arena& ar, const Knobs& K_, int prec, ConvKind kind, const float* w, const float* bias, int Cout, int Cin, int K,
                               int dil_or_stride) {
+  const int Cin_src = Cin;
+  if (kind == KIND_DOWN2) Cin = 2 * Cin;   // Downsample1D on the time-folded input (s2d_cast_kernel): 2C channels, taps n and n+1
   ConvLayer L;
   L.Cin = Cin; L.Cout = Cout; L.prec = prec;
   WeffRecipe rc;
@@ -347,6 +349,10 @@ static ConvLayer prepare_conv(Arena& ar, const Knobs& K_, int prec, ConvKind kin
       if (s < u) { L.tap_off[r][0] = 0; rc.src_k[r][0][0] = s; L.tap_off[r][1] = -1; rc.src_k[r][1][0] = s + u; }
       else       { L.tap_off[r][0] = 1; rc.src_k[r][0][0] = s - u; L.tap_off[r][1] = 0; rc.src_k[r][1][0] = s; }
     }
+  } else if (kind == KIND_DOWN2) {
+    REQUIRE(K == 3 && dil_or_stride == 2, "downsample conv: k=3, stride 2 only");
+    L.nphase = 1; L.ntaps = 2;
+    L.tap_off[0][0] = 0; L.tap_off[0][1] = 1;
   } else {
     REQUIRE(K == 3, "upsample conv: k=3 only");
     L.nphase = 2; L.ntaps = 2;
@@ -368,7 +374,8 @@ static ConvLayer prepare_conv(Arena& ar, const Knobs& K_, int prec, ConvKind kin
   Arena tmp;
   Arena& weff_owner = (prec == ALCM_PREC_FP32) ? ar : tmp;
   L.weff = static_cast<float*>(weff_owner.alloc(nweff * 4, false));
-  weff_kernel<<<(unsigned)std::min<size_t>((nweff + 255) / 256, 4096), 256>>>(w, L.weff, rc, Cout, Cin, K, kind == KIND_CONVT);
+  if (kind == KIND_DOWN2) weff_down2_kernel<<<(unsigned)std::min<size_t>((nweff + 255) / 256, 4096), 256>>>(w, L.weff, Cout, Cin_src);
+  else weff_kernel<<<(unsigned)std::min<size_t>((nweff + 255) / 256, 4096), 256>>>(w, L.weff, rc, Cout, Cin, K, kind == KIND_CONVT);
   CUDA_CHECK(cudaGetLastError());
 
   if (prec == ALCM_PREC_FP32) {
@@ -1420,6 +1427,72 @@ static void vae_run(alcm_vae* v, VaePlan* P, const float* z, float inv_scale, cu
   CUDA_CHECK(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------ VAE encoder
+// AutoencoderKL.encode up to the posterior's parameters (autoencoder1d.py:52-56): Encoder1D.forward (:391-413) + quant_conv.
+// Same kernel families as the decoder; the only new op is Downsample1D (:296-316), run as a 2-tap conv on the
+// time-folded input (s2d_cast_kernel).  The encoder's ResnetBlocks DO get kernel_size (k = 5), unlike the decoder's.
+struct EncLevel { std::vector<ResBlock> blocks; bool has_down = false; ConvLayer down; int C; };
+struct EncPlan : PlanBase {
+  PlaneT x_in, mom_out;
+};
+struct alcm_vae_encoder {
+  alcm_ctx* ctx;
+  Env env;
+  alcm_vae_enc_cfg cfg;
+  int prec;
+  Arena war;
+  ConvLayer conv_in, conv_out, quant;
+  std::vector<EncLevel> levels;
+  ResBlock mid1, mid2;
+  AttnBlk attn;
+  GnP norm_out;
+  int down_factor = 1;
+  RetileCache retiled;
+  std::map<std::pair<int, int>, std::unique_ptr<EncPlan>> plans;
+  PlanCache pcache;
+};
+
+static void enc_build(const alcm_vae_encoder* v, EncPlan& P) {
+  const int B = P.B, T = P.T;
+  P.ol.cur_stage = 0;
+  const int prec = v->prec, oe = opnd_esz(prec), rtf = prec == ALCM_PREC_TF32;
+  P.x_in = make_planes(P.ar, B, v->cfg.in_channels, T, oe);
+  PlaneT h = make_planes(P.ar, B, v->conv_in.Cout, T, 4);
+  P.ol.conv(v->conv_in, P.x_in, h, nullptr);
+  for (const EncLevel& lv : v->levels) {
+    for (const ResBlock& rb : lv.blocks) h = op_resblock(P.ol, P.ar, rb, h, prec);
+    if (lv.has_down) {
+      REQUIRE(h.T % 2 == 0, "vae_encode: the sequence length must be even at every Downsample1D");
+      const int To = h.T / 2, C = lv.C;
+      PlaneT x2 = make_planes(P.ar, B, 2 * C, To, oe);
+      {
+        const PlaneT hc = h, xc = x2;
+        Op op;
+        op.cls = ALCM_CLS_MISC; op.flops = 0; op.bytes = (double)B * h.T * C * (4.0 + oe);
+        op.fn = [=](cudaStream_t st) {
+          dim3 grid((To + 255) / 256, xc.g.nchunk, B);
+          if (oe == 2) launch_k(s2d_cast_kernel<8>, grid, dim3(256), 0, st, hc.f(), hc.g, (void*)xc.p, xc.g, C, To, 0);
+          else launch_k(s2d_cast_kernel<4>, grid, dim3(256), 0, st, hc.f(), hc.g, (void*)xc.p, xc.g, C, To, rtf);
+        };
+        P.ol.push(op);
+      }
+      PlaneT d = make_planes(P.ar, B, C, To, 4);
+      P.ol.conv(lv.down, x2, d, nullptr);
+      h = d;
+    }
+  }
+  h = op_resblock(P.ol, P.ar, v->mid1, h, prec);
+  h = op_attn(P.ol, P.ar, v->attn, h, prec);
+  h = op_resblock(P.ol, P.ar, v->mid2, h, prec);
+  PlaneT a = make_planes(P.ar, B, h.C, h.T, oe);
+  op_gn(P.ol, P.ar, h, a, v->norm_out, 1, prec);
+  PlaneT m0 = make_planes(P.ar, B, v->conv_out.Cout, h.T, 4);
+  P.ol.conv(v->conv_out, a, m0, nullptr);
+  P.mom_out = make_planes(P.ar, B, v->quant.Cout, h.T, 4);
+  P.ol.conv(v->quant, as_operand(P.ol, P.ar, m0, prec), P.mom_out, nullptr);
+  P.Tout = h.T;
+}
+
 // ------------------------------------------------------------------------------------------ C-ABI
 static void set_kernel_attrs() {
   const int mx = 227 * 1024;
@@ -1730,6 +1803,131 @@ int alcm_vae_decode(alcm_vae* v, const float* z, int B, int T, float inv_scale, 
     PlanUse use(P, st);
     vae_run(v, P, z, inv_scale, st);
     launch_unpack(P->mel_out, mel, v->cfg.out_ch, P->Tout, st);
+    CUDA_CHECK(cudaGetLastError());
+    use.finish();
+  });
+}
+
+// ---- VAE encoder
+static int enc_resblock_tensors(int cin, int cout) { return 8 + (cin != cout ? 2 : 0); }
+int alcm_vae_encoder_num_tensors(const alcm_vae_enc_cfg* c) {
+  if (!c) return -1;
+  int n = 2, block_in = c->ch;
+  for (int lv = 0; lv < c->n_levels; ++lv) {
+    const int block_out = c->ch * c->ch_mult[lv];
+    for (int i = 0; i < c->num_res_blocks; ++i) { n += enc_resblock_tensors(block_in, block_out); block_in = block_out; }
+    if (c->downsample_levels[lv]) n += 2;
+  }
+  return n + 2 * enc_resblock_tensors(block_in, block_in) + 10 + 2 + 2 + 2;
+}
+
+int alcm_vae_encoder_create(alcm_ctx* ctx, const alcm_vae_enc_cfg* cfg, const float* const* t, int n_tensors, int precision,
+                            alcm_vae_encoder** out) {
+  return guarded([&] {
+    REQUIRE(ctx && cfg && t && out, "vae_encoder_create: NULL argument");
+    REQUIRE(precision >= 0 && precision <= 2, "vae_encoder_create: bad precision");
+    REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= 8 && cfg->num_res_blocks >= 1, "vae_encoder_create: bad config");
+    REQUIRE(n_tensors == alcm_vae_encoder_num_tensors(cfg), "vae_encoder_create: wrong tensor count");
+    for (int i = 0; i < n_tensors; ++i) REQUIRE(t[i] != nullptr, "vae_encoder_create: NULL tensor");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    std::unique_ptr<alcm_vae_encoder> v(new alcm_vae_encoder());
+    v->ctx = ctx; v->cfg = *cfg; v->prec = precision;
+    v->env.cx = ctx; v->env.k = Knobs::from_env();
+    v->war.guard = v->env.k.guard != 0;
+    const Knobs& K = v->env.k;
+    const int ks = cfg->kernel_size;
+    int ti = 0;
+    auto conv = [&](int cout, int cin, int k, ConvKind kind = KIND_CONV, int p = 1) {
+      ConvLayer L = prepare_conv(v->war, K, precision, kind, t[ti], t[ti + 1], cout, cin, k, p);
+      ti += 2;
+      return L;
+    };
+    auto gn = [&](int C) {
+      GnP g = make_gn(v->war, t[ti], t[ti + 1], C);
+      ti += 2;
+      return g;
+    };
+    auto resblock = [&](int cin, int cout) {
+      ResBlock rb;
+      rb.Cin = cin; rb.Cout = cout;
+      rb.n1 = gn(cin);
+      rb.c1 = conv(cout, cin, ks);
+      rb.n2 = gn(cout);
+      rb.c2 = conv(cout, cout, ks);
+      rb.has_nin = cin != cout;
+      if (rb.has_nin) rb.nin = conv(cout, cin, 1);
+      return rb;
+    };
+    v->conv_in = conv(cfg->ch, cfg->in_channels, ks);
+    int block_in = cfg->ch;
+    for (int lv = 0; lv < cfg->n_levels; ++lv) {
+      EncLevel L;
+      const int block_out = cfg->ch * cfg->ch_mult[lv];
+      for (int i = 0; i < cfg->num_res_blocks; ++i) { L.blocks.push_back(resblock(block_in, block_out)); block_in = block_out; }
+      L.C = block_in;
+      L.has_down = cfg->downsample_levels[lv] != 0;
+      if (L.has_down) {
+        REQUIRE(block_in % 8 == 0, "vae_encoder_create: Downsample1D needs a multiple of 8 channels");
+        L.down = conv(block_in, block_in, 3, KIND_DOWN2, 2);
+        v->down_factor *= 2;
+      }
+      v->levels.push_back(std::move(L));
+    }
+    v->mid1 = resblock(block_in, block_in);
+    v->attn.C = block_in;
+    v->attn.norm = gn(block_in);
+    {
+      const size_t wn = (size_t)block_in * block_in, bn = (size_t)block_in;
+      Arena tmpq;
+      float* wcat = static_cast<float*>(tmpq.alloc(3 * wn * 4, false));
+      float* bcat = static_cast<float*>(tmpq.alloc(3 * bn * 4, false));
+      for (int i = 0; i < 3; ++i) {
+        CUDA_CHECK(cudaMemcpy(wcat + i * wn, t[ti + 2 * i], wn * 4, cudaMemcpyDeviceToDevice));
+        CUDA_CHECK(cudaMemcpy(bcat + i * bn, t[ti + 2 * i + 1], bn * 4, cudaMemcpyDeviceToDevice));
+      }
+      v->attn.qkv = prepare_conv(v->war, K, precision, KIND_CONV, wcat, bcat, 3 * block_in, block_in, 1, 1);
+      ti += 6;
+    }
+    v->attn.proj = conv(block_in, block_in, 1);
+    v->mid2 = resblock(block_in, block_in);
+    v->norm_out = gn(block_in);
+    const int zc2 = (cfg->double_z ? 2 : 1) * cfg->z_channels;
+    v->conv_out = conv(zc2, block_in, ks);
+    v->quant = conv(2 * cfg->embed_dim, zc2, 1);
+    REQUIRE(ti == n_tensors, "vae_encoder_create: tensor walk mismatch");
+    CUDA_CHECK(sync_setup());
+    *out = v.release();
+  });
+}
+void alcm_vae_encoder_destroy(alcm_vae_encoder* v) {
+  if (!v) return;
+  cudaSetDevice(v->ctx->device);
+  wait_plans(v->plans, v->pcache);
+  delete v;
+}
+int alcm_vae_encode(alcm_vae_encoder* v, const float* x, int B, int T, float* moments, void* stream) {
+  return guarded([&] {
+    REQUIRE(v && x && moments, "vae_encode: NULL argument");
+    REQUIRE(B >= 1 && T >= 1 && T % v->down_factor == 0, "vae_encode: T must be a positive multiple of the down-sampling factor");
+    CUDA_CHECK(cudaSetDevice(v->ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto key = std::make_pair(B, T);
+    auto it = v->plans.find(key);
+    EncPlan* P = nullptr;
+    if (it != v->plans.end()) {
+      P = it->second.get();
+    } else {
+      v->pcache.make_room(v->plans, (size_t)v->env.k.max_plans, st);
+      std::unique_ptr<EncPlan> pl = build_plan<EncPlan>(v->env, &v->war, &v->retiled, B, T, st, false, nullptr, [&](EncPlan& R) { enc_build(v, R); });
+      P = pl.get();
+      v->plans[key] = std::move(pl);
+    }
+    P->stamp = ++v->ctx->plan_clock;
+    PlanUse use(P, st);
+    launch_pack(x, P->x_in, v->cfg.in_channels, T, 1.f, v->prec, st);
+    if (P->ge.exec) CUDA_CHECK(cudaGraphLaunch(P->ge.exec, st));
+    else P->ol.run(st);
+    launch_unpack(P->mom_out, moments, v->quant.Cout, P->Tout, st);
     CUDA_CHECK(cudaGetLastError());
     use.finish();
   });

@@ -143,7 +143,48 @@ __global__ void sum_planes_kernel(SumArgs a) {
   }
 }
 
+// Downsample1D (autoencoder1d.py:296-316: right zero pad + Conv1d k3 stride 2) reads x at 2n, 2n+1, 2n+2.  With the time
+// axis folded into channels - x2[parity*C + c][n] = x[c][2n + parity] - it is a 2-tap stride-1 conv (rows n, n+1) over 2C
+// channels, which conv_umma_kernel handles.  This kernel writes x2 as operand planes (bf16 cast / tf32 rounding
+// included).  C must be a multiple of E.
+template <int E>
+__global__ void s2d_cast_kernel(const float* __restrict__ in, PlaneGeom ig, void* __restrict__ out, PlaneGeom og, int C, int Tout,
+                                int rtf32) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oc = blockIdx.y, b = blockIdx.z;
+  if (n >= Tout) return;
+  const int c0 = oc * E, parity = c0 / C, c = c0 - parity * C, t = 2 * n + parity;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out) + plane_row_off(og, b, oc, n);
+  const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, c >> 2, t));
+  if (E == 8) {
+    const float4 d = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, (c >> 2) + 1, t));
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(d.x, d.y); o.w = pack_bf16x2(d.z, d.w);
+    *reinterpret_cast<uint4*>(dst) = o;
+  } else {
+    float4 v = a;
+    if (rtf32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    *reinterpret_cast<float4*>(dst) = v;
+  }
+}
+
 // ------------------------------------------------------------------------------- weights
+// Effective weights of Downsample1D on the folded input (see s2d_cast_kernel): src (Cout,C,3) -> dst [2 taps][Cout][2C]
+//   tap 0 (row n)  : [ w[.,.,0] | w[.,.,1] ]      tap 1 (row n+1): [ w[.,.,2] | 0 ]
+__global__ void weff_down2_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int C) {
+  const size_t n = (size_t)2 * Cout * 2 * C;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    const int ci2 = idx % (2 * C);
+    const int co = (idx / (2 * C)) % Cout;
+    const int tap = idx / ((size_t)2 * C * Cout);
+    const int parity = ci2 / C, ci = ci2 - parity * C;
+    const int k = tap == 0 ? parity : (parity == 0 ? 2 : -1);
+    dst[idx] = k >= 0 ? src[((size_t)co * C + ci) * 3 + k] : 0.f;
+  }
+}
+
 // weight_norm fold (torch.nn.utils.weight_norm dim=0; models.py:36-51,143,152,174):
 // w[i,:,:] = g[i] * v[i,:,:] / ||v[i,:,:]||.  One block per dim-0 slice.
 __global__ void wn_fold_kernel(const float* __restrict__ v, const float* __restrict__ g, float* __restrict__ w, int inner) {

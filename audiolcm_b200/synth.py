@@ -167,6 +167,42 @@ def vae_decoder_state_dict(dd, embed_dim: int = VAE_EMBED_DIM, seed: int = 0) ->
     return sd
 
 
+def _resblock_k(rng, sd, p, cin, cout, k):
+    _gn(rng, sd, p + ".norm1", cin)
+    _conv(rng, sd, p + ".conv1", cout, cin, k)
+    _gn(rng, sd, p + ".norm2", cout)
+    _conv(rng, sd, p + ".conv2", cout, cout, k)
+    if cin != cout:
+        _conv(rng, sd, p + ".nin_shortcut", cout, cin, 1)
+
+
+def vae_encoder_state_dict(dd, embed_dim: int = VAE_EMBED_DIM, seed: int = 0) -> dict:
+    """Synthetic state_dict for ``encoder`` + ``quant_conv`` (numpy fp32), reference key names
+    (ldm/models/autoencoder1d.py:319-413,34): encoder ResnetBlocks DO get kernel_size (k = 5), unlike the decoder's."""
+    rng = np.random.default_rng(seed + 2000)
+    sd = {}
+    ch, mult, nrb, ks = dd["ch"], list(dd["ch_mult"]), dd["num_res_blocks"], dd["kernel_size"]
+    _conv(rng, sd, "encoder.conv_in", ch, dd["in_channels"], ks)
+    block_in = ch
+    for i_level in range(len(mult)):
+        block_out = ch * mult[i_level]
+        for i_block in range(nrb):
+            _resblock_k(rng, sd, f"encoder.down.{i_level}.block.{i_block}", block_in, block_out, ks)
+            block_in = block_out
+        if i_level in dd["down_layers"]:
+            _conv(rng, sd, f"encoder.down.{i_level}.downsample.conv", block_in, block_in, 3)
+    _resblock_k(rng, sd, "encoder.mid.block_1", block_in, block_in, ks)
+    _gn(rng, sd, "encoder.mid.attn_1.norm", block_in)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(rng, sd, f"encoder.mid.attn_1.{n}", block_in, block_in, 1)
+    _resblock_k(rng, sd, "encoder.mid.block_2", block_in, block_in, ks)
+    _gn(rng, sd, "encoder.norm_out", block_in)
+    zc2 = 2 * dd["z_channels"] if dd.get("double_z", True) else dd["z_channels"]
+    _conv(rng, sd, "encoder.conv_out", zc2, block_in, ks)
+    _conv(rng, sd, "quant_conv", 2 * embed_dim, zc2, 1)
+    return sd
+
+
 def synth_mel(B: int, T: int, seed: int = 0, n_mels: int = 80) -> np.ndarray:
     """log10-mel shaped input: clamp(N(-2.5, 1.5^2), -5, 1.5)."""
     rng = np.random.default_rng(seed + 7)

@@ -43,6 +43,7 @@ typedef struct alcm_ctx alcm_ctx;
 typedef struct alcm_vocoder alcm_vocoder;
 typedef struct alcm_vae alcm_vae;
 typedef struct alcm_conv1d alcm_conv1d;
+typedef struct alcm_vae_encoder alcm_vae_encoder;
 
 /* arithmetic used by the conv GEMMs */
 enum {
@@ -131,6 +132,31 @@ void alcm_vae_destroy(alcm_vae* v);
 int alcm_vae_decode(alcm_vae* v, const float* z, int B, int T, float inv_scale, float* mel, void* stream);
 int alcm_vae_plan(alcm_vae* v, int B, int T, void* stream);
 int alcm_vae_workspace_bytes(alcm_vae* v, int B, int T, size_t* bytes);
+
+/* ---- 1-D KL-VAE encoder (the step on the other side of the path, used by reconstruct_audio.py:115):
+ * AutoencoderKL.encode up to the posterior's parameters (ldm/models/autoencoder1d.py:52-56,319-413).
+ * downsample_levels[l] = 1 when level l ends with a Downsample1D (l in down_layers).  `tensors` order (conv = weight,bias;
+ * norm = weight,bias; resblock = norm1, conv1, norm2, conv2[, nin_shortcut]):
+ *   encoder.conv_in, for level = 0 .. n_levels-1: block.0 .. block.num_res_blocks-1, [downsample.conv],
+ *   mid.block_1, mid.attn_1 (norm, q, k, v, proj_out), mid.block_2, norm_out, conv_out, quant_conv. */
+typedef struct {
+  int ch;
+  int in_channels;
+  int z_channels;
+  int embed_dim;
+  int kernel_size;
+  int num_res_blocks;
+  int n_levels;
+  int double_z;
+  int ch_mult[8];
+  int downsample_levels[8];
+} alcm_vae_enc_cfg;
+int alcm_vae_encoder_num_tensors(const alcm_vae_enc_cfg* cfg);
+int alcm_vae_encoder_create(alcm_ctx* ctx, const alcm_vae_enc_cfg* cfg, const float* const* tensors, int n_tensors, int precision,
+                            alcm_vae_encoder** out);
+void alcm_vae_encoder_destroy(alcm_vae_encoder* v);
+/* mel [B,in_channels,T] -> moments [B, 2*embed_dim, T / 2^n_down] = (mean | logvar) of the posterior */
+int alcm_vae_encode(alcm_vae_encoder* v, const float* x, int B, int T, float* moments, void* stream);
 
 /* latent -> waveform with the mel kept on the device (mel_out may be NULL) */
 int alcm_decode_to_wav(alcm_vae* vae, alcm_vocoder* voc, const float* z, int B, int T, float inv_scale, float* mel_out,

@@ -206,6 +206,36 @@ def vae_decode(sd, dd, z, dtype=torch.float32):
     return _conv(sd, "decoder.conv_out", x, dtype, ks // 2)
 
 
+def vae_encode_moments(sd, dd, x, dtype=torch.float32):
+    """AutoencoderKL.encode autoencoder1d.py:52-56 up to the posterior's parameters (mean | logvar):
+    Encoder1D.forward :391-413 (ResnetBlocks with k = kernel_size, Downsample1D :296-316 = right zero pad + Conv1d k3
+    stride 2) then quant_conv :34."""
+    nl, nrb, ks = len(dd["ch_mult"]), dd["num_res_blocks"], dd["kernel_size"]
+
+    def res(p, h):
+        y = _conv(sd, p + ".conv1", _gn_swish(sd, p + ".norm1", h, dtype), dtype, ks // 2)
+        y = _conv(sd, p + ".conv2", _gn_swish(sd, p + ".norm2", y, dtype), dtype, ks // 2)
+        if (p + ".nin_shortcut.weight") in sd:
+            h = _conv(sd, p + ".nin_shortcut", h, dtype, 0)
+        return h + y
+
+    with torch.no_grad():
+        h = _conv(sd, "encoder.conv_in", _t(x, dtype), dtype, ks // 2)
+        for i_level in range(nl):
+            for i_block in range(nrb):
+                h = res(f"encoder.down.{i_level}.block.{i_block}", h)
+                if i_level in dd["attn_layers"]:
+                    raise NotImplementedError("down-level attention is not on the shipped config's path")
+            if i_level in dd["down_layers"]:
+                p = f"encoder.down.{i_level}.downsample.conv"
+                h = F.conv1d(F.pad(h, (0, 1)), _t(sd[p + ".weight"], dtype), _t(sd[p + ".bias"], dtype), stride=2)
+        h = res("encoder.mid.block_1", h)
+        h = attn_block(sd, "encoder.mid.attn_1", h, dtype)
+        h = res("encoder.mid.block_2", h)
+        h = _conv(sd, "encoder.conv_out", _gn_swish(sd, "encoder.norm_out", h, dtype), dtype, ks // 2)
+        return _conv(sd, "quant_conv", h, dtype, 0)
+
+
 def decode_first_stage(sd, dd, z, scale_factor: float = 1.0, dtype=torch.float32):
     """LCM_audio.decode_first_stage, ldm/models/diffusion/lcm_audio.py:392-406 (KL branch)."""
     with torch.no_grad():

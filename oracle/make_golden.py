@@ -67,7 +67,7 @@ def ref_bigvgan(h, sd_np):
     return g
 
 
-def ref_vae(dd, sd_np, embed_dim=synth.VAE_EMBED_DIM):
+def ref_vae(dd, sd_np, embed_dim=synth.VAE_EMBED_DIM, strict=False):
     _, AutoencoderKL, _, _ = import_reference()
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
@@ -75,13 +75,31 @@ def ref_vae(dd, sd_np, embed_dim=synth.VAE_EMBED_DIM):
     missing, unexpected = vae.load_state_dict(_to_torch(sd_np), strict=False)
     assert not unexpected, unexpected
     assert all(k.startswith(("encoder.", "quant_conv.")) for k in missing), missing
+    assert not (strict and missing), missing
     return vae
+
+
+def encoder_goldens():
+    """VAE encoder: AutoencoderKL.encode(x).parameters = (mean | logvar)."""
+    for tag, ch, T, B in (("ch32", 32, 40, 2), ("full_T64", 384, 64, 1)):
+        dd = synth.vae_config(ch)
+        esd = synth.vae_encoder_state_dict(dd, seed=5)
+        vae = ref_vae(dd, {**synth.vae_decoder_state_dict(dd, seed=3), **esd}, strict=True)
+        x = synth.synth_mel(B, T, seed=6)
+        with torch.no_grad():
+            mom = vae.encode(torch.from_numpy(x)).parameters.numpy()
+        np.savez(os.path.join(OUT, f"vae_enc_{tag}.npz"), ch=ch, T=T, B=B, wseed=5, xseed=6, moments=mom)
+        print("vae encode", tag, mom.shape, float(np.abs(mom).max()))
 
 
 def main():
     assert reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
+    if "--encoder-only" in sys.argv:
+        with torch.no_grad():
+            encoder_goldens()
+        return
     torch.set_grad_enabled(False)
     _, _, Activation1d, SnakeBeta = import_reference()
 
@@ -149,6 +167,8 @@ def main():
             taps = {}
         np.savez(os.path.join(OUT, f"vae_{tag}.npz"), ch=ch, T=T, B=B, wseed=3, xseed=4, mel=mel, **taps)
         print("vae", tag, mel.shape, float(np.abs(mel).max()), float(mel.std()))
+
+    encoder_goldens()
 
     # ---- full path latent -> mel -> wav (config 2), short clip to keep the fixture small -----
     dd = synth.vae_config()

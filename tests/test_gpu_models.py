@@ -519,3 +519,25 @@ def test_vae_attention_paths(golden_dir, monkeypatch, attn_tc):
         z3 = np.concatenate([z, z * 0.5, z * 1.5], axis=0)
         got3 = dec.decode(torch.from_numpy(z3).to(DEV)).cpu().numpy()
         assert np.abs(got3[: z.shape[0]] - got).max() <= MEL_TOL[precision]
+
+
+# ----------------------------------------------------------------------------------- VAE encoder
+@pytest.mark.parametrize("tag", ["ch32", "full_T64"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_vae_encode_vs_reference(golden_dir, tag, precision):
+    """AutoencoderKLEncoder against AutoencoderKL.encode(x).parameters of the unmodified reference (Encoder1D with its
+    k = 5 ResnetBlocks, Downsample1D as a 2-tap conv on the time-folded input, mid attention, quant_conv)."""
+    from audiolcm_b200 import AutoencoderKLEncoder
+    g = np.load(os.path.join(golden_dir, f"vae_enc_{tag}.npz"))
+    dd = synth.vae_config(int(g["ch"]))
+    sd = synth.vae_encoder_state_dict(dd, seed=int(g["wseed"]))
+    x = torch.from_numpy(synth.synth_mel(int(g["B"]), int(g["T"]), seed=int(g["xseed"]))).to(DEV)
+    enc = AutoencoderKLEncoder(sd, dd, synth.VAE_EMBED_DIM, DEV, precision)
+    mom = enc.moments(x).cpu().numpy()
+    err = np.abs(mom - g["moments"]).max()
+    print(f"\n[vae encode {tag} {precision}] max-abs {err:.3e} (ref abs-max {np.abs(g['moments']).max():.3f})")
+    assert mom.shape == g["moments"].shape and err <= MEL_TOL[precision]
+    mean, logvar = enc.encode(x)
+    assert mean.shape == (int(g["B"]), synth.VAE_EMBED_DIM, int(g["T"]) // 2) and float(logvar.max()) <= 20.0
+    with pytest.raises(ValueError):
+        enc.moments(x[..., :-1])          # odd length

@@ -110,3 +110,18 @@ def test_polyphase_closed_forms():
     b = rng.standard_normal(7)
     ref = F.conv1d(F.interpolate(torch.from_numpy(x), scale_factor=2.0, mode="nearest"), torch.from_numpy(w), torch.from_numpy(b), padding=1).numpy()
     np.testing.assert_allclose(NP.nearest2x_conv3_polyphase(x, w, b), ref, atol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["ch32", "full_T64"])
+def test_oracle_vae_encode_matches_reference(golden_dir, tag):
+    """oracle.vae_encode_moments == AutoencoderKL.encode(x).parameters of the unmodified reference."""
+    import torch
+    from audiolcm_b200 import synth
+    from oracle import decode_oracle as O
+    g = np.load(os.path.join(golden_dir, f"vae_enc_{tag}.npz"))
+    dd = synth.vae_config(int(g["ch"]))
+    sd = {k: torch.from_numpy(v) for k, v in synth.vae_encoder_state_dict(dd, seed=int(g["wseed"])).items()}
+    x = synth.synth_mel(int(g["B"]), int(g["T"]), seed=int(g["xseed"]))
+    mom = O.vae_encode_moments(sd, dd, x).numpy()
+    assert mom.shape == g["moments"].shape
+    assert np.abs(mom - g["moments"]).max() <= 2e-6
