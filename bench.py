@@ -535,6 +535,36 @@ def config5(pipe, device, precision, prompts=256, chunk=64):
                      "rest = device->host copies, WAV writing, Python")
 
 
+def encoder_leg(device, precision, flush, steps=5):
+    """SURVEY 8f row 4 (the step on the other side of the path): VAE encoder, 64 mels [80,624] -> posterior moments
+    [40,312], same kernels as the decoder (audiolcm_b200.AutoencoderKLEncoder).  Device-timed, FLOPs counted per conv."""
+    import torch
+    from audiolcm_b200 import AutoencoderKLEncoder, synth
+    dd = synth.vae_config()
+    enc = AutoencoderKLEncoder(synth.vae_encoder_state_dict(dd, seed=5), dd, synth.VAE_EMBED_DIM, device, precision)
+    B, T = CLIPS, T_LAT * VAE_UP
+    x = torch.from_numpy(synth.synth_mel(B, T, seed=3)).to(device)
+    enc.moments(x)
+    torch.cuda.synchronize()
+    dev_s = time_steps(lambda: enc.moments(x), steps, 2, flush)
+    ch, mult, nrb, ks = dd["ch"], dd["ch_mult"], dd["num_res_blocks"], dd["kernel_size"]
+    fl, t, cin = 2.0 * dd["in_channels"] * ch * ks * T, T, ch
+    for lv, m in enumerate(mult):
+        cout = ch * m
+        for _ in range(nrb):
+            fl += 2.0 * t * (cin * cout * ks + cout * cout * ks + (cin * cout if cin != cout else 0))
+            cin = cout
+        if lv in dd["down_layers"]:
+            t //= 2
+            fl += 2.0 * t * cin * cin * 3
+    fl += 4 * 2.0 * t * cin * cin * ks + 4 * 2.0 * t * cin * cin + 2 * 2.0 * t * t * cin      # mid blocks, q/k/v/proj, attention
+    fl += 2.0 * t * cin * 2 * dd["z_channels"] * ks + 2.0 * t * (2 * dd["z_channels"]) * (2 * synth.VAE_EMBED_DIM)
+    ms = 1e3 * dev_s / steps
+    return dict(workload=f"VAE encoder (autoencoder1d.py:52-56,319-413): {B} mels [80,{T}] -> moments [40,{T // 2}], {precision}",
+                ms_per_step=round(ms, 3), clips_per_second=round(B / (ms * 1e-3), 1), audio_seconds_per_second=round(audio_seconds(B, T_LAT) / (ms * 1e-3), 1),
+                gflop_per_clip=round(fl / 1e9, 1), tflops=round(B * fl / (ms * 1e-3) / 1e12, 1))
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -583,6 +613,7 @@ def run_gpu(args):
             extra[mode]["kernel_rooflines"] = kernel_rooflines(mode, peaks, local)
         if rank == 0 and world == 1 and not args.no_config5 and mode == modes[-1]:
             extra["config5"] = config5(pipe, device, mode)
+            extra["encoder"] = encoder_leg(device, mode, flush)
         del pipe
         torch.cuda.empty_cache()
     if rank == 0:
@@ -608,6 +639,8 @@ def run_gpu(args):
             line["longform"] = extra["longform"]
         if "config5" in extra:
             line["configs4_end_to_end_batch256"] = extra["config5"]
+        if "encoder" in extra:
+            line["vae_encoder"] = extra["encoder"]
         parity = {mode: dict(max_abs_item_vs_batch1=extra[mode]["max_abs_item_vs_batch1"]) for mode in modes}
         if not args.no_cpu:
             cb, ref = cpu_baseline()

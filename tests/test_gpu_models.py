@@ -541,3 +541,25 @@ def test_vae_encode_vs_reference(golden_dir, tag, precision):
     assert mean.shape == (int(g["B"]), synth.VAE_EMBED_DIM, int(g["T"]) // 2) and float(logvar.max()) <= 20.0
     with pytest.raises(ValueError):
         enc.moments(x[..., :-1])          # odd length
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_mel_front_end_vs_nat_mel_restatement(precision):
+    """MelSpectrogramB200 (STFT and mel projection as conv_umma_kernel GEMMs) against tests/util.log_mel, the torch.stft
+    restatement of MelNet.forward (NAT_mel.py:64-85; librosa is absent, so this half of SURVEY 8f row 4 is pinned to the
+    restatement, not to the reference class).  Broadband test signal (a decoded waveform plus noise): every mel bin
+    carries energy, so the log10 is well conditioned."""
+    from audiolcm_b200.melspec import MelSpectrogramB200
+    from tests.util import log_mel
+    rng = np.random.default_rng(3)
+    L = 256 * 97
+    t = np.arange(L) / 16000.0
+    wav = (0.3 * np.sin(2 * np.pi * 440 * t) + 0.2 * np.sin(2 * np.pi * 3100 * t * (1 + 0.1 * t)) + 0.05 * rng.standard_normal(L)).astype(np.float32)
+    ref = log_mel(wav)
+    got = MelSpectrogramB200(DEV, precision)(torch.from_numpy(np.stack([wav, wav[::-1].copy()]))).cpu().numpy()
+    assert got.shape == (2, 80, 97)
+    err = np.abs(got[0] - ref)
+    print(f"\n[mel front-end {precision}] log10-mel error: mean {err.mean():.2e}, max {err.max():.2e}")
+    mean_tol, max_tol = {"fp32": (1e-5, 2e-4), "tf32": (1e-3, 2e-2), "bf16": (6e-3, 1e-1)}[precision]
+    assert err.mean() <= mean_tol and err.max() <= max_tol
+    np.testing.assert_allclose(got[1], log_mel(wav[::-1].copy()), atol=max_tol)

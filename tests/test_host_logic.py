@@ -170,3 +170,14 @@ def test_bench_reference_arm_prints_one_json_line():
         ours = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                               timeout=600, cwd=root)
         assert ours.returncode != 0 and "no CPU fallback" in (ours.stderr + ours.stdout)
+
+
+def test_slaney_mel_basis_matches_torchaudio():
+    """The numpy restatement of librosa.filters.mel (slaney scale and norm) used by the GPU mel front-end equals
+    torchaudio's slaney filterbank (librosa itself is not in the image)."""
+    import torchaudio
+    from audiolcm_b200.melspec import slaney_mel_basis
+    a = slaney_mel_basis(16000, 1024, 80, 0.0, 8000.0)
+    b = torchaudio.functional.melscale_fbanks(513, 0.0, 8000.0, 80, 16000, norm="slaney", mel_scale="slaney").T.numpy()
+    assert a.shape == b.shape == (80, 513)
+    assert np.abs(a - b).max() <= 1e-6
