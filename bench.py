@@ -645,9 +645,17 @@ def run_gpu(args):
         if not args.no_cpu:
             cb, ref = cpu_baseline()
             line["cpu_baseline"] = cb
+            from audiolcm_b200.melspec import MelSpectrogramB200
+            melnet = MelSpectrogramB200(device, "fp32")                     # on-GPU log10-mel (NAT_mel.py:64-85), exact-fp32 GEMMs
+            mel_ref = melnet(torch.from_numpy(ref[None]))
             for mode in modes:
-                parity[mode]["max_abs_clip0_vs_cpu_oracle"] = float(np.abs(extra[mode]["clip0"] - ref).max())
-            parity["gates"] = "tf32: max-abs <= 1e-3; bf16: max-abs <= 5e-3 and SNR >= 35 dB (tests/test_gpu_models.py)"
+                got = extra[mode]["clip0"]
+                parity[mode]["max_abs_clip0_vs_cpu_oracle"] = float(np.abs(got - ref).max())
+                parity[mode]["snr_db_clip0_vs_cpu_oracle"] = round(float(10 * np.log10((ref.astype(np.float64) ** 2).sum() /
+                                                                                        max(((got.astype(np.float64) - ref) ** 2).sum(), 1e-300))), 2)
+                parity[mode]["log_mel_l1_clip0_vs_cpu_oracle"] = float((melnet(torch.from_numpy(got[None])) - mel_ref).abs().mean())
+            parity["gates"] = ("tf32: max-abs <= 1e-3; bf16: max-abs <= 5e-3, SNR >= 35 dB, mean |log10-mel difference| <= 0.05 "
+                               "(tests/test_gpu_models.py; the log-mel here is computed on the GPU by audiolcm_b200.melspec)")
             parity["ref_abs_max"] = float(np.abs(ref).max())
         line["parity_check"] = parity
         emit(line)
