@@ -455,10 +455,25 @@ def longform(pipe, device, world, rank, steps, barrier, precision):
     with torch.no_grad():
         o = O.bigvgan_forward(gsd, h, mel_all[..., w0 - halo:w1 + halo]).reshape(-1).numpy()[halo * hop:(halo + w1 - w0) * hop]
     got = full[0, w0 * hop:w1 * hop].cpu().numpy()
+    # the replicated half of the long-form path (GroupNorm statistics and the mid attention span all of T, so the
+    # VAE decoder does not shard along time): z [1,20,T/2] -> mel [1,80,T] un-sharded on this GPU, device-timed
+    zl = torch.from_numpy(synth.synth_latent(1, T // 2, seed=9)).to(device)
+    pipe.vae.decode(zl)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        pipe.vae.decode(zl)
+    ev1.record()
+    torch.cuda.synchronize()
+    vae_ms = ev0.elapsed_time(ev1) / steps
     return dict(workload=f"configs[3]: one {T * hop / SR:.0f} s clip (mel [1,80,{T}]), vocoder time-sharded over {world} GPU(s), "
                          f"{halo}-frame halo per interior edge exchanged with NCCL P2P inside the timed region",
                 precision=precision, ms_per_step=round(ms, 3), value=round(T * hop / SR / (ms * 1e-3), 1), unit="audio-s/s", steps=steps,
                 max_abs_vs_unsharded=err_unsharded, max_abs_vs_oracle=float(np.abs(got - o).max()),
+                vae_replicated_ms=round(vae_ms, 3),
+                vae_note=f"z [1,20,{T // 2}] -> mel [1,80,{T}] on ONE GPU (replicas only; {T // 2} x {T // 2} attention on the tensor cores); "
+                         "parity of this path at T_lat = 1100: tests/test_gpu_models.py::test_vae_long_sequence_paths",
                 oracle_window=f"frames [{w0},{w1}) (straddles the rank-0/1 boundary)" if world > 1 else f"frames [{w0},{w1})",
                 abs_max=float(ref.abs().max()))
 

@@ -563,3 +563,19 @@ def test_mel_front_end_vs_nat_mel_restatement(precision):
     mean_tol, max_tol = {"fp32": (1e-5, 2e-4), "tf32": (1e-3, 2e-2), "bf16": (6e-3, 1e-1)}[precision]
     assert err.mean() <= mean_tol and err.max() <= max_tol
     np.testing.assert_allclose(got[1], log_mel(wav[::-1].copy()), atol=max_tol)
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_vae_long_sequence_paths(precision):
+    """Long-form VAE decode (the replicated half of BASELINE.json configs[3]): at T_lat = 1100 the GroupNorm groups no
+    longer fit in shared memory (two-kernel statistics + apply path) and the attention scores are 1100 x 1100 per item
+    (tensor-core attention with per-item operands).  Full-size decoder against the CPU oracle."""
+    dd = synth.vae_config()
+    sd = synth.vae_decoder_state_dict(dd, seed=3)
+    z = synth.synth_latent(1, 1100, seed=8)
+    with torch.no_grad():
+        ref = O.vae_decode({k: torch.from_numpy(v) for k, v in sd.items()}, dd, torch.from_numpy(z)).numpy()
+    got = _vae(dd, sd, precision).decode(torch.from_numpy(z).to(DEV)).cpu().numpy()
+    err = np.abs(got - ref).max()
+    print(f"\n[vae T=1100 {precision}] max-abs {err:.3e} (ref abs-max {np.abs(ref).max():.2f})")
+    assert got.shape == (1, 80, 2200) and err <= MEL_TOL[precision]
