@@ -974,14 +974,25 @@ static void wait_plans(Map& plans, PlanCache& pc) {
   pc.retired.clear();
 }
 
+static bool stream_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+}
+
+// Replay a plan: its own CUDA graph normally; kernel by kernel (serial lanes) when the caller's stream is being captured -
+// the launches then become nodes of the CALLER's graph (a graph launch inside a capture invalidated it on this driver).
+static void run_plan(const PlanBase& P, cudaStream_t st) {
+  if (P.ge.exec && !stream_capturing(st)) CUDA_CHECK(cudaGraphLaunch(P.ge.exec, st));
+  else P.ol.run(st);
+}
+
 // Order a plan's launches after its previous use (other stream) and keep the retire event current.
 struct PlanUse {
   PlanBase* P;
   cudaStream_t st;
   bool capturing = false;
   PlanUse(PlanBase* p, cudaStream_t s) : P(p), st(s) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) capturing = true;
+    capturing = stream_capturing(st);
     if (capturing) { P->pinned = true; return; }
     if (P->used && P->last_stream != st) CUDA_CHECK(cudaStreamWaitEvent(st, P->done, 0));
   }
@@ -1173,8 +1184,7 @@ static VocPlan* voc_plan(alcm_vocoder* v, int B, int T, cudaStream_t st) {
 static void voc_run(alcm_vocoder* v, VocPlan* P, const float* mel, void* out, int pcm16, cudaStream_t st) {
   // mel either as [B,C,T] device tensor (packed here) or already resident in P->mel_in (decode_to_wav)
   if (mel) launch_pack(mel, P->mel_in, v->cfg.num_mels, P->T, 1.f, v->prec, st);
-  if (P->ge.exec) CUDA_CHECK(cudaGraphLaunch(P->ge.exec, st));
-  else P->ol.run(st);
+  run_plan(*P, st);
   const int threads = 256;
   dim3 grid((P->Tout + threads - 1) / threads, P->B);
   const size_t sm = (size_t)7 * P->post_in.g.nchunk * 4 * sizeof(float);
@@ -1422,8 +1432,7 @@ static VaePlan* vae_plan(alcm_vae* v, int B, int T, cudaStream_t st) {
 
 static void vae_run(alcm_vae* v, VaePlan* P, const float* z, float inv_scale, cudaStream_t st) {
   launch_pack(z, P->z_in, v->cfg.embed_dim, P->T, inv_scale, v->prec, st);
-  if (P->ge.exec) CUDA_CHECK(cudaGraphLaunch(P->ge.exec, st));
-  else P->ol.run(st);
+  run_plan(*P, st);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -1925,8 +1934,7 @@ int alcm_vae_encode(alcm_vae_encoder* v, const float* x, int B, int T, float* mo
     P->stamp = ++v->ctx->plan_clock;
     PlanUse use(P, st);
     launch_pack(x, P->x_in, v->cfg.in_channels, T, 1.f, v->prec, st);
-    if (P->ge.exec) CUDA_CHECK(cudaGraphLaunch(P->ge.exec, st));
-    else P->ol.run(st);
+    run_plan(*P, st);
     launch_unpack(P->mom_out, moments, v->quant.Cout, P->Tout, st);
     CUDA_CHECK(cudaGetLastError());
     use.finish();
@@ -2057,8 +2065,7 @@ int alcm_conv1d_run(alcm_conv1d* c, const float* x, const float* res, float* y, 
     PlanUse use(P, st);
     launch_pack(x, P->x_in, c->Cin, T, 1.f, c->prec, st);
     if (res) launch_pack(res, P->res_in, c->Cout, T, 1.f, ALCM_PREC_FP32, st);
-    if (P->ge.exec) CUDA_CHECK(cudaGraphLaunch(P->ge.exec, st));
-    else P->ol.run(st);
+    run_plan(*P, st);
     launch_unpack(P->out, y, c->Cout, T, st);
     CUDA_CHECK(cudaGetLastError());
     use.finish();

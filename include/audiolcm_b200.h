@@ -21,6 +21,7 @@
  * call that uses it.  Once a shape is planned, the decode calls perform NO allocation and NO
  * synchronisation: they enqueue kernels on `stream` and return.  Plan memory is stream-ordered
  * (cudaMallocAsync); the least recently used plans beyond ALCM_MAX_PLANS are retired without waiting.
+ * A pre-planned call may be recorded into the caller's own CUDA graph (stream capture): plan first, capture after.
  * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Functions return
  * 0 on success or a negative code; alcm_last_error() gives the message (per calling thread).  Nothing
  * aborts or throws across this boundary.
