@@ -4,9 +4,10 @@
 1 + 154 + T tokens whose feed-forward is a pair of 9-tap ``Conv1d`` layers (``Conv1dFeedForward`` with GEGLU,
 /root/reference/ldm/modules/new_attention.py:48-74): 576 -> 4608 and 2304 -> 576 channels.  Those two convs are 93 % of
 the denoiser's FLOPs and have exactly the shape ``conv_umma_kernel`` handles, so here they run on tcgen05 through
-persistent ``alcm_conv1d`` layer handles (weights packed once, one plan per (B,T)); the sampler's ``step()``
+persistent ``alcm_conv1d`` layer handles (weights packed once, one plan per (B,T)), and so do the q/k/v and output
+projections of the two self-attentions of every block (Linear over tokens = 1x1 conv); the sampler's ``step()``
 (scheduling_lcm.py:411-494) is the fused ``alcm_lcm_step`` kernel.  Everything else of the DiT (timestep / condition
-embedders, LayerNorm, the two 8-head self-attentions over 467 tokens, GroupNorm, 1x1 projections, GEGLU) is small
+embedders, LayerNorm, the softmax(QK^T)V core of the 8-head self-attentions over 467 tokens, GroupNorm, GEGLU) is small
 and stays in PyTorch: this module is the HYBRID the scope table calls "next", not a from-scratch denoiser.
 
 Pinned to the unmodified reference classes through tests/golden/lcm_denoiser.npz (made with the real LCM_audio,
@@ -74,13 +75,18 @@ class ConcatDiT2MLPB200(object):
     ``state_dict``: the reference module's (``model.unet.diffusion_model.state_dict()``), numpy or torch values."""
 
     def __init__(self, state_dict, device="cuda", precision="bf16", cfg=DIT_CFG):
-        self.cfg, self.device = dict(cfg), torch.device(device)
+        self.cfg, self.device, self.precision = dict(cfg), torch.device(device), precision
         self.sd = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).detach().to(self.device, torch.float32) for k, v in state_dict.items()}
-        self.ff_in, self.ff_out = [], []
+        self.ff_in, self.ff_out, self.qkv, self.attn_out = [], [], [], []
         for i in range(cfg["depth"]):
-            p = f"blocks.{i}.transformer_blocks.0.ff.net"
-            self.ff_in.append(Conv1dLayer(self.sd[f"{p}.0.proj.weight"], self.sd[f"{p}.0.proj.bias"], 1, device, precision))
-            self.ff_out.append(Conv1dLayer(self.sd[f"{p}.2.weight"], self.sd[f"{p}.2.bias"], 1, device, precision))
+            tb = f"blocks.{i}.transformer_blocks.0"
+            self.ff_in.append(Conv1dLayer(self.sd[f"{tb}.ff.net.0.proj.weight"], self.sd[f"{tb}.ff.net.0.proj.bias"], 1, device, precision))
+            self.ff_out.append(Conv1dLayer(self.sd[f"{tb}.ff.net.2.weight"], self.sd[f"{tb}.ff.net.2.bias"], 1, device, precision))
+            for a in ("attn1", "attn2"):   # to_q | to_k | to_v as ONE 1x1 conv (576 -> 1728), to_out as another: Linear over tokens = 1x1 conv
+                wqkv = torch.cat([self.sd[f"{tb}.{a}.to_{n}.weight"] for n in "qkv"], dim=0).unsqueeze(-1).contiguous()
+                self.qkv.append(Conv1dLayer(wqkv, None, 1, device, precision))
+                self.attn_out.append(Conv1dLayer(self.sd[f"{tb}.{a}.to_out.0.weight"].unsqueeze(-1).contiguous(), self.sd[f"{tb}.{a}.to_out.0.bias"],
+                                                 1, device, precision))
 
     @staticmethod
     def _timestep_embedding(t, dim=256, max_period=10000):            # concatDiT.py:49-69
@@ -89,13 +95,20 @@ class ConcatDiT2MLPB200(object):
         args = t[:, None].float() * freqs[None]
         return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
-    def _attn(self, p, x):                                              # new_attention.py:107-130 (self-attention)
-        sd, heads = self.sd, self.cfg["num_heads"]
-        B, N, Cc = x.shape
+    def _attn(self, idx, xn, res_cf):
+        """new_attention.py:107-130 (self-attention): xn (B,N,C) normalised tokens, res_cf (B,C,N) residual stream.
+        Returns to_out(attention) + residual, channels-first; both projections run on conv_umma_kernel."""
+        heads = self.cfg["num_heads"]
+        B, N, Cc = xn.shape
         d = Cc // heads
-        q, k, v = (F.linear(x, sd[f"{p}.to_{n}.weight"]).view(B, N, heads, d).transpose(1, 2) for n in "qkv")
-        out = F.scaled_dot_product_attention(q, k, v, scale=d ** -0.5).transpose(1, 2).reshape(B, N, Cc)
-        return F.linear(out, sd[f"{p}.to_out.0.weight"], sd[f"{p}.to_out.0.bias"])
+        qkv = self.qkv[idx](xn.permute(0, 2, 1))                                       # (B, 3C, N)
+        # one transposing copy makes q|k|v (B, heads, N, d) with unit stride in d: PyTorch's fused attention kernels
+        # need that (strided heads fall back to its 3-kernel math path); bf16 mode takes the flash kernel
+        dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        q, k, v = qkv.reshape(B, 3, heads, d, N).permute(1, 0, 2, 4, 3).to(dt, memory_format=torch.contiguous_format)
+        out = F.scaled_dot_product_attention(q, k, v, scale=d ** -0.5).float()        # (B, heads, N, d)
+        out_cf = out.transpose(2, 3).reshape(B, Cc, N)                                 # channel = head*d + dd, as 'b n (h d)'
+        return self.attn_out[idx](out_cf, res=res_cf)                                  # + bias + residual in the epilogue
 
     def _cond(self, p, c):                                              # concatDiT.py:93-104
         sd = self.sd
@@ -123,11 +136,11 @@ class ConcatDiT2MLPB200(object):
             x_in = h
             y = F.group_norm(h, 32, sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], eps=1e-6)
             y = F.conv1d(y, sd[f"{p}.proj_in.weight"], sd[f"{p}.proj_in.bias"]).permute(0, 2, 1)
-            ln = lambda v, n: F.layer_norm(v, v.shape[-1:], sd[f"{tb}.{n}.weight"], sd[f"{tb}.{n}.bias"])
-            y = self._attn(f"{tb}.attn1", ln(y, "norm1")) + y
-            y = self._attn(f"{tb}.attn2", ln(y, "norm2")) + y
-            yc = y.permute(0, 2, 1).contiguous()                          # residual stream, channels-first
-            f = self.ff_in[i](ln(y, "norm3").permute(0, 2, 1))            # Conv1d 576 -> 4608, k9 on tcgen05
+            ln = lambda v_cf, n: F.layer_norm(v_cf.permute(0, 2, 1), v_cf.shape[1:2], sd[f"{tb}.{n}.weight"], sd[f"{tb}.{n}.bias"])
+            yc = y.permute(0, 2, 1).contiguous()                          # residual stream, channels-first from here on
+            yc = self._attn(2 * i, ln(yc, "norm1"), yc)
+            yc = self._attn(2 * i + 1, ln(yc, "norm2"), yc)
+            f = self.ff_in[i](ln(yc, "norm3").permute(0, 2, 1))           # Conv1d 576 -> 4608, k9 on tcgen05
             a, gate = f.chunk(2, dim=1)
             y = self.ff_out[i](a * F.gelu(gate), res=yc)                  # Conv1d 2304 -> 576, k9, + residual fused in the epilogue
             h = F.conv1d(y, sd[f"{p}.proj_out.weight"], sd[f"{p}.proj_out.bias"]) + x_in
