@@ -97,6 +97,10 @@ SYMBOLS = {
     "alcm_conv1d_create": (C.c_int, [_P, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "alcm_conv1d_destroy": (None, [_P]),
     "alcm_conv1d_run": (C.c_int, [_P, _FP, _FP, _FP, C.c_int, C.c_int, _P]),
+    "alcm_layernorm_cf": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
+    "alcm_ffn1d_create": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "alcm_ffn1d_destroy": (None, [_P]),
+    "alcm_ffn1d_run": (C.c_int, [_P, _FP, _FP, _FP, C.c_int, C.c_int, _P]),
     "alcm_lcm_step": (C.c_int, [_P, _FP, _FP, _FP, _FP, _FP, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _P]),
     "alcm_activation1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "alcm_conv1d_fwd": (C.c_int, [_P, _FP, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -792,6 +792,22 @@ struct OpList {
     };
     push(op);
   }
+  // GEGLU of the DiT feed-forward: fp32 planes of 2*inner channels -> operand planes of inner channels
+  void geglu(const PlaneT& x, const PlaneT& out, int inner, int round_tf) {
+    const int E = 16 / out.esz;
+    REQUIRE(x.esz == 4 && x.T == out.T && x.B == out.B, "geglu: bad planes");
+    REQUIRE(inner % E == 0 && x.g.nchunk * 4 >= 2 * inner && out.g.nchunk * E >= inner, "geglu: channel mismatch");
+    const int B = x.B, T = x.T, oesz = out.esz;
+    PlaneT xc = x, oc = out;
+    Op op;
+    op.cls = ALCM_CLS_MISC; op.flops = 0; op.bytes = (double)B * T * inner * (8.0 + oesz);
+    op.fn = [=](cudaStream_t st) {
+      dim3 grid((T + 127) / 128, inner / E, B);
+      if (oesz == 2) launch_k(geglu_planes_kernel<8>, grid, dim3(128), 0, st, xc.f(), xc.g, oc.p, oc.g, T, inner, 0);
+      else launch_k(geglu_planes_kernel<4>, grid, dim3(128), 0, st, xc.f(), xc.g, oc.p, oc.g, T, inner, round_tf);
+    };
+    push(op);
+  }
   // n-way sum of fp32 planes (block mean of the AMP blocks, models.py:190-196, when the blocks ran as
   // parallel lanes); writes fp32 planes and/or operand planes for the next conv
   void sum(const std::vector<PlaneT>& in, const PlaneT* out32, const PlaneT* out_op, int round_tf) {
@@ -2000,6 +2016,18 @@ int alcm_lcm_step(alcm_ctx* ctx, const float* sample, const float* eps, const fl
   });
 }
 
+// nn.LayerNorm(C) of a channels-first tensor (the DiT token stream in conv layout), see layernorm_cf_kernel
+int alcm_layernorm_cf(alcm_ctx* ctx, const float* x, const float* gamma, const float* beta, float* y, int B, int C, int T, float eps,
+                      void* stream) {
+  return guarded([&] {
+    REQUIRE(ctx && x && gamma && beta && y, "layernorm_cf: NULL argument");
+    REQUIRE(B >= 1 && C >= 1 && T >= 1 && B <= 65535, "layernorm_cf: bad shape");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    launch_k(layernorm_cf_kernel, dim3((T + 127) / 128, B), dim3(128), 0, static_cast<cudaStream_t>(stream), x, gamma, beta, y, C, T, eps);
+    CUDA_CHECK(cudaGetLastError());
+  });
+}
+
 // ---- stand-alone Conv1d layer handle (the 9-tap Conv1dFeedForward convs of the DiT denoiser,
 //      ldm/modules/new_attention.py:48-74, are 93 % of its FLOPs and have exactly the shape conv_umma_kernel handles) ----
 struct ConvRunPlan : PlanBase {
@@ -2067,6 +2095,80 @@ int alcm_conv1d_run(alcm_conv1d* c, const float* x, const float* res, float* y, 
     if (res) launch_pack(res, P->res_in, c->Cout, T, 1.f, ALCM_PREC_FP32, st);
     run_plan(*P, st);
     launch_unpack(P->out, y, c->Cout, T, st);
+    CUDA_CHECK(cudaGetLastError());
+    use.finish();
+  });
+}
+
+// ---- the DiT's Conv1dFeedForward (glu=True) as ONE plan: Conv1d(dim -> 2*inner, k) -> x * gelu(gate) -> Conv1d(inner -> dim_out, k)
+//      (+ residual), ldm/modules/new_attention.py:48-74; the 2*inner-channel intermediate stays in planes ----
+struct alcm_ffn1d {
+  alcm_ctx* ctx;
+  Env env;
+  int prec, dim, inner, dim_out;
+  Arena war;
+  ConvLayer L1, L2;
+  RetileCache retiled;
+  std::map<std::tuple<int, int, int>, std::unique_ptr<ConvRunPlan>> plans;   // (B, T, has_res)
+  PlanCache pcache;
+};
+
+int alcm_ffn1d_create(alcm_ctx* ctx, const float* w_in, const float* b_in, const float* w_out, const float* b_out, int dim, int inner,
+                      int dim_out, int K, int precision, alcm_ffn1d** out) {
+  return guarded([&] {
+    REQUIRE(ctx && w_in && w_out && out, "ffn1d_create: NULL argument");
+    REQUIRE(dim >= 1 && inner >= 8 && inner % 8 == 0 && dim_out >= 1 && K >= 1 && (K & 1), "ffn1d_create: bad shape (inner % 8 == 0, odd K)");
+    REQUIRE(precision >= 0 && precision <= 2, "ffn1d_create: bad precision");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    std::unique_ptr<alcm_ffn1d> c(new alcm_ffn1d());
+    c->ctx = ctx; c->prec = precision; c->dim = dim; c->inner = inner; c->dim_out = dim_out;
+    c->env.cx = ctx; c->env.k = Knobs::from_env();
+    c->war.guard = c->env.k.guard != 0;
+    c->L1 = prepare_conv(c->war, c->env.k, precision, KIND_CONV, w_in, b_in, 2 * inner, dim, K, 1);
+    c->L2 = prepare_conv(c->war, c->env.k, precision, KIND_CONV, w_out, b_out, dim_out, inner, K, 1);
+    *out = c.release();
+  });
+}
+void alcm_ffn1d_destroy(alcm_ffn1d* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  wait_plans(c->plans, c->pcache);
+  delete c;
+}
+int alcm_ffn1d_run(alcm_ffn1d* c, const float* x, const float* res, float* y, int B, int T, void* stream) {
+  return guarded([&] {
+    REQUIRE(c && x && y, "ffn1d_run: NULL argument");
+    REQUIRE(B >= 1 && T >= 1, "ffn1d_run: B and T must be positive");
+    CUDA_CHECK(cudaSetDevice(c->ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto key = std::make_tuple(B, T, res ? 1 : 0);
+    auto it = c->plans.find(key);
+    ConvRunPlan* P = nullptr;
+    if (it != c->plans.end()) {
+      P = it->second.get();
+    } else {
+      c->pcache.make_room(c->plans, (size_t)c->env.k.max_plans, st);
+      const bool has_res = res != nullptr;
+      std::unique_ptr<ConvRunPlan> pl = build_plan<ConvRunPlan>(c->env, &c->war, &c->retiled, B, T, st, false, nullptr, [&](ConvRunPlan& R) {
+        R.x_in = make_planes(R.ar, B, c->dim, T, opnd_esz(c->prec));
+        PlaneT mid = make_planes(R.ar, B, 2 * c->inner, T, 4);
+        PlaneT act = make_planes(R.ar, B, c->inner, T, opnd_esz(c->prec));
+        R.out = make_planes(R.ar, B, c->dim_out, T, 4);
+        if (has_res) R.res_in = make_planes(R.ar, B, c->dim_out, T, 4);
+        R.ol.conv(c->L1, R.x_in, mid, nullptr);
+        R.ol.geglu(mid, act, c->inner, c->prec == ALCM_PREC_TF32);
+        R.ol.conv(c->L2, act, R.out, has_res ? &R.res_in : nullptr);
+        R.Tout = T;
+      });
+      P = pl.get();
+      c->plans[key] = std::move(pl);
+    }
+    P->stamp = ++c->ctx->plan_clock;
+    PlanUse use(P, st);
+    launch_pack(x, P->x_in, c->dim, T, 1.f, c->prec, st);
+    if (res) launch_pack(res, P->res_in, c->dim_out, T, 1.f, ALCM_PREC_FP32, st);
+    run_plan(*P, st);
+    launch_unpack(P->out, y, c->dim_out, T, st);
     CUDA_CHECK(cudaGetLastError());
     use.finish();
   });

@@ -97,6 +97,68 @@ __global__ void cast_planes_kernel(const float* __restrict__ in, PlaneGeom ig, v
   }
 }
 
+// nn.LayerNorm(C) over the channel axis of a CHANNELS-FIRST tensor x[b][c][t] (the DiT keeps its token stream in the conv
+// layout; the reference normalises (B,T,C) tokens, ldm/modules/new_attention.py:246-248).  One thread per (b, t) column,
+// threads along t (coalesced rows); mean, then centred variance, then the affine output: the second and third sweeps of
+// a column tile (C x 128 x 4 bytes) come from L2.
+__global__ void __launch_bounds__(128) layernorm_cf_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ y, int C, int T, float eps) {
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= T) return;
+  const float* xp = x + (size_t)blockIdx.y * C * T + t;
+  float* yp = y + (size_t)blockIdx.y * C * T + t;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int c = 0;
+  for (; c + 4 <= C; c += 4) {
+    s0 += xp[(size_t)c * T]; s1 += xp[(size_t)(c + 1) * T]; s2 += xp[(size_t)(c + 2) * T]; s3 += xp[(size_t)(c + 3) * T];
+  }
+  for (; c < C; ++c) s0 += xp[(size_t)c * T];
+  const float mean = ((s0 + s1) + (s2 + s3)) / (float)C;
+  s0 = s1 = s2 = s3 = 0.f;
+  for (c = 0; c + 4 <= C; c += 4) {
+    const float d0 = xp[(size_t)c * T] - mean, d1 = xp[(size_t)(c + 1) * T] - mean, d2 = xp[(size_t)(c + 2) * T] - mean,
+                d3 = xp[(size_t)(c + 3) * T] - mean;
+    s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s2 = fmaf(d2, d2, s2); s3 = fmaf(d3, d3, s3);
+  }
+  for (; c < C; ++c) { const float d = xp[(size_t)c * T] - mean; s0 = fmaf(d, d, s0); }
+  const float rstd = rsqrtf(((s0 + s1) + (s2 + s3)) / (float)C + eps);
+#pragma unroll 4
+  for (c = 0; c < C; ++c) yp[(size_t)c * T] = (xp[(size_t)c * T] - mean) * rstd * gamma[c] + beta[c];
+}
+
+// GEGLU between the two convs of the DiT's Conv1dFeedForward (ldm/modules/new_attention.py:48-55):
+// out[c] = in[c] * gelu(in[inner + c]) with the exact (erf) GELU of F.gelu; fp32 planes of 2*inner channels ->
+// operand planes of inner channels (bf16 E=8, or fp32 E=4 optionally rounded to tf32).  inner % E == 0.
+__device__ __forceinline__ float geglu1(float v, float g) { return v * (0.5f * g * (1.f + erff(g * 0.70710678118654752f))); }
+template <int E>
+__global__ void geglu_planes_kernel(const float* __restrict__ in, PlaneGeom ig, void* __restrict__ out, PlaneGeom og, int T, int inner,
+                                    int round_tf) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oc = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(in);
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out) + plane_row_off(og, b, oc, t);
+  const int gch = inner / 4;   // first gate chunk
+  if (E == 8) {
+    const float4 v0 = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, 2 * oc, t));
+    const float4 v1 = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, 2 * oc + 1, t));
+    const float4 g0 = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, gch + 2 * oc, t));
+    const float4 g1 = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, gch + 2 * oc + 1, t));
+    uint4 o;
+    o.x = pack_bf16x2(geglu1(v0.x, g0.x), geglu1(v0.y, g0.y)); o.y = pack_bf16x2(geglu1(v0.z, g0.z), geglu1(v0.w, g0.w));
+    o.z = pack_bf16x2(geglu1(v1.x, g1.x), geglu1(v1.y, g1.y)); o.w = pack_bf16x2(geglu1(v1.z, g1.z), geglu1(v1.w, g1.w));
+    *reinterpret_cast<uint4*>(dst) = o;
+  } else {
+    const float4 v = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, oc, t));
+    const float4 g = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, gch + oc, t));
+    float4 o = make_float4(geglu1(v.x, g.x), geglu1(v.y, g.y), geglu1(v.z, g.z), geglu1(v.w, g.w));
+    if (round_tf) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
+    *reinterpret_cast<float4*>(dst) = o;
+  }
+}
+
 // n-way sum of fp32 planes -> fp32 planes and/or operand planes (bf16 E=8 or tf32-rounded fp32).
 // One thread handles two adjacent fp32 chunks (= one bf16 chunk) of one time step.
 struct SumArgs {

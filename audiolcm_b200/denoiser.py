@@ -4,10 +4,10 @@
 1 + 154 + T tokens whose feed-forward is a pair of 9-tap ``Conv1d`` layers (``Conv1dFeedForward`` with GEGLU,
 /root/reference/ldm/modules/new_attention.py:48-74): 576 -> 4608 and 2304 -> 576 channels.  Those two convs are 93 % of
 the denoiser's FLOPs and have exactly the shape ``conv_umma_kernel`` handles, so here they run on tcgen05 through
-persistent ``alcm_conv1d`` layer handles (weights packed once, one plan per (B,T)), and so do the q/k/v and output
+persistent handles (weights packed once, one plan per (B,T): ``alcm_ffn1d`` = conv, GEGLU, conv + residual), and so do the q/k/v and output
 projections of the two self-attentions of every block (Linear over tokens = 1x1 conv); the sampler's ``step()``
 (scheduling_lcm.py:411-494) is the fused ``alcm_lcm_step`` kernel.  Everything else of the DiT (timestep / condition
-embedders, LayerNorm, the softmax(QK^T)V core of the 8-head self-attentions over 467 tokens, GroupNorm, GEGLU) is small
+embedders, the softmax(QK^T)V core of the 8-head self-attentions over 467 tokens, GroupNorm) is small
 and stays in PyTorch: this module is the HYBRID the scope table calls "next", not a from-scratch denoiser.
 
 Pinned to the unmodified reference classes through tests/golden/lcm_denoiser.npz (made with the real LCM_audio,
@@ -69,6 +69,51 @@ class Conv1dLayer(object):
         return y
 
 
+class Conv1dFeedForwardLayer(object):
+    """``Conv1dFeedForward(dim, mult=4, glu=True)`` (new_attention.py:48-74) as one native plan: conv -> GEGLU -> conv (+ res)."""
+
+    def __init__(self, w_in, b_in, w_out, b_out, device="cuda", precision="bf16"):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.AlcmError("audiolcm_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        t = lambda v: None if v is None else (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).detach().to(dev, torch.float32).contiguous()
+        w_in, b_in, w_out, b_out = t(w_in), t(b_in), t(w_out), t(b_out)
+        self.device, self.dim, self.inner, self.dim_out, self.k = dev, int(w_in.shape[1]), int(w_out.shape[1]), int(w_out.shape[0]), int(w_in.shape[2])
+        if w_in.shape[0] != 2 * self.inner or w_out.shape[2] != self.k:
+            raise ValueError("Conv1dFeedForward weights: expected [2*inner,dim,K] and [dim_out,inner,K]")
+        h = C.c_void_p()
+        ptr = lambda v: None if v is None else v.data_ptr()
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize()
+            _lib.check(_lib.load().alcm_ffn1d_create(_lib.ctx(dev.index), ptr(w_in), ptr(b_in), ptr(w_out), ptr(b_out), self.dim, self.inner,
+                                                     self.dim_out, self.k, _lib.PREC[precision], C.byref(h)))
+        self._h = h.value
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.load().alcm_ffn1d_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def __call__(self, x, res=None):
+        x = x.to(dtype=torch.float32, device=self.device).contiguous()
+        if x.dim() != 3 or x.shape[1] != self.dim:
+            raise ValueError(f"expected (B,{self.dim},T), got {tuple(x.shape)}")
+        B, _, T = x.shape
+        if res is not None:
+            res = res.to(dtype=torch.float32, device=self.device).contiguous()
+        y = torch.empty((B, self.dim_out, T), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().alcm_ffn1d_run(self._h, x.data_ptr(), None if res is None else res.data_ptr(), y.data_ptr(), B, T,
+                                                  torch.cuda.current_stream().cuda_stream))
+        return y
+
+
 class ConcatDiT2MLPB200(object):
     """``ConcatDiT2MLP.forward(x, t, context, w_cond)`` with the feed-forward convs on the B200 conv kernel.
 
@@ -77,11 +122,13 @@ class ConcatDiT2MLPB200(object):
     def __init__(self, state_dict, device="cuda", precision="bf16", cfg=DIT_CFG):
         self.cfg, self.device, self.precision = dict(cfg), torch.device(device), precision
         self.sd = {k: (torch.from_numpy(v) if isinstance(v, np.ndarray) else v).detach().to(self.device, torch.float32) for k, v in state_dict.items()}
-        self.ff_in, self.ff_out, self.qkv, self.attn_out = [], [], [], []
+        self.ff, self.qkv, self.attn_out, self.blk_in, self.blk_out = [], [], [], [], []
         for i in range(cfg["depth"]):
             tb = f"blocks.{i}.transformer_blocks.0"
-            self.ff_in.append(Conv1dLayer(self.sd[f"{tb}.ff.net.0.proj.weight"], self.sd[f"{tb}.ff.net.0.proj.bias"], 1, device, precision))
-            self.ff_out.append(Conv1dLayer(self.sd[f"{tb}.ff.net.2.weight"], self.sd[f"{tb}.ff.net.2.bias"], 1, device, precision))
+            self.ff.append(Conv1dFeedForwardLayer(self.sd[f"{tb}.ff.net.0.proj.weight"], self.sd[f"{tb}.ff.net.0.proj.bias"],
+                                                  self.sd[f"{tb}.ff.net.2.weight"], self.sd[f"{tb}.ff.net.2.bias"], device, precision))
+            self.blk_in.append(Conv1dLayer(self.sd[f"blocks.{i}.proj_in.weight"], self.sd[f"blocks.{i}.proj_in.bias"], 1, device, precision))
+            self.blk_out.append(Conv1dLayer(self.sd[f"blocks.{i}.proj_out.weight"], self.sd[f"blocks.{i}.proj_out.bias"], 1, device, precision))
             for a in ("attn1", "attn2"):   # to_q | to_k | to_v as ONE 1x1 conv (576 -> 1728), to_out as another: Linear over tokens = 1x1 conv
                 wqkv = torch.cat([self.sd[f"{tb}.{a}.to_{n}.weight"] for n in "qkv"], dim=0).unsqueeze(-1).contiguous()
                 self.qkv.append(Conv1dLayer(wqkv, None, 1, device, precision))
@@ -95,19 +142,19 @@ class ConcatDiT2MLPB200(object):
         args = t[:, None].float() * freqs[None]
         return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
-    def _attn(self, idx, xn, res_cf):
-        """new_attention.py:107-130 (self-attention): xn (B,N,C) normalised tokens, res_cf (B,C,N) residual stream.
-        Returns to_out(attention) + residual, channels-first; both projections run on conv_umma_kernel."""
+    def _attn(self, idx, xn_cf, res_cf):
+        """new_attention.py:107-130 (self-attention): xn_cf (B,C,N) normalised tokens and res_cf (B,C,N) residual stream, both
+        channels-first.  Returns to_out(attention) + residual; both projections run on conv_umma_kernel."""
         heads = self.cfg["num_heads"]
-        B, N, Cc = xn.shape
+        B, Cc, N = xn_cf.shape
         d = Cc // heads
-        qkv = self.qkv[idx](xn.permute(0, 2, 1))                                       # (B, 3C, N)
+        qkv = self.qkv[idx](xn_cf)                                                     # (B, 3C, N)
         # one transposing copy makes q|k|v (B, heads, N, d) with unit stride in d: PyTorch's fused attention kernels
         # need that (strided heads fall back to its 3-kernel math path); bf16 mode takes the flash kernel
         dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
         q, k, v = qkv.reshape(B, 3, heads, d, N).permute(1, 0, 2, 4, 3).to(dt, memory_format=torch.contiguous_format)
-        out = F.scaled_dot_product_attention(q, k, v, scale=d ** -0.5).float()        # (B, heads, N, d)
-        out_cf = out.transpose(2, 3).reshape(B, Cc, N)                                 # channel = head*d + dd, as 'b n (h d)'
+        out = F.scaled_dot_product_attention(q, k, v, scale=d ** -0.5)                 # (B, heads, N, d)
+        out_cf = out.transpose(2, 3).reshape(B, Cc, N).float()                         # channel = head*d + dd, as 'b n (h d)'
         return self.attn_out[idx](out_cf, res=res_cf)                                  # + bias + residual in the epilogue
 
     def _cond(self, p, c):                                              # concatDiT.py:93-104
@@ -118,6 +165,7 @@ class ConcatDiT2MLPB200(object):
 
     @torch.no_grad()
     def __call__(self, x, t, context, w_cond=None):
+        from . import ops
         sd = self.sd
         t_freq = self._timestep_embedding(t, 256)
         if w_cond is not None:
@@ -135,15 +183,12 @@ class ConcatDiT2MLPB200(object):
             p, tb = f"blocks.{i}", f"blocks.{i}.transformer_blocks.0"
             x_in = h
             y = F.group_norm(h, 32, sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], eps=1e-6)
-            y = F.conv1d(y, sd[f"{p}.proj_in.weight"], sd[f"{p}.proj_in.bias"]).permute(0, 2, 1)
-            ln = lambda v_cf, n: F.layer_norm(v_cf.permute(0, 2, 1), v_cf.shape[1:2], sd[f"{tb}.{n}.weight"], sd[f"{tb}.{n}.bias"])
-            yc = y.permute(0, 2, 1).contiguous()                          # residual stream, channels-first from here on
+            yc = self.blk_in[i](y)                                         # 1x1 proj_in; residual stream, channels-first from here on
+            ln = lambda v_cf, n: ops.layernorm_cf(v_cf, sd[f"{tb}.{n}.weight"], sd[f"{tb}.{n}.bias"])   # LayerNorm over channels, layout kept
             yc = self._attn(2 * i, ln(yc, "norm1"), yc)
             yc = self._attn(2 * i + 1, ln(yc, "norm2"), yc)
-            f = self.ff_in[i](ln(yc, "norm3").permute(0, 2, 1))           # Conv1d 576 -> 4608, k9 on tcgen05
-            a, gate = f.chunk(2, dim=1)
-            y = self.ff_out[i](a * F.gelu(gate), res=yc)                  # Conv1d 2304 -> 576, k9, + residual fused in the epilogue
-            h = F.conv1d(y, sd[f"{p}.proj_out.weight"], sd[f"{p}.proj_out.bias"]) + x_in
+            y = self.ff[i](ln(yc, "norm3"), res=yc)       # Conv1d 576 -> 4608 k9, GEGLU, Conv1d 2304 -> 576 k9, + residual: one plan
+            h = self.blk_out[i](y, res=x_in)                              # 1x1 proj_out + the block's skip connection
         h = h[..., extra:]
         h = F.group_norm(h, 16, sd["final_layer.norm_final.weight"], sd["final_layer.norm_final.bias"])
         return F.conv1d(h, sd["final_layer.conv1d.weight"], sd["final_layer.conv1d.bias"])

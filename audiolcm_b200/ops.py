@@ -111,3 +111,13 @@ def lcm_step(sample, eps, noise, sqrt_alpha_prod_t, sqrt_beta_prod_t, c_out, c_s
                                              float(sqrt_alpha_prod_t), float(sqrt_beta_prod_t), float(c_out), float(c_skip),
                                              float(sqrt_alpha_prod_prev), float(sqrt_beta_prod_prev), int(bool(last_step)), _stream()))
     return prev, den
+
+
+def layernorm_cf(x, gamma, beta, eps=1e-5):
+    """``nn.LayerNorm(C)`` over the channel axis of a channels-first (B,C,T) tensor (the DiT's norm1/2/3, new_attention.py:246-248)."""
+    (x, gamma, beta), dev = _prep(x, gamma, beta)
+    B, Cc, T = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().alcm_layernorm_cf(_lib.ctx(dev.index), _p(x), _p(gamma), _p(beta), _p(y), B, Cc, T, float(eps), _stream()))
+    return y

@@ -485,9 +485,9 @@ def config5(pipe, device, precision, prompts=256, chunk=64):
       reference  the reference's sampler and ConcatDiT2MLP in eager PyTorch (baseline/lcm_denoiser_port.py - the reference
                  Python cannot travel to this box; the port is pinned to it by tests/golden/lcm_denoiser.npz): the
                  configuration BASELINE.json names ("denoiser left as reference PyTorch");
-      hybrid     SURVEY 8f row 2: the DiT's 9-tap feed-forward convs (93 % of its FLOPs) and its attention projections on
-                 conv_umma_kernel, the sampler step as one kernel (audiolcm_b200/denoiser.py), the rest of the DiT
-                 (LayerNorm, GEGLU, the fused-SDPA attention core) still PyTorch."""
+      hybrid     SURVEY 8f row 2: the DiT's feed-forward (conv - GEGLU - conv + residual as one plan, 93 % of its FLOPs), its
+                 1x1 / attention projections and LayerNorms native, the sampler step as one kernel
+                 (audiolcm_b200/denoiser.py); the fused-SDPA attention core, GroupNorm and the embedders still PyTorch."""
     import shutil
     import tempfile
     import torch

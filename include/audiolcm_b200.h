@@ -44,6 +44,7 @@ typedef struct alcm_ctx alcm_ctx;
 typedef struct alcm_vocoder alcm_vocoder;
 typedef struct alcm_vae alcm_vae;
 typedef struct alcm_conv1d alcm_conv1d;
+typedef struct alcm_ffn1d alcm_ffn1d;
 typedef struct alcm_vae_encoder alcm_vae_encoder;
 
 /* arithmetic used by the conv GEMMs */
@@ -175,6 +176,11 @@ int alcm_lcm_step(alcm_ctx* ctx, const float* sample, const float* eps, const fl
                   float sqrt_alpha_prod_t, float sqrt_beta_prod_t, float c_out, float c_skip, float sqrt_alpha_prod_prev,
                   float sqrt_beta_prod_prev, int last_step, void* stream);
 
+/* nn.LayerNorm(C) (new_attention.py:246-248 norm1/2/3, eps 1e-5) applied over the channel axis of a channels-first
+ * tensor: y[b,:,t] = (x[b,:,t] - mean) * rsqrt(var + eps) * gamma + beta.  x, y [B,C,T], gamma, beta [C]: device fp32. */
+int alcm_layernorm_cf(alcm_ctx* ctx, const float* x, const float* gamma, const float* beta, float* y, int B, int C, int T, float eps,
+                      void* stream);
+
 /* ---- a Conv1d layer as a persistent handle: weights packed once, one plan per (B,T) shape.  Used for the 9-tap
  * Conv1dFeedForward convs of the DiT denoiser (ldm/modules/new_attention.py:48-74; ConcatDiT2MLP blocks,
  * concatDiT.py:108-130), 93 % of the denoiser's FLOPs.  w [Cout,Cin,K] and bias [Cout] are device fp32; padding is
@@ -184,6 +190,16 @@ int alcm_conv1d_create(alcm_ctx* ctx, const float* w, const float* bias, int Cou
                        alcm_conv1d** out);
 void alcm_conv1d_destroy(alcm_conv1d* c);
 int alcm_conv1d_run(alcm_conv1d* c, const float* x, const float* res, float* y, int B, int T, void* stream);
+
+/* ---- Conv1dFeedForward(dim, mult, glu=True, kernel_size=K) of the DiT blocks as ONE handle / one plan per (B,T)
+ * (ldm/modules/new_attention.py:38-74): h = Conv1d(dim -> 2*inner, K)(x); y = Conv1d(inner -> dim_out, K)(h[:inner] *
+ * gelu(h[inner:])) (+ res).  The 2*inner-channel intermediate never leaves the operand layout (GEGLU is one kernel
+ * between the two tcgen05 convs).  w_in [2*inner,dim,K], b_in [2*inner], w_out [dim_out,inner,K], b_out [dim_out]:
+ * device fp32 (biases may be NULL); inner % 8 == 0, K odd <= 11.  x [B,dim,T], res (may be NULL), y [B,dim_out,T]. */
+int alcm_ffn1d_create(alcm_ctx* ctx, const float* w_in, const float* b_in, const float* w_out, const float* b_out, int dim, int inner,
+                      int dim_out, int K, int precision, alcm_ffn1d** out);
+void alcm_ffn1d_destroy(alcm_ffn1d* c);
+int alcm_ffn1d_run(alcm_ffn1d* c, const float* x, const float* res, float* y, int B, int T, void* stream);
 
 /* ---- single-op entry points (tests / micro-benchmarks); tensors are [B,C,T] fp32 on device -----*/
 /* Activation1d(SnakeBeta logscale): act.py:23-28.  precision BF16 returns bf16-rounded values. */

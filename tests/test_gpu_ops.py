@@ -269,6 +269,43 @@ def test_conv1d_layer_handle(precision):
         assert float((y.double() - ref).abs().max()) < 3e-5 * max(1.0, float(ref.abs().max()))
 
 
+def test_layernorm_channels_first():
+    """alcm_layernorm_cf = nn.LayerNorm(C) of the DiT blocks (new_attention.py:246-248) applied to the channels-first stream."""
+    from audiolcm_b200 import ops
+    for (B, Cc, T) in ((2, 576, 467), (1, 3, 1), (3, 130, 129), (1, 64, 1000)):
+        x = _rand(B, Cc, T, seed=90 + T) + 0.5
+        g, b = _rand(Cc, seed=91) + 1.0, _rand(Cc, seed=92)
+        ref = F.layer_norm(x.double().permute(0, 2, 1), (Cc,), g.double(), b.double(), 1e-5).permute(0, 2, 1)
+        y = ops.layernorm_cf(x.to(DEV), g.to(DEV), b.to(DEV)).cpu()
+        assert float((y.double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_conv1d_feedforward_handle(precision):
+    """alcm_ffn1d_* = Conv1dFeedForward(glu=True) (new_attention.py:38-74): conv k9 -> x * gelu(gate) -> conv k9 (+ res) as one plan,
+    against the same ops in float64 (operands of the second conv rounded as the kernel rounds them)."""
+    from audiolcm_b200.denoiser import Conv1dFeedForwardLayer
+    dim, inner, K = 64, 136, 9      # inner % 16 != 0: the gate half starts inside a 16-channel padding group
+    w1 = _rand(2 * inner, dim, K, seed=80, scale=1.0 / np.sqrt(dim * K))
+    b1 = _rand(2 * inner, seed=81, scale=0.1)
+    w2 = _rand(dim, inner, K, seed=82, scale=1.0 / np.sqrt(inner * K))
+    b2 = _rand(dim, seed=83, scale=0.1)
+    layer = Conv1dFeedForwardLayer(w1, b1, w2, b2, DEV, precision)
+    for (B, T, with_res) in ((2, 467, True), (1, 50, False), (3, 129, True), (2, 467, True)):
+        x = _rand(B, dim, T, seed=84 + T)
+        res = _rand(B, dim, T, seed=85) if with_res else None
+        h = F.conv1d(round_operand(x, precision).double(), round_operand(w1, precision).double(), b1.double(), padding=K // 2)
+        a, gate = h.chunk(2, dim=1)
+        mid = (a * F.gelu(gate)).float()
+        ref = F.conv1d(round_operand(mid, precision).double(), round_operand(w2, precision).double(), b2.double(), padding=K // 2)
+        if with_res:
+            ref = ref + res.double()
+        y = layer(x.to(DEV), None if res is None else res.to(DEV)).cpu()
+        # the intermediate is re-rounded to the operand type: a 1-ulp flip of it moves the output by ~ulp * |w|
+        tol = {"fp32": 3e-5, "tf32": 1e-3, "bf16": 4e-3}[precision]
+        assert float((y.double() - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("precision", ["tf32", "bf16"])
 def test_hybrid_dit_and_sampler_match_reference_golden(golden_dir, precision):
     """ConcatDiT2MLPB200 (feed-forward convs on conv_umma_kernel, the rest PyTorch) and LCMSamplerB200 (fused step kernel)
