@@ -26,6 +26,8 @@ class BigVGANCfg(C.Structure):
         ("upsample_kernel_sizes", C.c_int * 8),
         ("resblock_kernel_sizes", C.c_int * 4),
         ("resblock_dilation_sizes", (C.c_int * 3) * 4),
+        ("resblock2", C.c_int),
+        ("snake_linear", C.c_int),
     ]
 
 

@@ -1092,12 +1092,12 @@ struct alcm_vocoder {
   PlanCache pcache;
 };
 
-static SnakeP make_snake(Arena& ar, const float* alpha, const float* beta, int C) {
+static SnakeP make_snake(Arena& ar, const float* alpha, const float* beta, int C, int linear) {
   const int Cpad = round_up(C, 16);
   SnakeP s;
   s.ea = static_cast<float*>(ar.alloc((size_t)Cpad * 4, false));
   s.ib = static_cast<float*>(ar.alloc((size_t)Cpad * 4, false));
-  snake_params_kernel<<<(Cpad + 127) / 128, 128>>>(alpha, beta, s.ea, s.ib, C, Cpad);
+  snake_params_kernel<<<(Cpad + 127) / 128, 128>>>(alpha, beta, s.ea, s.ib, C, Cpad, linear);
   CUDA_CHECK(cudaGetLastError());
   return s;
 }
@@ -1149,18 +1149,27 @@ static void voc_build(const alcm_vocoder* v, VocPlan& P) {
       }
       if (parallel) P.ol.lane(j);
       const PlaneT* cur = &X;
-      for (int l = 0; l < 3; ++l) {  // models.py:72-81
-        P.ol.act(*cur, A, bk.a[2 * l].ea, bk.a[2 * l].ib, rtf, fast);
-        P.ol.conv(bk.c1[l], A, Y, nullptr);
-        P.ol.act(Y, A, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, rtf, fast);
-        if (l < 2) {
-          P.ol.conv(bk.c2[l], A, R, cur);
+      const bool rb2 = v->cfg.resblock2 != 0;
+      const int nl = rb2 ? 2 : 3;
+      for (int l = 0; l < nl; ++l) {  // AMPBlock1 models.py:72-81: x += c2(a(c1(a(x)))); AMPBlock2 :119-126: x += c(a(x))
+        const ConvLayer* tail;
+        if (rb2) {
+          P.ol.act(*cur, A, bk.a[l].ea, bk.a[l].ib, rtf, fast);
+          tail = &bk.c1[l];
+        } else {
+          P.ol.act(*cur, A, bk.a[2 * l].ea, bk.a[2 * l].ib, rtf, fast);
+          P.ol.conv(bk.c1[l], A, Y, nullptr);
+          P.ol.act(Y, A, bk.a[2 * l + 1].ea, bk.a[2 * l + 1].ib, rtf, fast);
+          tail = &bk.c2[l];
+        }
+        if (l < nl - 1) {
+          P.ol.conv(*tail, A, R, cur);
           cur = &R;
         } else if (parallel) {  // block output in place of its residual stream (same thread reads then writes)
-          P.ol.conv(bk.c2[l], A, R, cur, 1.0f / nk, 0);
+          P.ol.conv(*tail, A, R, cur, 1.0f / nk, 0);
           Z.push_back(R);
         } else {  // x = xs / num_kernels, models.py:190-196, folded into the last conv of each block
-          P.ol.conv(bk.c2[l], A, XS, cur, 1.0f / nk, j > 0);
+          P.ol.conv(*tail, A, XS, cur, 1.0f / nk, j > 0);
         }
       }
     }
@@ -1553,7 +1562,8 @@ void alcm_ctx_destroy(alcm_ctx* ctx) { delete ctx; }
 
 int alcm_vocoder_num_tensors(const alcm_bigvgan_cfg* c) {
   if (!c) return -1;
-  return 3 + c->num_upsamples * (3 + c->num_kernels * (18 + 12)) + 2 + 3;
+  const int per_block = c->resblock2 ? (2 * 3 + 2 * 2) : (18 + 12);   // AMPBlock2: 2 convs + 2 activations (models.py:90-126)
+  return 3 + c->num_upsamples * (3 + c->num_kernels * per_block) + 2 + 3;
 }
 
 int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float* const* t, int n_tensors, int precision,
@@ -1596,18 +1606,19 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
       for (int j = 0; j < cfg->num_kernels; ++j) {
         AmpBlock bk;
         const int kk = cfg->resblock_kernel_sizes[j];
-        for (int l = 0; l < 3; ++l) {
+        const int nl = cfg->resblock2 ? 2 : 3;
+        for (int l = 0; l < nl; ++l) {
           const float* w = fold_wn(tmp, t[ti], t[ti + 1], C, C * kk);
           bk.c1[l] = prepare_conv(v->war, K, precision, KIND_CONV, w, t[ti + 2], C, C, kk, cfg->resblock_dilation_sizes[j][l]);
           ti += 3;
         }
-        for (int l = 0; l < 3; ++l) {
+        for (int l = 0; l < 3 && !cfg->resblock2; ++l) {
           const float* w = fold_wn(tmp, t[ti], t[ti + 1], C, C * kk);
           bk.c2[l] = prepare_conv(v->war, K, precision, KIND_CONV, w, t[ti + 2], C, C, kk, 1);
           ti += 3;
         }
-        for (int m = 0; m < 6; ++m) {
-          bk.a[m] = make_snake(v->war, t[ti], t[ti + 1], C);
+        for (int m = 0; m < (cfg->resblock2 ? 2 : 6); ++m) {
+          bk.a[m] = make_snake(v->war, t[ti], t[ti + 1], C, cfg->snake_linear);
           ti += 2;
         }
         S.blocks.push_back(bk);
@@ -1615,7 +1626,7 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
       }
       v->stages.push_back(std::move(S));
     }
-    v->act_post = make_snake(v->war, t[ti], t[ti + 1], C);
+    v->act_post = make_snake(v->war, t[ti], t[ti + 1], C, cfg->snake_linear);
     ti += 2;
     {  // conv_post (1,C,7) -> tap-major [7][Cpad] fp32 on device
       const float* w = fold_wn(tmp, t[ti], t[ti + 1], 1, C * 7);
@@ -2191,7 +2202,7 @@ int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, con
     Arena ar;
     ar.guard = env_int("ALCM_GUARD", 0) != 0;
     PlaneT xin = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, opnd_esz(precision));
-    SnakeP sp = make_snake(ar, alpha, beta, C);
+    SnakeP sp = make_snake(ar, alpha, beta, C, 0);
     CUDA_CHECK(sync_setup());
     launch_pack(x, xin, C, T, 1.f, ALCM_PREC_FP32, st);
     OpList ol;
@@ -2480,7 +2491,7 @@ int alcm_bench_act(alcm_ctx* ctx, int B, int C, int T, int precision, int iters,
     float* be = static_cast<float*>(ar.alloc((size_t)round_up(C, 16) * 4, false));
     fill_uniform(al, (size_t)round_up(C, 16), 0, -0.9f, 0.9f, 6u);   // alpha, beta ~ spread of N(0, 0.5)
     fill_uniform(be, (size_t)round_up(C, 16), 0, -0.9f, 0.9f, 7u);
-    SnakeP sp = make_snake(ar, al, be, C);
+    SnakeP sp = make_snake(ar, al, be, C, 0);
     OpList ol;
     ol.env = Env{ctx, Knobs::from_env()};
     ol.act(x, out, sp.ea, sp.ib, precision == ALCM_PREC_TF32, precision != ALCM_PREC_FP32);

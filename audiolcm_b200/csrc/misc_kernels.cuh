@@ -346,13 +346,15 @@ __global__ void repack_nt_kernel(const uint4* __restrict__ src, uint4* __restric
   }
 }
 
-// SnakeBeta parameters (activations.py:113-118, logscale): ea = exp(alpha), ib = 1/(exp(beta)+1e-9)
+// Snake / SnakeBeta parameters (activations.py:56-62,113-120): ea = exp(alpha), ib = 1/(exp(beta)+1e-9) with
+// alpha_logscale, ea = alpha, ib = 1/(beta+1e-9) without.  Snake is the beta = alpha case (the caller passes alpha twice).
 __global__ void snake_params_kernel(const float* __restrict__ alpha, const float* __restrict__ beta, float* __restrict__ ea,
-                                    float* __restrict__ ib, int C, int Cpad) {
+                                    float* __restrict__ ib, int C, int Cpad, int linear) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cpad) return;
-  ea[c] = (c < C) ? expf(alpha[c]) : 1.f;
-  ib[c] = (c < C) ? 1.0f / (expf(beta[c]) + 1e-9f) : 1.f;
+  if (c >= C) { ea[c] = 1.f; ib[c] = 1.f; return; }
+  ea[c] = linear ? alpha[c] : expf(alpha[c]);
+  ib[c] = 1.0f / ((linear ? beta[c] : expf(beta[c])) + 1e-9f);
 }
 
 // ------------------------------------------------------------------------------- conv_post + tanh

@@ -91,6 +91,15 @@ def _wn_conv(rng, sd, name, cout, cin, k, transposed=False):
     sd[name + ".bias"] = _uniform(rng, (cout,), 1.0 / np.sqrt(fan_in))
 
 
+def _snake_params(rng, sd, p, ch, h):
+    """alpha (and beta for snakebeta): N(0, 0.5) in log scale; U(0.6, 1.6) in linear scale, where the reference initialises
+    them to 1 (activations.py:33-42,88-98) and 1/beta must stay bounded for a well-conditioned test network."""
+    draw = (lambda: 0.5 * rng.standard_normal(ch)) if h["snake_logscale"] else (lambda: rng.uniform(0.6, 1.6, size=ch))
+    sd[p + ".alpha"] = draw().astype(np.float32)
+    if h["activation"] == "snakebeta":
+        sd[p + ".beta"] = draw().astype(np.float32)
+
+
 def bigvgan_state_dict(h, seed: int = 0) -> dict:
     """Synthetic generator state_dict (numpy fp32), reference key names.
     The 218 constant ``filter`` buffers are omitted (load with strict=False)."""
@@ -105,15 +114,19 @@ def bigvgan_state_dict(h, seed: int = 0) -> dict:
         _wn_conv(rng, sd, f"ups.{i}.0", ch, cin, k, transposed=True)
         for j, kk in enumerate(h["resblock_kernel_sizes"]):
             p = f"resblocks.{i * nk + j}"
-            for l in range(3):
-                _wn_conv(rng, sd, f"{p}.convs1.{l}", ch, ch, kk)
-            for l in range(3):
-                _wn_conv(rng, sd, f"{p}.convs2.{l}", ch, ch, kk)
-            for m in range(6):
-                sd[f"{p}.activations.{m}.act.alpha"] = (0.5 * rng.standard_normal(ch)).astype(np.float32)
-                sd[f"{p}.activations.{m}.act.beta"] = (0.5 * rng.standard_normal(ch)).astype(np.float32)
-    sd["activation_post.act.alpha"] = (0.5 * rng.standard_normal(ch)).astype(np.float32)
-    sd["activation_post.act.beta"] = (0.5 * rng.standard_normal(ch)).astype(np.float32)
+            if str(h["resblock"]) == "1":
+                for l in range(3):
+                    _wn_conv(rng, sd, f"{p}.convs1.{l}", ch, ch, kk)
+                for l in range(3):
+                    _wn_conv(rng, sd, f"{p}.convs2.{l}", ch, ch, kk)
+                nact = 6
+            else:                                       # AMPBlock2: two convs, two activations
+                for l in range(2):
+                    _wn_conv(rng, sd, f"{p}.convs.{l}", ch, ch, kk)
+                nact = 2
+            for m in range(nact):
+                _snake_params(rng, sd, f"{p}.activations.{m}.act", ch, h)
+    _snake_params(rng, sd, "activation_post.act", ch, h)
     _wn_conv(rng, sd, "conv_post", 1, ch, 7)
     return sd
 

@@ -35,22 +35,31 @@ def _as_cuda_f32(t, device):
 
 
 def bigvgan_tensor_names(h):
-    """state_dict keys in the order alcm_vocoder_create expects (include/audiolcm_b200.h)."""
+    """state_dict keys in the order alcm_vocoder_create expects (include/audiolcm_b200.h).  ``activation: snake`` has no
+    ``beta`` parameters (activations.py:9-62): its alpha is listed twice, Snake being SnakeBeta with beta = alpha."""
     names = []
     wn = lambda p: [p + ".weight_g", p + ".weight_v", p + ".bias"]
+    ab = (lambda p: [p + ".alpha", p + ".beta"]) if _get(h, "activation") == "snakebeta" else (lambda p: [p + ".alpha", p + ".alpha"])
+    rb2 = str(_get(h, "resblock")) == "2"
     names += wn("conv_pre")
     nk = len(_get(h, "resblock_kernel_sizes"))
     for i in range(len(_get(h, "upsample_rates"))):
         names += wn(f"ups.{i}.0")
         for j in range(nk):
             p = f"resblocks.{i * nk + j}"
+            if rb2:                                   # AMPBlock2, models.py:90-126
+                for l in range(2):
+                    names += wn(f"{p}.convs.{l}")
+                for m in range(2):
+                    names += ab(f"{p}.activations.{m}.act")
+                continue
             for l in range(3):
                 names += wn(f"{p}.convs1.{l}")
             for l in range(3):
                 names += wn(f"{p}.convs2.{l}")
             for m in range(6):
-                names += [f"{p}.activations.{m}.act.alpha", f"{p}.activations.{m}.act.beta"]
-    names += ["activation_post.act.alpha", "activation_post.act.beta"]
+                names += ab(f"{p}.activations.{m}.act")
+    names += ab("activation_post.act")
     names += wn("conv_post")
     return names
 
@@ -108,11 +117,10 @@ class VocoderBigVGAN(object):
     def _setup(self, sd, h, device, precision):
         if precision not in _lib.PREC:
             raise ValueError(f"precision must be one of {sorted(_lib.PREC)}")
-        if str(_get(h, "resblock")) != "1":
-            raise NotImplementedError("only resblock '1' (AMPBlock1) is implemented (the 16k config)")
-        if _get(h, "activation") != "snakebeta" or not _get(h, "snake_logscale"):
-            # reference raises NotImplementedError for unknown activations (models.py:70,172)
-            raise NotImplementedError("activation incorrectly specified: only snakebeta with snake_logscale is implemented")
+        if _get(h, "activation") not in ("snake", "snakebeta"):
+            # the reference raises the same for unknown activations (models.py:70,115,172)
+            raise NotImplementedError("activation incorrectly specified. check the config file and look for 'activation'.")
+        rb2 = str(_get(h, "resblock")) != "1"          # models.py:146: anything but '1' selects AMPBlock2
         dev = torch.device(device)
         if dev.type != "cuda":
             raise _lib.AlcmError("audiolcm_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
@@ -121,11 +129,12 @@ class VocoderBigVGAN(object):
         self.device = dev
         self.precision = precision
         self.h = {k: _get(h, k) for k in _GEN_KEYS}
+        self.h["resblock"] = "2" if rb2 else "1"
         rates = [int(u) for u in self.h["upsample_rates"]]
         ksz = [int(k) for k in self.h["upsample_kernel_sizes"]]
         rks = [int(k) for k in self.h["resblock_kernel_sizes"]]
         rds = [[int(d) for d in dd] for dd in self.h["resblock_dilation_sizes"]]
-        if len(rates) > 8 or len(rks) > 4 or any(len(d) != 3 for d in rds):
+        if len(rates) > 8 or len(rks) > 4 or any(len(d) != (2 if rb2 else 3) for d in rds):
             raise NotImplementedError("unsupported BigVGAN topology")
         self.num_mels = int(self.h["num_mels"])
         self.hop = int(np.prod(rates))
@@ -134,6 +143,8 @@ class VocoderBigVGAN(object):
         cfg.upsample_initial_channel = int(self.h["upsample_initial_channel"])
         cfg.num_upsamples = len(rates)
         cfg.num_kernels = len(rks)
+        cfg.resblock2 = int(rb2)
+        cfg.snake_linear = int(not _get(h, "snake_logscale"))
         for i, (u, k) in enumerate(zip(rates, ksz)):
             cfg.upsample_rates[i] = u
             cfg.upsample_kernel_sizes[i] = k

@@ -67,8 +67,10 @@ void alcm_ctx_destroy(alcm_ctx* ctx);
 const char* alcm_last_error(void);
 
 /* ---- BigVGAN vocoder ------------------------------------------------------------------------
- * cfg mirrors the generator keys of bigvgan_audioset16khz_80band.json (resblock "1", snakebeta,
- * snake_logscale true are the only supported choices - models.py:146,60-70).
+ * cfg mirrors the generator keys of bigvgan_audioset16khz_80band.json.  resblock "1" (AMPBlock1, models.py:28-81) or
+ * "2" (AMPBlock2, :90-126; `resblock2` = 1, two dilations per kernel size); activation "snakebeta" or "snake"
+ * (activations.py:9-120; for "snake" pass each alpha twice, as alpha and as beta); snake_logscale true or false
+ * (`snake_linear` = 1).  A zero-filled tail of the struct is the 16k config: AMPBlock1, log-scale parameters.
  * `tensors` lists device fp32 pointers in this order (state_dict names in brackets):
  *   conv_pre:   weight_g, weight_v, bias
  *   for i in 0..num_upsamples-1:
@@ -77,6 +79,7 @@ const char* alcm_last_error(void);
  *       convs1.0..2: (weight_g, weight_v, bias) x3
  *       convs2.0..2: (weight_g, weight_v, bias) x3
  *       activations.0..5.act: (alpha, beta) x6
+ *       [resblock2: convs.0..1 x (weight_g, weight_v, bias), activations.0..1.act x (alpha, beta) instead]
  *   activation_post.act: alpha, beta
  *   conv_post:  weight_g, weight_v, bias
  */
@@ -89,6 +92,8 @@ typedef struct {
   int upsample_kernel_sizes[8];
   int resblock_kernel_sizes[4];
   int resblock_dilation_sizes[4][3];
+  int resblock2;     /* 0: AMPBlock1 (3 dilations), 1: AMPBlock2 (resblock_dilation_sizes[j][0..1]) */
+  int snake_linear;  /* 0: alpha_logscale (exp of the stored parameters), 1: parameters used as stored */
 } alcm_bigvgan_cfg;
 
 int alcm_vocoder_num_tensors(const alcm_bigvgan_cfg* cfg);

@@ -51,10 +51,10 @@ def kaiser_sinc_filter(cutoff: float = 0.25, half_width: float = 0.3, kernel_siz
 
 
 # --------------------------------------------------------------------------- Activation1d
-def snake_beta(x, alpha, beta):
-    """vocoder/bigvgan/activations.py:107-120 with alpha_logscale=True."""
-    a = torch.exp(alpha).view(1, -1, 1)
-    b = torch.exp(beta).view(1, -1, 1)
+def snake_beta(x, alpha, beta, logscale=True):
+    """vocoder/bigvgan/activations.py:107-120 (SnakeBeta); Snake (:46-62) is the beta = alpha case."""
+    a = (torch.exp(alpha) if logscale else alpha).view(1, -1, 1)
+    b = (torch.exp(beta) if logscale else beta).view(1, -1, 1)
     return x + (1.0 / (b + 1e-9)) * torch.sin(x * a) ** 2
 
 
@@ -78,11 +78,11 @@ def downsample2x(x, filt):
     return F.conv1d(x, filt.view(1, 1, -1).expand(C, -1, -1), stride=2, groups=C)
 
 
-def activation1d(x, alpha, beta, filt=None):
-    """alias_free_torch/act.py:23-28: upsample -> SnakeBeta -> downsample."""
+def activation1d(x, alpha, beta, filt=None, logscale=True):
+    """alias_free_torch/act.py:23-28: upsample -> Snake / SnakeBeta -> downsample."""
     if filt is None:
         filt = kaiser_sinc_filter(dtype=x.dtype)
-    return downsample2x(snake_beta(upsample2x(x, filt), alpha, beta), filt)
+    return downsample2x(snake_beta(upsample2x(x, filt), alpha, beta, logscale), filt)
 
 
 # --------------------------------------------------------------------------- weight norm
@@ -100,25 +100,44 @@ def _wn(sd, name, dtype):
 
 
 # --------------------------------------------------------------------------- BigVGAN
-def amp_block1(sd, p, x, k, dils, filt, dtype):
+def _snake(sd, p, h, dtype):
+    """(alpha, beta, logscale) of one activation; ``activation: snake`` has alpha only."""
+    a = _t(sd[p + ".alpha"], dtype)
+    b = _t(sd[p + ".beta"], dtype) if h["activation"] == "snakebeta" else a
+    return a, b, bool(h["snake_logscale"])
+
+
+def amp_block1(sd, h, p, x, k, dils, filt, dtype):
     """vocoder/bigvgan/models.py:72-81."""
     for l, d in enumerate(dils):
-        a1 = (_t(sd[f"{p}.activations.{2 * l}.act.alpha"], dtype), _t(sd[f"{p}.activations.{2 * l}.act.beta"], dtype))
-        a2 = (_t(sd[f"{p}.activations.{2 * l + 1}.act.alpha"], dtype), _t(sd[f"{p}.activations.{2 * l + 1}.act.beta"], dtype))
+        a1, b1_, ls = _snake(sd, f"{p}.activations.{2 * l}.act", h, dtype)
+        a2, b2_, _ = _snake(sd, f"{p}.activations.{2 * l + 1}.act", h, dtype)
         w1, b1 = _wn(sd, f"{p}.convs1.{l}", dtype)
         w2, b2 = _wn(sd, f"{p}.convs2.{l}", dtype)
-        xt = activation1d(x, *a1, filt)
+        xt = activation1d(x, a1, b1_, filt, ls)
         xt = F.conv1d(xt, w1, b1, dilation=d, padding=(k * d - d) // 2)
-        xt = activation1d(xt, *a2, filt)
+        xt = activation1d(xt, a2, b2_, filt, ls)
         xt = F.conv1d(xt, w2, b2, dilation=1, padding=(k - 1) // 2)
+        x = xt + x
+    return x
+
+
+def amp_block2(sd, h, p, x, k, dils, filt, dtype):
+    """vocoder/bigvgan/models.py:119-126."""
+    for l, d in enumerate(dils):
+        a, b_, ls = _snake(sd, f"{p}.activations.{l}.act", h, dtype)
+        w, b = _wn(sd, f"{p}.convs.{l}", dtype)
+        xt = activation1d(x, a, b_, filt, ls)
+        xt = F.conv1d(xt, w, b, dilation=d, padding=(k * d - d) // 2)
         x = xt + x
     return x
 
 
 def bigvgan_forward(sd, h, mel, dtype=torch.float32):
     """vocoder/bigvgan/models.py:181-203.  mel (B,num_mels,T) -> (B,1,T*prod(upsample_rates))."""
-    if h["resblock"] != "1" or h["activation"] != "snakebeta" or not h["snake_logscale"]:
-        raise NotImplementedError("oracle covers AMPBlock1 + snakebeta(logscale) only (the 16k config)")
+    if h["activation"] not in ("snake", "snakebeta"):
+        raise NotImplementedError("activation incorrectly specified. check the config file and look for 'activation'.")
+    block = amp_block1 if str(h["resblock"]) == "1" else amp_block2       # models.py:146
     x = _t(mel, dtype)
     filt = kaiser_sinc_filter(dtype=dtype).to(x.device)  # (the GPU tests also run this port as "ATen eager on the same B200")
     w, b = _wn(sd, "conv_pre", dtype)
@@ -129,10 +148,11 @@ def bigvgan_forward(sd, h, mel, dtype=torch.float32):
         x = F.conv_transpose1d(x, w, b, stride=u, padding=(k - u) // 2)
         xs = None
         for j, (kk, dd) in enumerate(zip(h["resblock_kernel_sizes"], h["resblock_dilation_sizes"])):
-            y = amp_block1(sd, f"resblocks.{i * nk + j}", x, kk, dd, filt, dtype)
+            y = block(sd, h, f"resblocks.{i * nk + j}", x, kk, dd, filt, dtype)
             xs = y if xs is None else xs + y
         x = xs / nk
-    x = activation1d(x, _t(sd["activation_post.act.alpha"], dtype), _t(sd["activation_post.act.beta"], dtype), filt)
+    a, b_, ls = _snake(sd, "activation_post.act", h, dtype)
+    x = activation1d(x, a, b_, filt, ls)
     w, b = _wn(sd, "conv_post", dtype)
     x = F.conv1d(x, w, b, padding=3)
     return torch.tanh(x)

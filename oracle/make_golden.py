@@ -92,6 +92,26 @@ def encoder_goldens():
         print("vae encode", tag, mom.shape, float(np.abs(mom).max()))
 
 
+VARIANTS = {   # the other generator choices BigVGAN.__init__ accepts (models.py:146,158-172; activations.py:9-120)
+    "rb2_snake": dict(resblock="2", activation="snake", snake_logscale=True, resblock_dilation_sizes=[[1, 3], [1, 3], [1, 3]]),
+    "rb1_linear": dict(resblock="1", activation="snakebeta", snake_logscale=False),
+    "rb2_snakebeta_linear": dict(resblock="2", activation="snakebeta", snake_logscale=False,
+                                 resblock_dilation_sizes=[[1, 3], [1, 3], [1, 3]]),
+}
+
+
+def variant_goldens():
+    """BigVGAN(h) of the unmodified reference for AMPBlock2 / Snake / linear-scale parameters, narrow (c0 = 64)."""
+    for tag, over in VARIANTS.items():
+        h = synth.bigvgan_config(64, **over)
+        sd = synth.bigvgan_state_dict(h, seed=5)
+        g = ref_bigvgan(h, sd)
+        mel = synth.synth_mel(2, 21, seed=6)
+        wav = g(torch.from_numpy(mel)).numpy()
+        np.savez(os.path.join(OUT, f"bigvgan_c64_{tag}.npz"), c0=64, T=21, B=2, wseed=5, xseed=6, wav=wav)
+        print("bigvgan variant", tag, wav.shape, float(np.abs(wav).max()))
+
+
 def main():
     assert reference_available(), "needs /root/reference"
     os.makedirs(OUT, exist_ok=True)
@@ -99,6 +119,10 @@ def main():
     if "--encoder-only" in sys.argv:
         with torch.no_grad():
             encoder_goldens()
+        return
+    if "--variants-only" in sys.argv:
+        with torch.no_grad():
+            variant_goldens()
         return
     torch.set_grad_enabled(False)
     _, _, Activation1d, SnakeBeta = import_reference()
@@ -169,6 +193,7 @@ def main():
         print("vae", tag, mel.shape, float(np.abs(mel).max()), float(mel.std()))
 
     encoder_goldens()
+    variant_goldens()
 
     # ---- full path latent -> mel -> wav (config 2), short clip to keep the fixture small -----
     dd = synth.vae_config()

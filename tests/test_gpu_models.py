@@ -56,6 +56,24 @@ def test_vocode_small_vs_reference(golden_dir, tag, precision):
     assert np.all(np.abs(wav) < 1.0)
 
 
+@pytest.mark.parametrize("tag", ["rb2_snake", "rb1_linear", "rb2_snakebeta_linear"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+def test_vocode_config_variants_vs_reference(golden_dir, tag, precision):
+    """The other generator choices BigVGAN.__init__ accepts - AMPBlock2 (models.py:90-126), Snake (activations.py:9-62),
+    linear-scale alpha / beta - against outputs of the unmodified reference (oracle/make_golden.py VARIANTS)."""
+    from oracle.make_golden import VARIANTS
+    g = np.load(os.path.join(golden_dir, f"bigvgan_c64_{tag}.npz"))
+    h = synth.bigvgan_config(int(g["c0"]), **VARIANTS[tag])
+    sd = synth.bigvgan_state_dict(h, seed=int(g["wseed"]))
+    mel = synth.synth_mel(int(g["B"]), int(g["T"]), seed=int(g["xseed"]))
+    wav = _voc(h, sd, precision).vocode(torch.from_numpy(mel))
+    ref = g["wav"].squeeze()
+    err = np.abs(wav - ref).max()
+    print(f"\n[vocode {tag} {precision}] max-abs {err:.3e} (ref abs-max {np.abs(ref).max():.3f}) SNR {snr_db(ref, wav):.1f} dB")
+    assert wav.shape == ref.shape and err <= WAV_TOL[precision], err
+    assert snr_db(ref, wav) >= SNR_MIN[precision]
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("tag", ["T40", "T625"])
 def test_vocode_full_config_vs_reference(golden_dir, tag, precision):
@@ -325,7 +343,7 @@ def test_shape_errors():
     with pytest.raises(ValueError):
         voc.vocode(torch.zeros(0, 80, 10))
     bad = dict(h)
-    bad["activation"] = "snake"
+    bad["activation"] = "relu"          # the reference raises the same for anything but snake / snakebeta (models.py:170-172)
     with pytest.raises(NotImplementedError):
         _voc(bad, synth.bigvgan_state_dict(h, seed=0), "tf32")
 

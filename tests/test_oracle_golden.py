@@ -51,6 +51,20 @@ def test_bigvgan_small_matches_reference(golden_dir, tag):
     assert out.dtype == np.float32 and out.shape == tuple(s for s in g["wav"].shape if s != 1)
 
 
+@pytest.mark.parametrize("tag", ["rb2_snake", "rb1_linear", "rb2_snakebeta_linear"])
+def test_bigvgan_config_variants_match_reference(golden_dir, tag):
+    """AMPBlock2, Snake and linear-scale parameters (models.py:90-126,146,158-172; activations.py:9-62) against the
+    unmodified reference BigVGAN (oracle/make_golden.py VARIANTS)."""
+    from oracle.make_golden import VARIANTS
+    g = _load(golden_dir, f"bigvgan_c64_{tag}.npz")
+    h = synth.bigvgan_config(int(g["c0"]), **VARIANTS[tag])
+    sd = synth.bigvgan_state_dict(h, seed=int(g["wseed"]))
+    mel = synth.synth_mel(int(g["B"]), int(g["T"]), seed=int(g["xseed"]))
+    with torch.no_grad():
+        wav = O.bigvgan_forward(sd, h, mel).numpy()
+    np.testing.assert_allclose(wav, g["wav"], atol=2e-6)
+
+
 def test_bigvgan_full_T40_matches_reference(golden_dir):
     g = _load(golden_dir, "bigvgan_full_T40.npz")
     h = synth.bigvgan_config()
