@@ -754,8 +754,10 @@ struct OpList {
     op.cls = ALCM_CLS_ACT;
     op.flops = 0;
     op.bytes = (double)B * T * x.C * (4.0 + oesz);  // algorithmic: unpadded channels, one read + one write
-    // One kernel (act1d.cuh); three block sizes for measurements (ALCM_ACT_VARIANT): 0 = 128 threads (635 outputs per
-    // block), 1 = 64 threads (315), 2 = 32 threads (155).  Default: 64 - measured best at every launch size.
+    // One kernel (act1d.cuh); block sizes for measurements (ALCM_ACT_VARIANT): 0 = 128 threads (635 outputs per block),
+    // 1 = 64 threads (315) compiled for 14 blocks per SM (72 registers, no spills), 2 = 32 threads (155), 3 = 64 threads
+    // at 96 registers / 10 blocks.  Default 1 - measured best at every launch size; against 3 the fp32-out form (15 KB
+    // of shared memory per block) gains 3-5 % from the extra resident warps, the bf16-out form (21 KB: 10 blocks) ~1 %.
     int variant = 1;
     if (env.k.act_variant >= 0) variant = env.k.act_variant;
     op.fn = [=](cudaStream_t st) {
@@ -774,7 +776,8 @@ struct OpList {
       };
       if (variant == 0) go(std::integral_constant<int, 128>{}, std::integral_constant<int, 5>{});
       else if (variant == 2) go(std::integral_constant<int, 32>{}, std::integral_constant<int, 20>{});
-      else go(std::integral_constant<int, 64>{}, std::integral_constant<int, 10>{});
+      else if (variant == 3) go(std::integral_constant<int, 64>{}, std::integral_constant<int, 10>{});
+      else go(std::integral_constant<int, 64>{}, std::integral_constant<int, 14>{});
     };
     push(op);
   }
@@ -1535,6 +1538,13 @@ static void set_kernel_attrs() {
   CUDA_CHECK(cudaFuncSetAttribute(gn_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
   CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+  // the activation blocks are small (15-21 KB, 64 threads): their occupancy is bounded by shared memory, so ask for the
+  // largest shared-memory carve-out instead of leaving the split to the driver's heuristic
+  auto carve = [](auto kern) { CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); };
+  carve(act1d_kernel<1, true, 5, 128, 5>); carve(act1d_kernel<1, false, 5, 128, 5>); carve(act1d_kernel<2, true, 5, 128, 5>);
+  carve(act1d_kernel<1, true, 5, 64, 10>); carve(act1d_kernel<1, false, 5, 64, 10>); carve(act1d_kernel<2, true, 5, 64, 10>);
+  carve(act1d_kernel<1, true, 5, 64, 14>); carve(act1d_kernel<1, false, 5, 64, 14>); carve(act1d_kernel<2, true, 5, 64, 14>);
+  carve(act1d_kernel<1, true, 5, 32, 20>); carve(act1d_kernel<1, false, 5, 32, 20>); carve(act1d_kernel<2, true, 5, 32, 20>);
 }
 
 extern "C" {

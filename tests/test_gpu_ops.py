@@ -177,7 +177,7 @@ def test_bad_arguments_raise(ops):
 
 
 # ----------------------------------------------------------------------------------- every Activation1d kernel form
-ACT_VARIANTS = {0: "128 threads, 635 outputs per block", 1: "64 threads, 315", 2: "32 threads, 155"}
+ACT_VARIANTS = {0: "128 threads, 635 outputs per block", 1: "64 threads, 315 (72 registers)", 2: "32 threads, 155", 3: "64 threads, 315 (96 registers)"}
 ACT_EDGE_SHAPES = [(1, 8, 1), (1, 8, 3), (2, 24, 4099), (1, 16, 635), (1, 16, 636), (1, 8, 630), (1, 8, 1283), (1, 8, 315), (1, 8, 316),
                    (1, 8, 311), (1, 8, 155), (1, 8, 156), (1, 8, 152), (1, 24, 6), (1, 40, 1925), (3, 16, 160000)]
 

@@ -1,5 +1,5 @@
 """Activation1d micro-benchmark: algorithmic GB/s (fp32 in + operand out, unpadded channels) of single launches on random
-operands.  ALCM_ACT_VARIANT=n forces the block size (0: 128 threads / 635 outputs, 1: 64 / 315 (default), 2: 32 / 155)."""
+operands.  ALCM_ACT_VARIANT=n forces the block size (0: 128 threads / 635 outputs, 1: 64 / 315 (default), 2: 32 / 155, 3: 64 / 315 at 96 registers)."""
 import ctypes as C
 import os
 import sys
