@@ -9,7 +9,7 @@ from bench import build_pipe, T_LAT  # noqa: E402
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 pipe = build_pipe(prec, "cuda:0")
 rows = {}
-Bs = (2, 4, 8, 16, 64)
+Bs = tuple(int(b) for b in os.environ.get("SWEEP_B", "2,4,8,16,64").split(","))
 for B in Bs:
     pipe.profile_stages(B, T_LAT, 1)
     for st, cl in pipe.profile_stages(B, T_LAT, 3).items():
