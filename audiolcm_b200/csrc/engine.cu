@@ -756,8 +756,8 @@ struct OpList {
     op.bytes = (double)B * T * x.C * (4.0 + oesz);  // algorithmic: unpadded channels, one read + one write
     // One kernel (act1d.cuh); block sizes for measurements (ALCM_ACT_VARIANT): 0 = 128 threads (635 outputs per block),
     // 1 = 64 threads (315) compiled for 14 blocks per SM (72 registers, no spills), 2 = 32 threads (155), 3 = 64 threads
-    // at 96 registers / 10 blocks.  Default 1 - measured best at every launch size; against 3 the fp32-out form (15 KB
-    // of shared memory per block) gains 3-5 % from the extra resident warps, the bf16-out form (21 KB: 10 blocks) ~1 %.
+    // at 96 registers / 10 blocks.  Default 1 - measured best at every launch size; against 3 both forms (15 KB of shared
+    // memory per block) gain 3-5 % from the extra resident warps.
     int variant = 1;
     if (env.k.act_variant >= 0) variant = env.k.act_variant;
     op.fn = [=](cudaStream_t st) {
