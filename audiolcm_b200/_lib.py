@@ -12,7 +12,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libaudiolcm_b200.so")
 
-PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
+PREC = {"fp32": 0, "tf32": 1, "bf16": 2, "fp16": 3}
 CLASSES = ("conv", "act", "norm", "attn", "misc")
 
 

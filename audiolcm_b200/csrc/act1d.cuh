@@ -260,8 +260,7 @@ __global__ void __launch_bounds__(THREADS, MINB) act1d_kernel(const __grid_const
       uint2 pk[UR];
 #pragma unroll
       for (int r = 0; r < UR; ++r) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(res[r].x, res[r].y), h1 = __floats2bfloat162_rn(res[r].z, res[r].w);
-        pk[r] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        pk[r] = make_uint2(pack16x2(a.og.fmt, res[r].x, res[r].y), pack16x2(a.og.fmt, res[r].z, res[r].w));
       }
       if (p == 0) {
 #pragma unroll

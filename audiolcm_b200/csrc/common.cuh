@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace alcm {
@@ -21,10 +22,12 @@ constexpr int kPad = 32;  // >= largest conv half-span on the path (k=11, dilati
 constexpr int kMaxPhase = 4;   // polyphase outputs per conv launch (ConvTranspose1d stride <= 4)
 constexpr int kMaxTaps = 11;   // taps per phase
 
+enum { kFmtF32 = 0, kFmtBF16 = 1, kFmtF16 = 2 };   // element type of a plane (tf32 operands are kFmtF32 planes, rounded)
 struct PlaneGeom {
   int nchunk;  // 16-byte channel chunks per time step
   int Tp;      // rows per plane = T + 2*pad
   int pad;
+  int fmt;     // kFmt*: how a kernel WRITING 16-bit planes packs them (bf16, or fp16 with saturation)
 };
 
 __host__ __device__ inline size_t plane_row_off(const PlaneGeom& g, int b, int chunk, int t) {
@@ -212,6 +215,21 @@ __device__ __forceinline__ void tc_commit_pred(uint32_t bar, uint32_t leader) {
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader)
       : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// two fp32 -> one packed pair of 16-bit operands (a in the low half): bf16 (RNE), or fp16 (RNE, saturating at +-65504
+// instead of overflowing to inf: the "fp16" mode has tf32's 10-bit mantissa but not its range)
+__device__ __forceinline__ uint32_t pack16x2(int fmt, float a, float b) {
+  if (fmt == kFmtF16) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
+  return pack_bf16x2(a, b);
 }
 
 __device__ __forceinline__ float round_tf32(float x) {

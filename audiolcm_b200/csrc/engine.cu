@@ -133,6 +133,7 @@ struct Arena {
   // the repeat-call bit-identity tests catch).
   static constexpr size_t kGuard = 4096;
   bool guard = false;
+  bool f16 = false;   // 16-bit planes made from this arena are fp16 (precision "fp16"), else bf16
   std::vector<std::pair<uint8_t*, size_t>> gaps;
   static size_t align_up(size_t b) { return (std::max<size_t>(b, 16) + 255) & ~(size_t)255; }
   void* alloc(size_t bytes, bool zero = true) {
@@ -208,12 +209,15 @@ static PlaneT make_planes(Arena& ar, int B, int C, int T, int esz) {
   t.g.nchunk = plane_cpad(C) / E;
   t.g.pad = kPad;
   t.g.Tp = T + 2 * kPad;
+  t.g.fmt = esz == 2 ? (ar.f16 ? kFmtF16 : kFmtBF16) : kFmtF32;
   t.bytes = (size_t)B * t.g.nchunk * t.g.Tp * 16;
   t.p = static_cast<uint8_t*>(ar.alloc(t.bytes, true));
   return t;
 }
 
-static inline int opnd_esz(int prec) { return prec == ALCM_PREC_BF16 ? 2 : 4; }
+static inline bool is16(int prec) { return prec == ALCM_PREC_BF16 || prec == ALCM_PREC_FP16; }   // 16-bit operands, kind::f16
+static inline int opnd_esz(int prec) { return is16(prec) ? 2 : 4; }
+static inline int umma_fmt(int prec) { return prec == ALCM_PREC_FP16 ? 0 : prec == ALCM_PREC_BF16 ? 1 : 2; }   // idesc a/b format
 
 long long Arena::guard_violations() const {
   if (gaps.empty()) return 0;
@@ -288,7 +292,7 @@ struct ConvLayer {
 // channel counts, taps and arithmetic mode.
 static void conv_tiling(ConvLayer& L, const Knobs& K_) {
   const int prec = L.prec, Cout = L.Cout, Cin = L.Cin;
-  const int E = (prec == ALCM_PREC_BF16) ? 8 : 4;
+  const int E = is16(prec) ? 8 : 4;
   const int cout_pad = round_up(Cout, 16);
   int nt_pref = K_.nt;
   if (cout_pad == 192 && K_.nt192 > 0 && 192 % K_.nt192 == 0) nt_pref = K_.nt192 < 192 ? K_.nt192 : nt_pref;
@@ -304,7 +308,7 @@ static void conv_tiling(ConvLayer& L, const Knobs& K_) {
   else for (int d = std::min(12, K_.kblk_max); d >= 2; d -= 2) if (L.kchunks % d == 0) { L.kblk = d; break; }
   REQUIRE(L.kblk >= 2 && L.kblk % 2 == 0 && L.kblk <= 12, "bad k-block");
   L.nkb = L.kchunks / L.kblk;
-  L.idesc = umma_idesc(prec == ALCM_PREC_BF16 ? 1 : 2, L.NT);
+  L.idesc = umma_idesc(umma_fmt(prec), L.NT);
   L.w_stages = 0;  // chosen per launch (pick_pipeline)
   L.smem = 0;
   L.phase_stride = (size_t)L.n_tiles * L.nkb * L.ntaps * L.kblk * L.NT * 16;
@@ -387,13 +391,13 @@ static ConvLayer prepare_conv(Arena& ar, const Knobs& K_, int prec, ConvKind kin
     CUDA_CHECK(sync_setup());
     return L;
   }
-  const int E = (prec == ALCM_PREC_BF16) ? 8 : 4;
+  const int E = is16(prec) ? 8 : 4;
   conv_tiling(L, K_);
   L.wpack = static_cast<uint8_t*>(ar.alloc(L.phase_stride * L.nphase, false));
   const size_t units = L.phase_stride * L.nphase / 16;
   const unsigned blocks = (unsigned)std::min<size_t>((units + 255) / 256, 8192);
-  if (E == 8) pack_w_kernel<8><<<blocks, 256>>>(L.weff, L.wpack, L.nphase, L.ntaps, Cout, Cin, L.NT, L.n_tiles, L.kblk, L.nkb);
-  else pack_w_kernel<4><<<blocks, 256>>>(L.weff, L.wpack, L.nphase, L.ntaps, Cout, Cin, L.NT, L.n_tiles, L.kblk, L.nkb);
+  if (E == 8) pack_w_kernel<8><<<blocks, 256>>>(L.weff, L.wpack, L.nphase, L.ntaps, Cout, Cin, L.NT, L.n_tiles, L.kblk, L.nkb, prec == ALCM_PREC_FP16);
+  else pack_w_kernel<4><<<blocks, 256>>>(L.weff, L.wpack, L.nphase, L.ntaps, Cout, Cin, L.NT, L.n_tiles, L.kblk, L.nkb, 0);
   CUDA_CHECK(cudaGetLastError());
   L.bias = static_cast<float*>(ar.alloc((size_t)L.n_tiles * L.NT * 4, true));
   if (bias) CUDA_CHECK(cudaMemcpy(L.bias, bias, (size_t)Cout * 4, cudaMemcpyDeviceToDevice));
@@ -443,7 +447,7 @@ static void conv_kernel_for(int prec, void (**kern)(ConvArgs), int* threads);
 // Cached in the ctx (per device).
 static long cluster_capacity(const Env& env, int prec, int ks) {
   long (&cap)[2][9] = env.cx->cluster_cap;
-  const int pi = prec == ALCM_PREC_BF16 ? 0 : 1;
+  const int pi = is16(prec) ? 0 : 1;
   if (ks <= 1) return env.sms();
   std::lock_guard<std::mutex> lock(env.cx->mu);
   if (cap[pi][ks] == 0) {
@@ -504,7 +508,7 @@ static const ConvLayer& retile(Arena& ar, RetileCache& cache, const ConvLayer& L
   R.n_tiles = (cout_pad + NT2 - 1) / NT2;
   R.tmem_cols = 32;
   while (R.tmem_cols < NT2) R.tmem_cols *= 2;
-  R.idesc = umma_idesc(L.prec == ALCM_PREC_BF16 ? 1 : 2, NT2);
+  R.idesc = umma_idesc(umma_fmt(L.prec), NT2);
   R.phase_stride = (size_t)R.n_tiles * L.nkb * L.ntaps * L.kblk * NT2 * 16;
   R.wpack = static_cast<uint8_t*>(ar.alloc(R.phase_stride * L.nphase, false));
   const size_t units = R.phase_stride * L.nphase / 16;
@@ -599,7 +603,7 @@ static void conv_kernel_for(int prec, void (**kern)(ConvArgs), int* threads) {
   // one register budget for every tile width (128/thread, 2 CTAs of 192 threads per SM): a narrower, spilling
   // 80-register build for N < 128 (4 CTAs/SM) measured slower at every batch size (batch 1: 3.31 -> 3.24 ms)
   *threads = 192;
-  *kern = (prec == ALCM_PREC_BF16) ? conv_umma_kernel<0, 2> : conv_umma_kernel<1, 2>;
+  *kern = is16(prec) ? conv_umma_kernel<0, 2> : conv_umma_kernel<1, 2>;
 }
 
 // One conv launch, fully decided at PLAN time (kernel, grid, shared memory, pipeline shape, cluster size): replaying
@@ -1110,6 +1114,7 @@ static void voc_build(const alcm_vocoder* v, VocPlan& P) {
   const int B = P.B, T = P.T;
   const Knobs& K = v->env.k;
   const int prec = v->prec, oe = opnd_esz(prec);
+  P.ar.f16 = (prec == ALCM_PREC_FP16);
   const int rtf = (prec == ALCM_PREC_TF32);
   const bool fast = (prec != ALCM_PREC_FP32);  // MUFU.COS snake; the exact-fp32 mode keeps the range-reduced sin
   const int nk = v->cfg.num_kernels;
@@ -1127,7 +1132,7 @@ static void voc_build(const alcm_vocoder* v, VocPlan& P) {
     if (have_next_up_in) {
       up_in = next_up_in;
       have_next_up_in = false;
-    } else if (prec == ALCM_PREC_BF16) {
+    } else if (is16(prec)) {
       up_in = make_planes(P.ar, B, C, Tc, 2);
       P.ol.cast(xprev, up_in);
     }
@@ -1179,7 +1184,7 @@ static void voc_build(const alcm_vocoder* v, VocPlan& P) {
     if (parallel) {
       P.ol.join();
       const bool last = (i + 1 == v->stages.size());
-      if (prec == ALCM_PREC_BF16 && !last) {  // the only consumer is the next upsampler: emit its bf16 operand directly
+      if (is16(prec) && !last) {  // the only consumer is the next upsampler: emit its bf16 operand directly
         next_up_in = make_planes(P.ar, B, C, Tc, 2);
         P.ol.sum(Z, nullptr, &next_up_in, 0);
         have_next_up_in = true;
@@ -1294,7 +1299,7 @@ static void op_gn(OpList& ol, Arena& ar, const PlaneT& x, const PlaneT& out, con
 
 // operand-dtype view of an fp32 tensor: bf16 needs a cast copy, tf32/fp32 read the fp32 planes directly
 static PlaneT as_operand(OpList& ol, Arena& ar, const PlaneT& x, int prec) {
-  if (prec != ALCM_PREC_BF16) return x;
+  if (!is16(prec)) return x;
   PlaneT o = make_planes(ar, x.B, x.C, x.T, 2);
   ol.cast(x, o);
   return o;
@@ -1370,8 +1375,8 @@ static void push_attention_tc(OpList& ol, Arena& ar, const PlaneT& q, const Plan
     const ConvLayer Lc = L;
     op.fn = [=](cudaStream_t st) {
       const dim3 grid((unsigned)std::min<size_t>((units + 255) / 256, 2048), B);
-      if (oe == 2) launch_k(pack_dyn_w_kernel<8>, grid, dim3(256), 0, st, sc.f(), sc.g, C, T, (void*)Lc.wpack, mode, Lc.NT, Lc.n_tiles, Lc.kblk, Lc.nkb, units);
-      else launch_k(pack_dyn_w_kernel<4>, grid, dim3(256), 0, st, sc.f(), sc.g, C, T, (void*)Lc.wpack, mode, Lc.NT, Lc.n_tiles, Lc.kblk, Lc.nkb, units);
+      if (oe == 2) launch_k(pack_dyn_w_kernel<8>, grid, dim3(256), 0, st, sc.f(), sc.g, C, T, (void*)Lc.wpack, mode, Lc.NT, Lc.n_tiles, Lc.kblk, Lc.nkb, units, (int)(prec == ALCM_PREC_FP16));
+      else launch_k(pack_dyn_w_kernel<4>, grid, dim3(256), 0, st, sc.f(), sc.g, C, T, (void*)Lc.wpack, mode, Lc.NT, Lc.n_tiles, Lc.kblk, Lc.nkb, units, 0);
     };
     ol.push(op);
   };
@@ -1422,6 +1427,7 @@ static void vae_build(const alcm_vae* v, VaePlan& P) {
   const int B = P.B, T = P.T;
   P.ol.cur_stage = 0;
   const int prec = v->prec, oe = opnd_esz(prec);
+  P.ar.f16 = (prec == ALCM_PREC_FP16);
   P.z_in = make_planes(P.ar, B, v->cfg.embed_dim, T, oe);
   PlaneT h0 = make_planes(P.ar, B, v->cfg.z_channels, T, 4);
   P.ol.conv(v->post_quant, P.z_in, h0, nullptr);
@@ -1493,6 +1499,7 @@ static void enc_build(const alcm_vae_encoder* v, EncPlan& P) {
   const int B = P.B, T = P.T;
   P.ol.cur_stage = 0;
   const int prec = v->prec, oe = opnd_esz(prec), rtf = prec == ALCM_PREC_TF32;
+  P.ar.f16 = (prec == ALCM_PREC_FP16);
   P.x_in = make_planes(P.ar, B, v->cfg.in_channels, T, oe);
   PlaneT h = make_planes(P.ar, B, v->conv_in.Cout, T, 4);
   P.ol.conv(v->conv_in, P.x_in, h, nullptr);
@@ -1580,7 +1587,7 @@ int alcm_vocoder_create(alcm_ctx* ctx, const alcm_bigvgan_cfg* cfg, const float*
                         alcm_vocoder** out) {
   return guarded([&] {
     REQUIRE(ctx && cfg && t && out, "vocoder_create: NULL argument");
-    REQUIRE(precision >= 0 && precision <= 2, "vocoder_create: bad precision");
+    REQUIRE(precision >= 0 && precision <= 3, "vocoder_create: bad precision");
     REQUIRE(cfg->num_upsamples >= 1 && cfg->num_upsamples <= 8 && cfg->num_kernels >= 1 && cfg->num_kernels <= 4,
             "vocoder_create: bad config");
     REQUIRE(n_tensors == alcm_vocoder_num_tensors(cfg), "vocoder_create: wrong tensor count");
@@ -1737,7 +1744,7 @@ int alcm_vae_num_tensors(const alcm_vae_cfg* c) {
 int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* t, int n_tensors, int precision, alcm_vae** out) {
   return guarded([&] {
     REQUIRE(ctx && cfg && t && out, "vae_create: NULL argument");
-    REQUIRE(precision >= 0 && precision <= 2, "vae_create: bad precision");
+    REQUIRE(precision >= 0 && precision <= 3, "vae_create: bad precision");
     REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= 8, "vae_create: bad n_levels");
     REQUIRE(n_tensors == alcm_vae_num_tensors(cfg), "vae_create: wrong tensor count");
     for (int i = 0; i < n_tensors; ++i) REQUIRE(t[i] != nullptr, "vae_create: NULL tensor");
@@ -1871,7 +1878,7 @@ int alcm_vae_encoder_create(alcm_ctx* ctx, const alcm_vae_enc_cfg* cfg, const fl
                             alcm_vae_encoder** out) {
   return guarded([&] {
     REQUIRE(ctx && cfg && t && out, "vae_encoder_create: NULL argument");
-    REQUIRE(precision >= 0 && precision <= 2, "vae_encoder_create: bad precision");
+    REQUIRE(precision >= 0 && precision <= 3, "vae_encoder_create: bad precision");
     REQUIRE(cfg->n_levels >= 1 && cfg->n_levels <= 8 && cfg->num_res_blocks >= 1, "vae_encoder_create: bad config");
     REQUIRE(n_tensors == alcm_vae_encoder_num_tensors(cfg), "vae_encoder_create: wrong tensor count");
     for (int i = 0; i < n_tensors; ++i) REQUIRE(t[i] != nullptr, "vae_encoder_create: NULL tensor");
@@ -2070,7 +2077,7 @@ int alcm_conv1d_create(alcm_ctx* ctx, const float* w, const float* bias, int Cou
   return guarded([&] {
     REQUIRE(ctx && w && out, "conv1d_create: NULL argument");
     REQUIRE(Cout >= 1 && Cin >= 1 && dilation >= 1, "conv1d_create: bad shape");
-    REQUIRE(precision >= 0 && precision <= 2, "conv1d_create: bad precision");
+    REQUIRE(precision >= 0 && precision <= 3, "conv1d_create: bad precision");
     CUDA_CHECK(cudaSetDevice(ctx->device));
     std::unique_ptr<alcm_conv1d> c(new alcm_conv1d());
     c->ctx = ctx; c->prec = precision; c->Cin = Cin; c->Cout = Cout;
@@ -2101,6 +2108,7 @@ int alcm_conv1d_run(alcm_conv1d* c, const float* x, const float* res, float* y, 
       c->pcache.make_room(c->plans, (size_t)c->env.k.max_plans, st);
       const bool has_res = res != nullptr;
       std::unique_ptr<ConvRunPlan> pl = build_plan<ConvRunPlan>(c->env, &c->war, &c->retiled, B, T, st, false, nullptr, [&](ConvRunPlan& R) {
+        R.ar.f16 = (c->prec == ALCM_PREC_FP16);
         R.x_in = make_planes(R.ar, B, c->Cin, T, opnd_esz(c->prec));
         R.out = make_planes(R.ar, B, c->Cout, T, 4);
         if (has_res) R.res_in = make_planes(R.ar, B, c->Cout, T, 4);
@@ -2139,7 +2147,7 @@ int alcm_ffn1d_create(alcm_ctx* ctx, const float* w_in, const float* b_in, const
   return guarded([&] {
     REQUIRE(ctx && w_in && w_out && out, "ffn1d_create: NULL argument");
     REQUIRE(dim >= 1 && inner >= 8 && inner % 8 == 0 && dim_out >= 1 && K >= 1 && (K & 1), "ffn1d_create: bad shape (inner % 8 == 0, odd K)");
-    REQUIRE(precision >= 0 && precision <= 2, "ffn1d_create: bad precision");
+    REQUIRE(precision >= 0 && precision <= 3, "ffn1d_create: bad precision");
     CUDA_CHECK(cudaSetDevice(ctx->device));
     std::unique_ptr<alcm_ffn1d> c(new alcm_ffn1d());
     c->ctx = ctx; c->prec = precision; c->dim = dim; c->inner = inner; c->dim_out = dim_out;
@@ -2171,6 +2179,7 @@ int alcm_ffn1d_run(alcm_ffn1d* c, const float* x, const float* res, float* y, in
       c->pcache.make_room(c->plans, (size_t)c->env.k.max_plans, st);
       const bool has_res = res != nullptr;
       std::unique_ptr<ConvRunPlan> pl = build_plan<ConvRunPlan>(c->env, &c->war, &c->retiled, B, T, st, false, nullptr, [&](ConvRunPlan& R) {
+        R.ar.f16 = (c->prec == ALCM_PREC_FP16);
         R.x_in = make_planes(R.ar, B, c->dim, T, opnd_esz(c->prec));
         PlaneT mid = make_planes(R.ar, B, 2 * c->inner, T, 4);
         PlaneT act = make_planes(R.ar, B, c->inner, T, opnd_esz(c->prec));
@@ -2206,11 +2215,12 @@ int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, con
   return guarded([&] {
     REQUIRE(ctx && x && alpha && beta && y, "activation1d: NULL argument");
     REQUIRE(B >= 1 && C >= 1 && T >= 1, "activation1d: empty tensor");
-    REQUIRE(precision >= 0 && precision <= 2, "activation1d: bad precision");
+    REQUIRE(precision >= 0 && precision <= 3, "activation1d: bad precision");
     CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar;
     ar.guard = env_int("ALCM_GUARD", 0) != 0;
+    ar.f16 = (precision == ALCM_PREC_FP16);
     PlaneT xin = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, opnd_esz(precision));
     SnakeP sp = make_snake(ar, alpha, beta, C, 0);
     CUDA_CHECK(sync_setup());
@@ -2219,7 +2229,7 @@ int alcm_activation1d_fwd(alcm_ctx* ctx, const float* x, const float* alpha, con
     ol.env = Env{ctx, Knobs::from_env()};
     ol.act(xin, out, sp.ea, sp.ib, precision == ALCM_PREC_TF32, precision != ALCM_PREC_FP32);
     ol.run(st);
-    if (precision == ALCM_PREC_BF16) {
+    if (is16(precision)) {
       dim3 grid((T + 255) / 256, out.g.nchunk, B);
       launch_k(unpack_cf_bf16_kernel, dim3(grid), dim3(256), 0, st, out.p, out.g, y, C, T);
     } else {
@@ -2234,10 +2244,11 @@ static void run_conv_test(alcm_ctx* ctx, ConvKind kind, const float* x, const fl
                           float* y, int B, int Cin, int Cout, int T, int K, int p, int precision, cudaStream_t st) {
   REQUIRE(ctx && x && w && y, "conv: NULL argument");
   REQUIRE(B >= 1 && Cin >= 1 && Cout >= 1 && T >= 1, "conv: empty tensor");
-  REQUIRE(precision >= 0 && precision <= 2, "conv: bad precision");
+  REQUIRE(precision >= 0 && precision <= 3, "conv: bad precision");
   CUDA_CHECK(cudaSetDevice(ctx->device));
   Arena ar;
   ar.guard = env_int("ALCM_GUARD", 0) != 0;
+  ar.f16 = (precision == ALCM_PREC_FP16);
   const Env env{ctx, Knobs::from_env()};
   ConvLayer L = prepare_conv(ar, env.k, precision, kind, w, bias, Cout, Cin, K, p);
   PlaneT xin = make_planes(ar, B, Cin, T, opnd_esz(precision));
@@ -2310,11 +2321,12 @@ int alcm_attn1d_fwd(alcm_ctx* ctx, const float* q, const float* k, const float* 
   return guarded([&] {
     REQUIRE(ctx && q && k && v && out, "attn: NULL argument");
     REQUIRE(B >= 1 && C >= 1 && T >= 1, "attn: empty tensor");
-    REQUIRE(precision >= 0 && precision <= 2, "attn: bad precision");
+    REQUIRE(precision >= 0 && precision <= 3, "attn: bad precision");
     CUDA_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     Arena ar;
     ar.guard = env_int("ALCM_GUARD", 0) != 0;
+    ar.f16 = (precision == ALCM_PREC_FP16);
     PlaneT pq = make_planes(ar, B, C, T, 4), pk = make_planes(ar, B, C, T, 4), pv = make_planes(ar, B, C, T, 4);
     PlaneT ph = make_planes(ar, B, C, T, 4);
     OpList ol;
@@ -2410,9 +2422,9 @@ int alcm_profile_stages(alcm_vae* vae, alcm_vocoder* voc, int B, int T, int iter
 
 // Micro-benchmarks run on RANDOM operands (seeded, generated on the device): zero-filled operands draw far less
 // power, so the SM clock - and with it the measured rate - would not be the one real data sees.
-static void fill_uniform(void* p, size_t n, int bf16, float lo, float hi, unsigned seed) {
+static void fill_uniform(void* p, size_t n, int fmt, float lo, float hi, unsigned seed) {
   const unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, 16384);
-  fill_uniform_kernel<<<blocks, 256>>>(p, n, bf16, lo, hi, seed);
+  fill_uniform_kernel<<<blocks, 256>>>(p, n, fmt, lo, hi, seed);
   CUDA_CHECK(cudaGetLastError());
 }
 
@@ -2420,10 +2432,11 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
                     float* ms_per_launch) {
   return guarded([&] {
     REQUIRE(ctx && ms_per_launch && iters >= 1, "bench_conv: bad argument");
-    REQUIRE(precision == ALCM_PREC_TF32 || precision == ALCM_PREC_BF16 || dbg == 0, "bench_conv: dbg flags need a tcgen05 mode");
+    REQUIRE(precision != ALCM_PREC_FP32 || dbg == 0, "bench_conv: dbg flags need a tcgen05 mode");
     CUDA_CHECK(cudaSetDevice(ctx->device));
     Arena ar;
     ar.guard = env_int("ALCM_GUARD", 0) != 0;
+    ar.f16 = (precision == ALCM_PREC_FP16);
     const Env env{ctx, Knobs::from_env()};
     // Kaiming-uniform-like weights, N(0,1)-like activations: the magnitudes of the real model
     const float wb = 1.0f / sqrtf((float)Cin * K);
@@ -2434,7 +2447,7 @@ int alcm_bench_conv(alcm_ctx* ctx, int B, int Cin, int Cout, int T, int K, int d
     ConvLayer L = prepare_conv(ar, env.k, precision, KIND_CONV, w, bias, Cout, Cin, K, dilation);
     PlaneT x = make_planes(ar, B, Cin, T, opnd_esz(precision)), out = make_planes(ar, B, Cout, T, 4);
     // fill whole planes (pads included - they only feed the first/last rows of each clip; irrelevant for timing)
-    fill_uniform(x.p, x.bytes / (size_t)x.esz, x.esz == 2, -1.7f, 1.7f, 3u);
+    fill_uniform(x.p, x.bytes / (size_t)x.esz, x.g.fmt, -1.7f, 1.7f, 3u);
     OpList ol;
     RetileCache rcache;
     ol.env = env;
@@ -2495,6 +2508,7 @@ int alcm_bench_act(alcm_ctx* ctx, int B, int C, int T, int precision, int iters,
     CUDA_CHECK(cudaSetDevice(ctx->device));
     Arena ar;
     ar.guard = env_int("ALCM_GUARD", 0) != 0;
+    ar.f16 = (precision == ALCM_PREC_FP16);
     PlaneT x = make_planes(ar, B, C, T, 4), out = make_planes(ar, B, C, T, opnd_esz(precision));
     fill_uniform(x.p, x.bytes / 4, 0, -1.7f, 1.7f, 5u);
     float* al = static_cast<float*>(ar.alloc((size_t)round_up(C, 16) * 4, false));

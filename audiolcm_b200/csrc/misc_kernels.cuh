@@ -6,11 +6,6 @@
 
 namespace alcm {
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
 // ------------------------------------------------------------------------------- layout
 // [B][C][T] fp32 channel-first  ->  planes (fp32 E=4, optional tf32 rounding, or bf16 E=8); x*mul
 template <int E>
@@ -36,8 +31,8 @@ __global__ void pack_cf_kernel(const float* __restrict__ in, void* __restrict__ 
     *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
     uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
+    o.x = pack16x2(og.fmt, v[0], v[1]); o.y = pack16x2(og.fmt, v[2], v[3]);
+    o.z = pack16x2(og.fmt, v[4 % E], v[5 % E]); o.w = pack16x2(og.fmt, v[6 % E], v[7 % E]);
     *reinterpret_cast<uint4*>(dst) = o;
   }
 }
@@ -58,7 +53,7 @@ __global__ void unpack_cf_kernel(const float* __restrict__ in, PlaneGeom ig, flo
   }
 }
 
-// bf16 planes (E=8) -> [B][C][T] fp32 channel-first (test entry points only)
+// 16-bit planes (E=8, bf16 or fp16 by ig.fmt) -> [B][C][T] fp32 channel-first (test entry points only)
 __global__ void unpack_cf_bf16_kernel(const uint8_t* __restrict__ in, PlaneGeom ig, float* __restrict__ out, int C, int T) {
   pdl_launch_dependents();
   pdl_wait();
@@ -70,8 +65,13 @@ __global__ void unpack_cf_bf16_kernel(const uint8_t* __restrict__ in, PlaneGeom 
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = chunk * 8 + e;
-    const uint32_t bits = (e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16);
-    if (c < C) out[((size_t)b * C + c) * T + t] = __uint_as_float(bits);
+    float f;
+    if (ig.fmt == kFmtF16) {
+      f = __half2float(__ushort_as_half((unsigned short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu))));
+    } else {
+      f = __uint_as_float((e & 1) ? (w[e >> 1] & 0xffff0000u) : (w[e >> 1] << 16));
+    }
+    if (c < C) out[((size_t)b * C + c) * T + t] = f;
   }
 }
 
@@ -88,7 +88,7 @@ __global__ void cast_planes_kernel(const float* __restrict__ in, PlaneGeom ig, v
     const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, 2 * oc, t));
     const float4 c = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, 2 * oc + 1, t));
     uint4 o;
-    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(c.x, c.y); o.w = pack_bf16x2(c.z, c.w);
+    o.x = pack16x2(og.fmt, a.x, a.y); o.y = pack16x2(og.fmt, a.z, a.w); o.z = pack16x2(og.fmt, c.x, c.y); o.w = pack16x2(og.fmt, c.z, c.w);
     *reinterpret_cast<uint4*>(dst) = o;
   } else {
     float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, oc, t));
@@ -147,8 +147,8 @@ __global__ void geglu_planes_kernel(const float* __restrict__ in, PlaneGeom ig, 
     const float4 g0 = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, gch + 2 * oc, t));
     const float4 g1 = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, gch + 2 * oc + 1, t));
     uint4 o;
-    o.x = pack_bf16x2(geglu1(v0.x, g0.x), geglu1(v0.y, g0.y)); o.y = pack_bf16x2(geglu1(v0.z, g0.z), geglu1(v0.w, g0.w));
-    o.z = pack_bf16x2(geglu1(v1.x, g1.x), geglu1(v1.y, g1.y)); o.w = pack_bf16x2(geglu1(v1.z, g1.z), geglu1(v1.w, g1.w));
+    o.x = pack16x2(og.fmt, geglu1(v0.x, g0.x), geglu1(v0.y, g0.y)); o.y = pack16x2(og.fmt, geglu1(v0.z, g0.z), geglu1(v0.w, g0.w));
+    o.z = pack16x2(og.fmt, geglu1(v1.x, g1.x), geglu1(v1.y, g1.y)); o.w = pack16x2(og.fmt, geglu1(v1.z, g1.z), geglu1(v1.w, g1.w));
     *reinterpret_cast<uint4*>(dst) = o;
   } else {
     const float4 v = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, oc, t));
@@ -191,8 +191,8 @@ __global__ void sum_planes_kernel(SumArgs a) {
   if (a.out_op) {
     if (a.op_bf16) {
       uint4 o;
-      o.x = pack_bf16x2(s[0].x, s[0].y); o.y = pack_bf16x2(s[0].z, s[0].w);
-      o.z = pack_bf16x2(s[1].x, s[1].y); o.w = pack_bf16x2(s[1].z, s[1].w);
+      o.x = pack16x2(a.og.fmt, s[0].x, s[0].y); o.y = pack16x2(a.og.fmt, s[0].z, s[0].w);
+      o.z = pack16x2(a.og.fmt, s[1].x, s[1].y); o.w = pack16x2(a.og.fmt, s[1].z, s[1].w);
       *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out_op) + plane_row_off(a.og, b, pc, t)) = o;
     } else {
 #pragma unroll
@@ -223,7 +223,7 @@ __global__ void s2d_cast_kernel(const float* __restrict__ in, PlaneGeom ig, void
   if (E == 8) {
     const float4 d = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, (c >> 2) + 1, t));
     uint4 o;
-    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w); o.z = pack_bf16x2(d.x, d.y); o.w = pack_bf16x2(d.z, d.w);
+    o.x = pack16x2(og.fmt, a.x, a.y); o.y = pack16x2(og.fmt, a.z, a.w); o.z = pack16x2(og.fmt, d.x, d.y); o.w = pack16x2(og.fmt, d.z, d.w);
     *reinterpret_cast<uint4*>(dst) = o;
   } else {
     float4 v = a;
@@ -295,7 +295,7 @@ __global__ void weff_kernel(const float* __restrict__ src, float* __restrict__ d
 // no-swizzle B operand: LBO = NT*16, SBO = 128).  One thread per 16-byte unit.
 template <int E>
 __global__ void pack_w_kernel(const float* __restrict__ weff, void* __restrict__ dst, int nphase, int ntaps, int Cout, int Cin,
-                              int NT, int n_tiles, int kblk, int nkb) {
+                              int NT, int n_tiles, int kblk, int nkb, int f16) {
   const size_t units = (size_t)nphase * n_tiles * nkb * ntaps * kblk * NT;
   for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < units; u += (size_t)gridDim.x * blockDim.x) {
     size_t r = u;
@@ -317,8 +317,8 @@ __global__ void pack_w_kernel(const float* __restrict__ weff, void* __restrict__
       *reinterpret_cast<float4*>(d) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
     } else {
       uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
+      o.x = pack16x2(f16 ? kFmtF16 : kFmtBF16, v[0], v[1]); o.y = pack16x2(f16 ? kFmtF16 : kFmtBF16, v[2], v[3]);
+      o.z = pack16x2(f16 ? kFmtF16 : kFmtBF16, v[4 % E], v[5 % E]); o.w = pack16x2(f16 ? kFmtF16 : kFmtBF16, v[6 % E], v[7 % E]);
       *reinterpret_cast<uint4*>(d) = o;
     }
   }
@@ -398,7 +398,7 @@ __global__ void conv_post_tanh_kernel(const float* __restrict__ x, PlaneGeom xg,
 //   mode 1: W[n][k] = src[b][channel n][time k]   (V of PV:   n = channel, k = key)
 template <int E>
 __global__ void pack_dyn_w_kernel(const float* __restrict__ src, PlaneGeom sg, int C, int T, void* __restrict__ dst, int mode, int NT,
-                                  int n_tiles, int kblk, int nkb, size_t units_per_item) {
+                                  int n_tiles, int kblk, int nkb, size_t units_per_item, int f16) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.y;
@@ -426,8 +426,8 @@ __global__ void pack_dyn_w_kernel(const float* __restrict__ src, PlaneGeom sg, i
       *reinterpret_cast<float4*>(d) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
     } else {
       uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
+      o.x = pack16x2(f16 ? kFmtF16 : kFmtBF16, v[0], v[1]); o.y = pack16x2(f16 ? kFmtF16 : kFmtBF16, v[2], v[3]);
+      o.z = pack16x2(f16 ? kFmtF16 : kFmtBF16, v[4 % E], v[5 % E]); o.w = pack16x2(f16 ? kFmtF16 : kFmtBF16, v[6 % E], v[7 % E]);
       *reinterpret_cast<uint4*>(d) = o;
     }
   }
@@ -482,8 +482,8 @@ __global__ void softmax_planes_kernel(const float* __restrict__ S, PlaneGeom sg,
       *reinterpret_cast<float4*>(d) = make_float4(o[0], o[1], o[2], o[3]);
     } else {
       uint4 w;
-      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
-      w.z = pack_bf16x2(o[4 % E], o[5 % E]); w.w = pack_bf16x2(o[6 % E], o[7 % E]);
+      w.x = pack16x2(pg.fmt, o[0], o[1]); w.y = pack16x2(pg.fmt, o[2], o[3]);
+      w.z = pack16x2(pg.fmt, o[4 % E], o[5 % E]); w.w = pack16x2(pg.fmt, o[6 % E], o[7 % E]);
       *reinterpret_cast<uint4*>(d) = w;
     }
   }
@@ -531,13 +531,14 @@ __global__ void count_nonzero_kernel(const uint4* __restrict__ p, size_t n, unsi
 }
 
 // Seeded uniform fill in [lo, hi) (micro-benchmark operands): counter-based hash, fp32 or bf16 elements.
-__global__ void fill_uniform_kernel(void* __restrict__ p, size_t n, int bf16, float lo, float hi, unsigned seed) {
+__global__ void fill_uniform_kernel(void* __restrict__ p, size_t n, int fmt, float lo, float hi, unsigned seed) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     unsigned h = (unsigned)i * 2654435761u ^ (unsigned)(i >> 32) * 40503u ^ seed * 0x9E3779B9u;
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
     const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
     const float v = lo + (hi - lo) * u;
-    if (bf16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+    if (fmt == kFmtBF16) reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+    else if (fmt == kFmtF16) reinterpret_cast<__half*>(p)[i] = __float2half(v);
     else reinterpret_cast<float*>(p)[i] = v;
   }
 }
@@ -647,8 +648,8 @@ __global__ void gn_apply_kernel(const float* __restrict__ x, PlaneGeom xg, void*
     *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
     uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
+    o.x = pack16x2(og.fmt, v[0], v[1]); o.y = pack16x2(og.fmt, v[2], v[3]);
+    o.z = pack16x2(og.fmt, v[4 % E], v[5 % E]); o.w = pack16x2(og.fmt, v[6 % E], v[7 % E]);
     *reinterpret_cast<uint4*>(dst) = o;
   }
 }
@@ -737,8 +738,8 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(const float* __restrict__
       *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
       uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4 % E], v[5 % E]); o.w = pack_bf16x2(v[6 % E], v[7 % E]);
+      o.x = pack16x2(og.fmt, v[0], v[1]); o.y = pack16x2(og.fmt, v[2], v[3]);
+      o.z = pack16x2(og.fmt, v[4 % E], v[5 % E]); o.w = pack16x2(og.fmt, v[6 % E], v[7 % E]);
       *reinterpret_cast<uint4*>(dst) = o;
     }
   }

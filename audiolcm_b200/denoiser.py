@@ -151,7 +151,7 @@ class ConcatDiT2MLPB200(object):
         qkv = self.qkv[idx](xn_cf)                                                     # (B, 3C, N)
         # one transposing copy makes q|k|v (B, heads, N, d) with unit stride in d: PyTorch's fused attention kernels
         # need that (strided heads fall back to its 3-kernel math path); bf16 mode takes the flash kernel
-        dt = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        dt = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(self.precision, torch.float32)
         q, k, v = qkv.reshape(B, 3, heads, d, N).permute(1, 0, 2, 4, 3).to(dt, memory_format=torch.contiguous_format)
         out = F.scaled_dot_product_attention(q, k, v, scale=d ** -0.5)                 # (B, heads, N, d)
         out_cf = out.transpose(2, 3).reshape(B, Cc, N).float()                         # channel = head*d + dd, as 'b n (h d)'

@@ -14,6 +14,8 @@ data-path collective -> STRONG scaling; value = 64 clips' audio seconds / max-ov
 Prints ONE JSON line (rank 0):
   value / dtype      the "fp32 mode" (tcgen05 kind::tf32, fp32 storage; parity gate max-abs <= 1e-3 vs the reference)
   bf16               the same measurement in bf16 mode (parity gate SNR >= 35 dB, log-mel L1 <= 0.05)
+  fp16               the same measurement with fp16 operands (kind::f16: tf32's 10-bit mantissa at bf16's tensor rate and
+                     bytes; held to the fp32-mode gate, max-abs <= 1e-3; conversions saturate at +-65504)
   e2e                the public API (LatentToWaveform.decode) with pinned host latents in and host waveforms out, every step
   roofline           dominant kernel class (conv_umma_kernel, all conv launches of the step, in-pipeline CUDA-event
                      time) against the measured sustained bf16 peak; roofline_act the same for Activation1d vs HBM;
@@ -45,7 +47,7 @@ CLIPS = 64                       # BASELINE.json configs[2]
 LONG_FRAMES = 18750              # configs[3]: 300 s x 62.5 mel frames/s
 SR, HOP, VAE_UP = 16000, 256, 2
 METRIC = "audio_seconds_per_second_latent_to_waveform_decode"
-DTYPE = {"bf16": "bf16", "tf32": "tf32", "fp32": "f32"}
+DTYPE = {"bf16": "bf16", "tf32": "tf32", "fp32": "f32", "fp16": "f16"}
 
 
 def audio_seconds(B, t_lat):
@@ -234,13 +236,13 @@ def kernel_rooflines(precision, peaks, local):
                                               launches=iters, clocks=clk),
                             peak_note="measured bf16 cuBLAS figures (burst / sustained)" + (", halved for tf32 operands" if precision == "tf32" else ""))
     B, Cc, T = 64, 24, 160000               # last-stage Activation1d, batch 64: 1.5-2.0 GB, far beyond L2
-    for key, p, osz in (("activation1d", precision, 2 if precision == "bf16" else 4), ("activation1d_fp32_out", "tf32", 4)):
+    for key, p, osz in (("activation1d", precision, 2 if precision in ("bf16", "fp16") else 4), ("activation1d_fp32_out", "tf32", 4)):
         if key == "activation1d_fp32_out" and precision != "bf16":
             continue
         bms, sms_, iters, clk = timed(lambda n: lib.alcm_bench_act(ctx, B, Cc, T, _lib.PREC[p], n, C.byref(ms)))
         byt = B * Cc * T * (4 + osz)          # algorithmic: UNPADDED channels, one fp32 read + one write
         gb, gs = byt / (bms * 1e-3) / 1e9, byt / (sms_ * 1e-3) / 1e9
-        out[key] = dict(kernel="act1d_kernel", shape=f"C={Cc} T={T} batch {B}, fp32 in / {'bf16' if osz == 2 else 'fp32'} out "
+        out[key] = dict(kernel="act1d_kernel", shape=f"C={Cc} T={T} batch {B}, fp32 in / {precision if osz == 2 else 'fp32'} out "
                                                       f"({byt / 1e6:.0f} MB algorithmic, unpadded)", operands="seeded random x, alpha, beta",
                         bound="hbm", achieved=round(gb, 1), peak=peaks["hbm"], unit="GB/s", frac=round(gb / peaks["hbm"], 4),
                         us_per_launch=round(bms * 1e3, 1),
@@ -606,7 +608,8 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    modes = ["tf32", "bf16"] if args.precision == "both" else [args.precision]
+    modes = ["tf32", "bf16", "fp16"] if args.precision == "both" else [args.precision]
+    side = "bf16" if "bf16" in modes else modes[-1]     # the mode the long-form / config-5 / encoder legs run in
     recs, extra = {}, {}
     for mode in modes:
         pipe, rec, wav = measure_mode(mode, device, z_host, z_dev, args, world, rank, local, flush, barrier, peaks, detailed=True)
@@ -621,13 +624,13 @@ def run_gpu(args):
             if world == 1 and not args.no_batch1:
                 x["batch1"] = batch1_latency(pipe, device, flush, args.steps, args.warmup)
             extra[mode] = x
-        if not args.no_longform and mode == modes[-1]:
+        if not args.no_longform and mode == side:
             lf = longform(pipe, device, world, rank, 3, barrier, mode)
             if rank == 0:
                 extra["longform"] = lf
         if rank == 0 and world == 1 and not args.no_micro:
             extra[mode]["kernel_rooflines"] = kernel_rooflines(mode, peaks, local)
-        if rank == 0 and world == 1 and not args.no_config5 and mode == modes[-1]:
+        if rank == 0 and world == 1 and not args.no_config5 and mode == side:
             extra["config5"] = config5(pipe, device, mode)
             extra["encoder"] = encoder_leg(device, mode, flush)
         del pipe
@@ -670,7 +673,7 @@ def run_gpu(args):
                 parity[mode]["snr_db_clip0_vs_cpu_oracle"] = round(float(10 * np.log10((ref.astype(np.float64) ** 2).sum() /
                                                                                         max(((got.astype(np.float64) - ref) ** 2).sum(), 1e-300))), 2)
                 parity[mode]["log_mel_l1_clip0_vs_cpu_oracle"] = float((melnet(torch.from_numpy(got[None])) - mel_ref).abs().mean())
-            parity["gates"] = ("tf32: max-abs <= 1e-3; bf16: max-abs <= 5e-3, SNR >= 35 dB, mean |log10-mel difference| <= 0.05 "
+            parity["gates"] = ("tf32 and fp16: max-abs <= 1e-3; bf16: max-abs <= 5e-3, SNR >= 35 dB, mean |log10-mel difference| <= 0.05 "
                                "(tests/test_gpu_models.py; the log-mel here is computed on the GPU by audiolcm_b200.melspec)")
             parity["ref_abs_max"] = float(np.abs(ref).max())
         line["parity_check"] = parity
@@ -707,8 +710,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("ALCM_BENCH_PRECISION", "both"), choices=["both", "bf16", "tf32", "fp32"],
-                    help="both (default): headline = tf32 ('fp32 mode'), sibling object = bf16")
+    ap.add_argument("--precision", default=os.environ.get("ALCM_BENCH_PRECISION", "both"), choices=["both", "bf16", "tf32", "fp32", "fp16"],
+                    help="both (default): headline = tf32 ('fp32 mode'), sibling objects = bf16 and fp16")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (and the oracle parity check)")
     ap.add_argument("--no-batch1", action="store_true", help="skip the configs[1] (batch 1) latency measurement")
     ap.add_argument("--no-longform", action="store_true", help="skip the configs[3] (300 s clip) measurement")

@@ -51,7 +51,9 @@ typedef struct alcm_vae_encoder alcm_vae_encoder;
 enum {
   ALCM_PREC_FP32 = 0, /* CUDA-core FFMA, fp32 end to end (exact mode; slow)                        */
   ALCM_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 storage, fp32 accumulate  ("fp32 mode")          */
-  ALCM_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 residual stream and accumulators  */
+  ALCM_PREC_BF16 = 2, /* tcgen05 kind::f16 (bf16 operands), fp32 residual stream and accumulators  */
+  ALCM_PREC_FP16 = 3  /* tcgen05 kind::f16 (fp16 operands: tf32's 10-bit mantissa at bf16's speed and bytes; conversions
+                         saturate at +-65504 - for networks whose activations stay in fp16 range), fp32 elsewhere */
 };
 
 enum {

@@ -18,12 +18,12 @@ from tests.util import log_mel_l1, snr_db
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-WAV_TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 5e-3}
-MEL_TOL = {"fp32": 1e-4, "tf32": 1e-2, "bf16": 6e-2}
-SNR_MIN = {"fp32": 90.0, "tf32": 55.0, "bf16": 35.0}
+WAV_TOL = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 5e-3, "fp16": 1e-3}     # fp16 operands: held to the fp32-mode gate
+MEL_TOL = {"fp32": 1e-4, "tf32": 1e-2, "bf16": 6e-2, "fp16": 1e-2}
+SNR_MIN = {"fp32": 90.0, "tf32": 55.0, "bf16": 35.0, "fp16": 55.0}
 # mean |log10-mel| distance between our waveform and the reference's (NAT_mel definition, tests/util.py): the
 # stated bf16 bound of the north star (SURVEY.md 8d suggests <= 0.05 log10 units)
-LOGMEL_MAX = {"fp32": 1e-4, "tf32": 5e-3, "bf16": 5e-2}
+LOGMEL_MAX = {"fp32": 1e-4, "tf32": 5e-3, "bf16": 5e-2, "fp16": 5e-3}
 
 
 def _voc(h, sd, precision):
@@ -37,7 +37,7 @@ def _vae(dd, sd, precision):
 
 
 @pytest.mark.parametrize("tag", ["c64", "c256"])
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_vocode_small_vs_reference(golden_dir, tag, precision):
     g = np.load(os.path.join(golden_dir, f"bigvgan_{tag}.npz"))
     h = synth.bigvgan_config(int(g["c0"]))
@@ -57,7 +57,7 @@ def test_vocode_small_vs_reference(golden_dir, tag, precision):
 
 
 @pytest.mark.parametrize("tag", ["rb2_snake", "rb1_linear", "rb2_snakebeta_linear"])
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_vocode_config_variants_vs_reference(golden_dir, tag, precision):
     """The other generator choices BigVGAN.__init__ accepts - AMPBlock2 (models.py:90-126), Snake (activations.py:9-62),
     linear-scale alpha / beta - against outputs of the unmodified reference (oracle/make_golden.py VARIANTS)."""
@@ -74,7 +74,7 @@ def test_vocode_config_variants_vs_reference(golden_dir, tag, precision):
     assert snr_db(ref, wav) >= SNR_MIN[precision]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 @pytest.mark.parametrize("tag", ["T40", "T625"])
 def test_vocode_full_config_vs_reference(golden_dir, tag, precision):
     if precision == "fp32" and tag == "T625":
@@ -99,7 +99,7 @@ def test_vocode_full_config_vs_reference(golden_dir, tag, precision):
 
 
 @pytest.mark.parametrize("tag", ["ch32", "full_T17", "full"])
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_vae_decode_vs_reference(golden_dir, tag, precision):
     g = np.load(os.path.join(golden_dir, f"vae_{tag}.npz"))
     dd = synth.vae_config(int(g["ch"]))
@@ -117,7 +117,7 @@ def test_vae_decode_vs_reference(golden_dir, tag, precision):
     assert np.abs(got2 - got).max() <= (1e-5 if precision == "fp32" else MEL_TOL[precision])
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_full_path_vs_reference(golden_dir, precision):
     from audiolcm_b200 import LatentToWaveform
     g = np.load(os.path.join(golden_dir, "path_full_T24.npz"))
@@ -135,7 +135,7 @@ def test_full_path_vs_reference(golden_dir, precision):
     assert pipe.decode(z).shape == (1, 24 * 512)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_batch_and_time_shard_properties(precision):
     """Size-independent properties at a mid-size config: batching does not mix samples and the
     34-frame-halo time sharding (config 4) reproduces the un-sharded result in the interior.
@@ -143,7 +143,7 @@ def test_batch_and_time_shard_properties(precision):
     numerically vanishing Kaiser-sinc tails: exact to rounding, not bit-exact).  tf32 / bf16: the split-K factor and
     the Activation1d kernel form of small launches depend on the launch geometry, and a 1-ulp fp32 difference can
     flip the rounding of an operand, so the bound is the mode's parity gate - mixing samples would be O(0.1)."""
-    tol = {"fp32": 2e-6, "tf32": 1e-3, "bf16": 5e-3}[precision]
+    tol = {"fp32": 2e-6, "tf32": 1e-3, "bf16": 5e-3, "fp16": 1e-3}[precision]
     h = synth.bigvgan_config(256)
     sd = synth.bigvgan_state_dict(h, seed=2)
     voc = _voc(h, sd, precision)
@@ -163,7 +163,7 @@ def test_batch_and_time_shard_properties(precision):
 
 
 # ----------------------------------------------------------------------------------- the plans the benchmark runs
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "fp16"])
 def test_batch64_full_size_decode_vs_oracle(precision):
     """BASELINE.json configs[2] at full size: 64 x 10 s clips in ONE call.  This shape takes a different plan than
     the batch-1 headline - AMP blocks back to back accumulating in place (accum = 1), persistent two-accumulator conv
@@ -230,7 +230,7 @@ def _nccl_worker(rank, world, port, T, precision, out_q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "fp16"])
 def test_time_sharded_vocode_over_nccl_vs_oracle(precision):
     """BASELINE.json configs[3] on real hardware: two ranks, two GPUs, the 34-frame halo exchanged with NCCL P2P
     (batch_isend_irecv), each rank vocoding its extended chunk; the stitched waveform is compared with the CPU oracle
@@ -541,7 +541,7 @@ def test_vae_attention_paths(golden_dir, monkeypatch, attn_tc):
 
 # ----------------------------------------------------------------------------------- VAE encoder
 @pytest.mark.parametrize("tag", ["ch32", "full_T64"])
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_vae_encode_vs_reference(golden_dir, tag, precision):
     """AutoencoderKLEncoder against AutoencoderKL.encode(x).parameters of the unmodified reference (Encoder1D with its
     k = 5 ResnetBlocks, Downsample1D as a 2-tap conv on the time-folded input, mid attention, quant_conv)."""
@@ -561,7 +561,7 @@ def test_vae_encode_vs_reference(golden_dir, tag, precision):
         enc.moments(x[..., :-1])          # odd length
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_mel_front_end_vs_nat_mel_restatement(precision):
     """MelSpectrogramB200 (STFT and mel projection as conv_umma_kernel GEMMs) against tests/util.log_mel, the torch.stft
     restatement of MelNet.forward (NAT_mel.py:64-85; librosa is absent, so this half of SURVEY 8f row 4 is pinned to the
@@ -578,12 +578,12 @@ def test_mel_front_end_vs_nat_mel_restatement(precision):
     assert got.shape == (2, 80, 97)
     err = np.abs(got[0] - ref)
     print(f"\n[mel front-end {precision}] log10-mel error: mean {err.mean():.2e}, max {err.max():.2e}")
-    mean_tol, max_tol = {"fp32": (1e-5, 2e-4), "tf32": (1e-3, 2e-2), "bf16": (6e-3, 1e-1)}[precision]
+    mean_tol, max_tol = {"fp32": (1e-5, 2e-4), "tf32": (1e-3, 2e-2), "bf16": (6e-3, 1e-1), "fp16": (1e-3, 2e-2)}[precision]
     assert err.mean() <= mean_tol and err.max() <= max_tol
     np.testing.assert_allclose(got[1], log_mel(wav[::-1].copy()), atol=max_tol)
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "fp16"])
 def test_vae_long_sequence_paths(precision):
     """Long-form VAE decode (the replicated half of BASELINE.json configs[3]): at T_lat = 1100 the GroupNorm groups no
     longer fit in shared memory (two-kernel statistics + apply path) and the attention scores are 1100 x 1100 per item

@@ -41,7 +41,7 @@ def test_activation1d_golden_fp32(ops, golden_dir, case):
 
 
 @pytest.mark.parametrize("shape", [(1, 768, 2500), (2, 24, 4099), (1, 17, 511), (1, 16, 513), (3, 40, 1030)])
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_activation1d_vs_oracle(ops, shape, precision):
     from oracle import decode_oracle as O
     B, C, T = shape
@@ -49,7 +49,7 @@ def test_activation1d_vs_oracle(ops, shape, precision):
     al, be = _rand(C, seed=2, scale=0.5), _rand(C, seed=3, scale=0.5)
     ref = O.activation1d(x.double(), al.double(), be.double(), O.kaiser_sinc_filter().double())
     y = ops.activation1d(x.to(DEV), al.to(DEV), be.to(DEV), precision).cpu()
-    tol = {"fp32": 1e-5, "tf32": 2.0 ** -11, "bf16": 2.0 ** -8}[precision]
+    tol = {"fp32": 1e-5, "tf32": 2.0 ** -11, "bf16": 2.0 ** -8, "fp16": 2.0 ** -11}[precision]
     err = (y.double() - ref).abs()
     assert float((err / (ref.abs() + 1.0)).max()) < tol * 1.01 + 1e-5, float(err.max())
     if precision != "fp32":  # output must be exactly representable in the operand type
@@ -78,7 +78,7 @@ CONV_CASES = [
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_conv1d(ops, case, precision):
     B, Cin, Cout, T, K, d = case
     x = _rand(B, Cin, T, seed=4)
@@ -96,7 +96,7 @@ def test_conv1d(ops, case, precision):
 
 
 @pytest.mark.parametrize("case", [(1, 1536, 768, 625, 4), (2, 96, 48, 333, 2), (1, 48, 24, 1000, 2), (1, 8, 4, 5, 4), (1, 4, 2, 1, 2)])
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_conv_transpose1d(ops, case, precision):
     B, Cin, Cout, T, u = case
     x = _rand(B, Cin, T, seed=8)
@@ -110,7 +110,7 @@ def test_conv_transpose1d(ops, case, precision):
 
 
 @pytest.mark.parametrize("case", [(1, 768, 768, 312), (2, 64, 64, 17), (1, 32, 32, 1)])
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_upsample_conv3(ops, case, precision):
     B, Cin, Cout, T = case
     x = _rand(B, Cin, T, seed=11)
@@ -148,7 +148,7 @@ def test_groupnorm_swish(ops, shape, swish):
 
 
 @pytest.mark.parametrize("shape", [(1, 1536, 312), (2, 128, 24), (1, 32, 1), (1, 64, 33), (3, 256, 130), (1, 1536, 624)])
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_attn1d(ops, shape, precision):
     """fp32: CUDA-core kernels; tf32 / bf16: QK^T and PV on conv_umma_kernel with per-item operands.  The reference is
     float64 on operands rounded as the device rounds them (q, k, v; the probabilities are rounded on the device too, which the
@@ -159,7 +159,7 @@ def test_attn1d(ops, shape, precision):
     w = torch.softmax(torch.bmm(qr.permute(0, 2, 1), kr) * (C ** -0.5), dim=2)
     ref = torch.bmm(vr, w.permute(0, 2, 1))
     y = ops.attn1d(q.to(DEV), k.to(DEV), v.to(DEV), precision).cpu()
-    tol = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 6e-3}[precision]
+    tol = {"fp32": 2e-5, "tf32": 1e-3, "bf16": 6e-3, "fp16": 1e-3}[precision]
     assert float((y.double() - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
 
 
@@ -183,14 +183,14 @@ ACT_EDGE_SHAPES = [(1, 8, 1), (1, 8, 3), (2, 24, 4099), (1, 16, 635), (1, 16, 63
 
 
 @pytest.mark.parametrize("variant", sorted(ACT_VARIANTS))
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_activation1d_every_kernel_form(ops, monkeypatch, variant, precision):
     """The plans pick one block size of the Activation1d kernel; here each of the three is forced
     (ALCM_ACT_VARIANT) and run over tile-boundary and tiny shapes (T = 1: every tap is replicate padding;
     T = tile, tile+1, tile-3: the halo'd edges of the staged tile) against the float64 oracle."""
     from oracle import decode_oracle as O
     monkeypatch.setenv("ALCM_ACT_VARIANT", str(variant))
-    tol = {"fp32": 1e-5, "tf32": 2.0 ** -11, "bf16": 2.0 ** -8}[precision]
+    tol = {"fp32": 1e-5, "tf32": 2.0 ** -11, "bf16": 2.0 ** -8, "fp16": 2.0 ** -11}[precision]
     for i, (B, C, T) in enumerate(ACT_EDGE_SHAPES):
         x = _rand(B, C, T, seed=30 + i, scale=1.5)
         al, be = _rand(C, seed=2, scale=0.5), _rand(C, seed=3, scale=0.5)
@@ -250,7 +250,7 @@ def test_lcm_step_matches_reference_golden(ops, golden_dir):
 
 
 # ----------------------------------------------------------------------------------- DiT feed-forward convs
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "fp16"])
 def test_conv1d_layer_handle(precision):
     """alcm_conv1d_* (persistent layer: weights packed once, a plan per (B,T)) on the DiT's feed-forward shape (k = 9)."""
     from audiolcm_b200.denoiser import Conv1dLayer
@@ -280,7 +280,7 @@ def test_layernorm_channels_first():
         assert float((y.double() - ref).abs().max()) < 2e-5 * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
 def test_conv1d_feedforward_handle(precision):
     """alcm_ffn1d_* = Conv1dFeedForward(glu=True) (new_attention.py:38-74): conv k9 -> x * gelu(gate) -> conv k9 (+ res) as one plan,
     against the same ops in float64 (operands of the second conv rounded as the kernel rounds them)."""
@@ -302,11 +302,11 @@ def test_conv1d_feedforward_handle(precision):
             ref = ref + res.double()
         y = layer(x.to(DEV), None if res is None else res.to(DEV)).cpu()
         # the intermediate is re-rounded to the operand type: a 1-ulp flip of it moves the output by ~ulp * |w|
-        tol = {"fp32": 3e-5, "tf32": 1e-3, "bf16": 4e-3}[precision]
+        tol = {"fp32": 3e-5, "tf32": 1e-3, "bf16": 4e-3, "fp16": 1e-3}[precision]
         assert float((y.double() - ref).abs().max()) < tol * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32", "bf16", "fp16"])
 def test_hybrid_dit_and_sampler_match_reference_golden(golden_dir, precision):
     """ConcatDiT2MLPB200 (feed-forward convs on conv_umma_kernel, the rest PyTorch) and LCMSamplerB200 (fused step kernel)
     against tests/golden/lcm_denoiser.npz = outputs of the REAL ConcatDiT2MLP / LCMSampler.lcm_sampling on CPU."""
@@ -317,7 +317,7 @@ def test_hybrid_dit_and_sampler_match_reference_golden(golden_dir, precision):
     x, ctx, t = torch.from_numpy(g["x"]).to(DEV), torch.from_numpy(g["ctx"]).to(DEV), torch.from_numpy(g["t"]).to(DEV)
     w_emb = LCMSamplerB200.guidance_embedding(torch.tensor(4.0).repeat(x.shape[0])).to(DEV)
     eps = dit(x, t, ctx, w_emb).cpu().numpy()
-    tol = {"tf32": 3e-3, "bf16": 3e-2}[precision]
+    tol = {"tf32": 3e-3, "bf16": 3e-2, "fp16": 3e-3}[precision]
     err = np.abs(eps - g["eps"]).max() / np.abs(g["eps"]).max()
     print(f"\n[hybrid DiT {precision}] eps max-abs error relative to abs-max: {err:.2e}")
     assert err <= tol

@@ -15,6 +15,8 @@ def round_operand(x: torch.Tensor, precision: str) -> torch.Tensor:
         return round_tf32(x.float())
     if precision == "bf16":
         return x.float().bfloat16().float()
+    if precision == "fp16":
+        return x.float().clamp(-65504.0, 65504.0).half().float()
     return x.float()
 
 
