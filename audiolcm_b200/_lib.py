@@ -99,6 +99,9 @@ SYMBOLS = {
     "alcm_conv1d_create": (C.c_int, [_P, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "alcm_conv1d_destroy": (None, [_P]),
     "alcm_conv1d_run": (C.c_int, [_P, _FP, _FP, _FP, C.c_int, C.c_int, _P]),
+    "alcm_melspec_create": (C.c_int, [_P, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "alcm_melspec_destroy": (None, [_P]),
+    "alcm_melspec_run": (C.c_int, [_P, _FP, _FP, C.c_int, C.c_int, _P]),
     "alcm_layernorm_cf": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_float, _P]),
     "alcm_ffn1d_create": (C.c_int, [_P, _FP, _FP, _FP, _FP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "alcm_ffn1d_destroy": (None, [_P]),

@@ -799,22 +799,24 @@ struct OpList {
     };
     push(op);
   }
-  // GEGLU of the DiT feed-forward: fp32 planes of 2*inner channels -> operand planes of inner channels
-  void geglu(const PlaneT& x, const PlaneT& out, int inner, int round_tf) {
+  // value/gate pair ops on fp32 planes of 2*inner channels -> operand planes of inner channels: GEGLU of the DiT feed-forward
+  // (op 0), STFT magnitude of the mel front-end (op 1)
+  void pair(const PlaneT& x, const PlaneT& out, int inner, int round_tf, int opk) {
     const int E = 16 / out.esz;
-    REQUIRE(x.esz == 4 && x.T == out.T && x.B == out.B, "geglu: bad planes");
-    REQUIRE(inner % E == 0 && x.g.nchunk * 4 >= 2 * inner && out.g.nchunk * E >= inner, "geglu: channel mismatch");
+    REQUIRE(x.esz == 4 && x.T == out.T && x.B == out.B, "pair op: bad planes");
+    REQUIRE(inner % E == 0 && x.g.nchunk * 4 >= 2 * inner && out.g.nchunk * E >= inner, "pair op: channel mismatch");
     const int B = x.B, T = x.T, oesz = out.esz;
     PlaneT xc = x, oc = out;
     Op op;
     op.cls = ALCM_CLS_MISC; op.flops = 0; op.bytes = (double)B * T * inner * (8.0 + oesz);
     op.fn = [=](cudaStream_t st) {
       dim3 grid((T + 127) / 128, inner / E, B);
-      if (oesz == 2) launch_k(geglu_planes_kernel<8>, grid, dim3(128), 0, st, xc.f(), xc.g, oc.p, oc.g, T, inner, 0);
-      else launch_k(geglu_planes_kernel<4>, grid, dim3(128), 0, st, xc.f(), xc.g, oc.p, oc.g, T, inner, round_tf);
+      if (oesz == 2) launch_k(opk ? geglu_planes_kernel<8, 1> : geglu_planes_kernel<8, 0>, grid, dim3(128), 0, st, xc.f(), xc.g, oc.p, oc.g, T, inner, 0);
+      else launch_k(opk ? geglu_planes_kernel<4, 1> : geglu_planes_kernel<4, 0>, grid, dim3(128), 0, st, xc.f(), xc.g, oc.p, oc.g, T, inner, round_tf);
     };
     push(op);
   }
+  void geglu(const PlaneT& x, const PlaneT& out, int inner, int round_tf) { pair(x, out, inner, round_tf, 0); }
   // n-way sum of fp32 planes (block mean of the AMP blocks, models.py:190-196, when the blocks ran as
   // parallel lanes); writes fp32 planes and/or operand planes for the next conv
   void sum(const std::vector<PlaneT>& in, const PlaneT* out32, const PlaneT* out_op, int round_tf) {
@@ -2199,6 +2201,92 @@ int alcm_ffn1d_run(alcm_ffn1d* c, const float* x, const float* res, float* y, in
     if (res) launch_pack(res, P->res_in, c->dim_out, T, 1.f, ALCM_PREC_FP32, st);
     run_plan(*P, st);
     launch_unpack(P->out, y, c->dim_out, T, st);
+    CUDA_CHECK(cudaGetLastError());
+    use.finish();
+  });
+}
+
+// ---- log10-mel front-end (ldm/data/preprocess/NAT_mel.py:64-85) as one plan: clamp + reflect pad + fold -> STFT as a
+//      (taps+1)-tap conv -> magnitude -> mel filterbank as a 1x1 conv -> log10(clamp); SURVEY 8f row 4 ----
+struct MelPlan : PlanBase {
+  PlaneT x_in, mel_out;
+};
+struct alcm_melspec {
+  alcm_ctx* ctx;
+  Env env;
+  int prec, hop, taps, nb_pad, n_mels;
+  Arena war;
+  ConvLayer stft, mel;
+  RetileCache retiled;
+  std::map<std::pair<int, int>, std::unique_ptr<MelPlan>> plans;   // (B, L)
+  PlanCache pcache;
+};
+
+int alcm_melspec_create(alcm_ctx* ctx, const float* stft_w, const float* mel_w, int hop, int taps, int nb_pad, int n_mels, int precision,
+                        alcm_melspec** out) {
+  return guarded([&] {
+    REQUIRE(ctx && stft_w && mel_w && out, "melspec_create: NULL argument");
+    REQUIRE(hop >= 8 && taps >= 1 && taps <= 10 && (taps & 1) == 0 && nb_pad >= 8 && nb_pad % 8 == 0 && n_mels >= 1,
+            "melspec_create: bad shape (even taps <= 10, nb_pad % 8 == 0)");
+    REQUIRE(precision >= 0 && precision <= 3, "melspec_create: bad precision");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+    std::unique_ptr<alcm_melspec> c(new alcm_melspec());
+    c->ctx = ctx; c->prec = precision; c->hop = hop; c->taps = taps; c->nb_pad = nb_pad; c->n_mels = n_mels;
+    c->env.cx = ctx; c->env.k = Knobs::from_env();
+    c->war.guard = c->env.k.guard != 0;
+    c->stft = prepare_conv(c->war, c->env.k, precision, KIND_CONV, stft_w, nullptr, 2 * nb_pad, hop, taps + 1, 1);
+    c->mel = prepare_conv(c->war, c->env.k, precision, KIND_CONV, mel_w, nullptr, n_mels, nb_pad, 1, 1);
+    *out = c.release();
+  });
+}
+void alcm_melspec_destroy(alcm_melspec* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  wait_plans(c->plans, c->pcache);
+  delete c;
+}
+int alcm_melspec_run(alcm_melspec* c, const float* y, float* mel, int B, int L, void* stream) {
+  return guarded([&] {
+    REQUIRE(c && y && mel, "melspec_run: NULL argument");
+    REQUIRE(B >= 1 && L >= c->hop * c->taps && L % c->hop == 0, "melspec_run: L must be a positive multiple of hop (>= one window)");
+    CUDA_CHECK(cudaSetDevice(c->ctx->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int frames = L / c->hop, rows = frames + c->taps - 1, padw = (c->taps - 1) * c->hop / 2;
+    auto key = std::make_pair(B, L);
+    auto it = c->plans.find(key);
+    MelPlan* P = nullptr;
+    if (it != c->plans.end()) {
+      P = it->second.get();
+    } else {
+      c->pcache.make_room(c->plans, (size_t)c->env.k.max_plans, st);
+      std::unique_ptr<MelPlan> pl = build_plan<MelPlan>(c->env, &c->war, &c->retiled, B, rows, st, false, nullptr, [&](MelPlan& R) {
+        R.ar.f16 = (c->prec == ALCM_PREC_FP16);
+        R.x_in = make_planes(R.ar, B, c->hop, rows, opnd_esz(c->prec));
+        PlaneT spec = make_planes(R.ar, B, 2 * c->nb_pad, rows, 4);
+        PlaneT mag = make_planes(R.ar, B, c->nb_pad, rows, opnd_esz(c->prec));
+        R.mel_out = make_planes(R.ar, B, c->n_mels, rows, 4);
+        R.ol.conv(c->stft, R.x_in, spec, nullptr);
+        R.ol.pair(spec, mag, c->nb_pad, c->prec == ALCM_PREC_TF32, 1);
+        R.ol.conv(c->mel, mag, R.mel_out, nullptr);
+        R.Tout = frames;
+      });
+      P = pl.get();
+      c->plans[key] = std::move(pl);
+    }
+    P->stamp = ++c->ctx->plan_clock;
+    PlanUse use(P, st);
+    {
+      const PlaneT& X = P->x_in;
+      dim3 grid((rows + 127) / 128, X.g.nchunk, B);
+      if (X.esz == 2) launch_k(mel_fold_kernel<8>, grid, dim3(128), 0, st, y, L, c->hop, padw, (void*)X.p, X.g, rows, 0);
+      else launch_k(mel_fold_kernel<4>, grid, dim3(128), 0, st, y, L, c->hop, padw, (void*)X.p, X.g, rows, (int)(c->prec == ALCM_PREC_TF32));
+    }
+    run_plan(*P, st);
+    {  // frame m = sum_i X[m+i] D[i] is row m + taps/2 of the 'same' (taps+1)-tap conv whose first tap is zero
+      const PlaneT& M = P->mel_out;
+      dim3 grid((frames + 255) / 256, (c->n_mels + 3) / 4, B);
+      launch_k(unpack_log10_kernel, grid, dim3(256), 0, st, M.f(), M.g, mel, c->n_mels, frames, c->taps / 2 - 1, 1e-5f);
+    }
     CUDA_CHECK(cudaGetLastError());
     use.finish();
   });

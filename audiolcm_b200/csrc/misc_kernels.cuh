@@ -130,7 +130,11 @@ __global__ void __launch_bounds__(128) layernorm_cf_kernel(const float* __restri
 // out[c] = in[c] * gelu(in[inner + c]) with the exact (erf) GELU of F.gelu; fp32 planes of 2*inner channels ->
 // operand planes of inner channels (bf16 E=8, or fp32 E=4 optionally rounded to tf32).  inner % E == 0.
 __device__ __forceinline__ float geglu1(float v, float g) { return v * (0.5f * g * (1.f + erff(g * 0.70710678118654752f))); }
-template <int E>
+// OP 1 (the mel front-end, NAT_mel.py:75-78): out[c] = sqrt(in[c]^2 + in[inner + c]^2 + 1e-9), the magnitude of an STFT whose
+// real parts are channels [0, inner) and imaginary parts [inner, 2*inner).
+template <int OP>
+__device__ __forceinline__ float pair_op(float v, float g) { return OP == 0 ? geglu1(v, g) : sqrtf(fmaf(v, v, fmaf(g, g, 1e-9f))); }
+template <int E, int OP>
 __global__ void geglu_planes_kernel(const float* __restrict__ in, PlaneGeom ig, void* __restrict__ out, PlaneGeom og, int T, int inner,
                                     int round_tf) {
   pdl_launch_dependents();
@@ -147,15 +151,65 @@ __global__ void geglu_planes_kernel(const float* __restrict__ in, PlaneGeom ig, 
     const float4 g0 = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, gch + 2 * oc, t));
     const float4 g1 = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, gch + 2 * oc + 1, t));
     uint4 o;
-    o.x = pack16x2(og.fmt, geglu1(v0.x, g0.x), geglu1(v0.y, g0.y)); o.y = pack16x2(og.fmt, geglu1(v0.z, g0.z), geglu1(v0.w, g0.w));
-    o.z = pack16x2(og.fmt, geglu1(v1.x, g1.x), geglu1(v1.y, g1.y)); o.w = pack16x2(og.fmt, geglu1(v1.z, g1.z), geglu1(v1.w, g1.w));
+    o.x = pack16x2(og.fmt, pair_op<OP>(v0.x, g0.x), pair_op<OP>(v0.y, g0.y)); o.y = pack16x2(og.fmt, pair_op<OP>(v0.z, g0.z), pair_op<OP>(v0.w, g0.w));
+    o.z = pack16x2(og.fmt, pair_op<OP>(v1.x, g1.x), pair_op<OP>(v1.y, g1.y)); o.w = pack16x2(og.fmt, pair_op<OP>(v1.z, g1.z), pair_op<OP>(v1.w, g1.w));
     *reinterpret_cast<uint4*>(dst) = o;
   } else {
     const float4 v = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, oc, t));
     const float4 g = *reinterpret_cast<const float4*>(src + plane_row_off(ig, b, gch + oc, t));
-    float4 o = make_float4(geglu1(v.x, g.x), geglu1(v.y, g.y), geglu1(v.z, g.z), geglu1(v.w, g.w));
+    float4 o = make_float4(pair_op<OP>(v.x, g.x), pair_op<OP>(v.y, g.y), pair_op<OP>(v.z, g.z), pair_op<OP>(v.w, g.w));
     if (round_tf) { o.x = round_tf32(o.x); o.y = round_tf32(o.y); o.z = round_tf32(o.z); o.w = round_tf32(o.w); }
     *reinterpret_cast<float4*>(dst) = o;
+  }
+}
+
+// Mel front-end input (ldm/data/preprocess/NAT_mel.py:68-73): clamp the waveform to [-1,1], reflect-pad it by `padw` samples
+// on both sides and fold it into hop-sized rows, X[b][c][n] = yp[hop*n + c], written as operand planes (C = hop channels,
+// T = rows): the STFT is then a stride-1 conv over n (audiolcm_b200/melspec.py).
+template <int E>
+__global__ void mel_fold_kernel(const float* __restrict__ y, int L, int hop, int padw, void* __restrict__ out, PlaneGeom og, int rows,
+                                int rtf32) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  if (n >= rows) return;
+  float v[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int c = chunk * E + e;
+    int i = hop * n + c - padw;
+    i = i < 0 ? -i : (i >= L ? 2 * (L - 1) - i : i);
+    v[e] = (c < hop) ? fminf(fmaxf(y[(size_t)b * L + i], -1.f), 1.f) : 0.f;
+  }
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out) + plane_row_off(og, b, chunk, n);
+  if (E == 4) {
+    if (rtf32) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) v[e] = round_tf32(v[e]);
+    }
+    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    uint4 o;
+    o.x = pack16x2(og.fmt, v[0], v[1]); o.y = pack16x2(og.fmt, v[2], v[3]);
+    o.z = pack16x2(og.fmt, v[4 % E], v[5 % E]); o.w = pack16x2(og.fmt, v[6 % E], v[7 % E]);
+    *reinterpret_cast<uint4*>(dst) = o;
+  }
+}
+
+// fp32 planes -> [B][C][T] channel-first, rows [t0, t0+T), as log10(max(x, floor)) (NAT_mel.py:83-84)
+__global__ void unpack_log10_kernel(const float* __restrict__ in, PlaneGeom ig, float* __restrict__ out, int C, int T, int t0, float floor_) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y, b = blockIdx.z;
+  if (t >= T) return;
+  const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(in) + plane_row_off(ig, b, chunk, t + t0));
+  const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = chunk * 4 + e;
+    if (c < C) out[((size_t)b * C + c) * T + t] = log10f(fmaxf(vv[e], floor_));
   }
 }
 

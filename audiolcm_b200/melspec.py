@@ -1,4 +1,4 @@
-"""log10-mel front-end with its two GEMMs on the sm_100a conv kernel (first half).
+"""log10-mel front-end on the sm_100a kernels (first half).
 
 Restates ``MelNet.forward`` (/root/reference/ldm/data/preprocess/NAT_mel.py:64-85) with the BigVGAN-16k analysis
 parameters (vocoder/bigvgan/bigvgan_audioset16khz_80band.json: n_fft = win = 1024, hop 256, 80 mels, 0-8000 Hz):
@@ -9,17 +9,20 @@ parameters (vocoder/bigvgan/bigvgan_audioset16khz_80band.json: n_fft = win = 102
 
 The STFT is a GEMM: with the padded waveform folded into hop-sized rows X[n] = y[256 n : 256 n + 256], frame n is
 sum_{i<4} X[n+i] . D[i] with D the windowed DFT basis cut into four 256-column blocks, i.e. a 4-tap stride-1 ``Conv1d`` with
-256 input and 2*513 output channels - exactly what ``conv_umma_kernel`` runs (as a 5-tap 'same' conv whose first tap is
-zero; frame n = output row n+1).  The mel projection is a 1x1 conv (513 -> 80).  Padding, |.| and log10 are
-elementwise PyTorch: like audiolcm_b200/denoiser.py this is a hybrid, written for the on-GPU log-mel parity metric
-and as the input stage of ``AutoencoderKLEncoder``.
+256 input and 2*520 output channels - exactly what ``conv_umma_kernel`` runs (as a 5-tap 'same' conv whose first tap is
+zero; frame n = output row n+1).  The mel projection is a 1x1 conv (513 -> 80).  One native plan per (B, L)
+(``alcm_melspec_*``): fold kernel, conv, magnitude kernel, conv, log10 + unpack kernel; the bases are built here in numpy
+and handed over as conv weights.  Used for the on-GPU log-mel parity metric and as the input stage of
+``AutoencoderKLEncoder``.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 import torch
 
-from .denoiser import Conv1dLayer
+from . import _lib
 
 
 def slaney_mel_basis(sr=16000, n_fft=1024, n_mels=80, fmin=0.0, fmax=8000.0):
@@ -50,22 +53,45 @@ class MelSpectrogramB200(object):
     """``MelNet(hparams)(y)`` for y (B, L) with L a multiple of hop -> (B, n_mels, L/hop) float32 CUDA tensor."""
 
     def __init__(self, device="cuda", precision="tf32", sr=16000, n_fft=1024, hop=256, win=1024, n_mels=80, fmin=0.0, fmax=8000.0):
-        if win != n_fft or n_fft % hop:
-            raise NotImplementedError("win_size == fft_size, a multiple of hop_size, is what the shipped configs use")
-        self.device, self.n_fft, self.hop, self.n_mels = torch.device(device), n_fft, hop, n_mels
+        if win != n_fft or n_fft % hop or (n_fft // hop) % 2:
+            raise NotImplementedError("win_size == fft_size, an even multiple of hop_size, is what the shipped configs use")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise _lib.AlcmError("audiolcm_b200 runs on a CUDA (sm_100a) device only; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.device, self.n_fft, self.hop, self.n_mels = dev, n_fft, hop, n_mels
         self.taps = n_fft // hop                                        # 4
         nb = n_fft // 2 + 1                                             # 513 bins
+        nbp = (nb + 7) // 8 * 8                                         # 520: the imaginary half starts on a 16-byte unit
         n = np.arange(n_fft, dtype=np.float64)
         window = 0.5 - 0.5 * np.cos(2.0 * np.pi * n / n_fft)            # torch.hann_window (periodic)
         ang = 2.0 * np.pi * np.outer(np.arange(nb), n) / n_fft
-        basis = np.concatenate([np.cos(ang), -np.sin(ang)], axis=0) * window[None, :]      # (2*513, 1024): re | im
-        # Conv1d weight (Cout = 1026, Cin = hop, K = taps + 1): tap 0 zero, tap j holds columns [(j-1)*hop, j*hop)
-        w = np.zeros((2 * nb, hop, self.taps + 1), np.float32)
+        basis = np.zeros((2 * nbp, n_fft))
+        basis[:nb], basis[nbp:nbp + nb] = np.cos(ang) * window[None, :], -np.sin(ang) * window[None, :]      # re | im
+        # Conv1d weight (Cout = 2*520, Cin = hop, K = taps + 1): tap 0 zero, tap j holds columns [(j-1)*hop, j*hop)
+        w = np.zeros((2 * nbp, hop, self.taps + 1), np.float32)
         for j in range(1, self.taps + 1):
             w[:, :, j] = basis[:, (j - 1) * hop:j * hop]
+        melw = np.zeros((n_mels, nbp, 1), np.float32)
+        melw[:, :nb, 0] = slaney_mel_basis(sr, n_fft, n_mels, fmin, fmax)
         self.nb = nb
-        self.stft = Conv1dLayer(w, None, 1, device, precision)
-        self.mel = Conv1dLayer(slaney_mel_basis(sr, n_fft, n_mels, fmin, fmax)[:, :, None].copy(), None, 1, device, precision)
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            wt, mt = torch.from_numpy(w).to(dev), torch.from_numpy(melw).to(dev)
+            torch.cuda.synchronize()
+            _lib.check(_lib.load().alcm_melspec_create(_lib.ctx(dev.index), wt.data_ptr(), mt.data_ptr(), hop, self.taps, nbp, n_mels,
+                                                       _lib.PREC[precision], C.byref(h)))
+        self._h = h.value
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.load().alcm_melspec_destroy(h)
+            except Exception:
+                pass
+            self._h = None
 
     @torch.no_grad()
     def __call__(self, y):
@@ -73,16 +99,11 @@ class MelSpectrogramB200(object):
             y = torch.from_numpy(y)
         if y.dim() == 1:
             y = y.unsqueeze(0)
-        y = y.to(self.device, torch.float32).clamp(-1.0, 1.0)
+        y = y.to(self.device, torch.float32).contiguous()
         B, L = y.shape
-        if L % self.hop:
-            raise ValueError(f"waveform length must be a multiple of hop_size {self.hop}")
-        pad = (self.n_fft - self.hop) // 2
-        yp = torch.nn.functional.pad(y.unsqueeze(1), [pad, pad], mode="reflect").squeeze(1)     # NAT_mel.py:71-73
-        rows = yp.shape[1] // self.hop                                    # frames + taps - 1
-        x = yp.view(B, rows, self.hop).transpose(1, 2).contiguous()      # (B, hop, rows): hop-sized rows as channels
-        # 'same' 5-tap conv with a zero first tap, rows shifted so that output row m+1 = sum_i X[m+i] D[i]
-        spec = self.stft(x)[..., 1:rows - self.taps + 2]                  # (B, 1026, frames)
-        mag = torch.sqrt(spec[:, :self.nb] ** 2 + spec[:, self.nb:] ** 2 + 1e-9)
-        mel = self.mel(mag.contiguous())
-        return torch.log10(torch.clamp(mel, min=1e-5))
+        if L % self.hop or L < self.n_fft:
+            raise ValueError(f"waveform length must be a multiple of hop_size {self.hop} and at least one window")
+        mel = torch.empty((B, self.n_mels, L // self.hop), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().alcm_melspec_run(self._h, y.data_ptr(), mel.data_ptr(), B, L, torch.cuda.current_stream().cuda_stream))
+        return mel

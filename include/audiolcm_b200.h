@@ -45,6 +45,7 @@ typedef struct alcm_vocoder alcm_vocoder;
 typedef struct alcm_vae alcm_vae;
 typedef struct alcm_conv1d alcm_conv1d;
 typedef struct alcm_ffn1d alcm_ffn1d;
+typedef struct alcm_melspec alcm_melspec;
 typedef struct alcm_vae_encoder alcm_vae_encoder;
 
 /* arithmetic used by the conv GEMMs */
@@ -207,6 +208,17 @@ int alcm_ffn1d_create(alcm_ctx* ctx, const float* w_in, const float* b_in, const
                       int dim_out, int K, int precision, alcm_ffn1d** out);
 void alcm_ffn1d_destroy(alcm_ffn1d* c);
 int alcm_ffn1d_run(alcm_ffn1d* c, const float* x, const float* res, float* y, int B, int T, void* stream);
+
+/* ---- log10-mel front-end, MelNet.forward (ldm/data/preprocess/NAT_mel.py:64-85), as one plan per (B,L):
+ * clamp to [-1,1] + reflect pad (n_fft-hop)/2 + fold into hop-sized rows (one kernel) -> |STFT| as a (taps+1)-tap Conv1d
+ * over the folded rows + magnitude kernel -> mel filterbank as a 1x1 Conv1d -> log10(max(., 1e-5)).  n_fft = taps*hop.
+ * stft_w [2*nb_pad, hop, taps+1]: the windowed DFT basis, real rows [0,nb) and imaginary rows [nb_pad, nb_pad+nb), tap 0
+ * zero, tap j = basis columns [(j-1)*hop, j*hop); mel_w [n_mels, nb_pad, 1]; nb_pad = n_fft/2+1 rounded up to 8.
+ * y [B,L] (L a multiple of hop), mel [B,n_mels,L/hop]: device fp32. */
+int alcm_melspec_create(alcm_ctx* ctx, const float* stft_w, const float* mel_w, int hop, int taps, int nb_pad, int n_mels, int precision,
+                        alcm_melspec** out);
+void alcm_melspec_destroy(alcm_melspec* c);
+int alcm_melspec_run(alcm_melspec* c, const float* y, float* mel, int B, int L, void* stream);
 
 /* ---- single-op entry points (tests / micro-benchmarks); tensors are [B,C,T] fp32 on device -----*/
 /* Activation1d(SnakeBeta logscale): act.py:23-28.  precision BF16 returns bf16-rounded values. */
