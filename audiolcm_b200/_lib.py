@@ -42,6 +42,7 @@ class VAECfg(C.Structure):
         ("n_levels", C.c_int),
         ("ch_mult", C.c_int * 8),
         ("upsample_levels", C.c_int * 8),
+        ("attn_levels", C.c_int * 8),
     ]
 
 
@@ -57,6 +58,7 @@ class VAEEncCfg(C.Structure):
         ("double_z", C.c_int),
         ("ch_mult", C.c_int * 8),
         ("downsample_levels", C.c_int * 8),
+        ("attn_levels", C.c_int * 8),
     ]
 
 

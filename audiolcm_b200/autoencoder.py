@@ -34,11 +34,15 @@ def vae_tensor_names(dd, prefix=""):
         names += wb(f"decoder.mid.attn_1.{n}")
     names += res("decoder.mid.block_2", block_in, block_in)
     down_layers = [i + 1 for i in dd["down_layers"]]  # autoencoder1d.py:427
+    attn_layers = [int(a) for a in dd["attn_layers"]]
     for lv in reversed(range(nl)):
         block_out = ch * mult[lv]
         for ib in range(nrb + 1):
             names += res(f"decoder.up.{lv}.block.{ib}", block_in, block_out)
             block_in = block_out
+            if lv in attn_layers:                       # autoencoder1d.py:466-468
+                for n in ("norm", "q", "k", "v", "proj_out"):
+                    names += wb(f"decoder.up.{lv}.attn.{ib}.{n}")
         if lv in down_layers:
             names += wb(f"decoder.up.{lv}.upsample.conv")
     return names + wb("decoder.norm_out") + wb("decoder.conv_out")
@@ -55,8 +59,7 @@ class AutoencoderKLDecoder(object):
         dd["ch_mult"] = [int(m) for m in dd["ch_mult"]]
         dd["down_layers"] = [int(i) for i in dd["down_layers"]]
         nl = len(dd["ch_mult"])
-        if any(int(a) in range(nl) for a in dd["attn_layers"]):
-            raise NotImplementedError("attention inside up levels is not on the shipped config's path (attn_layers: [3])")
+        dd["attn_layers"] = [int(a) for a in dd["attn_layers"]]
         for k in ("give_pre_end", "tanh_out"):
             try:
                 if _get(ddconfig, k):
@@ -80,6 +83,7 @@ class AutoencoderKLDecoder(object):
         for i, m in enumerate(dd["ch_mult"]):
             cfg.ch_mult[i] = m
             cfg.upsample_levels[i] = 1 if i in down_layers else 0
+            cfg.attn_levels[i] = 1 if i in dd["attn_layers"] else 0
         names = vae_tensor_names(dd, prefix)
         missing = [n for n in names if n not in state_dict]
         if missing:
@@ -160,6 +164,9 @@ def vae_encoder_tensor_names(dd, prefix=""):
         for ib in range(nrb):
             names += res(f"encoder.down.{lv}.block.{ib}", block_in, block_out)
             block_in = block_out
+            if lv in [int(a) for a in dd["attn_layers"]]:   # autoencoder1d.py:356-358
+                for n in ("norm", "q", "k", "v", "proj_out"):
+                    names += wb(f"encoder.down.{lv}.attn.{ib}.{n}")
         if lv in [int(i) for i in dd["down_layers"]]:
             names += wb(f"encoder.down.{lv}.downsample.conv")
     names += res("encoder.mid.block_1", block_in, block_in)
@@ -183,8 +190,7 @@ class AutoencoderKLEncoder(object):
         dd["ch_mult"] = [int(m) for m in dd["ch_mult"]]
         dd["down_layers"] = [int(i) for i in dd["down_layers"]]
         nl = len(dd["ch_mult"])
-        if any(int(a) in range(nl) for a in dd["attn_layers"]):
-            raise NotImplementedError("attention inside down levels is not on the shipped config's path (attn_layers: [3])")
+        dd["attn_layers"] = [int(a) for a in dd["attn_layers"]]
         try:
             double_z = bool(_get(ddconfig, "double_z"))
         except (AttributeError, KeyError):
@@ -203,6 +209,7 @@ class AutoencoderKLEncoder(object):
         for i, m in enumerate(dd["ch_mult"]):
             cfg.ch_mult[i] = m
             cfg.downsample_levels[i] = 1 if i in dd["down_layers"] else 0
+            cfg.attn_levels[i] = 1 if i in dd["attn_layers"] else 0
         names = vae_encoder_tensor_names(dd, prefix)
         missing = [n for n in names if n not in state_dict]
         if missing:

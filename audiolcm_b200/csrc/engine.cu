@@ -1237,7 +1237,7 @@ struct ResBlock {
   int Cin, Cout;
 };
 struct AttnBlk { GnP norm; ConvLayer qkv, proj; int C; };  // q, k, v 1x1 convs run as one launch (Cout = 3C)
-struct VaeLevel { std::vector<ResBlock> blocks; bool has_up = false; ConvLayer up; int C; };
+struct VaeLevel { std::vector<ResBlock> blocks; std::vector<AttnBlk> attn; bool has_up = false; ConvLayer up; int C; };   // attn: one per block, or none
 
 struct VaePlan : PlanBase {
   PlaneT z_in, mel_out;
@@ -1439,7 +1439,10 @@ static void vae_build(const alcm_vae* v, VaePlan& P) {
   h = op_attn(P.ol, P.ar, v->attn, h, prec);
   h = op_resblock(P.ol, P.ar, v->mid2, h, prec);
   for (const VaeLevel& lv : v->levels) {
-    for (const ResBlock& rb : lv.blocks) h = op_resblock(P.ol, P.ar, rb, h, prec);
+    for (size_t i = 0; i < lv.blocks.size(); ++i) {   // autoencoder1d.py:500-504
+      h = op_resblock(P.ol, P.ar, lv.blocks[i], h, prec);
+      if (!lv.attn.empty()) h = op_attn(P.ol, P.ar, lv.attn[i], h, prec);
+    }
     if (lv.has_up) {
       PlaneT up = make_planes(P.ar, B, lv.C, h.T * 2, 4);
       P.ol.conv(lv.up, as_operand(P.ol, P.ar, h, prec), up, nullptr);
@@ -1476,7 +1479,7 @@ static void vae_run(alcm_vae* v, VaePlan* P, const float* z, float inv_scale, cu
 // AutoencoderKL.encode up to the posterior's parameters (autoencoder1d.py:52-56): Encoder1D.forward (:391-413) + quant_conv.
 // Same kernel families as the decoder; the only new op is Downsample1D (:296-316), run as a 2-tap conv on the
 // time-folded input (s2d_cast_kernel).  The encoder's ResnetBlocks DO get kernel_size (k = 5), unlike the decoder's.
-struct EncLevel { std::vector<ResBlock> blocks; bool has_down = false; ConvLayer down; int C; };
+struct EncLevel { std::vector<ResBlock> blocks; std::vector<AttnBlk> attn; bool has_down = false; ConvLayer down; int C; };
 struct EncPlan : PlanBase {
   PlaneT x_in, mom_out;
 };
@@ -1506,7 +1509,10 @@ static void enc_build(const alcm_vae_encoder* v, EncPlan& P) {
   PlaneT h = make_planes(P.ar, B, v->conv_in.Cout, T, 4);
   P.ol.conv(v->conv_in, P.x_in, h, nullptr);
   for (const EncLevel& lv : v->levels) {
-    for (const ResBlock& rb : lv.blocks) h = op_resblock(P.ol, P.ar, rb, h, prec);
+    for (size_t i = 0; i < lv.blocks.size(); ++i) {   // autoencoder1d.py:391-396
+      h = op_resblock(P.ol, P.ar, lv.blocks[i], h, prec);
+      if (!lv.attn.empty()) h = op_attn(P.ol, P.ar, lv.attn[i], h, prec);
+    }
     if (lv.has_down) {
       REQUIRE(h.T % 2 == 0, "vae_encode: the sequence length must be even at every Downsample1D");
       const int To = h.T / 2, C = lv.C;
@@ -1727,6 +1733,29 @@ static GnP make_gn(Arena& ar, const float* w, const float* b, int C) {
 
 static int vae_resblock_tensors(int cin, int cout) { return 8 + (cin != cout ? 2 : 0); }
 
+// AttnBlock1D parameters (autoencoder1d.py:241-254) from 10 tensors: norm (w,b), q, k, v, proj_out (w,b each).  The three
+// [C,C,1] projections are concatenated into ONE conv with Cout = 3C.
+static AttnBlk load_attn(Arena& war, const Knobs& K, int precision, const float* const* t, int& ti, int C) {
+  AttnBlk a;
+  a.C = C;
+  a.norm = make_gn(war, t[ti], t[ti + 1], C);
+  ti += 2;
+  const size_t wn = (size_t)C * C, bn = (size_t)C;
+  Arena tmpq;
+  float* wcat = static_cast<float*>(tmpq.alloc(3 * wn * 4, false));
+  float* bcat = static_cast<float*>(tmpq.alloc(3 * bn * 4, false));
+  for (int i = 0; i < 3; ++i) {
+    CUDA_CHECK(cudaMemcpy(wcat + i * wn, t[ti + 2 * i], wn * 4, cudaMemcpyDeviceToDevice));
+    CUDA_CHECK(cudaMemcpy(bcat + i * bn, t[ti + 2 * i + 1], bn * 4, cudaMemcpyDeviceToDevice));
+  }
+  a.qkv = prepare_conv(war, K, precision, KIND_CONV, wcat, bcat, 3 * C, C, 1, 1);
+  ti += 6;
+  a.proj = prepare_conv(war, K, precision, KIND_CONV, t[ti], t[ti + 1], C, C, 1, 1);
+  ti += 2;
+  CUDA_CHECK(sync_setup());   // tmpq is freed on return
+  return a;
+}
+
 int alcm_vae_num_tensors(const alcm_vae_cfg* c) {
   if (!c) return -1;
   int n = 2 + 2;
@@ -1735,7 +1764,7 @@ int alcm_vae_num_tensors(const alcm_vae_cfg* c) {
   for (int lv = c->n_levels - 1; lv >= 0; --lv) {
     const int block_out = c->ch * c->ch_mult[lv];
     for (int i = 0; i <= c->num_res_blocks; ++i) {
-      n += vae_resblock_tensors(block_in, block_out);
+      n += vae_resblock_tensors(block_in, block_out) + (c->attn_levels[lv] ? 10 : 0);
       block_in = block_out;
     }
     if (c->upsample_levels[lv]) n += 2;
@@ -1782,21 +1811,7 @@ int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* 
     int block_in = cfg->ch * cfg->ch_mult[cfg->n_levels - 1];
     v->conv_in = conv(block_in, cfg->z_channels, cfg->kernel_size);
     v->mid1 = resblock(block_in, block_in);
-    v->attn.C = block_in;
-    v->attn.norm = gn(block_in);
-    {  // q, k, v (autoencoder1d.py:246-248): concatenate the three [C,C,1] weights -> one conv with Cout = 3C
-      const size_t wn = (size_t)block_in * block_in, bn = (size_t)block_in;
-      Arena tmpq;
-      float* wcat = static_cast<float*>(tmpq.alloc(3 * wn * 4, false));
-      float* bcat = static_cast<float*>(tmpq.alloc(3 * bn * 4, false));
-      for (int i = 0; i < 3; ++i) {
-        CUDA_CHECK(cudaMemcpy(wcat + i * wn, t[ti + 2 * i], wn * 4, cudaMemcpyDeviceToDevice));
-        CUDA_CHECK(cudaMemcpy(bcat + i * bn, t[ti + 2 * i + 1], bn * 4, cudaMemcpyDeviceToDevice));
-      }
-      v->attn.qkv = prepare_conv(v->war, K, precision, KIND_CONV, wcat, bcat, 3 * block_in, block_in, 1, 1);
-      ti += 6;
-    }
-    v->attn.proj = conv(block_in, block_in, 1);
+    v->attn = load_attn(v->war, K, precision, t, ti, block_in);
     v->mid2 = resblock(block_in, block_in);
     v->up_factor = 1;
     for (int lv = cfg->n_levels - 1; lv >= 0; --lv) {
@@ -1805,6 +1820,7 @@ int alcm_vae_create(alcm_ctx* ctx, const alcm_vae_cfg* cfg, const float* const* 
       for (int i = 0; i <= cfg->num_res_blocks; ++i) {
         L.blocks.push_back(resblock(block_in, block_out));
         block_in = block_out;
+        if (cfg->attn_levels[lv]) L.attn.push_back(load_attn(v->war, K, precision, t, ti, block_in));   // autoencoder1d.py:466-468
       }
       L.C = block_in;
       L.has_up = cfg->upsample_levels[lv] != 0;
@@ -1870,7 +1886,7 @@ int alcm_vae_encoder_num_tensors(const alcm_vae_enc_cfg* c) {
   int n = 2, block_in = c->ch;
   for (int lv = 0; lv < c->n_levels; ++lv) {
     const int block_out = c->ch * c->ch_mult[lv];
-    for (int i = 0; i < c->num_res_blocks; ++i) { n += enc_resblock_tensors(block_in, block_out); block_in = block_out; }
+    for (int i = 0; i < c->num_res_blocks; ++i) { n += enc_resblock_tensors(block_in, block_out) + (c->attn_levels[lv] ? 10 : 0); block_in = block_out; }
     if (c->downsample_levels[lv]) n += 2;
   }
   return n + 2 * enc_resblock_tensors(block_in, block_in) + 10 + 2 + 2 + 2;
@@ -1918,7 +1934,11 @@ int alcm_vae_encoder_create(alcm_ctx* ctx, const alcm_vae_enc_cfg* cfg, const fl
     for (int lv = 0; lv < cfg->n_levels; ++lv) {
       EncLevel L;
       const int block_out = cfg->ch * cfg->ch_mult[lv];
-      for (int i = 0; i < cfg->num_res_blocks; ++i) { L.blocks.push_back(resblock(block_in, block_out)); block_in = block_out; }
+      for (int i = 0; i < cfg->num_res_blocks; ++i) {
+        L.blocks.push_back(resblock(block_in, block_out));
+        block_in = block_out;
+        if (cfg->attn_levels[lv]) L.attn.push_back(load_attn(v->war, K, precision, t, ti, block_in));   // autoencoder1d.py:356-358
+      }
       L.C = block_in;
       L.has_down = cfg->downsample_levels[lv] != 0;
       if (L.has_down) {
@@ -1929,21 +1949,7 @@ int alcm_vae_encoder_create(alcm_ctx* ctx, const alcm_vae_enc_cfg* cfg, const fl
       v->levels.push_back(std::move(L));
     }
     v->mid1 = resblock(block_in, block_in);
-    v->attn.C = block_in;
-    v->attn.norm = gn(block_in);
-    {
-      const size_t wn = (size_t)block_in * block_in, bn = (size_t)block_in;
-      Arena tmpq;
-      float* wcat = static_cast<float*>(tmpq.alloc(3 * wn * 4, false));
-      float* bcat = static_cast<float*>(tmpq.alloc(3 * bn * 4, false));
-      for (int i = 0; i < 3; ++i) {
-        CUDA_CHECK(cudaMemcpy(wcat + i * wn, t[ti + 2 * i], wn * 4, cudaMemcpyDeviceToDevice));
-        CUDA_CHECK(cudaMemcpy(bcat + i * bn, t[ti + 2 * i + 1], bn * 4, cudaMemcpyDeviceToDevice));
-      }
-      v->attn.qkv = prepare_conv(v->war, K, precision, KIND_CONV, wcat, bcat, 3 * block_in, block_in, 1, 1);
-      ti += 6;
-    }
-    v->attn.proj = conv(block_in, block_in, 1);
+    v->attn = load_attn(v->war, K, precision, t, ti, block_in);
     v->mid2 = resblock(block_in, block_in);
     v->norm_out = gn(block_in);
     const int zc2 = (cfg->double_z ? 2 : 1) * cfg->z_channels;

@@ -151,6 +151,12 @@ def _resblock(rng, sd, p, cin, cout):
         _conv(rng, sd, p + ".nin_shortcut", cout, cin, 1)
 
 
+def _attn(rng, sd, p, c):
+    _gn(rng, sd, p + ".norm", c)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(rng, sd, f"{p}.{n}", c, c, 1)
+
+
 def vae_decoder_state_dict(dd, embed_dim: int = VAE_EMBED_DIM, seed: int = 0) -> dict:
     """Synthetic state_dict for ``post_quant_conv`` + ``decoder`` (numpy fp32)."""
     rng = np.random.default_rng(seed + 1000)
@@ -173,6 +179,8 @@ def vae_decoder_state_dict(dd, embed_dim: int = VAE_EMBED_DIM, seed: int = 0) ->
         for i_block in range(nrb + 1):
             _resblock(rng, sd, f"decoder.up.{i_level}.block.{i_block}", block_in, block_out)
             block_in = block_out
+            if i_level in dd["attn_layers"]:
+                _attn(rng, sd, f"decoder.up.{i_level}.attn.{i_block}", block_in)
         if i_level in down_layers:
             _conv(rng, sd, f"decoder.up.{i_level}.upsample.conv", block_in, block_in, 3)
     _gn(rng, sd, "decoder.norm_out", block_in)
@@ -202,6 +210,8 @@ def vae_encoder_state_dict(dd, embed_dim: int = VAE_EMBED_DIM, seed: int = 0) ->
         for i_block in range(nrb):
             _resblock_k(rng, sd, f"encoder.down.{i_level}.block.{i_block}", block_in, block_out, ks)
             block_in = block_out
+            if i_level in dd["attn_layers"]:
+                _attn(rng, sd, f"encoder.down.{i_level}.attn.{i_block}", block_in)
         if i_level in dd["down_layers"]:
             _conv(rng, sd, f"encoder.down.{i_level}.downsample.conv", block_in, block_in, 3)
     _resblock_k(rng, sd, "encoder.mid.block_1", block_in, block_in, ks)

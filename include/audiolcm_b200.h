@@ -132,6 +132,8 @@ typedef struct {
   int n_levels;
   int ch_mult[8];
   int upsample_levels[8];
+  int attn_levels[8];     /* attn_levels[l] = 1 when level l is in attn_layers: an AttnBlock1D (norm, q, k, v, proj_out) follows
+                             every ResnetBlock1D of that level (autoencoder1d.py:466-468,500-504); zero-filled = shipped config */
 } alcm_vae_cfg;
 
 int alcm_vae_num_tensors(const alcm_vae_cfg* cfg);
@@ -160,6 +162,7 @@ typedef struct {
   int double_z;
   int ch_mult[8];
   int downsample_levels[8];
+  int attn_levels[8];     /* same meaning as in the decoder configuration above: autoencoder1d.py:356-358,391-396 */
 } alcm_vae_enc_cfg;
 int alcm_vae_encoder_num_tensors(const alcm_vae_enc_cfg* cfg);
 int alcm_vae_encoder_create(alcm_ctx* ctx, const alcm_vae_enc_cfg* cfg, const float* const* tensors, int n_tensors, int precision,

@@ -216,9 +216,8 @@ def vae_decode(sd, dd, z, dtype=torch.float32):
     for i_level in reversed(range(nl)):
         for i_block in range(nrb + 1):
             x = resnet_block(sd, f"decoder.up.{i_level}.block.{i_block}", x, dtype)
-            # attn_layers never matches a level index for the shipped config
-            if i_level in dd["attn_layers"]:
-                raise NotImplementedError("up-level attention is not on the shipped config's path")
+            if i_level in dd["attn_layers"]:   # autoencoder1d.py:500-504 (never a level index in the shipped config)
+                x = attn_block(sd, f"decoder.up.{i_level}.attn.{i_block}", x, dtype)
         if i_level in down_layers:
             x = F.interpolate(x, scale_factor=2.0, mode="nearest")  # autoencoder1d.py:291-295
             x = _conv(sd, f"decoder.up.{i_level}.upsample.conv", x, dtype, 1)
@@ -244,8 +243,8 @@ def vae_encode_moments(sd, dd, x, dtype=torch.float32):
         for i_level in range(nl):
             for i_block in range(nrb):
                 h = res(f"encoder.down.{i_level}.block.{i_block}", h)
-                if i_level in dd["attn_layers"]:
-                    raise NotImplementedError("down-level attention is not on the shipped config's path")
+                if i_level in dd["attn_layers"]:   # autoencoder1d.py:391-396
+                    h = attn_block(sd, f"encoder.down.{i_level}.attn.{i_block}", h, dtype)
             if i_level in dd["down_layers"]:
                 p = f"encoder.down.{i_level}.downsample.conv"
                 h = F.conv1d(F.pad(h, (0, 1)), _t(sd[p + ".weight"], dtype), _t(sd[p + ".bias"], dtype), stride=2)

@@ -100,6 +100,19 @@ VARIANTS = {   # the other generator choices BigVGAN.__init__ accepts (models.py
 }
 
 
+def level_attention_goldens():
+    """Decoder1D / Encoder1D with an AttnBlock1D after every ResnetBlock1D of a level (attn_layers holding a level index:
+    autoencoder1d.py:356-358,466-468), narrow (ch = 32) - a choice the constructors accept and the shipped config does not use."""
+    dd = synth.vae_config(32, attn_layers=[1])
+    vae = ref_vae(dd, {**synth.vae_decoder_state_dict(dd, seed=21), **synth.vae_encoder_state_dict(dd, seed=21)}, strict=True)
+    z = synth.synth_latent(2, 24, seed=22)
+    mel = vae.decode(torch.from_numpy(z)).numpy()
+    x = synth.synth_mel(2, 48, seed=23)
+    mom = vae.encode(torch.from_numpy(x)).parameters.numpy()
+    np.savez(os.path.join(OUT, "vae_ch32_level_attn.npz"), ch=32, wseed=21, zseed=22, xseed=23, mel=mel, moments=mom)
+    print("vae level attention", mel.shape, float(np.abs(mel).max()), mom.shape, float(np.abs(mom).max()))
+
+
 def variant_goldens():
     """BigVGAN(h) of the unmodified reference for AMPBlock2 / Snake / linear-scale parameters, narrow (c0 = 64)."""
     for tag, over in VARIANTS.items():
@@ -123,6 +136,7 @@ def main():
     if "--variants-only" in sys.argv:
         with torch.no_grad():
             variant_goldens()
+            level_attention_goldens()
         return
     torch.set_grad_enabled(False)
     _, _, Activation1d, SnakeBeta = import_reference()
@@ -194,6 +208,7 @@ def main():
 
     encoder_goldens()
     variant_goldens()
+    level_attention_goldens()
 
     # ---- full path latent -> mel -> wav (config 2), short clip to keep the fixture small -----
     dd = synth.vae_config()

@@ -583,6 +583,24 @@ def test_mel_front_end_vs_nat_mel_restatement(precision):
     np.testing.assert_allclose(got[1], log_mel(wav[::-1].copy()), atol=max_tol)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "bf16", "fp16"])
+def test_vae_level_attention_vs_reference(golden_dir, precision):
+    """Decoder1D / Encoder1D with attn_layers = [1]: an AttnBlock1D after every ResnetBlock1D of level 1 (autoencoder1d.py:
+    356-358,466-468), against outputs of the unmodified reference AutoencoderKL (oracle/make_golden.py)."""
+    from audiolcm_b200 import AutoencoderKLDecoder, AutoencoderKLEncoder
+    g = np.load(os.path.join(golden_dir, "vae_ch32_level_attn.npz"))
+    dd = synth.vae_config(int(g["ch"]), attn_layers=[1])
+    sd = {**synth.vae_decoder_state_dict(dd, seed=int(g["wseed"])), **synth.vae_encoder_state_dict(dd, seed=int(g["wseed"]))}
+    mel = AutoencoderKLDecoder(sd, dd, synth.VAE_EMBED_DIM, DEV, precision).decode(
+        torch.from_numpy(synth.synth_latent(2, 24, seed=int(g["zseed"]))).to(DEV)).cpu().numpy()
+    mean, logvar = AutoencoderKLEncoder(sd, dd, synth.VAE_EMBED_DIM, DEV, precision).encode(
+        torch.from_numpy(synth.synth_mel(2, 48, seed=int(g["xseed"]))).to(DEV))
+    mom = torch.cat([mean, logvar], dim=1).cpu().numpy()
+    e1, e2 = np.abs(mel - g["mel"]).max(), np.abs(mom - g["moments"]).max()
+    print(f"\n[vae level attention {precision}] mel max-abs {e1:.3e} (abs-max {np.abs(g['mel']).max():.2f}), moments {e2:.3e}")
+    assert e1 <= MEL_TOL[precision] and e2 <= MEL_TOL[precision]
+
+
 @pytest.mark.parametrize("precision", ["tf32", "bf16", "fp16"])
 def test_vae_long_sequence_paths(precision):
     """Long-form VAE decode (the replicated half of BASELINE.json configs[3]): at T_lat = 1100 the GroupNorm groups no

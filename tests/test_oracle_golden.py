@@ -139,3 +139,18 @@ def test_oracle_vae_encode_matches_reference(golden_dir, tag):
     mom = O.vae_encode_moments(sd, dd, x).numpy()
     assert mom.shape == g["moments"].shape
     assert np.abs(mom - g["moments"]).max() <= 2e-6
+
+
+def test_vae_level_attention_matches_reference(golden_dir):
+    """attn_layers holding a level index: an AttnBlock1D after every ResnetBlock1D of that level, in Decoder1D and Encoder1D
+    (autoencoder1d.py:356-358,391-396,466-468,500-504) - accepted by the constructors, unused by the shipped config."""
+    g = _load(golden_dir, "vae_ch32_level_attn.npz")
+    dd = synth.vae_config(int(g["ch"]), attn_layers=[1])
+    sd = {**synth.vae_decoder_state_dict(dd, seed=int(g["wseed"])), **synth.vae_encoder_state_dict(dd, seed=int(g["wseed"]))}
+    sd = {k: torch.from_numpy(v) for k, v in sd.items()}
+    with torch.no_grad():
+        mel = O.vae_decode(sd, dd, torch.from_numpy(synth.synth_latent(2, 24, seed=int(g["zseed"])))).numpy()
+        mom = O.vae_encode_moments(sd, dd, torch.from_numpy(synth.synth_mel(2, 48, seed=int(g["xseed"])))).numpy()
+    np.testing.assert_allclose(mel, g["mel"], atol=2e-5)
+    np.testing.assert_allclose(mom, g["moments"], atol=2e-5)
+
