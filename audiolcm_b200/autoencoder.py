@@ -34,7 +34,7 @@ def vae_tensor_names(dd, prefix=""):
         names += wb(f"decoder.mid.attn_1.{n}")
     names += res("decoder.mid.block_2", block_in, block_in)
     down_layers = [i + 1 for i in dd["down_layers"]]  # autoencoder1d.py:427
-    attn_layers = [int(a) for a in dd["attn_layers"]]
+    attn_layers = [int(a) for a in dd.get("attn_layers", [])]   # constructor default: no level attention
     for lv in reversed(range(nl)):
         block_out = ch * mult[lv]
         for ib in range(nrb + 1):
@@ -164,7 +164,7 @@ def vae_encoder_tensor_names(dd, prefix=""):
         for ib in range(nrb):
             names += res(f"encoder.down.{lv}.block.{ib}", block_in, block_out)
             block_in = block_out
-            if lv in [int(a) for a in dd["attn_layers"]]:   # autoencoder1d.py:356-358
+            if lv in [int(a) for a in dd.get("attn_layers", [])]:   # autoencoder1d.py:356-358
                 for n in ("norm", "q", "k", "v", "proj_out"):
                     names += wb(f"encoder.down.{lv}.attn.{ib}.{n}")
         if lv in [int(i) for i in dd["down_layers"]]:
