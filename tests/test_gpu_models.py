@@ -162,6 +162,23 @@ def test_batch_and_time_shard_properties(precision):
         assert snr_db(full.cpu().numpy(), stitched.cpu().numpy()) >= SNR_MIN["bf16"]
 
 
+def test_micro_batched_decode_matches_one_plan():
+    """LatentToWaveform(micro_batch=n): consecutive slices through one smaller plan (a ragged last slice included) reproduce
+    the single-plan decode to the mode's tolerance; the int16 path too."""
+    from audiolcm_b200 import AutoencoderKLDecoder, LatentToWaveform, VocoderBigVGAN
+    dd, h = synth.vae_config(32), synth.bigvgan_config(64)
+    vae = AutoencoderKLDecoder(synth.vae_decoder_state_dict(dd, seed=1), dd, synth.VAE_EMBED_DIM, DEV, "tf32")
+    voc = VocoderBigVGAN.from_state_dict(synth.bigvgan_state_dict(h, seed=1), h, DEV, "tf32")
+    z = torch.from_numpy(synth.synth_latent(7, 16, seed=9)).to(DEV)
+    full, (w3, m3) = LatentToWaveform(vae, voc).decode_tensor(z), LatentToWaveform(vae, voc, micro_batch=3).decode_tensor(z, return_mel=True)
+    assert w3.shape == full.shape and m3.shape == (7, 80, 32)
+    assert float((w3 - full).abs().max()) < WAV_TOL["tf32"]
+    p3 = LatentToWaveform(vae, voc, micro_batch=3).decode_pcm16_tensor(z)
+    assert int((p3.int() - torch.round(full * 32767.0).int()).abs().max()) <= 40      # 1e-3 of full scale
+    with pytest.raises(ValueError):
+        LatentToWaveform(vae, voc, micro_batch=0)
+
+
 # ----------------------------------------------------------------------------------- the plans the benchmark runs
 @pytest.mark.parametrize("precision", ["tf32", "bf16", "fp16"])
 def test_batch64_full_size_decode_vs_oracle(precision):

@@ -56,6 +56,21 @@ def test_activation1d_vs_oracle(ops, shape, precision):
         assert torch.equal(round_operand(y, precision), y)
 
 
+def test_fp16_operands_saturate_instead_of_overflowing(ops):
+    """precision="fp16": a value beyond the fp16 range becomes +-65504 (cvt.rn.satfinite), never inf - an out-of-range
+    activation degrades the result, it cannot poison a whole accumulation with inf - inf = NaN."""
+    x = torch.full((1, 8, 64), 3.0e5)
+    x[:, 4:] = -3.0e5
+    z = torch.zeros(8)
+    y = ops.activation1d(x.to(DEV), z.to(DEV), z.to(DEV), "fp16").cpu()
+    assert torch.isfinite(y).all()
+    assert torch.equal(y[:, :4], torch.full((1, 4, 64), 65504.0)) and torch.equal(y[:, 4:], torch.full((1, 4, 64), -65504.0))
+    w = torch.zeros(8, 8, 1)
+    w[torch.arange(8), torch.arange(8), 0] = 1.0
+    c = ops.conv1d(x.to(DEV), w.to(DEV), None, None, 1, "fp16").cpu()      # identity conv: operands saturate, fp32 accumulate
+    assert torch.equal(c, y)
+
+
 # ----------------------------------------------------------------------------------- Conv1d
 CONV_CASES = [
     # B, Cin, Cout, T, K, d
